@@ -1,0 +1,563 @@
+"""CPU oracle: torch-fp64 restatement of the reference's local-energy hot path.
+
+THIS IS TEST INFRASTRUCTURE.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The
+product (``deepsolid_b200``) never does.
+
+PARITY UNPINNED: the reference (bytedance/DeepSolid @ 812a2b8) is pure JAX + pyscf
+and neither is installable in this image, and its own tests hold no golden numbers
+(test/test_network.py asserts three invariants only).  The oracle is therefore a
+line-by-line restatement, pinned by (i) those three invariants, (ii) finite
+differences of its own log psi, (iii) Madelung constants for the Ewald setup and
+(iv) an independent forward-Laplacian derivation (oracle/forward_laplacian.py).
+
+Every function cites the reference lines (relative to /root/reference/DeepSolid/)
+it follows.  The Laplacian is obtained with the *reference's algorithm*
+(forward-over-reverse: ``jvp`` of ``grad``, hamiltonian.py:45-70 and :127-159),
+via ``torch.func`` -- deliberately not the forward-Laplacian recursion the CUDA
+kernels use.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch.func import grad, jvp, vmap
+
+DT = torch.float64
+CT = torch.complex128
+
+
+def _t(x, dtype=DT):
+    if isinstance(x, torch.Tensor):
+        return x.to(dtype)
+    return torch.as_tensor(np.asarray(x), dtype=dtype)
+
+
+# ---------------------------------------------------------------------------
+# network.py
+# ---------------------------------------------------------------------------
+
+def enforce_pbc(latvec: torch.Tensor, epos: torch.Tensor):
+    """network.py:42-57."""
+    recpvecs = torch.linalg.inv(latvec)
+    frac = epos @ recpvecs
+    wrap = torch.floor(frac)                # `// 1`; zero derivative like JAX
+    return (frac - wrap) @ latvec, wrap
+
+
+def scaled_f(w):
+    """network.py:189-195."""
+    return torch.abs(w) * (1 - torch.abs(w / math.pi) ** 3 / 4.0)
+
+
+def scaled_g(w):
+    """network.py:198-204."""
+    return w * (1 - 3.0 / 2.0 * torch.abs(w / math.pi) + 1.0 / 2.0 * torch.abs(w / math.pi) ** 2)
+
+
+def nu_distance(xea, a, b):
+    """network.py:207-224."""
+    w = torch.einsum("...ijk,lk->...ijl", xea, b)
+    mod = torch.floor((w + math.pi) / (2 * math.pi))
+    w = w - mod * 2 * math.pi
+    r1 = (torch.linalg.norm(a, dim=-1) * scaled_f(w)) ** 2
+    sg = scaled_g(w)
+    rel = torch.einsum("...i,ij->...j", sg, a)
+    r2 = torch.einsum("ij,kj->ik", a, a) * (sg[..., :, None] * sg[..., None, :])
+    n = r2.shape[-1]
+    off = torch.ones(n, n, dtype=r2.dtype) - torch.eye(n, dtype=r2.dtype)
+    result = torch.sum(r1, dim=-1) + torch.sum(r2 * off, dim=(-1, -2))
+    sd = result ** 0.5
+    return sd, rel
+
+
+def tri_distance(xea, a, b):
+    """network.py:227-246."""
+    w = torch.einsum("...ijk,lk->...ijl", xea, b)
+    sg, cg = torch.sin(w), torch.cos(w)
+    rel = torch.cat([torch.einsum("...i,ij->...j", sg, a),
+                     torch.einsum("...i,ij->...j", cg, a)], dim=-1)
+    metric = torch.einsum("ij,kj->ik", a, a)
+    vector = (1 - cg[..., :, None]) * (1 - cg[..., None, :]) + sg[..., :, None] * sg[..., None, :]
+    sd = torch.einsum("...ij,ij->...", vector, metric) ** 0.5
+    return sd, rel
+
+
+def construct_periodic_input_features(x, atoms, simulation_cell, distance_type="nu"):
+    """network.py:249-302."""
+    if distance_type == "nu":
+        distance_func = nu_distance
+    elif distance_type == "tri":
+        distance_func = tri_distance
+    else:
+        raise ValueError("Unrecognized distance function.")
+    prim = simulation_cell.original_cell
+    x = x.reshape(-1, 3)
+    n = x.shape[0]
+    prim_x, _ = enforce_pbc(_t(prim.a), x)
+    prim_xea = prim_x[..., None, :] - atoms
+    sea, xea = distance_func(prim_xea, _t(prim.AV), _t(prim.BV))
+    sea = sea[..., None]
+    sim_x, _ = enforce_pbc(_t(simulation_cell.a), x)
+    sim_xee = sim_x[:, None, :] - sim_x[None, :, :]
+    eye = torch.eye(n, dtype=x.dtype)
+    see, xee = distance_func(sim_xee + eye[..., None], _t(simulation_cell.AV), _t(simulation_cell.BV))
+    see = (see * (1.0 - eye))[..., None]
+    xee = xee * (1.0 - eye)[..., None]
+    return xea, xee, sea, see
+
+
+def construct_symmetric_features(h_one, h_two, spins):
+    """network.py:305-332."""
+    n0 = spins[0]
+    h_ones = [h_one[:n0], h_one[n0:]]
+    h_twos = [h_two[:n0], h_two[n0:]]
+    g_one = [h.mean(dim=0, keepdim=True) for h in h_ones if h.numel() > 0]
+    g_two = [h.mean(dim=0) for h in h_twos if h.numel() > 0]
+    g_one = [g.expand(h_one.shape[0], -1) for g in g_one]
+    return torch.cat([h_one] + g_one + g_two, dim=1)
+
+
+def isotropic_envelope(ae, params):
+    """network.py:335-337."""
+    return torch.sum(torch.exp(-torch.abs(ae * params["sigma"])) * params["pi"], dim=1)
+
+
+def diagonal_envelope(ae, params):
+    """network.py:340-343."""
+    r_ae = torch.linalg.norm(ae[..., None] * params["sigma"], dim=2)
+    return torch.sum(torch.exp(-r_ae) * params["pi"], dim=1)
+
+
+def full_envelope(ae, params):
+    """network.py:349-364 (apply_covariance == einsum 'ijk,kmjn->ijmn')."""
+    r_ae = torch.einsum("ijk,kmjn->ijmn", ae, params["sigma"])
+    r_ae = torch.linalg.norm(r_ae, dim=2)
+    return torch.sum(torch.exp(-r_ae) * params["pi"], dim=1)
+
+
+def slogdet_op(x):
+    """network.py:375-392."""
+    if x.shape[-1] == 1:
+        v = x[..., 0, 0]
+        return torch.exp(1j * torch.angle(v)), torch.log(torch.abs(v))
+    sign, logdet = torch.linalg.slogdet(x)
+    return sign, logdet
+
+
+def logdet_matmul(xs: Sequence[torch.Tensor]):
+    """network.py:395-427 with w=None."""
+    slogdets = [slogdet_op(x) for x in xs]
+    sign_in, slogdet = slogdets[0]
+    for s, l in slogdets[1:]:
+        sign_in, slogdet = sign_in * s, slogdet + l
+    # argmax gather: the max carries its own gradient, like slogdet[max_idx] in JAX
+    slogdet_max = slogdet[torch.argmax(slogdet.detach())]
+    det = sign_in * torch.exp(slogdet - slogdet_max)
+    result = torch.sum(det)
+    sign_out = torch.exp(1j * torch.angle(result))
+    slog_out = torch.log(torch.abs(result)) + slogdet_max
+    return sign_out, slog_out
+
+
+def linear_layer(x, w, b=None):
+    """network.py:430-443 (the KFAC tag is the identity on values)."""
+    y = x @ w
+    return y + b if b is not None else y
+
+
+def eval_phase(x, klist, spins, full_det=False):
+    """network.py:449-458."""
+    x = x.reshape(-1, 3)
+    xs = [x[:spins[0]], x[spins[0]:]]
+    if full_det:
+        kall = torch.cat([_t(k) for k in klist], dim=0)
+        kdot = [xx @ kall.T for xx, ne in zip(xs, spins) if ne > 0]
+    else:
+        kdot = [xx @ _t(k).T for xx, k, ne in zip(xs, klist, spins) if ne > 0]
+    return [torch.exp(1j * kd) for kd in kdot]
+
+
+def solid_fermi_net_orbitals(params, x, simulation_cell, klist, atoms, spins,
+                             envelope_type="isotropic", full_det=False, distance_type="nu"):
+    """network.py:461-560."""
+    ae_, ee_, r_ae, r_ee = construct_periodic_input_features(
+        x, atoms, simulation_cell, distance_type=distance_type)
+    ae = torch.cat((r_ae, ae_), dim=2)
+    ae = ae.reshape(ae.shape[0], -1)
+    ee = torch.cat((r_ee, ee_), dim=2)
+    to_env = r_ae if envelope_type == "isotropic" else ae_
+    envelope = {"isotropic": isotropic_envelope, "diagonal": diagonal_envelope,
+                "full": full_envelope}.get(envelope_type)
+    h_one, h_two = ae, ee
+    residual = lambda a, b: (a + b) / math.sqrt(2.0) if a.shape == b.shape else b
+    nd, ns = len(params["double"]), len(params["single"])
+    for i in range(nd):
+        h_one_in = construct_symmetric_features(h_one, h_two, spins)
+        h_one_next = torch.tanh(linear_layer(h_one_in, params["single"][i]["w"], params["single"][i]["b"]))
+        h_two_next = torch.tanh(linear_layer(h_two, params["double"][i]["w"], params["double"][i]["b"]))
+        h_one = residual(h_one, h_one_next)
+        h_two = residual(h_two, h_two_next)
+    if nd != ns:
+        h_one_in = construct_symmetric_features(h_one, h_two, spins)
+        h_one_next = torch.tanh(linear_layer(h_one_in, params["single"][-1]["w"], params["single"][-1]["b"]))
+        h_one = residual(h_one, h_one_next)
+        h_to_orbitals = h_one
+    else:
+        h_to_orbitals = construct_symmetric_features(h_one, h_two, spins)
+    hs = [h_to_orbitals[:spins[0]], h_to_orbitals[spins[0]:]]
+    active = [s for s in spins if s > 0]
+    hs = [h for h, s in zip(hs, spins) if s > 0]
+    orbitals = [linear_layer(h, p["w"], p.get("b")) for h, p in zip(hs, params["orbital"])]
+    for i in range(len(active)):
+        npar = params["orbital"][i]["w"].shape[-1] // 2
+        orbitals[i] = orbitals[i][..., :npar] + 1j * orbitals[i][..., npar:]
+    if envelope is not None:
+        splits, o = [], 0
+        for s in active:
+            splits.append(to_env[o:o + s])
+            o += s
+        orbitals = [envelope(te, p) * orb for te, orb, p in zip(splits, orbitals, params["envelope"])]
+    ntot = sum(spins)
+    orbitals = [orb.reshape(s, -1, ntot if full_det else s).permute(1, 0, 2)
+                for s, orb in zip(active, orbitals)]
+    phases = eval_phase(x, klist, spins, full_det=full_det)
+    orbitals = [orb * p[None, :, :] for orb, p in zip(orbitals, phases)]
+    if full_det:
+        orbitals = [torch.cat(orbitals, dim=1)]
+    return orbitals, to_env
+
+
+def eval_func(params, x, klist, simulation_cell, atoms, spins, envelope_type="isotropic",
+              full_det=False, distance_type="nu", method_name="eval_slogdet"):
+    """network.py:563-606."""
+    orbitals, _ = solid_fermi_net_orbitals(params, x, simulation_cell, klist, atoms, spins,
+                                           envelope_type, full_det, distance_type)
+    if method_name == "eval_slogdet":
+        return logdet_matmul(orbitals)[1]
+    if method_name == "eval_logdet":
+        sign, slog = logdet_matmul(orbitals)
+        return torch.log(sign) + slog
+    if method_name == "eval_phase_and_slogdet":
+        return logdet_matmul(orbitals)
+    if method_name == "eval_mats":
+        return orbitals
+    raise ValueError("Unrecognized method name")
+
+
+def init_params(rng: np.random.Generator, natom: int, spins, envelope_type="isotropic",
+                bias_orbitals=False, use_last_layer=False, full_det=False,
+                hidden_dims=((256, 32),) * 3, determinants=8, distance_type="nu") -> Dict:
+    """Shapes and distributions of network.py:60-186 (numpy RNG instead of jax.random)."""
+    if distance_type == "nu":
+        in_dims = (natom * 4, 4)
+    elif distance_type == "tri":
+        in_dims = (natom * 7, 7)
+    else:
+        raise ValueError("Unrecognized distance function.")
+    active = [s for s in spins if s > 0]
+    nch = len(active)
+    dims_one_in = ([(nch + 1) * in_dims[0] + nch * in_dims[1]] +
+                   [(nch + 1) * h[0] + nch * h[1] for h in hidden_dims])
+    if not use_last_layer:
+        dims_one_in[-1] = hidden_dims[-1][0]
+    dims_one_out = [h[0] for h in hidden_dims]
+    dims_two = [in_dims[1]] + [h[1] for h in hidden_dims]
+    len_double = len(hidden_dims) if use_last_layer else len(hidden_dims) - 1
+    P = {"single": [], "double": [], "orbital": [], "envelope": []}
+    for s in active:
+        npar = sum(spins) * determinants if full_det else s * determinants
+        env = {"pi": np.ones((natom, npar))}
+        if envelope_type == "isotropic":
+            env["sigma"] = np.ones((natom, npar))
+        elif envelope_type == "diagonal":
+            env["sigma"] = np.ones((natom, 3, npar))
+        elif envelope_type == "full":
+            env["sigma"] = np.tile(np.eye(3)[..., None, None], [1, 1, natom, npar])
+        P["envelope"].append(env)
+    for i in range(len(hidden_dims)):
+        P["single"].append({
+            "w": rng.standard_normal((dims_one_in[i], dims_one_out[i])) / np.sqrt(float(dims_one_in[i])),
+            "b": rng.standard_normal((dims_one_out[i],))})
+        if i < len_double:
+            P["double"].append({
+                "w": rng.standard_normal((dims_two[i], dims_two[i + 1])) / np.sqrt(float(dims_two[i])),
+                "b": rng.standard_normal((dims_two[i + 1],))})
+    for s in active:
+        npar = sum(spins) * determinants if full_det else s * determinants
+        orb = {"w": rng.standard_normal((dims_one_in[-1], 2 * npar)) / np.sqrt(float(dims_one_in[-1]))}
+        if bias_orbitals:
+            orb["b"] = rng.standard_normal((2 * npar,))
+        P["orbital"].append(orb)
+    return P
+
+
+def params_to_torch(params) -> Dict:
+    def conv(v):
+        if isinstance(v, dict):
+            return {k: conv(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return [conv(x) for x in v]
+        return _t(v)
+    return conv(params)
+
+
+def make_solid_fermi_net(klist, simulation_cell, envelope_type="isotropic", bias_orbitals=False,
+                         use_last_layer=False, full_det=False, hidden_dims=((256, 32),) * 3,
+                         determinants=8, after_determinants=1, distance_type="nu",
+                         method_name="eval_logdet") -> Callable:
+    """network.py:609-667; returns apply(params, x) for ONE walker."""
+    if method_name not in ["eval_slogdet", "eval_logdet", "eval_mats", "eval_phase_and_slogdet"]:
+        raise ValueError("Method name is not in class dir.")
+    atoms = _t(simulation_cell.original_cell.atom_coords())
+    spins = tuple(simulation_cell.nelec)
+
+    def apply(params, x):
+        return eval_func(params, x, klist=klist, simulation_cell=simulation_cell, atoms=atoms,
+                         spins=spins, envelope_type=envelope_type, full_det=full_det,
+                         distance_type=distance_type, method_name=method_name)
+    return apply
+
+
+# ---------------------------------------------------------------------------
+# distance.py / ewaldsum.py
+# ---------------------------------------------------------------------------
+
+class MinimalImageDistance:
+    """distance.py:32-141 (torch)."""
+
+    def __init__(self, latvec):
+        from deepsolid_b200.ewald_tables import classify_lattice, min_image_point_list
+        lat = np.asarray(latvec, dtype=float)
+        self.kind = classify_lattice(lat)
+        self._latvec = _t(lat)
+        self._invvec = torch.linalg.inv(self._latvec)
+        self.point_list = _t(min_image_point_list())
+        self.shifts = self.point_list @ self._latvec
+
+    def dist_i(self, configs, vec):
+        configs = configs.reshape(1, -1, 3)
+        v = vec.reshape(-1, 1, 3)
+        d1 = v - configs
+        if self.kind == 0:      # distance.py:110-128
+            diag = torch.diagonal(self._latvec)
+            return torch.remainder(d1 + diag / 2, diag) - diag / 2
+        if self.kind == 1:      # distance.py:91-108
+            frac = d1 @ self._invvec
+            return (torch.remainder(frac + 0.5, 1.0) - 0.5) @ self._latvec
+        shifts = self.shifts.reshape(-1, 1, 1, 3)     # distance.py:70-89
+        d1all = d1[None] + shifts
+        dists = torch.linalg.norm(d1all, dim=-1)
+        mininds = torch.argmin(dists, dim=0)
+        return torch.gather(d1all, 0, mininds[None, ..., None].expand(1, *d1.shape))[0]
+
+    def dist_matrix(self, configs):
+        vs = self.dist_i(configs, configs)
+        n = vs.shape[0]
+        return vs * (1 - torch.eye(n, dtype=vs.dtype))[..., None]
+
+
+class EwaldSum:
+    """Per-walker half of ewaldsum.py (138-191); setup tables come from
+    deepsolid_b200.ewald_tables (which restates ewaldsum.py:33-136)."""
+
+    def __init__(self, cell, ewald_gmax=200, nlatvec=1):
+        from deepsolid_b200.ewald_tables import build_ewald_tables
+        tb = build_ewald_tables(cell, ewald_gmax, nlatvec)
+        self.tb = tb
+        self.nelec = tuple(cell.nelec)
+        self.atom_coords = _t(tb.atom_coords)
+        self.atom_charges = _t(tb.atom_charges)
+        self.dist = MinimalImageDistance(tb.latvec)
+        self.lattice_displacements = _t(tb.lattice_displacements)
+        self.alpha = tb.alpha
+        self.gpoints, self.gweight = _t(tb.gpoints), _t(tb.gweight)
+        self.ion_exp = torch.as_tensor(tb.ion_exp, dtype=CT)
+        self.ion_ion, self.ii_const = tb.ion_ion, tb.ii_const
+
+    def _real_cij(self, dists):
+        r = dists[:, :, None, :] + self.lattice_displacements
+        r = torch.linalg.norm(r, dim=-1)
+        return torch.sum(torch.erfc(self.alpha * r) / r, dim=-1)
+
+    def ewald_electron(self, configs):
+        nelec = sum(self.nelec)
+        ei_d = self.dist.dist_i(self.atom_coords.reshape(-1), configs)
+        ei_real = torch.sum(-self.atom_charges[None, :] * self._real_cij(ei_d))
+        ee_real = torch.zeros((), dtype=DT)
+        if nelec > 1:
+            ee_d = self.dist.dist_matrix(configs)
+            rvec = ee_d[None] + self.lattice_displacements[:, None, None, :]
+            r = torch.linalg.norm(rvec, dim=-1)
+            mask = torch.triu(torch.ones(nelec, nelec, dtype=torch.bool), diagonal=1)
+            ee_real = torch.sum(torch.where(mask[None], torch.erfc(self.alpha * r) / r,
+                                            torch.zeros((), dtype=DT)))
+        ee_rec, ei_rec = self.reciprocal_space_electron(configs)
+        return ee_real + ee_rec, ei_real + ei_rec
+
+    def reciprocal_space_electron(self, configs):
+        gr = configs.reshape(sum(self.nelec), -1) @ self.gpoints.T
+        ssin, scos = torch.sin(gr).sum(dim=0), torch.cos(gr).sum(dim=0)
+        ee = torch.dot(ssin ** 2 + scos ** 2, self.gweight)
+        cs = -self.ion_exp.real * scos - self.ion_exp.imag * ssin
+        return ee, 2 * torch.dot(cs, self.gweight)
+
+    def energy(self, configs):
+        ne = sum(self.nelec)
+        ee, ei = self.ewald_electron(configs)
+        return ee + self.tb.ee_const(ne), ei + self.tb.ei_const(ne), torch.tensor(self.tb.ii_total, dtype=DT)
+
+
+def enforce_pbc_batch(latvec, epos):
+    """distance.py:144-163 (vmapped over the batch): divmod(frac, 1)."""
+    lat = _t(latvec)
+    B = epos.shape[0]
+    frac = epos.reshape(B, -1, 3) @ torch.linalg.inv(lat)
+    wrap = torch.floor(frac)
+    return ((frac - wrap) @ lat).reshape(B, -1), wrap
+
+
+# ---------------------------------------------------------------------------
+# hamiltonian.py
+# ---------------------------------------------------------------------------
+
+def local_kinetic_energy_real_imag(f):
+    """hamiltonian.py:45-70 ('for' mode): per direction jvp(grad(Re f)) and jvp(grad(Im f))."""
+    def _lapl_over_f(params, x):
+        ne = x.shape[-1]
+        eye = torch.eye(ne, dtype=x.dtype)
+        g_re = grad(lambda y: f(params, y).real)
+        g_im = grad(lambda y: f(params, y).imag)
+        re = torch.zeros((), dtype=DT)
+        im = torch.zeros((), dtype=DT)
+        for i in range(ne):
+            p_re, t_re = jvp(g_re, (x,), (eye[i],))
+            p_im, t_im = jvp(g_im, (x,), (eye[i],))
+            re = re + t_re[i] + p_re[i] ** 2 - p_im[i] ** 2
+            im = im + t_im[i] + 2 * p_re[i] * p_im[i]
+        return [-0.5 * re, -0.5 * im * 1j]
+    return _lapl_over_f
+
+
+def local_kinetic_energy_partition(f, partition_number=3):
+    """hamiltonian.py:127-159 ('partition' mode): vmapped jvp over chunks of eye(3N)."""
+    def _lapl_over_f(params, x):
+        n = x.shape[0]
+        if n % partition_number:
+            raise ValueError("partition_number must divide 3*N_elec")   # jnp.asarray(array_split) would fail
+        eye = torch.eye(n, dtype=x.dtype)
+        g_re = grad(lambda y: f(params, y).real)
+        g_im = grad(lambda y: f(params, y).imag)
+        vjvp = lambda g, e: vmap(lambda t: jvp(g, (x,), (t,)))(e)
+        prs, pis, trs, tis = [], [], [], []
+        for e in eye.reshape(partition_number, n // partition_number, n):
+            pr, tr = vjvp(g_re, e)
+            pi_, ti = vjvp(g_im, e)
+            prs.append(pr); pis.append(pi_); trs.append(tr); tis.append(ti)
+        primal = [torch.cat(prs), torch.cat(pis)]
+        tangent = [torch.cat(trs), torch.cat(tis)]
+        real = torch.trace(tangent[0]) + torch.trace(primal[0] ** 2) - torch.trace(primal[1] ** 2)
+        imag = torch.trace(tangent[1]) + torch.trace(2 * primal[0] * primal[1])
+        return [-0.5 * real, -0.5 * 1j * imag]
+    return _lapl_over_f
+
+
+def local_kinetic_energy_dim_batch(f):
+    """hamiltonian.py:73-101."""
+    return local_kinetic_energy_partition(f, partition_number=1)
+
+
+def local_kinetic_energy_hessian(f):
+    """hamiltonian.py:104-124."""
+    from torch.func import hessian
+
+    def _lapl_over_f(params, x):
+        g_re = grad(lambda y: f(params, y).real)(x)
+        g_im = grad(lambda y: f(params, y).imag)(x)
+        h_re = hessian(lambda y: f(params, y).real)(x)
+        h_im = hessian(lambda y: f(params, y).imag)(x)
+        real = torch.trace(h_re) + torch.sum(g_re ** 2) - torch.sum(g_im ** 2)
+        imag = torch.trace(h_im) + torch.sum(2 * g_re * g_im)
+        return [-0.5 * real, -0.5 * 1j * imag]
+    return _lapl_over_f
+
+
+def local_ewald_energy(simulation_cell):
+    """hamiltonian.py:163-179 (the pyscf energy_nuc assertion is replaced by the
+    Madelung tests in tests/test_ewald_oracle.py)."""
+    ewald = EwaldSum(simulation_cell)
+
+    def _local_ewald_energy(x):
+        return sum(ewald.energy(x))
+    return _local_ewald_energy
+
+
+def local_energy_seperate(f, simulation_cell, mode="for", partition_number=3):
+    """hamiltonian.py:194-228."""
+    if mode == "for":
+        ke_ri = local_kinetic_energy_real_imag(f)
+    elif mode == "hessian":
+        ke_ri = local_kinetic_energy_hessian(f)
+    elif mode == "dim_batch":
+        ke_ri = local_kinetic_energy_dim_batch(f)
+    elif mode == "partition":
+        ke_ri = local_kinetic_energy_partition(f, partition_number=partition_number)
+    else:
+        raise ValueError("Unrecognized laplacian evaluation mode.")
+    ew = local_ewald_energy(simulation_cell)
+
+    def _local_energy(params, x):
+        parts = ke_ri(params, x)
+        return parts[0] + parts[1], ew(x)
+    return _local_energy
+
+
+# ---------------------------------------------------------------------------
+# qmc.py / train.py
+# ---------------------------------------------------------------------------
+
+def mh_update(params, f_batch, x1, lp_1, num_accepts, latvec, stddev, xi, u):
+    """qmc.py:153-224, symmetric branch, with the gaussian noise ``xi`` (B,3N) and the
+    uniforms ``u`` (B,) supplied by the caller instead of jax.random."""
+    x2 = x1 + stddev * xi
+    x2, _ = enforce_pbc_batch(latvec, x2)
+    lp_2 = 2.0 * f_batch(params, x2)
+    ratio = lp_2 - lp_1
+    rnd = torch.log(u)
+    cond = ratio > rnd
+    x_new = torch.where(cond[..., None], x2, x1)
+    lp_new = torch.where(cond, lp_2, lp_1)
+    return x_new, lp_new, num_accepts + cond.sum().to(DT), cond
+
+
+def make_mcmc_step(batch_slog_network, batch_per_device, latvec, steps=10):
+    """qmc.py:290-364 (Metropolis, all-electron moves).  ``noise`` = (xi[steps,B,3N], u[steps,B])
+    replaces the PRNG key; returns (data, pmove, accept_masks[steps,B])."""
+    def mcmc_step(params, data, noise, width):
+        xi, u = noise
+        logprob = 2.0 * batch_slog_network(params, data)
+        n_acc = torch.zeros((), dtype=DT)
+        masks = []
+        for s in range(steps):
+            data, logprob, n_acc, cond = mh_update(params, batch_slog_network, data, logprob, n_acc,
+                                                   latvec, width, xi[s], u[s])
+            masks.append(cond)
+        pmove = n_acc / (steps * batch_per_device)
+        return data, pmove, torch.stack(masks)
+    return mcmc_step
+
+
+def total_energy_stats(ke, ew):
+    """train.py:74-89, single device: loss, imaginary, variance from per-walker (ke, ew)."""
+    e_l = ke + ew
+    mean = e_l.mean()
+    variance = (e_l.abs() ** 2).mean() - mean.real.abs() ** 2
+    return mean.real, mean.imag, variance
+
+
+def batch_apply(apply, params, X):
+    """process.py:116-118: the caller vmaps apply over the batch; a loop is the oracle."""
+    return torch.stack([apply(params, x) for x in X])
