@@ -1,0 +1,761 @@
+// C ABI of deepsolid_b200: context, parameter upload, workspace, and the launch
+// sequences of log psi / local energy / Metropolis step.  See include/deepsolid_b200.h.
+#include "../../include/deepsolid_b200.h"
+#include "kernels.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+static thread_local char g_err[1024] = "";
+
+void ds_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* ds_last_error(void) { return g_err; }
+extern "C" int ds_version(void) { return 100; }
+
+namespace {
+
+struct DevBuf {
+    double* p = nullptr;
+    size_t n = 0;   // doubles
+};
+
+struct Region {
+    const char* name;
+    double* p;
+    size_t n;
+};
+
+struct Workspace {
+    double* base = nullptr;
+    size_t cap = 0;     // doubles
+    size_t used = 0;
+    std::vector<Region> regions;
+    void reset() { used = 0; regions.clear(); }
+    double* take(const char* name, size_t n) {
+        n = (n + 31) & ~size_t(31);     // 256-byte granules keep every buffer 16B aligned for cp.async
+        double* p = base ? base + used : nullptr;
+        used += n;
+        regions.push_back(Region{name, p, n});
+        return p;
+    }
+};
+
+struct ProfEvent {
+    cudaEvent_t a, b;
+    double flops;
+};
+
+}  // namespace
+
+struct ds_ctx {
+    int device = 0;
+    DsSys sys;
+    EwaldDev ew;
+    int npar[2] = {0, 0}, npar_max = 0, off_s[2] = {0, 0}, n_s[2] = {0, 0};
+    int nbuf = 2;
+    bool params_set = false;
+    std::vector<void*> owned;           // device allocations freed at destroy
+    // parameters (device)
+    double* B_am[DS_MAX_LAYERS] = {};   // [(C + 2Pl) x H] own + pair-mean rows
+    double* B_g[DS_MAX_LAYERS] = {};    // [2C x H] spin-mean rows
+    double* bias1[DS_MAX_LAYERS] = {};  // [H]
+    double* Wp[DS_MAX_LAYERS] = {};     // pair-stream weights
+    double* bp[DS_MAX_LAYERS] = {};
+    double* Worb[2] = {};               // [H x 2 npar_s], columns interleaved (re, im)
+    double* env_pi[2] = {};
+    double* env_sigma[2] = {};
+    double* klist[2] = {};
+    // workspace
+    Workspace ws;
+    size_t ws_limit = size_t(8) << 30;  // bytes
+    // mcmc scratch
+    DevBuf mc_x2, mc_lp, mc_lp2, host_stage;
+    // instrumentation
+    long long launches = 0;
+    bool prof_on = false;
+    std::vector<ProfEvent> prof;
+    cudaEvent_t tot_a = nullptr, tot_b = nullptr;
+    double tot_ms = 0.0;
+    int dbg_stop_layer = -1;
+    // layout of the last local-energy chunk (for ds_debug_buffer)
+    std::vector<Region> last_regions;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(ds_ctx* c, T** out, size_t count) {
+    void* p = nullptr;
+    DS_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    c->owned.push_back(p);
+    *out = (T*)p;
+    return 0;
+}
+
+int upload(ds_ctx* c, double** out, const double* host, size_t count) {
+    if (int rc = dev_alloc(c, out, count)) return rc;
+    DS_CUDA_CHECK(cudaMemcpy(*out, host, count * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void inv3(const double* a, double* o) {
+    double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+    double id = 1.0 / det;
+    o[0] = (a[4] * a[8] - a[5] * a[7]) * id; o[1] = (a[2] * a[7] - a[1] * a[8]) * id; o[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    o[3] = (a[5] * a[6] - a[3] * a[8]) * id; o[4] = (a[0] * a[8] - a[2] * a[6]) * id; o[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    o[6] = (a[3] * a[7] - a[4] * a[6]) * id; o[7] = (a[1] * a[6] - a[0] * a[7]) * id; o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
+void fill_lattice(DsLattice& L, const double* lat, const double* AV, const double* BV) {
+    memcpy(L.lat, lat, 9 * sizeof(double));
+    inv3(lat, L.inv);
+    memcpy(L.AV, AV, 9 * sizeof(double));
+    memcpy(L.BV, BV, 9 * sizeof(double));
+    for (int l = 0; l < 3; ++l) {
+        L.an2[l] = AV[l * 3] * AV[l * 3] + AV[l * 3 + 1] * AV[l * 3 + 1] + AV[l * 3 + 2] * AV[l * 3 + 2];
+        for (int m = 0; m < 3; ++m)
+            L.metric[l * 3 + m] = AV[l * 3] * AV[m * 3] + AV[l * 3 + 1] * AV[m * 3 + 1] + AV[l * 3 + 2] * AV[m * 3 + 2];
+    }
+}
+
+struct Guard {
+    int prev = -1;
+    explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+    ~Guard() { int cur; cudaGetDevice(&cur); if (cur != prev && prev >= 0) cudaSetDevice(prev); }
+};
+
+int gemm(ds_ctx* c, const GemmParams& p, int mode, bool res, cudaStream_t st, bool profile_as_jac = false) {
+    ProfEvent ev{};
+    bool rec = c->prof_on && profile_as_jac;
+    if (rec) {
+        DS_CUDA_CHECK(cudaEventCreate(&ev.a));
+        DS_CUDA_CHECK(cudaEventCreate(&ev.b));
+        DS_CUDA_CHECK(cudaEventRecord(ev.a, st));
+    }
+    int rc = ds_launch_gemm(p, mode, res, st);
+    if (rc) return rc;
+    c->launches++;
+    if (rec) {
+        DS_CUDA_CHECK(cudaEventRecord(ev.b, st));
+        ev.flops = 2.0 * (double)p.M * p.N * p.K;
+        c->prof.push_back(ev);
+    }
+    return 0;
+}
+
+// per-walker workspace size in doubles
+struct Layout {
+    bool lap;
+    int Wc;
+    double *A0V, *A0L, *A0J;
+    double *J[DS_MAX_LAYERS], *V[DS_MAX_LAYERS], *Lp[DS_MAX_LAYERS];
+    double *T, *S, *GIN, *GOUT, *RAE, *ETAB, *YV, *YL, *YOWN;
+    double *MAT[2], *LAPM[2], *DA[2];
+    double *LOGDET, *TAU, *TRSQ, *TRLAP;
+};
+
+void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap) {
+    const DsDims& d = c->sys.d;
+    const size_t W = (size_t)Wc, N = d.N;
+    ws.reset();
+    L.lap = lap; L.Wc = Wc;
+    L.A0V = ws.take("A0V", W * N * d.K0);
+    L.A0L = lap ? ws.take("A0L", W * N * d.K0) : nullptr;
+    L.A0J = lap ? ws.take("A0J", W * N * d.NDp * d.K0) : nullptr;
+    static const char* jn[] = {"J0", "J1", "J2", "J3"};
+    static const char* vn[] = {"V0", "V1", "V2", "V3"};
+    static const char* ln[] = {"L0", "L1", "L2", "L3"};
+    for (int b = 0; b < c->nbuf; ++b) {
+        L.V[b] = ws.take(vn[b], W * N * d.K1);
+        L.Lp[b] = lap ? ws.take(ln[b], W * N * d.K1) : nullptr;
+        L.J[b] = lap ? ws.take(jn[b], W * N * d.NDp * d.K1) : nullptr;
+    }
+    L.T = ws.take("T", W * N * d.H);
+    L.S = lap ? ws.take("S", W * N * d.H) : nullptr;
+    const size_t cmax = (size_t)std::max(d.C0, d.H);
+    L.GIN = ws.take("GIN", W * d.NDg * 2 * cmax);
+    L.GOUT = ws.take("GOUT", W * d.NDg * d.H);
+    L.RAE = ws.take("RAE", W * N * d.A * 5);
+    const size_t npm = c->npar_max;
+    L.ETAB = ws.take("ETAB", W * N * 5 * npm * 2);
+    L.YV = ws.take("YV", W * N * npm * 2);
+    L.YL = lap ? ws.take("YL", W * N * npm * 2) : nullptr;
+    L.YOWN = lap ? ws.take("YOWN", W * N * 3 * npm * 2) : nullptr;
+    static const char* mn[] = {"MAT0", "MAT1"};
+    static const char* lmn[] = {"LAPM0", "LAPM1"};
+    static const char* dn[] = {"DA0", "DA1"};
+    for (int s = 0; s < 2; ++s) {
+        size_t ns = c->n_s[s];
+        L.MAT[s] = ws.take(mn[s], W * d.D * ns * ns * 2);
+        L.LAPM[s] = lap ? ws.take(lmn[s], W * d.D * ns * ns * 2) : nullptr;
+        L.DA[s] = lap ? ws.take(dn[s], W * d.D * d.NDp * ns * ns * 2) : nullptr;
+    }
+    L.LOGDET = ws.take("LOGDET", W * 2 * d.D * 3);
+    L.TAU = lap ? ws.take("TAU", W * 2 * d.D * d.NDp * 2) : nullptr;
+    L.TRSQ = lap ? ws.take("TRSQ", W * 2 * d.D * 2) : nullptr;
+    L.TRLAP = lap ? ws.take("TRLAP", W * 2 * d.D * 2) : nullptr;
+}
+
+int plan_chunk(ds_ctx* c, long long batch, bool lap, int* Wc_out) {
+    Workspace probe;                      // base == nullptr: sizes only
+    Layout L;
+    carve(c, probe, L, 1, lap);
+    size_t per_walker = probe.used + 64;  // doubles (granule slack)
+    size_t limit = c->ws_limit / sizeof(double);
+    long long Wc = (long long)(limit / per_walker);
+    if (Wc < 1) {
+        ds_set_error("workspace limit %zu bytes is below the %zu bytes one walker needs", c->ws_limit,
+                     per_walker * sizeof(double));
+        return DS_ERR_NOMEM;
+    }
+    Wc = std::min<long long>(Wc, batch);
+    // keep the row counts of the Jacobian GEMM within int-friendly grid sizes
+    Wc = std::min<long long>(Wc, 1 << 15);
+    *Wc_out = (int)Wc;
+    carve(c, probe, L, (int)Wc, lap);
+    size_t need = probe.used;
+    if (need > c->ws.cap) {
+        if (c->ws.base) { DS_CUDA_CHECK(cudaFree(c->ws.base)); c->ws.base = nullptr; c->ws.cap = 0; }
+        cudaError_t e = cudaMalloc((void**)&c->ws.base, need * sizeof(double));
+        if (e != cudaSuccess) {
+            ds_set_error("cannot allocate %zu bytes of workspace: %s", need * sizeof(double), cudaGetErrorString(e));
+            return DS_ERR_NOMEM;
+        }
+        c->ws.cap = need;
+    }
+    return 0;
+}
+
+// One chunk of walkers through the network.  lap=false: log psi only.
+int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, double* phase, double* ke_re,
+              double* ke_im, double* mats_out, cudaStream_t st) {
+    const DsSys& sys = c->sys;
+    const DsDims& d = sys.d;
+    Layout Lo;
+    carve(c, c->ws, Lo, Wc, lap);
+    c->last_regions = c->ws.regions;
+    const int N = d.N, H = d.H, L = d.L;
+
+    // buffer of the inputs of layer l >= 1 is (l-1); the last layer writes into buffer `outb(L-1)`
+    auto inb = [&](int l) { return l - 1; };
+    auto outb = [&](int l) { return (l + 1 < L) ? l : ((L - 1 >= 2) ? 0 : 1); };
+
+    FeatParams fp{};
+    fp.X = X; fp.A0V = Lo.A0V; fp.A0L = Lo.A0L; fp.A0J = Lo.A0J; fp.RAE = Lo.RAE;
+    for (int l = 1; l < L; ++l) { fp.AV[l] = Lo.V[inb(l)]; fp.AL[l] = Lo.Lp[inb(l)]; fp.AJ[l] = Lo.J[inb(l)]; }
+    for (int l = 0; l < L - 1; ++l) { fp.Wp[l] = c->Wp[l]; fp.bp[l] = c->bp[l]; }
+    if (int rc = ds_launch_features(sys, fp, Wc, lap, st)) return rc;
+    c->launches++;
+
+    const double *hV = nullptr, *hJ = nullptr, *hL = nullptr;
+    for (int l = 0; l < L; ++l) {
+        const int C = (l == 0) ? d.C0 : H;
+        const int K = (l == 0) ? d.K0 : d.K1;
+        const double* AV = (l == 0) ? Lo.A0V : Lo.V[inb(l)];
+        const double* AL = (l == 0) ? Lo.A0L : Lo.Lp[inb(l)];
+        const double* AJ = (l == 0) ? Lo.A0J : Lo.J[inb(l)];
+        double* OV = Lo.V[outb(l)];
+        double* OL = Lo.Lp[outb(l)];
+        double* OJ = Lo.J[outb(l)];
+        const bool res = (C == H);
+        if (lap) DS_CUDA_CHECK(cudaMemsetAsync(Lo.S, 0, (size_t)Wc * N * H * sizeof(double), st));
+        if (int rc = ds_launch_means(d, Wc, C, AJ, K, AV, AL, K, Lo.GIN, 2 * C, lap, st)) return rc;
+        c->launches++;
+        {   // shared spin-mean contribution, once per walker and direction
+            GemmParams g{};
+            g.B = c->B_g[l]; g.ldb = H; g.N = H; g.K = 2 * C; g.rpg = 0;
+            if (lap) {
+                g.A = Lo.GIN; g.lda = 2 * C; g.M = (long long)Wc * d.NDg; g.C = Lo.GOUT; g.ldc = H;
+            } else {    // only the value row d = NDp of every walker
+                g.A = Lo.GIN + (size_t)d.NDp * 2 * C; g.lda = d.NDg * 2 * C; g.M = Wc;
+                g.C = Lo.GOUT + (size_t)d.NDp * H; g.ldc = d.NDg * H;
+            }
+            if (int rc = gemm(c, g, GEMM_PLAIN, false, st)) return rc;
+        }
+        GemmParams p{};
+        p.B = c->B_am[l]; p.ldb = H; p.N = H; p.K = K; p.rpg = 0;
+        p.G = Lo.GOUT; p.ldg = H; p.n_elec = N; p.NDp = d.NDp; p.NDg = d.NDg;
+        p.T = Lo.T; p.ldt = H; p.S = Lo.S; p.colbias = c->bias1[l];
+        {
+            GemmParams v = p;
+            v.A = AV; v.lda = K; v.M = (long long)Wc * N; v.C = OV; v.ldc = d.K1; v.R = AV; v.ldr = K;
+            if (int rc = gemm(c, v, GEMM_VALUE, res, st)) return rc;
+        }
+        if (lap) {
+            GemmParams j = p;
+            j.A = AJ; j.lda = K; j.M = (long long)Wc * N * d.NDp; j.C = OJ; j.ldc = d.K1; j.R = AJ; j.ldr = K;
+            if (int rc = gemm(c, j, GEMM_JAC, res, st, /*profile*/ l > 0)) return rc;
+            GemmParams q = p;
+            q.A = AL; q.lda = K; q.M = (long long)Wc * N; q.C = OL; q.ldc = d.K1; q.R = AL; q.ldr = K;
+            if (int rc = gemm(c, q, GEMM_LAP, res, st)) return rc;
+        }
+        hV = OV; hJ = OJ; hL = OL;
+        if (c->dbg_stop_layer == l) return 0;
+    }
+
+    // ---- orbitals --------------------------------------------------------
+    SlaterBufs sb{};
+    sb.X = X; sb.RAE = Lo.RAE; sb.ETAB = Lo.ETAB; sb.YV = Lo.YV; sb.YL = Lo.YL; sb.YOWN = Lo.YOWN;
+    for (int s = 0; s < 2; ++s) {
+        sb.MAT[s] = Lo.MAT[s]; sb.LAPM[s] = Lo.LAPM[s]; sb.DA[s] = Lo.DA[s];
+        sb.env_pi[s] = c->env_pi[s]; sb.env_sigma[s] = c->env_sigma[s]; sb.klist[s] = c->klist[s];
+    }
+    sb.LOGDET = Lo.LOGDET; sb.TAU = Lo.TAU; sb.TRSQ = Lo.TRSQ; sb.TRLAP = Lo.TRLAP;
+    if (int rc = ds_launch_etab(sys, sb, Wc, c->npar_max, lap, st)) return rc;
+    c->launches++;
+    for (int s = 0; s < 2; ++s) {
+        const int ns = c->n_s[s];
+        GemmParams o{};
+        o.B = c->Worb[s]; o.ldb = 2 * c->npar[s]; o.N = 2 * c->npar[s]; o.K = H;
+        o.lda = d.K1; o.cmap = 1; o.ldc = 2 * c->npar_max;
+        o.rpg = ns; o.gstride = N; o.goff = c->off_s[s];
+        o.M = (long long)Wc * ns;
+        o.A = hV; o.C = Lo.YV;
+        if (int rc = gemm(c, o, GEMM_PLAIN, false, st)) return rc;
+        if (lap) {
+            o.A = hL; o.C = Lo.YL;
+            if (int rc = gemm(c, o, GEMM_PLAIN, false, st)) return rc;
+            GemmParams j = o;
+            j.A = hJ; j.cmap = 0; j.C = nullptr;
+            j.rpg = (long long)ns * d.NDp; j.gstride = (long long)N * d.NDp; j.goff = (long long)c->off_s[s] * d.NDp;
+            j.M = (long long)Wc * ns * d.NDp;
+            j.n_elec = N; j.NDp = d.NDp; j.etab = Lo.ETAB; j.npar_max = c->npar_max;
+            j.n_s = ns; j.off_s = c->off_s[s]; j.n_det = d.D; j.DA = Lo.DA[s]; j.YOWN = Lo.YOWN;
+            if (int rc = gemm(c, j, GEMM_ORBJ, false, st, /*profile*/ true)) return rc;
+        }
+    }
+    if (int rc = ds_launch_orb_assemble(sys, sb, Wc, c->npar_max, lap, st)) return rc;
+    c->launches++;
+    if (mats_out) {
+        size_t off = 0;
+        for (int s = 0; s < 2; ++s) {
+            size_t per = (size_t)d.D * c->n_s[s] * c->n_s[s] * 2;
+            size_t tot = (size_t)d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
+            DS_CUDA_CHECK(cudaMemcpy2DAsync(mats_out + off, tot * sizeof(double), Lo.MAT[s], per * sizeof(double),
+                                            per * sizeof(double), Wc, cudaMemcpyDeviceToDevice, st));
+            off += per;
+        }
+        return 0;
+    }
+    if (int rc = ds_launch_det(sys, sb, Wc, lap, st)) return rc;
+    c->launches++;
+    if (int rc = ds_launch_combine(sys, sb, Wc, lap, log_abs, phase, ke_re, ke_im, st)) return rc;
+    c->launches++;
+    return 0;
+}
+
+int run_batched(ds_ctx* c, const double* X, long long batch, bool lap, double* log_abs, double* phase,
+                double* ke_re, double* ke_im, double* mats_out, cudaStream_t st) {
+    DS_REQUIRE(c && c->params_set, "parameters have not been set (ds_set_params)");
+    DS_REQUIRE(batch >= 0, "negative batch");
+    if (batch == 0) return 0;
+    DS_REQUIRE(X != nullptr, "null walker pointer");
+    int Wc = 0;
+    if (int rc = plan_chunk(c, batch, lap, &Wc)) return rc;
+    const int n3 = 3 * c->sys.d.N;
+    const size_t mat_per = (size_t)c->sys.d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
+    for (long long w0 = 0; w0 < batch; w0 += Wc) {
+        int wc = (int)std::min<long long>(Wc, batch - w0);
+        int rc = run_chunk(c, X + w0 * n3, wc, lap, log_abs ? log_abs + w0 : nullptr, phase ? phase + w0 : nullptr,
+                           ke_re ? ke_re + w0 : nullptr, ke_im ? ke_im + w0 : nullptr,
+                           mats_out ? mats_out + w0 * mat_per : nullptr, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int ensure(ds_ctx* c, DevBuf& b, size_t n) {
+    if (b.n >= n) return 0;
+    if (b.p) DS_CUDA_CHECK(cudaFree(b.p));
+    b.p = nullptr; b.n = 0;
+    DS_CUDA_CHECK(cudaMalloc((void**)&b.p, n * sizeof(double)));
+    b.n = n;
+    (void)c;
+    return 0;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, int device, ds_ctx** out) {
+    DS_REQUIRE(sd && nd && out, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        ds_set_error("no CUDA device available (%s); deepsolid_b200 has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return DS_ERR_CUDA;
+    }
+    DS_REQUIRE(device >= 0 && device < ndev, "device %d out of range (0..%d)", device, ndev - 1);
+    DS_REQUIRE(sd->n_up > 0 && sd->n_dn > 0,
+               "both spin channels must be occupied (n_up=%d n_dn=%d): spin-polarised cells are not implemented",
+               sd->n_up, sd->n_dn);
+    DS_REQUIRE(sd->n_atoms_prim > 0 && sd->n_atoms_prim <= DS_MAX_ATOMS_PRIM,
+               "primitive cell must have 1..%d atoms", DS_MAX_ATOMS_PRIM);
+    DS_REQUIRE(nd->n_layers >= 2 && nd->n_layers <= DS_MAX_LAYERS, "n_layers must be in 2..%d", DS_MAX_LAYERS);
+    DS_REQUIRE(nd->hidden_two >= 2 && nd->hidden_two <= 32 && nd->hidden_two % 2 == 0,
+               "two-electron stream width must be even and <= 32 (got %d)", nd->hidden_two);
+    DS_REQUIRE(nd->hidden_one >= 2 && nd->hidden_one % 2 == 0, "one-electron stream width must be even");
+    DS_REQUIRE(nd->n_det >= 1, "need at least one determinant");
+    DS_REQUIRE(sd->dist_kind >= 0 && sd->dist_kind <= 2, "dist_kind must be 0, 1 or 2");
+    DS_REQUIRE(sd->n_g >= 0 && sd->n_atoms_sim > 0, "bad Ewald table sizes");
+    DS_CUDA_CHECK(cudaSetDevice(device));
+    ds_ctx* c = new ds_ctx();
+    c->device = device;
+    DsDims& d = c->sys.d;
+    d.n_up = sd->n_up; d.n_dn = sd->n_dn; d.N = sd->n_up + sd->n_dn; d.A = sd->n_atoms_prim;
+    d.H = nd->hidden_one; d.P = nd->hidden_two; d.D = nd->n_det; d.L = nd->n_layers;
+    d.ND = 3 * d.N; d.NDp = (d.ND + 7) / 8 * 8; d.NDg = d.NDp + 8;
+    d.C0 = 4 * d.A; d.K0 = d.C0 + 8; d.K1 = d.H + 2 * d.P;
+    fill_lattice(c->sys.prim, sd->prim_latvec, sd->prim_AV, sd->prim_BV);
+    fill_lattice(c->sys.sim, sd->sim_latvec, sd->sim_AV, sd->sim_BV);
+    memcpy(c->sys.atoms, sd->prim_atoms, sizeof(double) * 3 * d.A);
+    c->n_s[0] = d.n_up; c->n_s[1] = d.n_dn; c->off_s[0] = 0; c->off_s[1] = d.n_up;
+    c->npar[0] = d.n_up * d.D; c->npar[1] = d.n_dn * d.D; c->npar_max = std::max(c->npar[0], c->npar[1]);
+    c->nbuf = std::max(2, d.L - 1);
+
+    EwaldDev& ew = c->ew;
+    ew.n_elec = d.N; ew.n_atoms = sd->n_atoms_sim; ew.dist_kind = sd->dist_kind; ew.n_g = sd->n_g;
+    memcpy(ew.lat, sd->sim_latvec, 9 * sizeof(double));
+    inv3(sd->sim_latvec, ew.inv);
+    ew.alpha = sd->alpha; ew.ee_const = sd->ee_const; ew.ei_const = sd->ei_const; ew.ii_total = sd->ii_total;
+    int rc = 0;
+    double* tmp = nullptr;
+    rc |= upload(c, &tmp, sd->sim_atoms, 3 * (size_t)sd->n_atoms_sim); ew.atoms = tmp;
+    rc |= upload(c, &tmp, sd->sim_charges, (size_t)sd->n_atoms_sim); ew.charges = tmp;
+    rc |= upload(c, &tmp, sd->mi_shifts, 81); ew.mi_shifts = tmp;
+    rc |= upload(c, &tmp, sd->lattice_displacements, 81); ew.disp = tmp;
+    rc |= upload(c, &tmp, sd->gpoints, 3 * (size_t)sd->n_g); ew.gpoints = tmp;
+    rc |= upload(c, &tmp, sd->gweight, (size_t)sd->n_g); ew.gweight = tmp;
+    rc |= upload(c, &tmp, sd->ion_exp_re, (size_t)sd->n_g); ew.ion_re = tmp;
+    rc |= upload(c, &tmp, sd->ion_exp_im, (size_t)sd->n_g); ew.ion_im = tmp;
+    rc |= upload(c, &c->klist[0], sd->klist_up, 3 * (size_t)d.n_up);
+    rc |= upload(c, &c->klist[1], sd->klist_dn, 3 * (size_t)d.n_dn);
+    if (rc) { ds_ctx_destroy(c); return DS_ERR_CUDA; }
+    *out = c;
+    return 0;
+}
+
+extern "C" int ds_ctx_destroy(ds_ctx* c) {
+    if (!c) return 0;
+    Guard g(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->owned) cudaFree(p);
+    if (c->ws.base) cudaFree(c->ws.base);
+    for (DevBuf* b : {&c->mc_x2, &c->mc_lp, &c->mc_lp2, &c->host_stage}) if (b->p) cudaFree(b->p);
+    for (auto& ev : c->prof) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    if (c->tot_a) cudaEventDestroy(c->tot_a);
+    if (c->tot_b) cudaEventDestroy(c->tot_b);
+    delete c;
+    return 0;
+}
+
+extern "C" int ds_set_workspace_limit(ds_ctx* c, size_t bytes) {
+    DS_REQUIRE(c, "null context");
+    DS_REQUIRE(bytes >= (size_t(1) << 20), "workspace limit must be at least 1 MiB");
+    c->ws_limit = bytes;
+    return 0;
+}
+
+extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64_t* sizes, int n_leaves) {
+    DS_REQUIRE(c && leaves && sizes, "null argument");
+    Guard g(c->device);
+    const DsDims& d = c->sys.d;
+    const int L = d.L, H = d.H, P = d.P;
+    const int expect = 2 * L + 2 * (L - 1) + 2 + 4;
+    DS_REQUIRE(n_leaves == expect, "expected %d parameter leaves for %d layers, got %d", expect, L, n_leaves);
+    // expected sizes
+    std::vector<int64_t> want;
+    for (int l = 0; l < L; ++l) {
+        int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? 4 : P;
+        want.push_back((int64_t)(3 * C + 2 * Pl) * H);
+        want.push_back(H);
+    }
+    for (int l = 0; l < L - 1; ++l) {
+        want.push_back((int64_t)((l == 0) ? 4 : P) * P);
+        want.push_back(P);
+    }
+    for (int s = 0; s < 2; ++s) want.push_back((int64_t)H * 2 * c->npar[s]);
+    for (int s = 0; s < 2; ++s) { want.push_back((int64_t)d.A * c->npar[s]); want.push_back((int64_t)d.A * c->npar[s]); }
+    for (int i = 0; i < n_leaves; ++i)
+        DS_REQUIRE(sizes[i] == want[i], "parameter leaf %d has %lld elements, expected %lld "
+                   "(only envelope_type='isotropic', full_det=False, use_last_layer=False, bias_orbitals=False are implemented)",
+                   i, (long long)sizes[i], (long long)want[i]);
+    // stage every leaf on the host (pointers may be host or device memory)
+    std::vector<std::vector<double>> h(n_leaves);
+    for (int i = 0; i < n_leaves; ++i) {
+        h[i].resize((size_t)sizes[i]);
+        DS_CUDA_CHECK(cudaMemcpy(h[i].data(), leaves[i], (size_t)sizes[i] * sizeof(double), cudaMemcpyDefault));
+    }
+    auto put = [&](double** dst, const std::vector<double>& v) -> int {
+        if (!*dst) { if (int rc = dev_alloc(c, dst, v.size())) return rc; }
+        DS_CUDA_CHECK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    int li = 0;
+    for (int l = 0; l < L; ++l) {
+        const int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? 4 : P;
+        const std::vector<double>& W = h[li++];
+        const std::vector<double>& b = h[li++];
+        std::vector<double> am((size_t)(C + 2 * Pl) * H), gg((size_t)2 * C * H);
+        std::copy(W.begin(), W.begin() + (size_t)C * H, am.begin());
+        std::copy(W.begin() + (size_t)3 * C * H, W.end(), am.begin() + (size_t)C * H);
+        std::copy(W.begin() + (size_t)C * H, W.begin() + (size_t)3 * C * H, gg.begin());
+        if (int rc = put(&c->B_am[l], am)) return rc;
+        if (int rc = put(&c->B_g[l], gg)) return rc;
+        if (int rc = put(&c->bias1[l], b)) return rc;
+    }
+    for (int l = 0; l < L - 1; ++l) {
+        if (int rc = put(&c->Wp[l], h[li++])) return rc;
+        if (int rc = put(&c->bp[l], h[li++])) return rc;
+    }
+    for (int s = 0; s < 2; ++s) {
+        const std::vector<double>& W = h[li++];
+        const int np = c->npar[s];
+        std::vector<double> wi((size_t)H * 2 * np);
+        for (int r = 0; r < H; ++r)
+            for (int p = 0; p < np; ++p) {
+                wi[(size_t)r * 2 * np + 2 * p] = W[(size_t)r * 2 * np + p];
+                wi[(size_t)r * 2 * np + 2 * p + 1] = W[(size_t)r * 2 * np + np + p];
+            }
+        if (int rc = put(&c->Worb[s], wi)) return rc;
+    }
+    for (int s = 0; s < 2; ++s) {
+        if (int rc = put(&c->env_pi[s], h[li++])) return rc;
+        if (int rc = put(&c->env_sigma[s], h[li++])) return rc;
+    }
+    c->params_set = true;
+    return 0;
+}
+
+extern "C" int ds_logpsi(ds_ctx* c, const double* x, int64_t batch, double* log_abs, double* phase, void* stream) {
+    DS_REQUIRE(c, "null context");
+    Guard g(c->device);
+    return run_batched(c, x, batch, false, log_abs, phase, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int64_t ds_orbitals_size(const ds_ctx* c) {
+    if (!c) return -1;
+    return (int64_t)c->sys.d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
+}
+
+extern "C" int ds_orbitals(ds_ctx* c, const double* x, int64_t batch, double* out, void* stream) {
+    DS_REQUIRE(c && out, "null argument");
+    Guard g(c->device);
+    return run_batched(c, x, batch, false, nullptr, nullptr, nullptr, nullptr, out, (cudaStream_t)stream);
+}
+
+extern "C" int ds_ewald(ds_ctx* c, const double* x, int64_t batch, double* ee, double* ei, void* stream) {
+    DS_REQUIRE(c && x, "null argument");
+    Guard g(c->device);
+    int rc = ds_launch_ewald(c->ew, x, batch, ee, ei, nullptr, (cudaStream_t)stream);
+    if (!rc) c->launches++;
+    return rc;
+}
+
+extern "C" double ds_ewald_ii(const ds_ctx* c) { return c ? c->ew.ii_total : 0.0; }
+
+extern "C" int ds_local_energy(ds_ctx* c, const double* x, int64_t batch, int mode, int partition_number,
+                               double* ke_re, double* ke_im, double* ewald, void* stream) {
+    DS_REQUIRE(c, "null context");
+    DS_REQUIRE(mode >= DS_LAP_FOR && mode <= DS_LAP_PARTITION, "Unrecognized laplacian evaluation mode.");
+    if (mode == DS_LAP_PARTITION)
+        DS_REQUIRE(partition_number >= 1 && (3 * c->sys.d.N) % partition_number == 0,
+                   "partition_number (%d) must divide 3*N_elec (%d)", partition_number, 3 * c->sys.d.N);
+    DS_REQUIRE(ke_re && ke_im && ewald, "null output pointer");
+    Guard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->prof_on) {
+        if (!c->tot_a) { DS_CUDA_CHECK(cudaEventCreate(&c->tot_a)); DS_CUDA_CHECK(cudaEventCreate(&c->tot_b)); }
+        DS_CUDA_CHECK(cudaEventRecord(c->tot_a, st));
+    }
+    int rc = run_batched(c, x, batch, true, nullptr, nullptr, ke_re, ke_im, nullptr, st);
+    if (rc) return rc;
+    rc = ds_launch_ewald(c->ew, x, batch, nullptr, nullptr, ewald, st);
+    if (rc) return rc;
+    c->launches++;
+    if (c->prof_on) {
+        DS_CUDA_CHECK(cudaEventRecord(c->tot_b, st));
+        DS_CUDA_CHECK(cudaEventSynchronize(c->tot_b));
+        float ms = 0.f;
+        DS_CUDA_CHECK(cudaEventElapsedTime(&ms, c->tot_a, c->tot_b));
+        c->tot_ms += ms;
+    }
+    return 0;
+}
+
+extern "C" int ds_mcmc_step(ds_ctx* c, double* x, int64_t batch, int steps, double width, uint64_t seed,
+                            const double* xi, const double* u, uint8_t* accept, double* n_accept, void* stream) {
+    DS_REQUIRE(c && x && n_accept, "null argument");
+    DS_REQUIRE(steps >= 0, "negative number of MCMC steps");
+    Guard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n3 = 3 * c->sys.d.N;
+    if (int rc = ensure(c, c->mc_x2, (size_t)batch * n3)) return rc;
+    if (int rc = ensure(c, c->mc_lp, (size_t)batch)) return rc;
+    if (int rc = ensure(c, c->mc_lp2, (size_t)batch)) return rc;
+    DS_CUDA_CHECK(cudaMemsetAsync(n_accept, 0, sizeof(double), st));
+    if (batch == 0) return 0;
+    // logprob = 2 log|psi|   (qmc.py:357)
+    if (int rc = run_batched(c, x, batch, false, c->mc_lp.p, nullptr, nullptr, nullptr, nullptr, st)) return rc;
+    if (int rc = ds_launch_scale(c->mc_lp.p, c->mc_lp.p, 2.0, batch, st)) return rc;
+    c->launches++;
+    for (int s = 0; s < steps; ++s) {
+        if (int rc = ds_launch_propose(c->sys.sim, x, c->mc_x2.p, batch, n3, width,
+                                       xi ? xi + (size_t)s * batch * n3 : nullptr, seed, (unsigned long long)s, st)) return rc;
+        if (int rc = run_batched(c, c->mc_x2.p, batch, false, c->mc_lp2.p, nullptr, nullptr, nullptr, nullptr, st)) return rc;
+        if (int rc = ds_launch_scale(c->mc_lp2.p, c->mc_lp2.p, 2.0, batch, st)) return rc;
+        if (int rc = ds_launch_accept(x, c->mc_x2.p, c->mc_lp.p, c->mc_lp2.p, batch, n3,
+                                      u ? u + (size_t)s * batch : nullptr, seed, (unsigned long long)s,
+                                      accept ? accept + (size_t)s * batch : nullptr, n_accept, st)) return rc;
+        c->launches += 3;
+    }
+    return 0;
+}
+
+extern "C" int ds_energy_stats(ds_ctx* c, const double* ke_re, const double* ke_im, const double* ew,
+                               int64_t batch, double* out6, void* stream) {
+    DS_REQUIRE(c && out6, "null argument");
+    Guard g(c->device);
+    int rc = ds_launch_stats(ke_re, ke_im, ew, batch, out6, (cudaStream_t)stream);
+    if (!rc) c->launches++;
+    return rc;
+}
+
+// ---- host-buffer forms ----------------------------------------------------
+extern "C" int ds_logpsi_host(ds_ctx* c, const double* x, int64_t batch, double* log_abs, double* phase) {
+    DS_REQUIRE(c && x, "null argument");
+    Guard g(c->device);
+    const size_t n3 = 3 * (size_t)c->sys.d.N;
+    if (int rc = ensure(c, c->host_stage, (size_t)batch * (n3 + 2))) return rc;
+    double* dx = c->host_stage.p;
+    double* dl = dx + (size_t)batch * n3;
+    double* dp = dl + batch;
+    DS_CUDA_CHECK(cudaMemcpyAsync(dx, x, (size_t)batch * n3 * sizeof(double), cudaMemcpyHostToDevice, 0));
+    if (int rc = ds_logpsi(c, dx, batch, dl, dp, nullptr)) return rc;
+    if (log_abs) DS_CUDA_CHECK(cudaMemcpyAsync(log_abs, dl, batch * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    if (phase) DS_CUDA_CHECK(cudaMemcpyAsync(phase, dp, batch * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    DS_CUDA_CHECK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+extern "C" int ds_local_energy_host(ds_ctx* c, const double* x, int64_t batch, int mode, int partition_number,
+                                    double* ke_re, double* ke_im, double* ewald) {
+    DS_REQUIRE(c && x && ke_re && ke_im && ewald, "null argument");
+    Guard g(c->device);
+    const size_t n3 = 3 * (size_t)c->sys.d.N;
+    if (int rc = ensure(c, c->host_stage, (size_t)batch * (n3 + 3))) return rc;
+    double* dx = c->host_stage.p;
+    double* d0 = dx + (size_t)batch * n3;
+    DS_CUDA_CHECK(cudaMemcpyAsync(dx, x, (size_t)batch * n3 * sizeof(double), cudaMemcpyHostToDevice, 0));
+    if (int rc = ds_local_energy(c, dx, batch, mode, partition_number, d0, d0 + batch, d0 + 2 * batch, nullptr)) return rc;
+    DS_CUDA_CHECK(cudaMemcpyAsync(ke_re, d0, batch * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    DS_CUDA_CHECK(cudaMemcpyAsync(ke_im, d0 + batch, batch * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    DS_CUDA_CHECK(cudaMemcpyAsync(ewald, d0 + 2 * batch, batch * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    DS_CUDA_CHECK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+extern "C" int ds_mcmc_step_host(ds_ctx* c, double* x, int64_t batch, int steps, double width, uint64_t seed,
+                                 const double* xi, const double* u, uint8_t* accept, double* n_accept) {
+    DS_REQUIRE(c && x && n_accept, "null argument");
+    Guard g(c->device);
+    const size_t n3 = 3 * (size_t)c->sys.d.N;
+    size_t need = (size_t)batch * n3 + 8;
+    if (xi) need += (size_t)steps * batch * n3;
+    if (u) need += (size_t)steps * batch;
+    need += ((size_t)steps * batch + 7) / 8 + 8;
+    if (int rc = ensure(c, c->host_stage, need)) return rc;
+    double* dx = c->host_stage.p;
+    double* dn = dx + (size_t)batch * n3;
+    double* p = dn + 8;
+    double *dxi = nullptr, *du = nullptr;
+    if (xi) { dxi = p; p += (size_t)steps * batch * n3; }
+    if (u) { du = p; p += (size_t)steps * batch; }
+    uint8_t* dacc = accept ? reinterpret_cast<uint8_t*>(p) : nullptr;
+    DS_CUDA_CHECK(cudaMemcpyAsync(dx, x, (size_t)batch * n3 * sizeof(double), cudaMemcpyHostToDevice, 0));
+    if (xi) DS_CUDA_CHECK(cudaMemcpyAsync(dxi, xi, (size_t)steps * batch * n3 * sizeof(double), cudaMemcpyHostToDevice, 0));
+    if (u) DS_CUDA_CHECK(cudaMemcpyAsync(du, u, (size_t)steps * batch * sizeof(double), cudaMemcpyHostToDevice, 0));
+    if (int rc = ds_mcmc_step(c, dx, batch, steps, width, seed, dxi, du, dacc, dn, nullptr)) return rc;
+    DS_CUDA_CHECK(cudaMemcpyAsync(x, dx, (size_t)batch * n3 * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    DS_CUDA_CHECK(cudaMemcpyAsync(n_accept, dn, sizeof(double), cudaMemcpyDeviceToHost, 0));
+    if (accept) DS_CUDA_CHECK(cudaMemcpyAsync(accept, dacc, (size_t)steps * batch, cudaMemcpyDeviceToHost, 0));
+    DS_CUDA_CHECK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+// ---- instrumentation ------------------------------------------------------
+extern "C" int64_t ds_launch_count(const ds_ctx* c) { return c ? c->launches : -1; }
+
+extern "C" int ds_profile_enable(ds_ctx* c, int on) {
+    DS_REQUIRE(c, "null context");
+    c->prof_on = on != 0;
+    return 0;
+}
+
+extern "C" int ds_profile_reset(ds_ctx* c) {
+    DS_REQUIRE(c, "null context");
+    Guard g(c->device);
+    for (auto& ev : c->prof) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    c->prof.clear();
+    c->tot_ms = 0.0;
+    return 0;
+}
+
+extern "C" int ds_profile_get(ds_ctx* c, double* jac_ms, int64_t* jac_launches, double* jac_flops, double* total_ms) {
+    DS_REQUIRE(c, "null context");
+    Guard g(c->device);
+    double ms = 0.0, fl = 0.0;
+    for (auto& ev : c->prof) {
+        DS_CUDA_CHECK(cudaEventSynchronize(ev.b));
+        float t = 0.f;
+        DS_CUDA_CHECK(cudaEventElapsedTime(&t, ev.a, ev.b));
+        ms += t; fl += ev.flops;
+    }
+    if (jac_ms) *jac_ms = ms;
+    if (jac_launches) *jac_launches = (int64_t)c->prof.size();
+    if (jac_flops) *jac_flops = fl;
+    if (total_ms) *total_ms = c->tot_ms;
+    return 0;
+}
+
+extern "C" int ds_debug_set_int(ds_ctx* c, const char* key, int value) {
+    DS_REQUIRE(c && key, "null argument");
+    if (!strcmp(key, "stop_layer")) { c->dbg_stop_layer = value; return 0; }
+    ds_set_error("unknown debug key %s", key);
+    return -1;
+}
+
+extern "C" int64_t ds_debug_buffer(ds_ctx* c, const char* name, double* dst, int64_t max_doubles) {
+    if (!c || !name) return -1;
+    Guard g(c->device);
+    for (const Region& r : c->last_regions) {
+        if (!strcmp(r.name, name)) {
+            if (!r.p) return 0;
+            int64_t n = std::min<int64_t>((int64_t)r.n, max_doubles);
+            if (dst && n > 0) {
+                if (cudaMemcpy(dst, r.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice) != cudaSuccess) return -2;
+            }
+            return (int64_t)r.n;
+        }
+    }
+    ds_set_error("no workspace region named %s", name);
+    return -1;
+}
+
+extern "C" int ds_dgemm_probe(int device, const double* a, const double* b, double* cc, int64_t m, int n, int k,
+                              void* stream) {
+    Guard g(device);
+    GemmParams p{};
+    p.A = a; p.lda = k; p.B = b; p.ldb = n; p.M = m; p.N = n; p.K = k; p.C = cc; p.ldc = n;
+    return ds_launch_gemm(p, GEMM_PLAIN, false, (cudaStream_t)stream);
+}

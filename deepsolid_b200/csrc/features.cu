@@ -1,0 +1,242 @@
+// Periodic input features (network.py:249-302), the two-electron stream
+// (network.py:525-528) and its spin-channel means (network.py:323,328), with analytic
+// value / gradient / Laplacian jets when JETS is set.
+//
+// h_two[j,i] depends on x_j - x_i only (the pair stream never mixes), so a pair's jet
+// w.r.t. r = x_j - x_i gives d/dx_j = +grad, d/dx_i = -grad, full Laplacian = 2 lap_r.
+//
+// Grid: one CTA per (walker w, electron i).  A warp owns a pair (j,i); lane = hidden
+// channel of the pair stream.  Outputs are written straight into the operand
+// matrices of the one-electron-stream GEMMs (own + pair-mean columns).
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int FEAT_THREADS = 256;
+
+__device__ __forceinline__ Jet pick4(const Jet f[4], int q) {
+    return (q == 0) ? f[0] : (q == 1) ? f[1] : (q == 2) ? f[2] : f[3];
+}
+
+template <bool JETS>
+__global__ void __launch_bounds__(FEAT_THREADS) features_pair_kernel(const DsSys sys, const FeatParams fp) {
+    const DsDims& dm = sys.d;
+    const int N = dm.N, A = dm.A, P = dm.P, L = dm.L, C0 = dm.C0, K0 = dm.K0, K1 = dm.K1, H = dm.H;
+    const int NDp = dm.NDp, ND = dm.ND;
+    const long long e = blockIdx.x;             // w*N + i
+    const int w = (int)(e / N), i = (int)(e % N);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+    extern __shared__ double sm[];
+    double* sx = sm;                            // [N*3] wrapped (simulation cell) positions
+    double* sums = sx + 3 * N;                  // [2 spins][L levels][5 comps][32 lanes]
+    double* wsm = sums + 2 * L * 5 * 32;        // pair weights: level l>=1: [P_in x P] + [P] bias
+    const double* x = fp.X + (long long)w * 3 * N;
+
+    for (int t = tid; t < N; t += blockDim.x) {
+        double xi[3] = {x[3 * t], x[3 * t + 1], x[3 * t + 2]}, o[3];
+        ds_wrap(sys.sim, xi, o);
+        sx[3 * t] = o[0]; sx[3 * t + 1] = o[1]; sx[3 * t + 2] = o[2];
+    }
+    for (int t = tid; t < 2 * L * 5 * 32; t += blockDim.x) sums[t] = 0.0;
+    {   // stage pair-stream weights
+        int off = 0;
+        for (int l = 0; l < L - 1; ++l) {
+            int pin = (l == 0) ? 4 : P;
+            for (int t = tid; t < pin * P; t += blockDim.x) wsm[off + t] = fp.Wp[l][t];
+            for (int t = tid; t < P; t += blockDim.x) wsm[off + pin * P + t] = fp.bp[l][t];
+            off += pin * P + P;
+        }
+    }
+    __syncthreads();
+
+    // ---- electron-atom features of electron i (primitive cell) ---------------
+    if (tid < A) {
+        double xi[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]}, px[3], d[3];
+        ds_wrap(sys.prim, xi, px);
+        for (int k = 0; k < 3; ++k) d[k] = px[k] - sys.atoms[3 * tid + k];
+        Jet f[4];
+        ds_nu_distance<JETS>(sys.prim, d, f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            fp.A0V[e * K0 + tid * 4 + q] = f[q].v;
+            if (JETS) {
+                fp.A0L[e * K0 + tid * 4 + q] = f[q].l;
+                long long r = e * NDp + 3 * i;
+                fp.A0J[(r + 0) * K0 + tid * 4 + q] = f[q].g0;
+                fp.A0J[(r + 1) * K0 + tid * 4 + q] = f[q].g1;
+                fp.A0J[(r + 2) * K0 + tid * 4 + q] = f[q].g2;
+            }
+        }
+        double* ra = fp.RAE + (e * A + tid) * 5;
+        ra[0] = f[0].v; ra[1] = f[0].g0; ra[2] = f[0].g1; ra[3] = f[0].g2; ra[4] = f[0].l;
+    }
+
+    // ---- pairs (j, i) ---------------------------------------------------------
+    const double inv_up = 1.0 / dm.n_up, inv_dn = 1.0 / dm.n_dn;
+    double acc[2][DS_MAX_LAYERS][5];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int l = 0; l < DS_MAX_LAYERS; ++l)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) acc[s][l][c] = 0.0;
+
+    for (int j = warp; j < N; j += nwarps) {
+        const int sj = (j < dm.n_up) ? 0 : 1;
+        const double invn = sj ? inv_dn : inv_up;
+        double d[3];
+        for (int k = 0; k < 3; ++k) d[k] = sx[3 * j + k] - sx[3 * i + k] + (j == i ? 1.0 : 0.0);
+        Jet f[4];
+        ds_nu_distance<JETS>(sys.sim, d, f);
+        if (j == i) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) f[q] = jet_const(0.0);
+        }
+        Jet cur = jet_const(0.0);
+        if (lane < 4) cur = pick4(f, lane);
+        const long long rj = e * NDp + 3 * j;      // Jacobian rows of directions (j, c)
+        int woff = 0;
+#pragma unroll
+        for (int l = 0; l < DS_MAX_LAYERS; ++l) {
+            if (l >= L) break;
+            const int Pl = (l == 0) ? 4 : P;
+            // accumulate spin-channel sums of level l
+            if (lane < Pl) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const double m = (s == sj) ? 1.0 : 0.0;
+                    acc[s][l][0] += m * cur.v;
+                    if (JETS) {
+                        acc[s][l][1] += m * cur.g0; acc[s][l][2] += m * cur.g1; acc[s][l][3] += m * cur.g2;
+                        acc[s][l][4] += m * cur.l;
+                    }
+                }
+            }
+            // Jacobian rows of directions (j,c), j != i: +grad / n_{s(j)} in the spin-of-j half
+            if (JETS && j != i) {
+                if (l == 0) {
+                    if (lane < K0) {
+                        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+                        if (lane >= C0) {
+                            int s = (lane - C0) >> 2, q = (lane - C0) & 3;
+                            Jet fq = pick4(f, q);
+                            if (s == sj) { v0 = fq.g0 * invn; v1 = fq.g1 * invn; v2 = fq.g2 * invn; }
+                        }
+                        fp.A0J[(rj + 0) * K0 + lane] = v0;
+                        fp.A0J[(rj + 1) * K0 + lane] = v1;
+                        fp.A0J[(rj + 2) * K0 + lane] = v2;
+                    }
+                } else if (lane < P) {
+                    double* aj = fp.AJ[l];
+                    long long c_on = H + sj * P + lane, c_off = H + (1 - sj) * P + lane;
+                    aj[(rj + 0) * K1 + c_on] = cur.g0 * invn; aj[(rj + 0) * K1 + c_off] = 0.0;
+                    aj[(rj + 1) * K1 + c_on] = cur.g1 * invn; aj[(rj + 1) * K1 + c_off] = 0.0;
+                    aj[(rj + 2) * K1 + c_on] = cur.g2 * invn; aj[(rj + 2) * K1 + c_off] = 0.0;
+                }
+            }
+            if (l == L - 1) break;
+            // pair layer l: z = cur . W + b ; tanh ; residual when shapes agree (l >= 1)
+            const double* W = wsm + woff;
+            const double* bb = W + Pl * P;
+            Jet z = jet_const(lane < P ? bb[lane] : 0.0);
+            for (int c = 0; c < Pl; ++c) {
+                double wv = (lane < P) ? W[c * P + lane] : 0.0;
+                double cv = __shfl_sync(0xffffffffu, cur.v, c);
+                z.v = fma(cv, wv, z.v);
+                if (JETS) {
+                    double c0 = __shfl_sync(0xffffffffu, cur.g0, c);
+                    double c1 = __shfl_sync(0xffffffffu, cur.g1, c);
+                    double c2 = __shfl_sync(0xffffffffu, cur.g2, c);
+                    double cl = __shfl_sync(0xffffffffu, cur.l, c);
+                    z.g0 = fma(c0, wv, z.g0); z.g1 = fma(c1, wv, z.g1); z.g2 = fma(c2, wv, z.g2);
+                    z.l = fma(cl, wv, z.l);
+                }
+            }
+            Jet t;
+            if (JETS) t = jet_tanh(z);
+            else t = jet_const(tanh(z.v));
+            if (l >= 1) {
+                const double rs2 = 0.70710678118654752440;
+                t = jet_scale(jet_add(cur, t), rs2);
+            }
+            cur = (lane < P) ? t : jet_const(0.0);
+            woff += Pl * P + P;
+        }
+    }
+    // cross-warp reduction of the spin-channel sums
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int l = 0; l < DS_MAX_LAYERS; ++l) {
+            if (l >= L) break;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                if (!JETS && c > 0) break;
+                atomicAdd(&sums[((s * L + l) * 5 + c) * 32 + lane], acc[s][l][c]);
+            }
+        }
+    __syncthreads();
+
+    // ---- finalize: value / Laplacian rows, own-direction Jacobian rows, padding rows
+#pragma unroll
+    for (int l = 0; l < DS_MAX_LAYERS; ++l) {
+        if (l >= L) break;
+        const int Pl = (l == 0) ? 4 : P;
+        for (int t = tid; t < 64; t += blockDim.x) {
+            const int lane_c = t & 31, s = t >> 5;
+            if (lane_c >= Pl) continue;
+            const double* sv = sums + ((s * L + l) * 5) * 32 + lane_c;
+            const double invn = s ? inv_dn : inv_up;
+            const long long r = e * NDp + 3 * i;
+            if (l == 0) {
+                long long col = C0 + s * 4 + lane_c;
+                fp.A0V[e * K0 + col] = sv[0] * invn;
+                if (JETS) {
+                    fp.A0L[e * K0 + col] = 2.0 * sv[4 * 32] * invn;
+                    fp.A0J[(r + 0) * K0 + col] = -sv[1 * 32] * invn;
+                    fp.A0J[(r + 1) * K0 + col] = -sv[2 * 32] * invn;
+                    fp.A0J[(r + 2) * K0 + col] = -sv[3 * 32] * invn;
+                }
+            } else {
+                long long col = H + s * P + lane_c;
+                fp.AV[l][e * K1 + col] = sv[0] * invn;
+                if (JETS) {
+                    fp.AL[l][e * K1 + col] = 2.0 * sv[4 * 32] * invn;
+                    fp.AJ[l][(r + 0) * K1 + col] = -sv[1 * 32] * invn;
+                    fp.AJ[l][(r + 1) * K1 + col] = -sv[2 * 32] * invn;
+                    fp.AJ[l][(r + 2) * K1 + col] = -sv[3 * 32] * invn;
+                }
+            }
+        }
+    }
+    if (JETS) {
+        // zero rows of the padding directions d in [ND, NDp)
+        const int npad = NDp - ND;
+        for (int t = tid; t < npad * K0; t += blockDim.x)
+            fp.A0J[(e * NDp + ND + t / K0) * K0 + t % K0] = 0.0;
+#pragma unroll
+        for (int l = 1; l < DS_MAX_LAYERS; ++l) {
+            if (l >= L) break;
+            for (int t = tid; t < npad * 2 * P; t += blockDim.x)
+                fp.AJ[l][(e * NDp + ND + t / (2 * P)) * K1 + H + t % (2 * P)] = 0.0;
+        }
+    }
+}
+
+}  // namespace
+
+size_t ds_features_smem(const DsDims& d) {
+    size_t n = 3 * d.N + 2 * d.L * 5 * 32;
+    for (int l = 0; l < d.L - 1; ++l) n += ((l == 0) ? 4 : d.P) * d.P + d.P;
+    return n * sizeof(double);
+}
+
+int ds_launch_features(const DsSys& sys, const FeatParams& fp, int Wc, bool jets, cudaStream_t stream) {
+    size_t smem = ds_features_smem(sys.d);
+    dim3 grid((unsigned)((long long)Wc * sys.d.N));
+    if (jets) features_pair_kernel<true><<<grid, FEAT_THREADS, smem, stream>>>(sys, fp);
+    else features_pair_kernel<false><<<grid, FEAT_THREADS, smem, stream>>>(sys, fp);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,78 @@
+// Kernel launchers of the deepsolid_b200 library (definitions in the .cu files).
+#pragma once
+#include "ds_common.cuh"
+#include "gemm_f64.cuh"
+
+#define DS_MAX_LAYERS 4
+
+// features.cu ---------------------------------------------------------------
+struct FeatParams {
+    const double* X;                 // [Wc, 3N]
+    double *A0V, *A0L, *A0J;         // layer-0 operand matrices, ld = K0
+    double* AV[DS_MAX_LAYERS];       // value rows of layer l >= 1 (ld K1); pair-mean columns written here
+    double* AL[DS_MAX_LAYERS];       // Laplacian rows
+    double* AJ[DS_MAX_LAYERS];       // Jacobian rows
+    double* RAE;                     // [(w*N+i)*A + a][5] jet of the electron-atom distance
+    const double* Wp[DS_MAX_LAYERS]; // pair-stream weights [in x P]
+    const double* bp[DS_MAX_LAYERS]; // pair-stream biases [P]
+};
+int ds_launch_features(const DsSys& sys, const FeatParams& fp, int Wc, bool jets, cudaStream_t stream);
+
+// stream.cu -----------------------------------------------------------------
+// spin-channel means of the one-electron stream: rows of the shared-mean operand
+// GIN[w, d, s*C + c] = mean_{i in s} src[(w,i,d), c]; d = NDp -> value, NDp+1 -> Laplacian.
+int ds_launch_means(const DsDims& dm, int Wc, int C, const double* AJ, int ldj, const double* AV,
+                    const double* AL, int ldv, double* GIN, int ldgin, bool jets, cudaStream_t stream);
+
+// slater.cu -----------------------------------------------------------------
+struct SlaterBufs {
+    const double* X;        // [Wc,3N]
+    const double* RAE;      // electron-atom distance jets
+    double* ETAB;           // complex [(w*N+i)][5][npar_max]
+    const double* YV;       // complex raw orbital values   [(w*N+i)][npar_max]
+    const double* YL;       // complex raw orbital Laplacians
+    const double* YOWN;     // complex raw own-gradient     [(w*N+i)][3][npar_max]
+    double* MAT[2];         // complex orbital matrices per spin [(w*D+k)][n_s][n_s]
+    double* LAPM[2];        // complex Laplacian of the matrices
+    double* DA[2];          // complex derivative matrices  [(w*D+k)][NDp][n_s][n_s]
+    double* LOGDET;         // [w][2][D][3] : log|det|, cos(arg), sin(arg)
+    double* TAU;            // complex [w][2][D][NDp]  tr(X dA_d)
+    double* TRSQ;           // complex [w][2][D]       sum_d tr((X dA_d)^2)
+    double* TRLAP;          // complex [w][2][D]       tr(X lapA)
+    const double* env_pi[2];
+    const double* env_sigma[2];     // [A][n_s*D]
+    const double* klist[2];         // [n_s][3]
+};
+int ds_launch_etab(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max, bool jets, cudaStream_t stream);
+int ds_launch_orb_assemble(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max, bool jets, cudaStream_t stream);
+int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cudaStream_t stream);
+int ds_launch_combine(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, double* log_abs, double* phase,
+                      double* ke_re, double* ke_im, cudaStream_t stream);
+
+// ewald.cu ------------------------------------------------------------------
+struct EwaldDev {
+    int n_elec, n_atoms, dist_kind, n_g;
+    double lat[9], inv[9], alpha;
+    const double* atoms;        // [n_atoms*3]
+    const double* charges;
+    const double* mi_shifts;    // [27*3]
+    const double* disp;         // [27*3]
+    const double* gpoints;      // [n_g*3]
+    const double* gweight;
+    const double* ion_re;
+    const double* ion_im;
+    double ee_const, ei_const, ii_total;
+};
+int ds_launch_ewald(const EwaldDev& ew, const double* X, long long batch, double* ee, double* ei,
+                    double* total_or_null, cudaStream_t stream);
+
+// mcmc.cu -------------------------------------------------------------------
+int ds_launch_propose(const DsLattice& sim, const double* x, double* x2, long long batch, int n3, double width,
+                      const double* xi_or_null, unsigned long long seed, unsigned long long step,
+                      cudaStream_t stream);
+int ds_launch_accept(double* x, const double* x2, double* lp, const double* lp2, long long batch, int n3,
+                     const double* u_or_null, unsigned long long seed, unsigned long long step,
+                     unsigned char* mask_or_null, double* n_accept, cudaStream_t stream);
+int ds_launch_scale(double* dst, const double* src, double a, long long n, cudaStream_t stream);
+int ds_launch_stats(const double* ke_re, const double* ke_im, const double* ew, long long n, double* out6,
+                    cudaStream_t stream);

@@ -1,0 +1,267 @@
+"""Device context of the hot path: one ``HotPath`` per (simulation cell, network
+configuration, CUDA device).  It owns the C-ABI context, uploads the parameter
+pytree when it changes, and exposes batched torch-tensor entry points that the
+reference-shaped closures in network.py / hamiltonian.py / qmc.py / train.py call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ewald_tables import build_ewald_tables
+
+LAP_MODES = {"for": 0, "hessian": 1, "dim_batch": 2, "partition": 3}
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_lib.c_double_p)
+
+
+def flatten_params(params) -> list:
+    """Leaf order of ds_set_params (include/deepsolid_b200.h)."""
+    leaves = []
+    for layer in params["single"]:
+        leaves += [layer["w"], layer["b"]]
+    for layer in params["double"]:
+        leaves += [layer["w"], layer["b"]]
+    for orb in params["orbital"]:
+        if "b" in orb:
+            raise ValueError("bias_orbitals=True is not implemented in the CUDA hot path")
+        leaves.append(orb["w"])
+    for env in params["envelope"]:
+        leaves += [env["pi"], env["sigma"]]
+    return leaves
+
+
+class HotPath:
+    def __init__(self, simulation_cell, klist, hidden_dims=((256, 32),) * 3, determinants: int = 8,
+                 device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("deepsolid_b200 needs a CUDA device: the local-energy hot path has no CPU fallback")
+        self.lib = _lib.load()
+        self.cell = simulation_cell
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.tdev = torch.device("cuda", self.device)
+        prim = simulation_cell.original_cell
+        hidden_dims = tuple(tuple(h) for h in hidden_dims)
+        if len({h[0] for h in hidden_dims}) != 1 or len({h[1] for h in hidden_dims}) != 1:
+            raise ValueError("the CUDA hot path needs equal widths in every layer of hidden_dims")
+        self.hidden_dims = hidden_dims
+        self.determinants = int(determinants)
+        self.n_up, self.n_dn = simulation_cell.nelec
+        self.nelec = self.n_up + self.n_dn
+        tb = build_ewald_tables(simulation_cell)
+        self.tables = tb
+        ne = self.nelec
+        keep = [_f64(prim.a), _f64(simulation_cell.a), _f64(prim.AV), _f64(prim.BV), _f64(simulation_cell.AV),
+                _f64(simulation_cell.BV), _f64(prim.atom_coords()), _f64(tb.atom_coords), _f64(tb.atom_charges),
+                _f64(klist[0]).reshape(-1, 3), _f64(klist[1]).reshape(-1, 3), _f64(tb.mi_shifts),
+                _f64(tb.lattice_displacements), _f64(tb.gpoints), _f64(tb.gweight),
+                _f64(tb.ion_exp.real), _f64(tb.ion_exp.imag)]
+        for m in keep[2:6]:
+            if m.shape != (3, 3):
+                raise ValueError("only sym_type='minimal' (3 reciprocal rows) is implemented")
+        if keep[9].shape[0] != self.n_up or keep[10].shape[0] != self.n_dn:
+            raise ValueError("klist must hold one k-point per occupied orbital of each spin")
+        sd = _lib.SystemDesc(
+            n_up=self.n_up, n_dn=self.n_dn, n_atoms_prim=prim.natm, n_atoms_sim=len(tb.atom_charges),
+            prim_latvec=_ptr(keep[0]), sim_latvec=_ptr(keep[1]), prim_AV=_ptr(keep[2]), prim_BV=_ptr(keep[3]),
+            sim_AV=_ptr(keep[4]), sim_BV=_ptr(keep[5]), prim_atoms=_ptr(keep[6]), sim_atoms=_ptr(keep[7]),
+            sim_charges=_ptr(keep[8]), klist_up=_ptr(keep[9]), klist_dn=_ptr(keep[10]),
+            dist_kind=int(tb.dist_kind), mi_shifts=_ptr(keep[11]), lattice_displacements=_ptr(keep[12]),
+            alpha=float(tb.alpha), n_g=int(len(tb.gweight)), gpoints=_ptr(keep[13]), gweight=_ptr(keep[14]),
+            ion_exp_re=_ptr(keep[15]), ion_exp_im=_ptr(keep[16]),
+            ee_const=float(tb.ee_const(ne)), ei_const=float(tb.ei_const(ne)), ii_total=float(tb.ii_total))
+        nd = _lib.NetDesc(n_layers=len(hidden_dims), hidden_one=hidden_dims[0][0], hidden_two=hidden_dims[0][1],
+                          n_det=self.determinants)
+        h = C.c_void_p()
+        _lib.check(self.lib.ds_ctx_create(C.byref(sd), C.byref(nd), self.device, C.byref(h)))
+        self.h = h
+        self._param_key = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.ds_ctx_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    def set_params(self, params) -> None:
+        """Upload the reference parameter pytree (network.py:135-184) if it changed."""
+        leaves = flatten_params(params)
+        tens = []
+        for lf in leaves:
+            t = lf if isinstance(lf, torch.Tensor) else torch.as_tensor(np.asarray(lf))
+            if t.dtype != torch.float64 or not t.is_contiguous():
+                t = t.to(torch.float64).contiguous()
+            tens.append(t)
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tens)
+        if key == self._param_key:
+            return
+        n = len(tens)
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tens])
+        sizes = (C.c_int64 * n)(*[t.numel() for t in tens])
+        _lib.check(self.lib.ds_set_params(self.h, ptrs, sizes, n))
+        self._param_key = key
+        self._keep_params = tens
+
+    def set_workspace_limit(self, nbytes: int) -> None:
+        _lib.check(self.lib.ds_set_workspace_limit(self.h, int(nbytes)))
+
+    # ------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def _prep(self, x) -> Tuple[torch.Tensor, bool, bool]:
+        """-> (2-D float64 contiguous tensor, was_1d, on_device)."""
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+        one = t.dim() == 1
+        if one:
+            t = t[None]
+        if t.dim() != 2 or t.shape[1] != 3 * self.nelec:
+            raise ValueError(f"walkers must have shape (batch, {3 * self.nelec}); got {tuple(t.shape)}")
+        t = t.to(torch.float64).contiguous()
+        on_dev = t.is_cuda
+        if on_dev and t.device != self.tdev:
+            raise ValueError(f"walkers live on {t.device}, context on {self.tdev}")
+        return t, one, on_dev
+
+    def logpsi(self, x):
+        """(log|psi|, angle) for a batch; device tensors stay on the device, host tensors go
+        through the C-ABI host entry point (copies included)."""
+        t, one, on_dev = self._prep(x)
+        B = t.shape[0]
+        if on_dev:
+            la = torch.empty(B, dtype=torch.float64, device=self.tdev)
+            ph = torch.empty_like(la)
+            _lib.check(self.lib.ds_logpsi(self.h, t.data_ptr(), B, la.data_ptr(), ph.data_ptr(), self._stream()))
+        else:
+            la = torch.empty(B, dtype=torch.float64)
+            ph = torch.empty_like(la)
+            _lib.check(self.lib.ds_logpsi_host(self.h, t.data_ptr(), B, la.data_ptr(), ph.data_ptr()))
+        return (la[0], ph[0]) if one else (la, ph)
+
+    def orbitals(self, x):
+        t, one, on_dev = self._prep(x)
+        B = t.shape[0]
+        td = t if on_dev else t.to(self.tdev)
+        per = int(self.lib.ds_orbitals_size(self.h))
+        out = torch.empty(B, per, dtype=torch.float64, device=self.tdev)
+        _lib.check(self.lib.ds_orbitals(self.h, td.data_ptr(), B, out.data_ptr(), self._stream()))
+        D = self.determinants
+        mats, o = [], 0
+        for ns in (self.n_up, self.n_dn):
+            n = D * ns * ns * 2
+            m = torch.view_as_complex(out[:, o:o + n].reshape(B, D, ns, ns, 2).contiguous())
+            mats.append(m if on_dev else m.cpu())
+            o += n
+        return [m[0] for m in mats] if one else mats
+
+    def local_energy(self, x, mode: str = "for", partition_number: int = 3):
+        """(kinetic complex128 [B], ewald float64 [B])."""
+        if mode not in LAP_MODES:
+            raise ValueError("Unrecognized laplacian evaluation mode.")
+        t, one, on_dev = self._prep(x)
+        B = t.shape[0]
+        dev = self.tdev if on_dev else torch.device("cpu")
+        out = torch.empty(3, B, dtype=torch.float64, device=dev)
+        if on_dev:
+            _lib.check(self.lib.ds_local_energy(self.h, t.data_ptr(), B, LAP_MODES[mode], int(partition_number),
+                                                out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                                self._stream()))
+        else:
+            _lib.check(self.lib.ds_local_energy_host(self.h, t.data_ptr(), B, LAP_MODES[mode], int(partition_number),
+                                                     out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr()))
+        ke = torch.complex(out[0], out[1])
+        ew = out[2]
+        return (ke[0], ew[0]) if one else (ke, ew)
+
+    def ewald(self, x):
+        t, one, on_dev = self._prep(x)
+        td = t if on_dev else t.to(self.tdev)
+        B = td.shape[0]
+        out = torch.empty(2, B, dtype=torch.float64, device=self.tdev)
+        _lib.check(self.lib.ds_ewald(self.h, td.data_ptr(), B, out[0].data_ptr(), out[1].data_ptr(), self._stream()))
+        ii = torch.full((B,), float(self.lib.ds_ewald_ii(self.h)), dtype=torch.float64, device=self.tdev)
+        res = (out[0], out[1], ii)
+        if not on_dev:
+            res = tuple(r.cpu() for r in res)
+        return tuple(r[0] for r in res) if one else res
+
+    def mcmc(self, data, steps: int, width: float, seed: int = 0, xi=None, u=None, return_masks: bool = False):
+        """In-place-free Metropolis sweep: returns (new_data, n_accept tensor[1], masks or None)."""
+        t, one, on_dev = self._prep(data)
+        if one:
+            raise ValueError("mcmc_step needs batched walkers (batch, 3N)")
+        B = t.shape[0]
+        if on_dev:
+            x = t.clone()
+            nacc = torch.zeros(1, dtype=torch.float64, device=self.tdev)
+            masks = torch.empty(steps, B, dtype=torch.uint8, device=self.tdev) if return_masks else None
+            xi_d = xi.to(self.tdev, torch.float64).contiguous() if xi is not None else None
+            u_d = u.to(self.tdev, torch.float64).contiguous() if u is not None else None
+            if xi_d is not None and tuple(xi_d.shape) != (steps, B, 3 * self.nelec):
+                raise ValueError("xi must have shape (steps, batch, 3N)")
+            if u_d is not None and tuple(u_d.shape) != (steps, B):
+                raise ValueError("u must have shape (steps, batch)")
+            _lib.check(self.lib.ds_mcmc_step(
+                self.h, x.data_ptr(), B, int(steps), float(width), int(seed) & (2 ** 64 - 1),
+                xi_d.data_ptr() if xi_d is not None else None, u_d.data_ptr() if u_d is not None else None,
+                masks.data_ptr() if masks is not None else None, nacc.data_ptr(), self._stream()))
+            return x, nacc, masks
+        x = t.clone()
+        nacc = torch.zeros(1, dtype=torch.float64)
+        masks = torch.empty(steps, B, dtype=torch.uint8) if return_masks else None
+        xi_h = xi.to(torch.float64).contiguous() if xi is not None else None
+        u_h = u.to(torch.float64).contiguous() if u is not None else None
+        _lib.check(self.lib.ds_mcmc_step_host(
+            self.h, x.data_ptr(), B, int(steps), float(width), int(seed) & (2 ** 64 - 1),
+            xi_h.data_ptr() if xi_h is not None else None, u_h.data_ptr() if u_h is not None else None,
+            masks.data_ptr() if masks is not None else None, nacc.data_ptr()))
+        return x, nacc, masks
+
+    def energy_stats(self, ke: torch.Tensor, ew: torch.Tensor) -> torch.Tensor:
+        """[sum Re e, sum Im e, sum |e|^2, sum Re ke, sum ew, n] on the device."""
+        kr = ke.real.contiguous()
+        ki = ke.imag.contiguous()
+        ew = ew.contiguous()
+        out = torch.empty(6, dtype=torch.float64, device=self.tdev)
+        _lib.check(self.lib.ds_energy_stats(self.h, kr.data_ptr(), ki.data_ptr(), ew.data_ptr(), kr.numel(),
+                                            out.data_ptr(), self._stream()))
+        return out
+
+    # ---- instrumentation ------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.lib.ds_launch_count(self.h))
+
+    def profile(self, on: bool):
+        _lib.check(self.lib.ds_profile_enable(self.h, 1 if on else 0))
+        _lib.check(self.lib.ds_profile_reset(self.h))
+
+    def profile_get(self) -> Dict[str, float]:
+        ms, fl, tot = C.c_double(), C.c_double(), C.c_double()
+        n = C.c_int64()
+        _lib.check(self.lib.ds_profile_get(self.h, C.byref(ms), C.byref(n), C.byref(fl), C.byref(tot)))
+        return {"jac_ms": ms.value, "jac_launches": n.value, "jac_flops": fl.value, "total_ms": tot.value}
+
+    def debug_buffer(self, name: str) -> torch.Tensor:
+        n = int(self.lib.ds_debug_buffer(self.h, name.encode(), None, 0))
+        if n < 0:
+            raise KeyError(name)
+        out = torch.empty(n, dtype=torch.float64, device=self.tdev)
+        if n:
+            self.lib.ds_debug_buffer(self.h, name.encode(), out.data_ptr(), n)
+        return out
+
+    def debug_set(self, key: str, value: int):
+        _lib.check(self.lib.ds_debug_set_int(self.h, key.encode(), int(value)))

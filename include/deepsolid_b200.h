@@ -1,0 +1,179 @@
+/*
+ * deepsolid_b200 -- C ABI of the B200-native local-energy hot path.
+ *
+ * The reference (bytedance/DeepSolid) has no FFI layer: its boundary is the set of
+ * Python closures process.py builds (process.py:112-118,183-198).  Each entry point
+ * below is what one of those closures computes for a whole batch of walkers, so
+ * that deepsolid_b200/{network,hamiltonian,qmc,train}.py can re-create the closures
+ * with the reference's names and argument meaning on top of this library.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative ds_status otherwise;
+ *    ds_last_error() returns a thread-local human-readable message.
+ *  - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*.
+ *  - "_dev" pointers are device memory on the context's device (owned by the
+ *    caller, e.g. a torch tensor); entry points suffixed _host take HOST buffers
+ *    and do the host<->device copies themselves on the given stream.
+ *  - walkers are (B, 3N) fp64, electron-major then xyz, spin-up electrons first
+ *    (network.py:322-323,451,537).
+ *  - one context per (process, device); calls on one context are not thread safe
+ *    (the reference driver is single-threaded, process.py:289-383).
+ *  - there is no CPU fallback: without a CUDA device ds_ctx_create fails.
+ */
+#ifndef DEEPSOLID_B200_H
+#define DEEPSOLID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define DS_API __attribute__((visibility("default")))
+#else
+#define DS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ds_ctx ds_ctx;
+
+typedef enum ds_status {
+    DS_OK = 0,
+    DS_ERR_INVALID = -1,      /* invalid argument -> Python ValueError          */
+    DS_ERR_CUDA = -2,         /* CUDA runtime error -> Python RuntimeError       */
+    DS_ERR_UNSUPPORTED = -3,  /* option outside the implemented path            */
+    DS_ERR_NOMEM = -4
+} ds_status;
+
+/* Laplacian evaluation modes of hamiltonian.local_energy_seperate (hamiltonian.py:209-218).
+ * All four denote the same quantity; they select how the 3N directions are tiled. */
+typedef enum ds_lap_mode {
+    DS_LAP_FOR = 0, DS_LAP_HESSIAN = 1, DS_LAP_DIM_BATCH = 2, DS_LAP_PARTITION = 3
+} ds_lap_mode;
+
+/* Geometry + Ewald tables of one simulation cell.  All pointers are HOST memory and
+ * are copied.  Replaces the attributes the hot path reads from the pyscf Cell
+ * (supercell.py:64-140) and the tables EwaldSum.__init__ builds (ewaldsum.py:33-136). */
+typedef struct ds_system_desc {
+    int32_t n_up, n_dn;              /* simulation_cell.nelec                          */
+    int32_t n_atoms_prim;            /* atoms of original_cell (network.py:643)        */
+    int32_t n_atoms_sim;             /* atoms of the simulation cell (ewaldsum.py:41)  */
+    const double *prim_latvec;       /* 3x3 row-major, rows = lattice vectors (Bohr)   */
+    const double *sim_latvec;
+    const double *prim_AV, *prim_BV; /* 3x3 (supercell.py:131-139, sym_type minimal)   */
+    const double *sim_AV, *sim_BV;
+    const double *prim_atoms;        /* n_atoms_prim x 3                               */
+    const double *sim_atoms;         /* n_atoms_sim x 3                                */
+    const double *sim_charges;       /* n_atoms_sim                                    */
+    const double *klist_up;          /* n_up x 3 occupied k per orbital (hf.py:84-104) */
+    const double *klist_dn;          /* n_dn x 3                                       */
+    int32_t dist_kind;               /* 0 diagonal, 1 orthogonal, 2 general (distance.py:41-59) */
+    const double *mi_shifts;         /* 27 x 3 minimal-image candidates (distance.py:64-67) */
+    const double *lattice_displacements; /* 27 x 3 real-space images (ewaldsum.py:48-56) */
+    double alpha;                    /* ewaldsum.py:63-64                              */
+    int32_t n_g;
+    const double *gpoints;           /* n_g x 3 (ewaldsum.py:68-89)                    */
+    const double *gweight;           /* n_g                                            */
+    const double *ion_exp_re, *ion_exp_im; /* n_g (ewaldsum.py:131-132)                */
+    double ee_const, ei_const, ii_total;   /* ewaldsum.py:109-113,188-190              */
+} ds_system_desc;
+
+/* Network hyper-parameters (base_config.py:129-139).  Only the reference's tested
+ * defaults for the structural switches are implemented: envelope_type='isotropic',
+ * full_det=False, use_last_layer=False, bias_orbitals=False, distance_type='nu'. */
+typedef struct ds_net_desc {
+    int32_t n_layers;     /* len(hidden_dims)            (3)   */
+    int32_t hidden_one;   /* one-electron stream width   (256) */
+    int32_t hidden_two;   /* two-electron stream width   (32)  */
+    int32_t n_det;        /* determinants                (8)   */
+} ds_net_desc;
+
+DS_API const char *ds_last_error(void);
+DS_API int ds_version(void);
+
+DS_API int ds_ctx_create(const ds_system_desc *sys, const ds_net_desc *net, int device, ds_ctx **out);
+DS_API int ds_ctx_destroy(ds_ctx *ctx);
+
+/* Upper bound (bytes) for the internal per-chunk workspace; walkers are processed
+ * in chunks that fit.  Default 8 GiB. */
+DS_API int ds_set_workspace_limit(ds_ctx *ctx, size_t bytes);
+
+/* Parameter pytree of init_solid_fermi_net_params (network.py:135-184), flattened in
+ * this order (L = n_layers):
+ *   single[0].w, single[0].b, ..., single[L-1].w, single[L-1].b,
+ *   double[0].w, double[0].b, ..., double[L-2].w, double[L-2].b,
+ *   orbital[0].w, orbital[1].w,
+ *   envelope[0].pi, envelope[0].sigma, envelope[1].pi, envelope[1].sigma
+ * Every leaf is row-major fp64; pointers may be host or device memory; the data is
+ * copied (and re-laid-out) so the caller may free or mutate it afterwards. */
+DS_API int ds_set_params(ds_ctx *ctx, const double *const *leaves, const int64_t *leaf_sizes, int n_leaves);
+
+/* network.eval_func, methods eval_slogdet / eval_logdet / eval_phase_and_slogdet
+ * (network.py:594-600), batched: log_abs[b] = log|psi|, phase[b] = angle(psi) in (-pi,pi].
+ * Either output may be NULL. */
+DS_API int ds_logpsi(ds_ctx *ctx, const double *x_dev, int64_t batch,
+              double *log_abs_dev, double *phase_dev, void *stream);
+
+/* method eval_mats (network.py:601-602): out = complex128 (re,im interleaved) of shape
+ * (batch, 2 spins, n_det, n_s, n_s) with spin blocks concatenated (n_up block first). */
+DS_API int ds_orbitals(ds_ctx *ctx, const double *x_dev, int64_t batch, double *out_dev, void *stream);
+DS_API int64_t ds_orbitals_size(const ds_ctx *ctx); /* doubles per walker written by ds_orbitals */
+
+/* hamiltonian.local_energy_seperate(f, cell, mode, partition_number)(params, x)
+ * (hamiltonian.py:194-228), batched: kinetic = ke_re + i ke_im, ewald = ee+ei+ii. */
+DS_API int ds_local_energy(ds_ctx *ctx, const double *x_dev, int64_t batch, int mode, int partition_number,
+                    double *ke_re_dev, double *ke_im_dev, double *ewald_dev, void *stream);
+
+/* EwaldSum.energy (ewaldsum.py:185-191): ee[b], ei[b] (constants included); ii via ds_ewald_ii. */
+DS_API int ds_ewald(ds_ctx *ctx, const double *x_dev, int64_t batch, double *ee_dev, double *ei_dev, void *stream);
+DS_API double ds_ewald_ii(const ds_ctx *ctx);
+
+/* qmc.make_mcmc_step(...).mcmc_step (qmc.py:335-362) with mh_update (qmc.py:153-224),
+ * symmetric all-electron Metropolis moves.
+ *   x_dev        in/out walkers (batch, 3N)
+ *   xi_dev,u_dev optional caller-supplied noise: gaussians (steps,batch,3N) and uniforms
+ *                (steps,batch).  When NULL, a Philox4x32-10 stream keyed by `seed`
+ *                generates them on the device.
+ *   accept_dev   optional (steps,batch) uint8 accept masks
+ *   n_accept_dev required: one double, number of accepted moves over all steps
+ * pmove = n_accept / (steps*batch) is formed (and all-reduced) by the caller. */
+DS_API int ds_mcmc_step(ds_ctx *ctx, double *x_dev, int64_t batch, int steps, double width, uint64_t seed,
+                 const double *xi_dev, const double *u_dev, uint8_t *accept_dev,
+                 double *n_accept_dev, void *stream);
+
+/* train.make_loss.total_energy forward statistics (train.py:74-80): out6 =
+ * [sum Re e_l, sum Im e_l, sum |e_l|^2, sum Re ke, sum ew, n] over the local batch;
+ * the caller all-reduces the vector (NCCL) and forms mean / variance. */
+DS_API int ds_energy_stats(ds_ctx *ctx, const double *ke_re_dev, const double *ke_im_dev,
+                    const double *ewald_dev, int64_t batch, double *out6_dev, void *stream);
+
+/* HOST-buffer forms: copy in, compute, copy out, synchronise the stream. */
+DS_API int ds_logpsi_host(ds_ctx *ctx, const double *x_host, int64_t batch, double *log_abs_host, double *phase_host);
+DS_API int ds_local_energy_host(ds_ctx *ctx, const double *x_host, int64_t batch, int mode, int partition_number,
+                         double *ke_re_host, double *ke_im_host, double *ewald_host);
+DS_API int ds_mcmc_step_host(ds_ctx *ctx, double *x_host, int64_t batch, int steps, double width, uint64_t seed,
+                      const double *xi_host, const double *u_host, uint8_t *accept_host, double *n_accept_host);
+
+/* ---- instrumentation (not part of the reference surface) ------------------------ */
+/* number of kernels this library has launched on the context since creation */
+DS_API int64_t ds_launch_count(const ds_ctx *ctx);
+/* device-time (ms, CUDA events on the launching stream) and launch count of the
+ * Jacobian-sweep GEMM kernel accumulated since the last reset; flops = executed DMMA flops */
+DS_API int ds_profile_reset(ds_ctx *ctx);
+DS_API int ds_profile_enable(ds_ctx *ctx, int on);
+DS_API int ds_profile_get(ds_ctx *ctx, double *jac_ms, int64_t *jac_launches, double *jac_flops,
+                   double *total_ms);
+/* Copy an internal per-chunk buffer of the last ds_local_energy call (first chunk) to
+ * dst_dev for stage-by-stage parity tests.  Returns number of doubles (or <0). */
+DS_API int64_t ds_debug_buffer(ds_ctx *ctx, const char *name, double *dst_dev, int64_t max_doubles);
+/* debug knobs: "stop_layer" = l stops ds_local_energy/ds_logpsi after one-electron layer l (-1: off) */
+DS_API int ds_debug_set_int(ds_ctx *ctx, const char *key, int value);
+/* Stand-alone run of the fp64 tensor-core GEMM kernel (C = A.B, row-major) for peak probes. */
+DS_API int ds_dgemm_probe(int device, const double *a_dev, const double *b_dev, double *c_dev,
+                   int64_t m, int n, int k, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPSOLID_B200_H */
