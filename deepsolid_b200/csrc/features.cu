@@ -235,6 +235,10 @@ size_t ds_features_smem(const DsDims& d) {
 int ds_launch_features(const DsSys& sys, const FeatParams& fp, int Wc, bool jets, cudaStream_t stream) {
     size_t smem = ds_features_smem(sys.d);
     dim3 grid((unsigned)((long long)Wc * sys.d.N));
+    if (smem > 48 * 1024) {
+        DS_CUDA_CHECK(cudaFuncSetAttribute(features_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DS_CUDA_CHECK(cudaFuncSetAttribute(features_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (jets) features_pair_kernel<true><<<grid, FEAT_THREADS, smem, stream>>>(sys, fp);
     else features_pair_kernel<false><<<grid, FEAT_THREADS, smem, stream>>>(sys, fp);
     DS_CUDA_CHECK(cudaGetLastError());

@@ -447,23 +447,16 @@ int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cuda
         while (G > 1 && (size_t)(np * np + np + 2 * G * np * np) * sizeof(cplx) > 100 * 1024) --G;
     }
     size_t smem = (size_t)(np * np + np + (lap ? 2 * G * np * np : 0)) * sizeof(cplx);
-    DS_REQUIRE(smem <= 227 * 1024, "determinant kernel needs %zu bytes of shared memory", smem);
+    DS_REQUIRE(smem <= 226 * 1024, "determinant kernel needs %zu bytes of shared memory", smem);
     dim3 grid((unsigned)((long long)Wc * 2 * sys.d.D));
-    if (lap) {
-        static bool cfg = false;
-        if (!cfg) {
-            DS_CUDA_CHECK(cudaFuncSetAttribute(det_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            cfg = true;
-        }
-        det_kernel<true><<<grid, DET_THREADS, smem, stream>>>(sys, sb, G);
-    } else {
-        static bool cfg = false;
-        if (!cfg) {
-            DS_CUDA_CHECK(cudaFuncSetAttribute(det_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            cfg = true;
-        }
-        det_kernel<false><<<grid, DET_THREADS, smem, stream>>>(sys, sb, G);
+    static size_t cfg_smem[2] = {0, 0};
+    if (smem > cfg_smem[lap ? 1 : 0]) {
+        if (lap) DS_CUDA_CHECK(cudaFuncSetAttribute(det_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else DS_CUDA_CHECK(cudaFuncSetAttribute(det_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg_smem[lap ? 1 : 0] = smem;
     }
+    if (lap) det_kernel<true><<<grid, DET_THREADS, smem, stream>>>(sys, sb, G);
+    else det_kernel<false><<<grid, DET_THREADS, smem, stream>>>(sys, sb, G);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
