@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- local-energies/sec of the DeepSolid local-energy hot path on B200.
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (torchrun for N>1)
+prints ONE JSON line on rank 0.  A "step" is one pass of the hot path over one batch of
+synthetic walkers: ``total_energy(params, data)`` = per-walker kinetic energy
+(forward-Laplacian sweep) + Ewald energy + packed statistics + one all-reduce
+(train.py:66-89 forward).  ``value`` times it with walkers resident in HBM; ``e2e``
+times the same call with pinned HOST walkers through the C-ABI host entry point
+(H2D of walkers and D2H of the per-walker energies inside the timed region).
+
+``--impl reference`` times the CPU oracle (torch-fp64 restatement of the reference
+algorithm, hamiltonian.py:127-159 'partition'/dim_batch mode = jvp-of-grad over all 3N
+directions) on all host threads; the reference itself needs JAX + pyscf which do not
+exist in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from deepsolid_b200 import cell as C
+
+METRIC = "local_energies_per_sec"
+UNIT = "local-energies/s"
+DEFAULT_SYSTEM = "graphite54"       # BASELINE.json configs[2]: the config `metric` is quoted on
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--system", default=DEFAULT_SYSTEM)
+    ap.add_argument("--batch", type=int, default=0, help="walkers per GPU (default: BASELINE batch of the system)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="walkers per CPU-baseline sample (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mcmc", action="store_true", help="also time the Metropolis step (extras)")
+    ap.add_argument("--equil", type=int, default=2, help="Metropolis calls (20 moves each) used to equilibrate walkers")
+    return ap.parse_args()
+
+
+def work_model(cell, D=8, H=256, P=32):
+    """SURVEY section 8d / BASELINE.md section 4 flop model per walker."""
+    nu, nd = cell.nelec
+    N = nu + nd
+    A = cell.original_cell.natm
+    f_one = 2 * N * H * ((12 * A + 8) + (3 * H + 2 * P) * 2)
+    f_two = 2 * N * N * (4 * P + P * P)
+    f_orb = sum(2 * ns * H * (2 * ns * D) for ns in (nu, nd))
+    f_det = sum(D * (8 / 3) * ns ** 3 for ns in (nu, nd))
+    f_fwd = f_one + f_two + f_orb + f_det
+    f_lap = (3 * N + 2) * (f_one + f_orb) + 8 * f_two + sum(D * 3 * N * 8 * ns ** 3 for ns in (nu, nd))
+    return {"F_fwd": f_fwd, "F_lap": f_lap, "F_EL": f_fwd + f_lap}
+
+
+def make_inputs(system, batch, seed=666):
+    cell = C.build_system(system)
+    klist = C.make_klist(cell)
+    X = C.init_walkers(cell, batch, seed=seed)
+    return cell, klist, X
+
+
+def oracle_params(cell):
+    from oracle import deepsolid_oracle as O      # parameters only (numpy RNG, seed 888)
+    return O.init_params(np.random.default_rng(888), cell.original_cell.natm, cell.nelec)
+
+
+def torch_params(pn):
+    def conv(v):
+        if isinstance(v, dict):
+            return {k: conv(x) for k, x in v.items()}
+        if isinstance(v, list):
+            return [conv(x) for x in v]
+        return torch.as_tensor(np.asarray(v, dtype=np.float64))
+    return conv(pn)
+
+
+# ---------------------------------------------------------------------------
+def cpu_oracle_rate(cell, klist, pn, X, n_walkers, threads):
+    """Local energies/s of the oracle (reference algorithm) on `threads` host threads."""
+    from oracle import deepsolid_oracle as O
+    torch.set_num_threads(threads)
+    P = O.params_to_torch(pn)
+    f = O.make_solid_fermi_net(klist, cell, method_name="eval_logdet")
+    el = O.local_energy_seperate(f, cell, mode="dim_batch")
+    Xs = torch.as_tensor(X[:n_walkers])
+    t0 = time.perf_counter()
+    out = [el(P, x) for x in Xs]
+    dt = time.perf_counter() - t0
+    return n_walkers / dt, dt, out
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/ds_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                       reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def measure_fp64_peak(dev):
+    """cuBLAS DGEMM 8192^3 (MEASURED_PEAKS.json carries no fp64 figure)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty_like(a)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12      # TFLOP/s
+
+
+def run_ours(args):
+    import torch.distributed as td
+    from deepsolid_b200 import network, train, qmc
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    system = args.system
+    batch = args.batch or C.SYSTEMS[system][1]
+    mode, pn = C.SYSTEMS[system][2], C.SYSTEMS[system][3]
+    cell, klist, X = make_inputs(system, batch, seed=666 + rank)        # every rank its own walkers
+    pnum = oracle_params(cell)
+    P = torch_params(pnum)
+    net = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=klist,
+                                       simulation_cell=cell, determinants=8, method_name="eval_logdet", device=local)
+    slog = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=klist,
+                                        simulation_cell=cell, determinants=8, method_name="eval_slogdet",
+                                        hotpath=net.apply.hotpath())
+    hp = net.apply.hotpath()
+    total_energy = train.make_loss(net.apply, net.apply, cell, mode=mode, partition_number=pn)
+    mcmc_step = qmc.make_mcmc_step(slog.apply, batch, cell.lattice_vectors(), steps=20)
+
+    Xd = torch.as_tensor(X).to(dev)
+    # short equilibration with the (parity-tested) GPU Metropolis kernel; mirrors the burn-in of process.py:256-260
+    for it in range(args.equil):
+        Xd, pm = mcmc_step(P, Xd, 1000 + it + 17 * rank, 0.05)
+    Xh = Xd.cpu().pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)     # 256 MB > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            tot += e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    fp64_peak = measure_fp64_peak(dev) if rank == 0 else None
+    keep = {}
+
+    def step_dev():
+        loss, aux = total_energy(P, Xd)
+        keep["loss"] = loss
+
+    def step_host():
+        loss, aux = total_energy(P, Xh)
+        keep["loss_h"] = float(loss)
+
+    sampler = ClockSampler(local)
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    torch.cuda.synchronize(dev)
+    hp.profile(True)
+    l0 = hp.launch_count()
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_dev, args.steps, 0)
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = hp.launch_count() - l0
+    prof = hp.profile_get()
+    hp.profile(False)
+    value = world * batch * args.steps / (ms / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_h = timed(step_host, args.steps, 1)
+        e2e = {"value": world * batch * args.steps / (ms_h / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(batch * X.shape[1] * 8), "d2h_bytes_per_step": int(3 * batch * 8),
+               "ms_per_step": ms_h / args.steps}
+    extras = {}
+    if args.mcmc:
+        keepx = {"x": Xd}
+
+        def step_mcmc():
+            keepx["x"], _ = mcmc_step(P, keepx["x"], 7, 0.02)
+        ms_m = timed(step_mcmc, max(1, args.steps // 2), 1)
+        extras["mcmc_moves_per_sec"] = world * batch * 20 * max(1, args.steps // 2) / (ms_m / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+    wm = work_model(cell)
+    jac_tf = prof["jac_flops"] / (prof["jac_ms"] / 1e3) / 1e12 if prof["jac_ms"] > 0 else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_f64_kernel<JAC|ORBJ> (fp64 DMMA Jacobian sweep)",
+        "achieved": jac_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": (jac_tf / fp64_peak) if jac_tf else None,
+        "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry; "
+                       f"its bf16 burst figure is {peaks.get('bf16_tflops')} TF/s, hbm {peaks.get('hbm_gbs')} GB/s)",
+        "launches": prof["jac_launches"], "kernel_ms_per_step": prof["jac_ms"] / args.steps,
+        "kernel_share_of_step": prof["jac_ms"] / ms,
+        "traffic": None,
+        "survey_model_tflops": wm["F_EL"] * batch * args.steps / (ms / 1e3) / 1e12,
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{system}: {cell.nelectron} e-, {cell.natm} atoms, batch {batch}/GPU, "
+                               f"laplacian mode {mode}, 8 dets, hidden ((256,32),)*3",
+                   "system": system, "batch_per_gpu": batch, "global_batch": batch * world,
+                   "walkers": f"gaussian init (seed 666+rank) + {20 * args.equil} GPU Metropolis moves; params N(0,1)/sqrt(fan_in) seed 888",
+                   "l2": "256 MB flush between timed steps; per-step workspace >> L2",
+                   "parallelism": f"walker-sharded dp{world}, one all-reduce of 4 doubles per step"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "roofline": roofline, "loss": float(keep["loss"]),
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if extras:
+        line["extras"] = extras
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        nsamp = args.cpu_sample or max(1, min(8, int(20.0 / max(0.02, 1.5e-3 * cell.nelectron ** 2))))
+        rate, dt, out = cpu_oracle_rate(cell, klist, pnum, Xh.numpy(), nsamp, threads)
+        # the same walkers through the GPU: report the agreement next to the rate
+        ke_g, ew_g = net.apply.hotpath().local_energy(Xd[:nsamp])
+        d = max(abs(complex(k) + float(e) - complex(kg) - float(eg)) for (k, e), kg, eg in
+                zip(out, ke_g.cpu(), ew_g.cpu()))
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{nsamp} walkers of the same batch, oracle dim_batch mode "
+                                          f"(jvp-of-grad over all 3N directions), {dt:.1f} s",
+                                "max_abs_diff_vs_gpu_Ha": d}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def run_reference(args):
+    """CPU oracle (reference algorithm) on the host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    system = args.system
+    batch = args.batch or C.SYSTEMS[system][1]
+    cell, klist, X = make_inputs(system, batch)
+    pnum = oracle_params(cell)
+    threads = os.cpu_count() or 1
+    nsamp = args.cpu_sample or max(1, min(4, int(10.0 / max(0.02, 1.5e-3 * cell.nelectron ** 2))))
+    rates = []
+    for it in range(args.warmup + args.steps):
+        rate, dt, _ = cpu_oracle_rate(cell, klist, pnum, X[it * nsamp:(it + 1) * nsamp], nsamp, threads)
+        if it >= args.warmup:
+            rates.append((nsamp, dt))
+        if it == 0 and dt * (args.warmup + args.steps) > 240 and args.warmup > 0:
+            args.warmup = 0     # keep the whole run within a few minutes
+            rates.append((nsamp, dt))
+    n = sum(r[0] for r in rates)
+    t = sum(r[1] for r in rates)
+    value = n / t
+    mode = C.SYSTEMS[system][2]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(rates), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{system}: {cell.nelectron} e-, {cell.natm} atoms, batch {batch}/GPU, "
+                               f"laplacian mode {mode}, 8 dets, hidden ((256,32),)*3",
+                   "system": system, "batch_per_gpu": batch, "global_batch": batch * args.gpus,
+                   "note": "CPU torch-fp64 restatement of the reference algorithm (JAX/pyscf absent from the image); "
+                           "each step = a bounded sample of the batch, rate is per walker"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{nsamp} walkers per step, oracle dim_batch mode"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

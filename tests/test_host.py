@@ -1,0 +1,153 @@
+"""CPU tests of the host logic: geometry, Ewald tables, error behaviour of the closures,
+the C-ABI surface (symbols, no-GPU failure), and the 2-rank gloo path of the statistics."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, system
+from deepsolid_b200 import cell as C
+from deepsolid_b200 import _lib, network, hamiltonian, qmc, train
+from deepsolid_b200.ewald_tables import build_ewald_tables
+
+
+def test_cells_match_baseline_configs():
+    want = {"h10": ((5, 5), 10, 2), "li24": ((12, 12), 8, 2), "graphite54": ((27, 27), 18, 2),
+            "diamond64": ((32, 32), 16, 2), "lih108": ((54, 54), 54, 2)}
+    for name, (nelec, natm, nprim) in want.items():
+        sc = C.build_system(name)
+        assert sc.nelec == nelec and sc.natm == natm and sc.original_cell.natm == nprim
+        for cc in (sc, sc.original_cell):       # a_i . b_j = 2 pi delta_ij ; AV = a / 2 pi
+            assert np.allclose(cc.a @ cc.BV.T, 2 * np.pi * np.eye(3), atol=1e-12)
+            assert np.allclose(cc.AV, cc.a / (2 * np.pi), atol=1e-12)
+        kl = C.make_klist(sc)
+        assert [k.shape for k in kl] == [(nelec[0], 3), (nelec[1], 3)]
+        assert abs(sc.vol - sc.scale * sc.original_cell.vol) < 1e-9
+        assert abs(sum(sc.charges) - sum(nelec)) < 1e-12        # neutral
+
+
+def test_supercell_kpts_are_supercell_reciprocal_vectors():
+    sc = C.build_system("graphite54")
+    k = C.get_supercell_kpts(sc)
+    assert k.shape == (9, 3)
+    frac = k @ sc.a.T / (2 * np.pi)       # integer combinations of the supercell reciprocal lattice
+    assert np.allclose(frac, np.round(frac), atol=1e-10)
+
+
+def test_ewald_table_sizes():
+    tb = build_ewald_tables(C.build_system("diamond64"))
+    assert tb.dist_kind == 2 and tb.lattice_displacements.shape == (27, 3)
+    assert len(tb.gweight) == len(tb.gpoints) == len(tb.ion_exp) and (tb.gweight > 1e-12).all()
+    # half space: no G and -G together
+    s = {tuple(np.round(g, 8)) for g in tb.gpoints}
+    assert not any(tuple(np.round(-np.array(g), 8)) in s for g in list(s)[:200])
+    assert build_ewald_tables(C.build_system("h10")).dist_kind == 0
+
+
+def test_walker_init_inside_cell():
+    sc = C.build_system("graphite54")
+    X = C.init_walkers(sc, 5)
+    frac = X.reshape(5, -1, 3) @ np.linalg.inv(sc.a)
+    assert X.shape == (5, 162) and (frac >= 0).all() and (frac < 1).all()
+
+
+def test_constructor_errors_match_reference():
+    sc, kl, _, _ = system("h4")
+    with pytest.raises(ValueError, match="Method name"):
+        network.make_solid_fermi_net(klist=kl, simulation_cell=sc, method_name="nope")
+    with pytest.raises(ValueError, match="distance"):
+        network.make_solid_fermi_net(klist=kl, simulation_cell=sc, distance_type="l2", envelope_type="isotropic", full_det=False)
+    with pytest.raises(ValueError, match="not implemented"):
+        network.make_solid_fermi_net(klist=kl, simulation_cell=sc)             # reference defaults full/full_det
+    net = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc, determinants=8)
+    with pytest.raises(ValueError, match="laplacian"):
+        hamiltonian.local_energy_seperate(net.apply, sc, mode="nope")
+    with pytest.raises(ValueError, match="one elec"):
+        qmc.make_mcmc_step(net.apply, 4, sc.a, importance_sampling=lambda *a: 0, one_electron_moves=True)
+    with pytest.raises(TypeError):
+        hamiltonian.local_energy_seperate(lambda p, x: 0, sc)(None, None)
+
+
+def test_init_params_shapes():
+    sc, kl, _, _ = system("graphite54")
+    net = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc, determinants=8)
+    p = net.init(0)
+    assert [tuple(l["w"].shape) for l in p["single"]] == [(32, 256), (832, 256), (832, 256)]
+    assert [tuple(l["w"].shape) for l in p["double"]] == [(4, 32), (32, 32)]
+    assert [tuple(o["w"].shape) for o in p["orbital"]] == [(256, 432), (256, 432)]
+    assert tuple(p["envelope"][0]["sigma"].shape) == (2, 216)
+    from deepsolid_b200.hotpath import flatten_params
+    assert len(flatten_params(p)) == 16
+
+
+def test_c_abi_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "deepsolid_b200.h")).read()
+    declared = set(re.findall(r"DS_API[^;(]*?\b(ds_\w+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert declared <= exported
+    assert not {e for e in exported if not e.startswith("ds_") and not e.startswith("_")}   # only the C ABI
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    sc, kl, _, P = system("h4")
+    net = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc, determinants=8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net.apply(P, torch.zeros(12, dtype=torch.float64))
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    sd, nd = _lib.SystemDesc(), _lib.NetDesc()
+    rc = lib.ds_ctx_create(ctypes.byref(sd), ctypes.byref(nd), 0, ctypes.byref(h))
+    assert rc != 0 and b"no CPU fallback" in lib.ds_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "deepsolid_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("oracle/", ""), fn
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as td
+sys.path.insert(0, sys.argv[1])
+from deepsolid_b200 import train, dist
+td.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
+r = td.get_rank()
+e = torch.tensor([[1 + 2j, 3 - 1j, 0.5 + 0j], [2 - 1j, -1 + 0.5j, 4 + 4j]], dtype=torch.complex128)[r]
+stats = torch.stack([e.real.sum(), e.imag.sum(), (e.abs() ** 2).sum(), e.real.sum(), torch.zeros(()).double(), torch.tensor(3.0).double()])
+loss, im, var = train.reduce_energy_stats(stats)
+pm = dist.pmean(torch.tensor([0.25 + 0.5 * r], dtype=torch.float64))
+if r == 0:
+    print("RESULT", float(loss), float(im), float(var), float(pm))
+td.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_statistics(tmp_path):
+    """world_size-2 path of train.py:76-80 / qmc.py:360-361 on CPU (gloo)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29577", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    vals = [float(v) for v in [l for l in outs[0][0].splitlines() if l.startswith("RESULT")][0].split()[1:]]
+    e = torch.tensor([[1 + 2j, 3 - 1j, 0.5 + 0j], [2 - 1j, -1 + 0.5j, 4 + 4j]], dtype=torch.complex128)
+    means = e.mean(1)
+    loss = float(means.real.mean()); im = float(means.imag.mean())
+    var = float(((e.abs() ** 2).mean(1) - means.real.abs() ** 2).mean())      # mean of per-device variances
+    assert abs(vals[0] - loss) < 1e-14 and abs(vals[1] - im) < 1e-14 and abs(vals[2] - var) < 1e-14
+    assert abs(vals[3] - 0.5) < 1e-15
