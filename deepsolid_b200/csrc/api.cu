@@ -555,7 +555,9 @@ extern "C" int ds_orbitals(ds_ctx* c, const double* x, int64_t batch, double* ou
 }
 
 extern "C" int ds_ewald(ds_ctx* c, const double* x, int64_t batch, double* ee, double* ei, void* stream) {
-    DS_REQUIRE(c && x, "null argument");
+    DS_REQUIRE(c, "null context");
+    if (batch == 0) return 0;
+    DS_REQUIRE(x, "null argument");
     Guard g(c->device);
     int rc = ds_launch_ewald(c->ew, x, batch, ee, ei, nullptr, (cudaStream_t)stream);
     if (!rc) c->launches++;
@@ -571,6 +573,8 @@ extern "C" int ds_local_energy(ds_ctx* c, const double* x, int64_t batch, int mo
     if (mode == DS_LAP_PARTITION)
         DS_REQUIRE(partition_number >= 1 && (3 * c->sys.d.N) % partition_number == 0,
                    "partition_number (%d) must divide 3*N_elec (%d)", partition_number, 3 * c->sys.d.N);
+    DS_REQUIRE(batch >= 0, "negative batch");
+    if (batch == 0) return 0;
     DS_REQUIRE(ke_re && ke_im && ewald, "null output pointer");
     Guard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -595,8 +599,9 @@ extern "C" int ds_local_energy(ds_ctx* c, const double* x, int64_t batch, int mo
 
 extern "C" int ds_mcmc_step(ds_ctx* c, double* x, int64_t batch, int steps, double width, uint64_t seed,
                             const double* xi, const double* u, uint8_t* accept, double* n_accept, void* stream) {
-    DS_REQUIRE(c && x && n_accept, "null argument");
+    DS_REQUIRE(c && n_accept, "null argument");
     DS_REQUIRE(steps >= 0, "negative number of MCMC steps");
+    DS_REQUIRE(x || batch == 0, "null walker pointer");
     Guard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int n3 = 3 * c->sys.d.N;
@@ -633,7 +638,9 @@ extern "C" int ds_energy_stats(ds_ctx* c, const double* ke_re, const double* ke_
 
 // ---- host-buffer forms ----------------------------------------------------
 extern "C" int ds_logpsi_host(ds_ctx* c, const double* x, int64_t batch, double* log_abs, double* phase) {
-    DS_REQUIRE(c && x, "null argument");
+    DS_REQUIRE(c, "null context");
+    if (batch == 0) return 0;
+    DS_REQUIRE(x, "null argument");
     Guard g(c->device);
     const size_t n3 = 3 * (size_t)c->sys.d.N;
     if (int rc = ensure(c, c->host_stage, (size_t)batch * (n3 + 2))) return rc;
@@ -650,7 +657,9 @@ extern "C" int ds_logpsi_host(ds_ctx* c, const double* x, int64_t batch, double*
 
 extern "C" int ds_local_energy_host(ds_ctx* c, const double* x, int64_t batch, int mode, int partition_number,
                                     double* ke_re, double* ke_im, double* ewald) {
-    DS_REQUIRE(c && x && ke_re && ke_im && ewald, "null argument");
+    DS_REQUIRE(c, "null context");
+    if (batch == 0) return ds_local_energy(c, x, 0, mode, partition_number, ke_re, ke_im, ewald, nullptr);
+    DS_REQUIRE(x && ke_re && ke_im && ewald, "null argument");
     Guard g(c->device);
     const size_t n3 = 3 * (size_t)c->sys.d.N;
     if (int rc = ensure(c, c->host_stage, (size_t)batch * (n3 + 3))) return rc;

@@ -44,4 +44,6 @@ def golden(name):
 
 
 def angle_diff(a, b):
-    return torch.angle(torch.exp(1j * (torch.as_tensor(a) - torch.as_tensor(b)))).abs()
+    a = torch.as_tensor(a, dtype=torch.float64)
+    b = torch.as_tensor(b, dtype=torch.float64)
+    return torch.angle(torch.exp(1j * (a - b))).abs()
