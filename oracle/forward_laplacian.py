@@ -23,6 +23,15 @@ import torch
 DT = torch.float64
 PI = math.pi
 
+#: optional hook ``f(A, W) -> A @ W`` applied to the two Jacobian-row contractions (one-electron
+#: stream and orbital projection).  Used by scripts/ozaki_study.py and the tests of the int8
+#: slice arithmetic to emulate the truncation of the tcgen05 path on the CPU.
+JAC_MATMUL = None
+
+
+def _jmm(A, W):
+    return A @ W if JAC_MATMUL is None else JAC_MATMUL(A, W)
+
 
 class Jet:
     """value v[...], gradient g[...,3], laplacian l[...] w.r.t. one 3-vector."""
@@ -179,7 +188,7 @@ def kinetic_forward_laplacian(params: Dict, X: torch.Tensor, sim_cell, klist, wa
         gJ = torch.stack([J[:, m].mean(1) for m in masks], 2)            # (B,3N,2,C)
         gl = torch.stack([hl[:, m].mean(1) for m in masks], 1)
         zv = hv @ Wown + torch.einsum("bsc,sco->bo", gv, Wg)[:, None] + torch.einsum("bisp,spo->bio", mv, Wm) + b
-        zJ = (J @ Wown + torch.einsum("bdsc,sco->bdo", gJ, Wg)[:, None]
+        zJ = (_jmm(J, Wown) + torch.einsum("bdsc,sco->bdo", gJ, Wg)[:, None]
               + torch.einsum("bidsp,spo->bido", mJ, Wm))
         zl = hl @ Wown + torch.einsum("bsc,sco->bo", gl, Wg)[:, None] + torch.einsum("bisp,spo->bio", ml, Wm)
         th = torch.tanh(zv)
@@ -209,7 +218,7 @@ def kinetic_forward_laplacian(params: Dict, X: torch.Tensor, sim_cell, klist, wa
         npar = ns * D
         sl = slice(o, o + ns)
         Yv = hv[:, sl] @ W                      # (B,ns,2npar)
-        YJ = J[:, sl] @ W                       # (B,ns,3N,2npar)
+        YJ = _jmm(J[:, sl], W)                       # (B,ns,3N,2npar)
         Yl = hl[:, sl] @ W
         cx = lambda y: torch.complex(y[..., :npar], y[..., npar:])
         Ov, OJ, Ol = cx(Yv), cx(YJ), cx(Yl)
