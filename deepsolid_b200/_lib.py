@@ -61,6 +61,8 @@ SIGNATURES = {
     "ds_profile_get": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64), c_double_p, c_double_p]),
     "ds_debug_buffer": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "ds_debug_set_int": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "ds_ozaki_dgemm_probe": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                       c_double_p, c_double_p, C.c_void_p]),
     "ds_dgemm_probe": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
 }
 

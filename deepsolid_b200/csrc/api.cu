@@ -2,6 +2,7 @@
 // sequences of log psi / local energy / Metropolis step.  See include/deepsolid_b200.h.
 #include "../../include/deepsolid_b200.h"
 #include "kernels.cuh"
+#include "ozaki.cuh"
 
 #include <stdarg.h>
 #include <string.h>
@@ -767,4 +768,46 @@ extern "C" int ds_dgemm_probe(int device, const double* a, const double* b, doub
     GemmParams p{};
     p.A = a; p.lda = k; p.B = b; p.ldb = n; p.M = m; p.N = n; p.K = k; p.C = cc; p.ldc = n;
     return ds_launch_gemm(p, GEMM_PLAIN, false, (cudaStream_t)stream);
+}
+
+// Stand-alone run of the tcgen05 int8-slice GEMM (C = A.B, row-major fp64 in / out): digits of A
+// and of B^T are formed on the device, then the GEMM is launched `reps` times; *gemm_ms = average
+// device time of one GEMM launch, *slice_ms = time of the digit kernel over A.
+extern "C" int ds_ozaki_dgemm_probe(int device, const double* a, const double* b, double* cc, int64_t m, int n, int k,
+                                    int reps, double* gemm_ms, double* slice_ms, void* stream) {
+    Guard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    DS_REQUIRE(m > 0 && n > 0 && k > 0 && reps >= 1, "bad probe sizes");
+    signed char *Ad = nullptr, *Wd = nullptr;
+    double *sa = nullptr, *sb = nullptr, *bt = nullptr;
+    DS_CUDA_CHECK(cudaMalloc((void**)&Ad, (size_t)m * OZ_S * k));
+    DS_CUDA_CHECK(cudaMalloc((void**)&Wd, (size_t)n * OZ_S * k));
+    DS_CUDA_CHECK(cudaMalloc((void**)&sa, (size_t)m * sizeof(double)));
+    DS_CUDA_CHECK(cudaMalloc((void**)&sb, (size_t)n * sizeof(double)));
+    DS_CUDA_CHECK(cudaMalloc((void**)&bt, (size_t)n * k * sizeof(double)));
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    int rc = ds_launch_transpose(b, k, n, bt, st);
+    if (!rc) rc = ds_launch_slice_rows(bt, k, n, k, Wd, sb, st);
+    cudaEventRecord(e0, st);
+    if (!rc) rc = ds_launch_slice_rows(a, k, m, k, Ad, sa, st);
+    cudaEventRecord(e1, st);
+    OzParams p{};
+    p.Ad = Ad; p.sa = sa; p.rpg = m; p.gstride = m; p.goff = 0; p.n_groups = 1;
+    p.Wd = Wd; p.sb = sb; p.N = n; p.K = k; p.C = cc; p.ldc = n;
+    if (!rc) rc = ds_launch_oz_gemm(p, OZ_PLAIN, false, st);        // warm-up (also configures the kernel)
+    cudaEventRecord(e2, st);
+    for (int i = 0; i < reps && !rc; ++i) rc = ds_launch_oz_gemm(p, OZ_PLAIN, false, st);
+    cudaEventRecord(e3, st);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    float t01 = 0.f, t23 = 0.f;
+    cudaEventElapsedTime(&t01, e0, e1);
+    cudaEventElapsedTime(&t23, e2, e3);
+    if (slice_ms) *slice_ms = t01;
+    if (gemm_ms) *gemm_ms = t23 / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    cudaFree(Ad); cudaFree(Wd); cudaFree(sa); cudaFree(sb); cudaFree(bt);
+    if (rc) return rc;
+    if (ce != cudaSuccess) { ds_set_error("ozaki probe failed: %s", cudaGetErrorString(ce)); return -2; }
+    return 0;
 }

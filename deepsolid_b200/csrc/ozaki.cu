@@ -1,0 +1,450 @@
+// tcgen05 / TMEM / TMA implementation of the sliced-integer fp64 GEMM.  See ozaki.cuh.
+#include "ozaki.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int OZ_THREADS = 192;                       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int STAGES = 3;
+constexpr int W_SLICE = OZ_TM * OZ_BK;                // 8192 B
+constexpr int A_SLICE = OZ_TN * OZ_BK;                // 4096 B
+constexpr int W_STAGE = OZ_S * W_SLICE;               // 49152 B
+constexpr int A_STAGE = OZ_S * A_SLICE;               // 24576 B
+constexpr int STAGE_BYTES = W_STAGE + A_STAGE;        // 73728 B
+constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024; // + alignment slack
+constexpr int TMEM_COLS = 512;                        // 6 x 64 used (power of two required)
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error traps (kernel fails) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// 16 consecutive int32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (rows of 64 bytes, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address
+    d |= (uint64_t)1 << 16;                     // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t)(512 >> 4) << 32;            // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                     // descriptor version of sm_100
+    d |= (uint64_t)4 << 61;                     // SWIZZLE_64B
+    return d;
+}
+// kind::i8 instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_TM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------
+// digits of fp64 rows: one warp per row
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ A, int lda, long long rows, int K,
+                                                         signed char* __restrict__ Ad, double* __restrict__ sa) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const double* a = A + r * (long long)lda;
+    double v[2][8];
+    double mx = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int c0 = it * 256 + lane * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[it][j] = 0.0;
+        if (c0 < K) {
+            const double2* p = reinterpret_cast<const double2*>(a + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double2 t = p[j];
+                v[it][2 * j] = t.x; v[it][2 * j + 1] = t.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double f = fabs(v[it][j]);
+                bad |= !(f <= 1.7e308);           // inf or nan
+                mx = fmax(mx, f);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    bad = __any_sync(0xffffffffu, bad);
+    int e = 0;
+    if (mx > 0.0) e = ilogb(mx) + 1;              // mx < 2^e
+    if (e < -900) e = -900;
+    const double f = scalbn(1.0, 8 * OZ_S - 2 - e);
+    if (lane == 0) sa[r] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 6);
+    signed char* out = Ad + r * (long long)OZ_S * K;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int c0 = it * 256 + lane * 8;
+        if (c0 >= K) continue;
+        unsigned long long w[OZ_S];
+#pragma unroll
+        for (int s = 0; s < OZ_S; ++s) w[s] = 0ull;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            long long q = bad ? 0ll : __double2ll_rn(v[it][j] * f);
+#pragma unroll
+            for (int s = OZ_S - 1; s >= 1; --s) {
+                const long long d = ((q + 128) & 255) - 128;
+                w[s] |= (unsigned long long)(d & 255) << (8 * j);
+                q = (q - d) >> 8;
+            }
+            w[0] |= (unsigned long long)(q & 255) << (8 * j);
+        }
+#pragma unroll
+        for (int s = 0; s < OZ_S; ++s)
+            *reinterpret_cast<unsigned long long*>(out + (long long)s * K + c0) = w[s];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// the GEMM
+// ---------------------------------------------------------------------------
+template <int MODE, bool RES>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const OzParams p,
+               const int tiles_per_group, const int n_cb, const long long n_tiles) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.K / OZ_BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        mbar_init(&tmem_empty_bar, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            long long cnt = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int cb = (int)(tile % n_cb);
+                const long long rt = tile / n_cb;
+                const int grp = (int)(rt / tiles_per_group);
+                const int q0 = (int)(rt % tiles_per_group) * OZ_TN;
+                for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+                    const int st = (int)(cnt % STAGES);
+                    const uint32_t ph = (uint32_t)((cnt / STAGES) & 1);
+                    mbar_wait(&empty_bar[st], ph ^ 1u);
+                    unsigned char* sW = smem + st * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+                    tma_load_4d(sW, &tmW, &full_bar[st], kb * OZ_BK, cb * OZ_TM, 0, 0);
+                    tma_load_4d(sW + W_STAGE, &tmA, &full_bar[st], kb * OZ_BK, q0, 0, grp);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            long long cnt = 0;
+            uint32_t it = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                mbar_wait(&tmem_empty_bar, (it & 1u) ^ 1u);
+                tc_fence_after();
+                for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+                    const int st = (int)(cnt % STAGES);
+                    const uint32_t ph = (uint32_t)((cnt / STAGES) & 1);
+                    mbar_wait(&full_bar[st], ph);
+                    tc_fence_after();
+                    const uint32_t sW = smem_u32(smem + st * STAGE_BYTES);
+                    const uint32_t sA = sW + W_STAGE;
+#pragma unroll
+                    for (int ks = 0; ks < OZ_BK / 32; ++ks) {
+#pragma unroll
+                        for (int t = 0; t < OZ_S; ++t) {
+                            // W_t x [A_0 .. A_{5-t}] -> diagonals t .. 5 (TMEM column blocks of 64)
+                            const uint64_t wdesc = make_desc(sW + t * W_SLICE + ks * 32);
+                            const int nsl = OZ_S - t;
+                            const int n1 = (nsl > 4 ? 4 : nsl) * OZ_TN;
+                            const uint32_t acc = (kb > 0 || ks > 0 || t > 0) ? 1u : 0u;
+                            umma_i8(tmem_base + t * OZ_TN, wdesc, make_desc(sA + ks * 32), make_idesc(n1), acc);
+                            if (nsl > 4)
+                                umma_i8(tmem_base + (t + 4) * OZ_TN, wdesc, make_desc(sA + 4 * A_SLICE + ks * 32),
+                                        make_idesc((nsl - 4) * OZ_TN), acc);
+                        }
+                    }
+                    umma_commit(&empty_bar[st]);          // frees the smem stage when the MMAs have read it
+                }
+                umma_commit(&tmem_full_bar);              // accumulators complete
+            }
+        }
+    } else {
+        // ===================== epilogue: thread = output channel =====================
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t it = 0;
+        const double rs2 = 0.70710678118654752440;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int cb = (int)(tile % n_cb);
+            const long long rt = tile / n_cb;
+            const long long grp = rt / tiles_per_group;
+            const long long q0 = (rt % tiles_per_group) * OZ_TN;
+            const int n = cb * OZ_TM + q * 32 + lane;
+            const bool nv = n < p.N;
+            const double sbn = nv ? p.sb[n] : 0.0;
+            const long long prow0 = grp * p.gstride + p.goff + q0;      // physical row of column 0
+
+            // per-mode running state
+            long long cur_e = -1;
+            double sacc = 0.0, d1 = 0.0;
+            double Ex = 0.0, Ey = 0.0;
+            int cur_is = -1;
+
+            mbar_wait(&tmem_full_bar, it & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < OZ_TN; c0 += 16) {
+                int v[OZ_S][16];
+#pragma unroll
+                for (int g = 0; g < OZ_S; ++g) tmem_ld16(lane_addr + g * OZ_TN + c0, v[g]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const long long qq = q0 + c0 + j;                   // row within the group
+                    if (qq >= p.rpg) continue;                          // warp-uniform
+                    const long long pr = prow0 + c0 + j;
+                    double acc = (double)v[OZ_S - 1][j];
+#pragma unroll
+                    for (int g = OZ_S - 2; g >= 0; --g) acc = fma(acc, 1.0 / 256.0, (double)v[g][j]);
+                    const double z = acc * (p.sa[pr] * sbn);
+                    if (MODE == OZ_PLAIN) {
+                        if (nv) p.C[pr * (long long)p.ldc + n] = z;
+                    } else if (MODE == OZ_JAC) {
+                        const long long e = pr / p.NDp;
+                        const int d = (int)(pr - e * p.NDp);
+                        if (e != cur_e) {
+                            if (cur_e >= 0 && nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc);
+                            sacc = 0.0;
+                            cur_e = e;
+                            if (nv) { const double t = p.T[e * (long long)p.ldt + n]; d1 = 1.0 - t * t; }
+                        }
+                        if (nv) {
+                            const long long w = e / p.n_elec;
+                            const double zj = z + p.G[(w * p.NDg + d) * (long long)p.ldg + n];
+                            sacc = fma(zj, zj, sacc);
+                            double o = d1 * zj;
+                            if (RES) o = (p.R[pr * (long long)p.ldr + n] + o) * rs2;
+                            p.C[pr * (long long)p.ldc + n] = o;
+                        }
+                    } else {   // OZ_ORBJ: group = walker, row in group = is*NDp + d, channel = 2*pp + (re|im)
+                        const int is = (int)(qq / p.NDp);
+                        const int d = (int)(qq - (long long)is * p.NDp);
+                        const double zp = __shfl_xor_sync(0xffffffffu, z, 1);
+                        if (d >= 3 * p.n_elec) continue;                // padding directions (warp-uniform)
+                        const long long e = grp * p.n_elec + p.off_s + is;
+                        const int pp = n >> 1, im = n & 1;
+                        if (is != cur_is) {
+                            cur_is = is;
+                            if (nv) {
+                                const double2 E = *reinterpret_cast<const double2*>(p.etab + e * 10LL * p.npar_max + 2 * pp);
+                                Ex = E.x; Ey = E.y;
+                            }
+                        }
+                        if (nv) {
+                            const int k = pp / p.n_s, o = pp - k * p.n_s;
+                            // (vr + i vi)(Ex + i Ey): re = vr Ex - vi Ey, im = vr Ey + vi Ex
+                            const double out = im ? fma(zp, Ey, z * Ex) : fma(-zp, Ey, z * Ex);
+                            const long long di = (((grp * p.n_det + k) * p.NDp + d) * p.n_s + is) * (long long)p.n_s + o;
+                            p.DA[2 * di + im] = out;
+                            if (d / 3 == p.off_s + is) {
+                                const int c = d - 3 * (d / 3);
+                                p.YOWN[2 * ((e * 3 + c) * (long long)p.npar_max + pp) + im] = z;
+                            }
+                        }
+                    }
+                }
+            }
+            if (MODE == OZ_JAC && cur_e >= 0 && nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ B, int K, int N, double* __restrict__ Bt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // index into Bt [N][K]
+    if (i >= (long long)K * N) return;
+    const int n = (int)(i / K), k = (int)(i - (long long)n * K);
+    Bt[i] = B[(long long)k * N + n];
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// 4-D map over int8 digits [group][row][slice][k]: dims (k, row, slice, group)
+int make_map(CUtensorMap* tm, const signed char* base, int K, long long rows, long long group_stride_rows, int n_groups,
+             int box_rows) {
+    auto enc = get_encode();
+    if (!enc) { ds_set_error("cuTensorMapEncodeTiled is not available from the driver"); return -2; }
+    cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)OZ_S, (cuuint64_t)n_groups};
+    cuuint64_t strides[3] = {(cuuint64_t)OZ_S * K, (cuuint64_t)K, (cuuint64_t)group_stride_rows * OZ_S * K};
+    cuuint32_t box[4] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, (cuuint32_t)OZ_S, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<signed char*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ds_set_error("cuTensorMapEncodeTiled failed with code %d (K=%d rows=%lld groups=%d)", (int)r, K, rows, n_groups);
+        return -2;
+    }
+    return 0;
+}
+
+template <int MODE, bool RES>
+int launch(const OzParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    static int n_sm = 0;
+    if (!configured) {
+        DS_CUDA_CHECK(cudaFuncSetAttribute(oz_gemm_kernel<MODE, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+        int dev = 0;
+        DS_CUDA_CHECK(cudaGetDevice(&dev));
+        DS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    CUtensorMap tmW, tmA;
+    if (int rc = make_map(&tmW, p.Wd, p.K, p.N, p.N, 1, OZ_TM)) return rc;
+    if (int rc = make_map(&tmA, p.Ad + p.goff * (long long)OZ_S * p.K, p.K, p.rpg, p.gstride, p.n_groups, OZ_TN)) return rc;
+    const int tpg = (int)((p.rpg + OZ_TN - 1) / OZ_TN);
+    const int n_cb = (p.N + OZ_TM - 1) / OZ_TM;
+    const long long n_tiles = (long long)tpg * p.n_groups * n_cb;
+    const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
+    oz_gemm_kernel<MODE, RES><<<grid, OZ_THREADS, SMEM_DYN, stream>>>(tmW, tmA, p, tpg, n_cb, n_tiles);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int ds_launch_slice_rows(const double* A, int lda, long long rows, int K, signed char* Ad, double* sa,
+                         cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    DS_REQUIRE(K % 8 == 0 && K <= 512 && lda % 2 == 0, "slice_rows: K must be a multiple of 8 and <= 512 (K=%d lda=%d)", K, lda);
+    const int wpb = 8;
+    slice_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(A, lda, rows, K, Ad, sa);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_transpose(const double* B, int K, int N, double* Bt, cudaStream_t stream) {
+    const long long tot = (long long)K * N;
+    if (tot <= 0) return 0;
+    transpose_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(B, K, N, Bt);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t stream) {
+    if (p.rpg <= 0 || p.n_groups <= 0 || p.N <= 0) return 0;
+    DS_REQUIRE(p.K % OZ_BK == 0 && p.K >= OZ_BK, "oz_gemm: K must be a multiple of %d (K=%d)", OZ_BK, p.K);
+    DS_REQUIRE((reinterpret_cast<uintptr_t>(p.Ad) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Wd) & 15) == 0,
+               "oz_gemm: digit buffers must be 16-byte aligned");
+    switch (mode) {
+        case OZ_PLAIN: return launch<OZ_PLAIN, false>(p, stream);
+        case OZ_JAC: return residual ? launch<OZ_JAC, true>(p, stream) : launch<OZ_JAC, false>(p, stream);
+        case OZ_ORBJ: return launch<OZ_ORBJ, false>(p, stream);
+    }
+    ds_set_error("oz_gemm: unknown mode %d", mode);
+    return -1;
+}

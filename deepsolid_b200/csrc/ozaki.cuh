@@ -1,0 +1,60 @@
+// fp64-accurate GEMM on the 5th-generation tensor cores (tcgen05.mma kind::i8, TMEM
+// accumulators, TMA-fed shared memory).
+//
+// tcgen05 has no f64 kind, so the Jacobian-sweep GEMMs  Z[r,n] = sum_k A[r,k] W[k,n]  are
+// evaluated with error-free integer slices (Ozaki scheme I):
+//     A[r,k] ~ sa[r] * sum_s dA_s[r,k] 256^-s ,   W[k,n] ~ sb[n] * sum_t dW_t[k,n] 256^-t ,
+// dA_s, dW_t balanced base-256 digits (int8), S = 6 digits each (46 bits below the row /
+// column maximum).  Digit products accumulate EXACTLY in int32 (|sum| < 2^26), and the
+// diagonals g = s+t < 6 are recombined in fp64 in the epilogue:
+//     Z[r,n] = sa[r] sb[n] sum_g 256^-g C_g[r,n],   C_g = sum_{s+t=g} dA_s . dW_t      (21 int8 GEMMs).
+//
+// The product is formed TRANSPOSED: the UMMA M side (128 TMEM lanes) holds 128 output channels
+// n, the N side holds 64 rows r of A.  All six digit matrices of a K block are staged in one
+// shared-memory stage, slice-major, so that ONE instruction  W_t x [A_0 .. A_{5-t}]  (N up to
+// 256) adds W_t.A_s into the TMEM column block of diagonal s+t: 8 tcgen05.mma per K=32 step
+// instead of 21.  TMEM: 6 diagonals x 64 columns of int32.  Epilogue thread = output channel,
+// loop over columns = rows of A (consecutive directions d of one electron), so the
+// sum over d of zJ^2, the shared-mean addend G[d,:], tanh factors and stores are all coalesced
+// across lanes and sequential in a thread.
+#pragma once
+#include "ds_common.cuh"
+
+#define OZ_S 6            // digits per operand
+#define OZ_BK 64          // K bytes per pipeline stage (SWIZZLE_64B rows)
+#define OZ_TM 128         // output channels per tile (UMMA M)
+#define OZ_TN 64          // rows of A per tile (UMMA N per digit)
+
+enum OzMode {
+    OZ_PLAIN = 0,   // C[r, n] = Z
+    OZ_JAC = 1,     // one-electron stream Jacobian rows (see gemm_f64.cuh GEMM_JAC)
+    OZ_ORBJ = 2     // orbital-layer Jacobian rows (see gemm_f64.cuh GEMM_ORBJ)
+};
+
+struct OzParams {
+    // digits of A: int8 [rows][OZ_S][K] (row pitch OZ_S*K bytes), scales sa[rows]
+    const signed char* Ad; const double* sa;
+    // A rows are addressed as (group w, row-in-group q): physical row = w*gstride + goff + q, q < rpg.
+    // Plain matrices: n_groups = 1, rpg = M.
+    long long rpg, gstride, goff; int n_groups;
+    // digits of W^T: int8 [N][OZ_S][K], scales sb[N]
+    const signed char* Wd; const double* sb;
+    int N, K;
+    // outputs / epilogue operands (same meaning as GemmParams)
+    double* C; int ldc;
+    const double* G; int ldg;
+    int n_elec, NDp, NDg;
+    const double* T; int ldt;
+    double* S;
+    const double* R; int ldr;
+    const double* etab; int npar_max;
+    int n_s, off_s, n_det;
+    double* DA; double* YOWN;
+};
+
+// digits + scales of `rows` rows of a row-major fp64 matrix (leading dimension lda, K columns)
+int ds_launch_slice_rows(const double* A, int lda, long long rows, int K, signed char* Ad, double* sa,
+                         cudaStream_t stream);
+// Bt[N][K] = B[K][N]^T
+int ds_launch_transpose(const double* B, int K, int N, double* Bt, cudaStream_t stream);
+int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t stream);

@@ -173,6 +173,11 @@ DS_API int ds_debug_set_int(ds_ctx *ctx, const char *key, int value);
 DS_API int ds_dgemm_probe(int device, const double *a_dev, const double *b_dev, double *c_dev,
                    int64_t m, int n, int k, void *stream);
 
+/* Stand-alone run of the tcgen05 (kind::i8, TMEM, TMA) sliced-integer fp64 GEMM (C = A.B, row-major).
+ * gemm_ms: average device time of one GEMM launch over `reps`; slice_ms: digit kernel over A. */
+DS_API int ds_ozaki_dgemm_probe(int device, const double *a_dev, const double *b_dev, double *c_dev,
+                         int64_t m, int n, int k, int reps, double *gemm_ms, double *slice_ms, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
