@@ -5,6 +5,7 @@
 #include "ozaki.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -72,6 +73,13 @@ struct ds_ctx {
     double* Wp[DS_MAX_LAYERS] = {};     // pair-stream weights
     double* bp[DS_MAX_LAYERS] = {};
     double* Worb[2] = {};               // [H x 2 npar_s], columns interleaved (re, im)
+    // int8 digits of the transposed weights for the tcgen05 path (ozaki.cuh): [N][OZ_S][K] + scales [N]
+    signed char* Wd_am[DS_MAX_LAYERS] = {};
+    double* sb_am[DS_MAX_LAYERS] = {};
+    signed char* Wd_orb[2] = {};
+    double* sb_orb[2] = {};
+    bool use_i8 = true;                 // Jacobian-sweep GEMMs on tcgen05 (false: fp64 DMMA kernels)
+    bool i8_ok = false;                 // stream widths are multiples of the tcgen05 K block
     double* env_pi[2] = {};
     double* env_sigma[2] = {};
     double* klist[2] = {};
@@ -153,6 +161,16 @@ int gemm(ds_ctx* c, const GemmParams& p, int mode, bool res, cudaStream_t st, bo
     return 0;
 }
 
+// Jacobian-sweep GEMM on the tcgen05 path: digits of the fp64 operand rows, then the int8 GEMM.
+// Profiled like the DMMA kernels it replaces (flops = fp64-equivalent 2 M N K).
+struct ProfScope {
+    ds_ctx* c; cudaStream_t st; ProfEvent ev{}; bool rec;
+    ProfScope(ds_ctx* c_, cudaStream_t st_, bool on, double flops) : c(c_), st(st_), rec(c_->prof_on && on) {
+        if (rec) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); cudaEventRecord(ev.a, st); ev.flops = flops; }
+    }
+    ~ProfScope() { if (rec) { cudaEventRecord(ev.b, st); c->prof.push_back(ev); } }
+};
+
 // per-walker workspace size in doubles
 struct Layout {
     bool lap;
@@ -162,6 +180,7 @@ struct Layout {
     double *T, *S, *GIN, *GOUT, *RAE, *ETAB, *YV, *YL, *YOWN;
     double *MAT[2], *LAPM[2], *DA[2];
     double *LOGDET, *TAU, *TRSQ, *TRLAP;
+    double *AD, *SA;        // int8 digits of the current Jacobian operand (as bytes) and its row scales
 };
 
 void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap) {
@@ -204,6 +223,9 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap) {
     L.TAU = lap ? ws.take("TAU", W * 2 * d.D * d.NDp * 2) : nullptr;
     L.TRSQ = lap ? ws.take("TRSQ", W * 2 * d.D * 2) : nullptr;
     L.TRLAP = lap ? ws.take("TRLAP", W * 2 * d.D * 2) : nullptr;
+    const bool i8 = lap && c->use_i8 && c->i8_ok;
+    L.AD = i8 ? ws.take("AD", (W * N * d.NDp * OZ_S * d.K1 + 7) / 8) : nullptr;
+    L.SA = i8 ? ws.take("SA", W * N * d.NDp) : nullptr;
 }
 
 int plan_chunk(ds_ctx* c, long long batch, bool lap, int* Wc_out) {
@@ -291,10 +313,24 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             v.A = AV; v.lda = K; v.M = (long long)Wc * N; v.C = OV; v.ldc = d.K1; v.R = AV; v.ldr = K;
             if (int rc = gemm(c, v, GEMM_VALUE, res, st)) return rc;
         }
-        if (lap) {
+        if (lap && c->use_i8 && c->i8_ok && l > 0) {
+            const long long rows = (long long)Wc * N * d.NDp;
+            ProfScope ps(c, st, true, 2.0 * (double)rows * H * K);
+            signed char* Ad = reinterpret_cast<signed char*>(Lo.AD);
+            if (int rc = ds_launch_slice_rows(AJ, K, rows, K, Ad, Lo.SA, st)) return rc;
+            OzParams o{};
+            o.Ad = Ad; o.sa = Lo.SA; o.rpg = rows; o.gstride = rows; o.goff = 0; o.n_groups = 1;
+            o.Wd = c->Wd_am[l]; o.sb = c->sb_am[l]; o.N = H; o.K = K;
+            o.C = OJ; o.ldc = d.K1; o.G = Lo.GOUT; o.ldg = H; o.n_elec = N; o.NDp = d.NDp; o.NDg = d.NDg;
+            o.T = Lo.T; o.ldt = H; o.S = Lo.S; o.R = AJ; o.ldr = K;
+            if (int rc = ds_launch_oz_gemm(o, OZ_JAC, res, st)) return rc;
+            c->launches += 2;
+        } else if (lap) {
             GemmParams j = p;
             j.A = AJ; j.lda = K; j.M = (long long)Wc * N * d.NDp; j.C = OJ; j.ldc = d.K1; j.R = AJ; j.ldr = K;
             if (int rc = gemm(c, j, GEMM_JAC, res, st, /*profile*/ l > 0)) return rc;
+        }
+        if (lap) {
             GemmParams q = p;
             q.A = AL; q.lda = K; q.M = (long long)Wc * N; q.C = OL; q.ldc = d.K1; q.R = AL; q.ldr = K;
             if (int rc = gemm(c, q, GEMM_LAP, res, st)) return rc;
@@ -313,6 +349,13 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
     sb.LOGDET = Lo.LOGDET; sb.TAU = Lo.TAU; sb.TRSQ = Lo.TRSQ; sb.TRLAP = Lo.TRLAP;
     if (int rc = ds_launch_etab(sys, sb, Wc, c->npar_max, lap, st)) return rc;
     c->launches++;
+    const bool i8 = lap && c->use_i8 && c->i8_ok;
+    const long long jrows = (long long)Wc * N * d.NDp;
+    if (i8) {     // digits of the last layer's Jacobian rows (own columns), shared by both spins
+        ProfScope ps(c, st, true, 0.0);
+        if (int rc = ds_launch_slice_rows(hJ, d.K1, jrows, H, reinterpret_cast<signed char*>(Lo.AD), Lo.SA, st)) return rc;
+        c->launches++;
+    }
     for (int s = 0; s < 2; ++s) {
         const int ns = c->n_s[s];
         GemmParams o{};
@@ -325,6 +368,19 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         if (lap) {
             o.A = hL; o.C = Lo.YL;
             if (int rc = gemm(c, o, GEMM_PLAIN, false, st)) return rc;
+        }
+        if (i8) {
+            ProfScope ps(c, st, true, 2.0 * (double)Wc * ns * d.NDp * H * 2.0 * c->npar[s]);
+            OzParams z{};
+            z.Ad = reinterpret_cast<signed char*>(Lo.AD); z.sa = Lo.SA;
+            z.rpg = (long long)ns * d.NDp; z.gstride = (long long)N * d.NDp; z.goff = (long long)c->off_s[s] * d.NDp;
+            z.n_groups = Wc;
+            z.Wd = c->Wd_orb[s]; z.sb = c->sb_orb[s]; z.N = 2 * c->npar[s]; z.K = H;
+            z.n_elec = N; z.NDp = d.NDp; z.etab = Lo.ETAB; z.npar_max = c->npar_max;
+            z.n_s = ns; z.off_s = c->off_s[s]; z.n_det = d.D; z.DA = Lo.DA[s]; z.YOWN = Lo.YOWN;
+            if (int rc = ds_launch_oz_gemm(z, OZ_ORBJ, false, st)) return rc;
+            c->launches++;
+        } else if (lap) {
             GemmParams j = o;
             j.A = hJ; j.cmap = 0; j.C = nullptr;
             j.rpg = (long long)ns * d.NDp; j.gstride = (long long)N * d.NDp; j.goff = (long long)c->off_s[s] * d.NDp;
@@ -412,6 +468,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     DS_CUDA_CHECK(cudaSetDevice(device));
     ds_ctx* c = new ds_ctx();
     c->device = device;
+    if (const char* ev = getenv("DS_NO_I8")) c->use_i8 = atoi(ev) == 0;
     DsDims& d = c->sys.d;
     d.n_up = sd->n_up; d.n_dn = sd->n_dn; d.N = sd->n_up + sd->n_dn; d.A = sd->n_atoms_prim;
     d.H = nd->hidden_one; d.P = nd->hidden_two; d.D = nd->n_det; d.L = nd->n_layers;
@@ -533,6 +590,29 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
     for (int s = 0; s < 2; ++s) {
         if (int rc = put(&c->env_pi[s], h[li++])) return rc;
         if (int rc = put(&c->env_sigma[s], h[li++])) return rc;
+    }
+    // int8 digits of the transposed weights for the tcgen05 path
+    {
+        auto digits = [&](const double* Bdev, int K, int Nn, signed char** Wd, double** sbp) -> int {
+            double* bt = nullptr;
+            DS_CUDA_CHECK(cudaMalloc((void**)&bt, (size_t)K * Nn * sizeof(double)));
+            if (!*Wd) { if (int rc = dev_alloc(c, Wd, (size_t)Nn * OZ_S * K)) return rc; }
+            if (!*sbp) { if (int rc = dev_alloc(c, sbp, (size_t)Nn)) return rc; }
+            int rc = ds_launch_transpose(Bdev, K, Nn, bt, 0);
+            if (!rc) rc = ds_launch_slice_rows(bt, K, Nn, K, *Wd, *sbp, 0);
+            cudaError_t e = cudaStreamSynchronize(0);
+            cudaFree(bt);
+            if (rc) return rc;
+            DS_CUDA_CHECK(e);
+            return 0;
+        };
+        c->i8_ok = (H % OZ_BK == 0) && (d.K1 % OZ_BK == 0);
+        if (c->i8_ok) {
+            for (int l = 1; l < L; ++l)
+                if (int rc = digits(c->B_am[l], d.K1, H, &c->Wd_am[l], &c->sb_am[l])) return rc;
+            for (int s = 0; s < 2; ++s)
+                if (int rc = digits(c->Worb[s], H, 2 * c->npar[s], &c->Wd_orb[s], &c->sb_orb[s])) return rc;
+        }
     }
     c->params_set = true;
     return 0;
@@ -741,6 +821,7 @@ extern "C" int ds_profile_get(ds_ctx* c, double* jac_ms, int64_t* jac_launches, 
 extern "C" int ds_debug_set_int(ds_ctx* c, const char* key, int value) {
     DS_REQUIRE(c && key, "null argument");
     if (!strcmp(key, "stop_layer")) { c->dbg_stop_layer = value; return 0; }
+    if (!strcmp(key, "i8")) { c->use_i8 = value != 0; return 0; }
     ds_set_error("unknown debug key %s", key);
     return -1;
 }
@@ -795,6 +876,7 @@ extern "C" int ds_ozaki_dgemm_probe(int device, const double* a, const double* b
     OzParams p{};
     p.Ad = Ad; p.sa = sa; p.rpg = m; p.gstride = m; p.goff = 0; p.n_groups = 1;
     p.Wd = Wd; p.sb = sb; p.N = n; p.K = k; p.C = cc; p.ldc = n;
+    if (const char* dv = getenv("DS_OZ_DBG")) p.dbg = atoi(dv);
     if (!rc) rc = ds_launch_oz_gemm(p, OZ_PLAIN, false, st);        // warm-up (also configures the kernel)
     cudaEventRecord(e2, st);
     for (int i = 0; i < reps && !rc; ++i) rc = ds_launch_oz_gemm(p, OZ_PLAIN, false, st);

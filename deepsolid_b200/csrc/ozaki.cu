@@ -6,7 +6,7 @@
 
 namespace {
 
-constexpr int OZ_THREADS = 192;                       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int OZ_THREADS = 320;                       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
 constexpr int STAGES = 3;
 constexpr int W_SLICE = OZ_TM * OZ_BK;                // 8192 B
 constexpr int A_SLICE = OZ_TN * OZ_BK;                // 4096 B
@@ -87,6 +87,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -188,7 +194,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&tmem_full_bar, 1);
-        mbar_init(&tmem_empty_bar, 4);
+        mbar_init(&tmem_empty_bar, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -211,6 +217,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     const uint32_t ph = (uint32_t)((cnt / STAGES) & 1);
                     mbar_wait(&empty_bar[st], ph ^ 1u);
                     unsigned char* sW = smem + st * STAGE_BYTES;
+                    if (p.dbg & 4) { mbar_arrive(&full_bar[st]); continue; }
                     mbar_expect_tx(&full_bar[st], STAGE_BYTES);
                     tma_load_4d(sW, &tmW, &full_bar[st], kb * OZ_BK, cb * OZ_TM, 0, 0);
                     tma_load_4d(sW + W_STAGE, &tmA, &full_bar[st], kb * OZ_BK, q0, 0, grp);
@@ -232,6 +239,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t sW = smem_u32(smem + st * STAGE_BYTES);
                     const uint32_t sA = sW + W_STAGE;
+                    if (!(p.dbg & 2))
 #pragma unroll
                     for (int ks = 0; ks < OZ_BK / 32; ++ks) {
 #pragma unroll
@@ -254,94 +262,152 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue: thread = output channel =====================
+        // 8 warps: two per TMEM lane quarter, each owning 32 of the tile's 64 columns (= rows of A).
+        // Phase A (holds TMEM): read the six diagonals, pack them EXACTLY into two int64 per output
+        //   hi = c0 2^16 + c1 2^8 + c2,  lo = c3 2^16 + c4 2^8 + c5   (|c_g| < 2^26),
+        // round hi + lo 2^-24 ONCE to fp64 (the only rounding of the whole product) and release the
+        // accumulators so the next tile's MMAs start.  Phase B: scales, fused epilogue math, stores.
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int half = (warp - 2) >> 2;                 // which 32 columns
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 32;
         uint32_t it = 0;
         const double rs2 = 0.70710678118654752440;
+        const double MAGIC = 6755399441055744.0;          // 2^52 + 2^51
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int cb = (int)(tile % n_cb);
             const long long rt = tile / n_cb;
             const long long grp = rt / tiles_per_group;
-            const long long q0 = (rt % tiles_per_group) * OZ_TN;
+            const long long q0 = (rt % tiles_per_group) * OZ_TN + half * 32;    // first row (in group) of this warp
             const int n = cb * OZ_TM + q * 32 + lane;
             const bool nv = n < p.N;
-            const double sbn = nv ? p.sb[n] : 0.0;
-            const long long prow0 = grp * p.gstride + p.goff + q0;      // physical row of column 0
+            const double sbn = nv ? p.sb[n] * (1.0 / 65536.0) : 0.0;
+            const long long prow0 = grp * p.gstride + p.goff + q0;              // physical row of column 0
+
+            double zz[32];
+            mbar_wait(&tmem_full_bar, it & 1u);
+            tc_fence_after();
+            if (!(MODE == OZ_PLAIN && (p.dbg & 1))) {
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 8) {
+                    int v[OZ_S][8];
+#pragma unroll
+                    for (int g = 0; g < OZ_S; ++g) tmem_ld8(lane_addr + g * OZ_TN + c0, v[g]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const long long hi = ((long long)v[0][j] << 16) + ((long long)v[1][j] << 8) + (long long)v[2][j];
+                        const long long lo = ((long long)v[3][j] << 16) + ((long long)v[4][j] << 8) + (long long)v[5][j];
+                        const double dh = __longlong_as_double(hi + 0x4338000000000000LL) - MAGIC;
+                        const double dl = __longlong_as_double(lo + 0x4338000000000000LL) - MAGIC;
+                        zz[c0 + j] = fma(dl, 1.0 / 16777216.0, dh);     // one fp64 rounding of the exact integer sum
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar);
+            if (MODE == OZ_PLAIN && (p.dbg & 1)) continue;
+
+            // scales of this warp's 32 rows: one coalesced load, broadcast per column
+            const int nvalid = (int)((p.rpg - q0) < 32 ? (p.rpg - q0) : 32);          // warp-uniform, may be <= 0
+            const double sa_l = (lane < nvalid) ? p.sa[prow0 + lane] : 0.0;
 
             // per-mode running state
             long long cur_e = -1;
             double sacc = 0.0, d1 = 0.0;
             double Ex = 0.0, Ey = 0.0;
-            int cur_is = -1;
-
-            mbar_wait(&tmem_full_bar, it & 1u);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < OZ_TN; c0 += 16) {
-                int v[OZ_S][16];
+            // JAC: (electron row e, direction d) of column 0, advanced incrementally
+            long long je = 0; int jd = 0;
+            if (MODE == OZ_JAC) { je = prow0 / p.NDp; jd = (int)(prow0 - je * p.NDp); }
+            int ois = 0, od = 0;
+            if (MODE == OZ_ORBJ) { ois = (int)(q0 / p.NDp); od = (int)(q0 - (long long)ois * p.NDp); }
+            double* cptr = (MODE == OZ_ORBJ) ? nullptr : p.C + prow0 * (long long)p.ldc + n;
+            const double* rptr = (MODE == OZ_JAC && RES) ? p.R + prow0 * (long long)p.ldr + n : nullptr;
+            if (MODE == OZ_JAC) {
+                // blocks of 8 columns: issue the G / residual loads of the block first (independent of the
+                // stores of earlier columns), then the arithmetic and the stores
+                const double* __restrict__ Gp = p.G;
+                const double* __restrict__ Tp = p.T;
+                int jw = (int)(je / p.n_elec);
+                int ji = (int)(je - (long long)jw * p.n_elec);
 #pragma unroll
-                for (int g = 0; g < OZ_S; ++g) tmem_ld16(lane_addr + g * OZ_TN + c0, v[g]);
-                tmem_ld_wait();
+                for (int j0 = 0; j0 < 32; j0 += 8) {
+                    double gv[8], rv[8];
+                    int dflag[8];                                   // 1: first column of a new electron row
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const long long qq = q0 + c0 + j;                   // row within the group
-                    if (qq >= p.rpg) continue;                          // warp-uniform
-                    const long long pr = prow0 + c0 + j;
-                    double acc = (double)v[OZ_S - 1][j];
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const bool ok = nv && (j0 + jj < nvalid);
+                        gv[jj] = ok ? Gp[((long long)jw * p.NDg + jd) * p.ldg + n] : 0.0;
+                        rv[jj] = (RES && ok) ? rptr[(long long)(j0 + jj) * p.ldr] : 0.0;
+                        dflag[jj] = (j0 + jj == 0) || (jd == 0);
+                        if (++jd == p.NDp) { jd = 0; if (++ji == p.n_elec) { ji = 0; ++jw; } }
+                    }
 #pragma unroll
-                    for (int g = OZ_S - 2; g >= 0; --g) acc = fma(acc, 1.0 / 256.0, (double)v[g][j]);
-                    const double z = acc * (p.sa[pr] * sbn);
-                    if (MODE == OZ_PLAIN) {
-                        if (nv) p.C[pr * (long long)p.ldc + n] = z;
-                    } else if (MODE == OZ_JAC) {
-                        const long long e = pr / p.NDp;
-                        const int d = (int)(pr - e * p.NDp);
-                        if (e != cur_e) {
-                            if (cur_e >= 0 && nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc);
-                            sacc = 0.0;
-                            cur_e = e;
-                            if (nv) { const double t = p.T[e * (long long)p.ldt + n]; d1 = 1.0 - t * t; }
-                        }
-                        if (nv) {
-                            const long long w = e / p.n_elec;
-                            const double zj = z + p.G[(w * p.NDg + d) * (long long)p.ldg + n];
-                            sacc = fma(zj, zj, sacc);
-                            double o = d1 * zj;
-                            if (RES) o = (p.R[pr * (long long)p.ldr + n] + o) * rs2;
-                            p.C[pr * (long long)p.ldc + n] = o;
-                        }
-                    } else {   // OZ_ORBJ: group = walker, row in group = is*NDp + d, channel = 2*pp + (re|im)
-                        const int is = (int)(qq / p.NDp);
-                        const int d = (int)(qq - (long long)is * p.NDp);
-                        const double zp = __shfl_xor_sync(0xffffffffu, z, 1);
-                        if (d >= 3 * p.n_elec) continue;                // padding directions (warp-uniform)
-                        const long long e = grp * p.n_elec + p.off_s + is;
-                        const int pp = n >> 1, im = n & 1;
-                        if (is != cur_is) {
-                            cur_is = is;
-                            if (nv) {
-                                const double2 E = *reinterpret_cast<const double2*>(p.etab + e * 10LL * p.npar_max + 2 * pp);
-                                Ex = E.x; Ey = E.y;
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int j = j0 + jj;
+                        const double z = zz[j] * (__shfl_sync(0xffffffffu, sa_l, j) * sbn);
+                        if (j < nvalid) {
+                            if (dflag[jj]) {
+                                if (cur_e >= 0) { if (nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc); ++cur_e; }
+                                else cur_e = je;
+                                sacc = 0.0;
+                                if (nv) { const double t = Tp[cur_e * (long long)p.ldt + n]; d1 = 1.0 - t * t; }
                             }
-                        }
-                        if (nv) {
-                            const int k = pp / p.n_s, o = pp - k * p.n_s;
-                            // (vr + i vi)(Ex + i Ey): re = vr Ex - vi Ey, im = vr Ey + vi Ex
-                            const double out = im ? fma(zp, Ey, z * Ex) : fma(-zp, Ey, z * Ex);
-                            const long long di = (((grp * p.n_det + k) * p.NDp + d) * p.n_s + is) * (long long)p.n_s + o;
-                            p.DA[2 * di + im] = out;
-                            if (d / 3 == p.off_s + is) {
-                                const int c = d - 3 * (d / 3);
-                                p.YOWN[2 * ((e * 3 + c) * (long long)p.npar_max + pp) + im] = z;
+                            if (nv) {
+                                const double zj = z + gv[jj];
+                                sacc = fma(zj, zj, sacc);
+                                double o = d1 * zj;
+                                if (RES) o = (rv[jj] + o) * rs2;
+                                cptr[(long long)j * p.ldc] = o;
                             }
                         }
                     }
                 }
+            } else if (MODE == OZ_PLAIN) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double z = zz[j] * (__shfl_sync(0xffffffffu, sa_l, j) * sbn);
+                    if (nv && j < nvalid) *cptr = z;
+                    cptr += p.ldc;
+                }
+            } else {
+                // OZ_ORBJ: group = walker, row in group = is*NDp + d, channel n = 2*pp + (re|im), pp = k*n_s + o.
+                // All column-dependent offsets are warp-uniform and advanced incrementally.
+                const int pp = n >> 1, im = n & 1;
+                const int kdet = pp / p.n_s, oo = pp - kdet * p.n_s;
+                const int ND = 3 * p.n_elec;
+                const long long ns2 = 2LL * p.n_s * p.n_s;
+                double* dap = p.DA + 2 * ((((long long)grp * p.n_det + kdet) * p.NDp) * p.n_s * p.n_s + oo) + im;
+                long long coff = od * ns2 + 2LL * ois * p.n_s;
+                int own0 = 3 * (p.off_s + ois);
+                long long e = grp * p.n_elec + p.off_s + ois;
+                const double* ep = p.etab + e * 10LL * p.npar_max + 2 * pp;
+                double* yp = p.YOWN + 2 * (e * 3LL * p.npar_max + pp) + im;
+                bool newis = true;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double z = zz[j] * (__shfl_sync(0xffffffffu, sa_l, j) * sbn);
+                    const double zp = __shfl_xor_sync(0xffffffffu, z, 1);
+                    if (j < nvalid && od < ND) {                        // warp-uniform
+                        if (newis) {
+                            newis = false;
+                            if (nv) { const double2 E = *reinterpret_cast<const double2*>(ep); Ex = E.x; Ey = E.y; }
+                        }
+                        if (nv) {
+                            // (vr + i vi)(Ex + i Ey): re = vr Ex - vi Ey, im = vr Ey + vi Ex
+                            dap[coff] = im ? fma(zp, Ey, z * Ex) : fma(-zp, Ey, z * Ex);
+                            const unsigned c = (unsigned)(od - own0);
+                            if (c < 3u) yp[2LL * c * p.npar_max] = z;
+                        }
+                    }
+                    ++od; coff += ns2;
+                    if (od == p.NDp) {
+                        od = 0; ++ois; coff = 2LL * ois * p.n_s; own0 += 3;
+                        ep += 10LL * p.npar_max; yp += 6LL * p.npar_max; newis = true;
+                    }
+                }
             }
             if (MODE == OZ_JAC && cur_e >= 0 && nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar);
         }
     }
     tc_fence_before();

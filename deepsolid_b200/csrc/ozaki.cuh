@@ -50,6 +50,7 @@ struct OzParams {
     const double* etab; int npar_max;
     int n_s, off_s, n_det;
     double* DA; double* YOWN;
+    int dbg;                 // probe only: 1 = epilogue skips TMEM reads/stores, 2 = no MMA issue, 4 = no TMA
 };
 
 // digits + scales of `rows` rows of a row-major fp64 matrix (leading dimension lda, K columns)

@@ -167,7 +167,9 @@ DS_API int ds_profile_get(ds_ctx *ctx, double *jac_ms, int64_t *jac_launches, do
 /* Copy an internal per-chunk buffer of the last ds_local_energy call (first chunk) to
  * dst_dev for stage-by-stage parity tests.  Returns number of doubles (or <0). */
 DS_API int64_t ds_debug_buffer(ds_ctx *ctx, const char *name, double *dst_dev, int64_t max_doubles);
-/* debug knobs: "stop_layer" = l stops ds_local_energy/ds_logpsi after one-electron layer l (-1: off) */
+/* debug knobs: "stop_layer" = l stops ds_local_energy/ds_logpsi after one-electron layer l (-1: off);
+ * "i8" = 0 runs the Jacobian-sweep GEMMs on the fp64 DMMA kernels instead of the tcgen05 int8-slice
+ * kernels (default 1; environment DS_NO_I8=1 selects 0 at context creation). */
 DS_API int ds_debug_set_int(ds_ctx *ctx, const char *key, int value);
 /* Stand-alone run of the fp64 tensor-core GEMM kernel (C = A.B, row-major) for peak probes. */
 DS_API int ds_dgemm_probe(int device, const double *a_dev, const double *b_dev, double *c_dev,
