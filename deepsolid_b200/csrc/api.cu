@@ -80,6 +80,7 @@ struct ds_ctx {
     double* sb_orb[2] = {};
     bool use_i8 = true;                 // Jacobian-sweep GEMMs on tcgen05 (false: fp64 DMMA kernels)
     bool i8_ok = false;                 // stream widths are multiples of the tcgen05 K block
+    bool use_l0_kernel = true;          // layer-0 Jacobian rows by the streaming kernel (false: DMMA GEMM)
     double* env_pi[2] = {};
     double* env_sigma[2] = {};
     double* klist[2] = {};
@@ -315,9 +316,9 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         }
         if (lap && c->use_i8 && c->i8_ok && l > 0) {
             const long long rows = (long long)Wc * N * d.NDp;
-            ProfScope ps(c, st, true, 2.0 * (double)rows * H * K);
             signed char* Ad = reinterpret_cast<signed char*>(Lo.AD);
             if (int rc = ds_launch_slice_rows(AJ, K, rows, K, Ad, Lo.SA, st)) return rc;
+            ProfScope ps(c, st, true, 2.0 * (double)rows * H * K);     // the tcgen05 GEMM alone
             OzParams o{};
             o.Ad = Ad; o.sa = Lo.SA; o.rpg = rows; o.gstride = rows; o.goff = 0; o.n_groups = 1;
             o.Wd = c->Wd_am[l]; o.sb = c->sb_am[l]; o.N = H; o.K = K;
@@ -325,6 +326,9 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             o.T = Lo.T; o.ldt = H; o.S = Lo.S; o.R = AJ; o.ldr = K;
             if (int rc = ds_launch_oz_gemm(o, OZ_JAC, res, st)) return rc;
             c->launches += 2;
+        } else if (lap && l == 0 && !res && c->use_l0_kernel) {
+            if (int rc = ds_launch_l0_jac(d, Wc, AJ, c->B_am[0], Lo.GOUT, H, Lo.T, H, Lo.S, OJ, d.K1, st)) return rc;
+            c->launches++;
         } else if (lap) {
             GemmParams j = p;
             j.A = AJ; j.lda = K; j.M = (long long)Wc * N * d.NDp; j.C = OJ; j.ldc = d.K1; j.R = AJ; j.ldr = K;
@@ -352,7 +356,6 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
     const bool i8 = lap && c->use_i8 && c->i8_ok;
     const long long jrows = (long long)Wc * N * d.NDp;
     if (i8) {     // digits of the last layer's Jacobian rows (own columns), shared by both spins
-        ProfScope ps(c, st, true, 0.0);
         if (int rc = ds_launch_slice_rows(hJ, d.K1, jrows, H, reinterpret_cast<signed char*>(Lo.AD), Lo.SA, st)) return rc;
         c->launches++;
     }
@@ -469,6 +472,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     ds_ctx* c = new ds_ctx();
     c->device = device;
     if (const char* ev = getenv("DS_NO_I8")) c->use_i8 = atoi(ev) == 0;
+    if (const char* ev = getenv("DS_L0_GEMM")) c->use_l0_kernel = atoi(ev) == 0;
     DsDims& d = c->sys.d;
     d.n_up = sd->n_up; d.n_dn = sd->n_dn; d.N = sd->n_up + sd->n_dn; d.A = sd->n_atoms_prim;
     d.H = nd->hidden_one; d.P = nd->hidden_two; d.D = nd->n_det; d.L = nd->n_layers;
@@ -822,6 +826,7 @@ extern "C" int ds_debug_set_int(ds_ctx* c, const char* key, int value) {
     DS_REQUIRE(c && key, "null argument");
     if (!strcmp(key, "stop_layer")) { c->dbg_stop_layer = value; return 0; }
     if (!strcmp(key, "i8")) { c->use_i8 = value != 0; return 0; }
+    if (!strcmp(key, "l0_kernel")) { c->use_l0_kernel = value != 0; return 0; }
     ds_set_error("unknown debug key %s", key);
     return -1;
 }

@@ -171,7 +171,7 @@ void ds_set_error(const char* fmt, ...);
         }                                                                                 \
     } while (0)
 
-struct cplx {
+struct __align__(16) cplx {
     double re, im;
 };
 __host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {

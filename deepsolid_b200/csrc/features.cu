@@ -19,7 +19,7 @@ __device__ __forceinline__ Jet pick4(const Jet f[4], int q) {
 }
 
 template <bool JETS>
-__global__ void __launch_bounds__(FEAT_THREADS) features_pair_kernel(const DsSys sys, const FeatParams fp) {
+__global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const DsSys sys, const FeatParams fp) {
     const DsDims& dm = sys.d;
     const int N = dm.N, A = dm.A, P = dm.P, L = dm.L, C0 = dm.C0, K0 = dm.K0, K1 = dm.K1, H = dm.H;
     const int NDp = dm.NDp, ND = dm.ND;
@@ -74,17 +74,17 @@ __global__ void __launch_bounds__(FEAT_THREADS) features_pair_kernel(const DsSys
 
     // ---- pairs (j, i) ---------------------------------------------------------
     const double inv_up = 1.0 / dm.n_up, inv_dn = 1.0 / dm.n_dn;
-    double acc[2][DS_MAX_LAYERS][5];
+    // one spin channel of partners j at a time: the per-lane sums of a channel stay in 5 registers per level
+    for (int sj = 0; sj < 2; ++sj) {
+    const int jbeg = sj ? dm.n_up : 0, jend = sj ? N : dm.n_up;
+    const double invn = sj ? inv_dn : inv_up;
+    double acc[DS_MAX_LAYERS][5];
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int l = 0; l < DS_MAX_LAYERS; ++l)
 #pragma unroll
-        for (int l = 0; l < DS_MAX_LAYERS; ++l)
-#pragma unroll
-            for (int c = 0; c < 5; ++c) acc[s][l][c] = 0.0;
+        for (int c = 0; c < 5; ++c) acc[l][c] = 0.0;
 
-    for (int j = warp; j < N; j += nwarps) {
-        const int sj = (j < dm.n_up) ? 0 : 1;
-        const double invn = sj ? inv_dn : inv_up;
+    for (int j = jbeg + warp; j < jend; j += nwarps) {
         double d[3];
         for (int k = 0; k < 3; ++k) d[k] = sx[3 * j + k] - sx[3 * i + k] + (j == i ? 1.0 : 0.0);
         Jet f[4];
@@ -103,15 +103,8 @@ __global__ void __launch_bounds__(FEAT_THREADS) features_pair_kernel(const DsSys
             const int Pl = (l == 0) ? 4 : P;
             // accumulate spin-channel sums of level l
             if (lane < Pl) {
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const double m = (s == sj) ? 1.0 : 0.0;
-                    acc[s][l][0] += m * cur.v;
-                    if (JETS) {
-                        acc[s][l][1] += m * cur.g0; acc[s][l][2] += m * cur.g1; acc[s][l][3] += m * cur.g2;
-                        acc[s][l][4] += m * cur.l;
-                    }
-                }
+                acc[l][0] += cur.v;
+                if (JETS) { acc[l][1] += cur.g0; acc[l][2] += cur.g1; acc[l][3] += cur.g2; acc[l][4] += cur.l; }
             }
             // Jacobian rows of directions (j,c), j != i: +grad / n_{s(j)} in the spin-of-j half
             if (JETS && j != i) {
@@ -164,18 +157,17 @@ __global__ void __launch_bounds__(FEAT_THREADS) features_pair_kernel(const DsSys
             woff += Pl * P + P;
         }
     }
-    // cross-warp reduction of the spin-channel sums
+    // cross-warp reduction of the sums of this spin channel
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int l = 0; l < DS_MAX_LAYERS; ++l) {
+        if (l >= L) break;
 #pragma unroll
-        for (int l = 0; l < DS_MAX_LAYERS; ++l) {
-            if (l >= L) break;
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                if (!JETS && c > 0) break;
-                atomicAdd(&sums[((s * L + l) * 5 + c) * 32 + lane], acc[s][l][c]);
-            }
+        for (int c = 0; c < 5; ++c) {
+            if (!JETS && c > 0) break;
+            atomicAdd(&sums[((sj * L + l) * 5 + c) * 32 + lane], acc[l][c]);
         }
+    }
+    }   // spin channel
     __syncthreads();
 
     // ---- finalize: value / Laplacian rows, own-direction Jacobian rows, padding rows
@@ -239,8 +231,18 @@ int ds_launch_features(const DsSys& sys, const FeatParams& fp, int Wc, bool jets
         DS_CUDA_CHECK(cudaFuncSetAttribute(features_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DS_CUDA_CHECK(cudaFuncSetAttribute(features_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if (jets) features_pair_kernel<true><<<grid, FEAT_THREADS, smem, stream>>>(sys, fp);
-    else features_pair_kernel<false><<<grid, FEAT_THREADS, smem, stream>>>(sys, fp);
+    // warps per CTA: a warp owns one partner j at a time, one spin channel after the other; 4 or 8 warps
+    // (whole warps per SM sub-partition, 128 registers each), whichever wastes fewer warp-rounds
+    int best_w = 8;
+    double best_eff = -1.0;
+    for (int w = 8; w >= 4; w -= 4) {
+        const int rounds = (sys.d.n_up + w - 1) / w + (sys.d.n_dn + w - 1) / w;
+        const double eff = (double)sys.d.N / ((double)rounds * w);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_w = w; }
+    }
+    const int threads = jets ? 32 * best_w : FEAT_THREADS;
+    if (jets) features_pair_kernel<true><<<grid, threads, smem, stream>>>(sys, fp);
+    else features_pair_kernel<false><<<grid, threads, smem, stream>>>(sys, fp);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

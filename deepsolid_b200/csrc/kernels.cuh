@@ -24,6 +24,10 @@ int ds_launch_features(const DsSys& sys, const FeatParams& fp, int Wc, bool jets
 int ds_launch_means(const DsDims& dm, int Wc, int C, const double* AJ, int ldj, const double* AV,
                     const double* AL, int ldv, double* GIN, int ldgin, bool jets, cudaStream_t stream);
 
+// layer-0 Jacobian rows (no GEMM): J1 = (1-T^2)(A0J.B + G), S = sum_d (A0J.B + G)^2
+int ds_launch_l0_jac(const DsDims& dm, int Wc, const double* A0J, const double* B, const double* G, int ldg,
+                     const double* T, int ldt, double* S, double* OJ, int ldc, cudaStream_t stream);
+
 // slater.cu -----------------------------------------------------------------
 struct SlaterBufs {
     const double* X;        // [Wc,3N]

@@ -6,7 +6,9 @@
 
 namespace {
 
-constexpr int OZ_THREADS = 320;                       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
+constexpr int EPI_WARPS = 16;                         // four per TMEM lane quarter
+constexpr int EPI_COLS = OZ_TN / (EPI_WARPS / 4);     // columns (rows of A) per epilogue warp
+constexpr int OZ_THREADS = 64 + EPI_WARPS * 32;       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..: epilogue
 constexpr int STAGES = 3;
 constexpr int W_SLICE = OZ_TM * OZ_BK;                // 8192 B
 constexpr int A_SLICE = OZ_TN * OZ_BK;                // 4096 B
@@ -112,7 +114,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 }
 
 // ---------------------------------------------------------------------------
-// digits of fp64 rows: one warp per row
+// digits of fp64 rows: one warp per row.
+//   e      = exponent of the row maximum + 1 (taken from the IEEE exponent field: integer max of the
+//            high words, no fp64 compares),  sa[r] = 2^(e-6)
+//   q[k]   = rn(A[r,k] * 2^(46-e))           (|q| < 2^46; formed with the 2^52+2^51 magic add)
+//   digits = balanced base-256 digits of q: the bytes of q + 0x8080808080 with their top bit flipped
+//            (adding 128 to every byte position propagates exactly the balanced carries); the top
+//            digit is the signed remainder byte.
+// 8 consecutive k per lane; a byte transpose (PRMT) turns them into one 8-byte word per slice, so a
+// warp stores 256 contiguous bytes per slice.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ A, int lda, long long rows, int K,
                                                          signed char* __restrict__ Ad, double* __restrict__ sa) {
@@ -121,8 +131,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     const int lane = threadIdx.x & 31;
     const double* a = A + r * (long long)lda;
     double v[2][8];
-    double mx = 0.0;
-    bool bad = false;
+    unsigned mxh = 0u;                                // max over the row of the high words of |A|
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const int c0 = it * 256 + lane * 8;
@@ -136,43 +145,100 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
                 v[it][2 * j] = t.x; v[it][2 * j + 1] = t.y;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                double f = fabs(v[it][j]);
-                bad |= !(f <= 1.7e308);           // inf or nan
-                mx = fmax(mx, f);
-            }
+            for (int j = 0; j < 8; ++j) mxh = max(mxh, (unsigned)__double2hiint(v[it][j]) & 0x7fffffffu);
         }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    bad = __any_sync(0xffffffffu, bad);
-    int e = 0;
-    if (mx > 0.0) e = ilogb(mx) + 1;              // mx < 2^e
+    for (int off = 16; off > 0; off >>= 1) mxh = max(mxh, __shfl_xor_sync(0xffffffffu, mxh, off));
+    const bool bad = mxh >= 0x7ff00000u;              // inf or nan somewhere in the row
+    int e = (int)(mxh >> 20) - 1022;                  // row max < 2^e (subnormal rows: e = -1022)
     if (e < -900) e = -900;
-    const double f = scalbn(1.0, 8 * OZ_S - 2 - e);
-    if (lane == 0) sa[r] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e - 6);
+    // 2^(46-e) as an IEEE double (46-e in [-978, 946]: always a normal number)
+    const double f = __hiloint2double((1023 + 8 * OZ_S - 2 - e) << 20, 0);
+    if (lane == 0) sa[r] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __hiloint2double((1023 + e - 6) << 20, 0);
     signed char* out = Ad + r * (long long)OZ_S * K;
+    const double MAGIC = 6755399441055744.0;          // 2^52 + 2^51
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const int c0 = it * 256 + lane * 8;
         if (c0 >= K) continue;
-        unsigned long long w[OZ_S];
-#pragma unroll
-        for (int s = 0; s < OZ_S; ++s) w[s] = 0ull;
+        unsigned lo[8], hi[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            long long q = bad ? 0ll : __double2ll_rn(v[it][j] * f);
+            const double t = bad ? MAGIC : fma(v[it][j], f, MAGIC);     // low 48 bits = q (two's complement)
+            unsigned l = (unsigned)__double2loint(t), h = (unsigned)__double2hiint(t);
+            const unsigned l2 = l + 0x80808080u;
+            h += 0x80u + (l2 < l ? 1u : 0u);
+            lo[j] = l2 ^ 0x80808080u;                 // digits 2..5 (bytes 3..0)
+            hi[j] = h ^ 0x80u;                        // digit 1 (byte 0), digit 0 = signed byte 1
+        }
+        unsigned w[OZ_S][2];
 #pragma unroll
-            for (int s = OZ_S - 1; s >= 1; --s) {
-                const long long d = ((q + 128) & 255) - 128;
-                w[s] |= (unsigned long long)(d & 255) << (8 * j);
-                q = (q - d) >> 8;
-            }
-            w[0] |= (unsigned long long)(q & 255) << (8 * j);
+        for (int hf = 0; hf < 2; ++hf) {
+            const unsigned *L = lo + 4 * hf, *H = hi + 4 * hf;
+            const unsigned t01 = __byte_perm(L[0], L[1], 0x5140), t23 = __byte_perm(L[2], L[3], 0x5140);   // bytes 0,1
+            const unsigned u01 = __byte_perm(L[0], L[1], 0x7362), u23 = __byte_perm(L[2], L[3], 0x7362);   // bytes 2,3
+            const unsigned h01 = __byte_perm(H[0], H[1], 0x5140), h23 = __byte_perm(H[2], H[3], 0x5140);
+            w[5][hf] = __byte_perm(t01, t23, 0x5410);
+            w[4][hf] = __byte_perm(t01, t23, 0x7632);
+            w[3][hf] = __byte_perm(u01, u23, 0x5410);
+            w[2][hf] = __byte_perm(u01, u23, 0x7632);
+            w[1][hf] = __byte_perm(h01, h23, 0x5410);
+            w[0][hf] = __byte_perm(h01, h23, 0x7632);
         }
 #pragma unroll
         for (int s = 0; s < OZ_S; ++s)
-            *reinterpret_cast<unsigned long long*>(out + (long long)s * K + c0) = w[s];
+            *reinterpret_cast<uint2*>(out + (long long)s * K + c0) = make_uint2(w[s][0], w[s][1]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// epilogue blocks: 8 consecutive rows of A (one electron) for one output channel.  FULL: the whole
+// 128-channel block is inside N (no per-lane predicates, straight-line code the scheduler can
+// interleave across the 8 columns); all loads are issued before the first use.
+// ---------------------------------------------------------------------------
+template <bool RES, bool FULL>
+__device__ __forceinline__ double jac_block8(const double* zz8, const double* __restrict__ gp, long long ldg,
+                                             const double* __restrict__ rp, long long ldr, double* __restrict__ cp,
+                                             long long ldc, const double* __restrict__ sap, double sbn, double d1,
+                                             bool nv, double sacc) {
+    const double rs2 = 0.70710678118654752440;
+    double gv[8], rv[8], sc[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        sc[jj] = __ldg(sap + jj);                              // same address in every lane: one broadcast transaction
+        gv[jj] = (FULL || nv) ? gp[jj * ldg] : 0.0;
+        rv[jj] = (RES && (FULL || nv)) ? rp[jj * ldr] : 0.0;
+    }
+    double s1 = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const double zj = fma(zz8[jj], sc[jj] * sbn, gv[jj]);
+        if (jj & 1) s1 = fma(zj, zj, s1); else sacc = fma(zj, zj, sacc);
+        double o = d1 * zj;
+        if (RES) o = (rv[jj] + o) * rs2;
+        if (FULL || nv) cp[jj * ldc] = o;
+    }
+    return sacc + s1;
+}
+
+template <bool FULL>
+__device__ __forceinline__ void orbj_block8(const double* zz8, const double* __restrict__ sap, double sbn, double Ex,
+                                            double Ey, int im, double* __restrict__ dp, long long ns2,
+                                            double* __restrict__ yp, long long ystride, int d, int ND, int c0, bool nv) {
+    double sc[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) sc[jj] = __ldg(sap + jj);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const double z = zz8[jj] * (sc[jj] * sbn);
+        const double zp = __shfl_xor_sync(0xffffffffu, z, 1);
+        if ((FULL || nv) && d + jj < ND) {
+            // (vr + i vi)(Ex + i Ey): re = vr Ex - vi Ey, im = vr Ey + vi Ex
+            dp[jj * ns2] = im ? fma(zp, Ey, z * Ex) : fma(-zp, Ey, z * Ex);
+            const unsigned c = (unsigned)(c0 + jj);
+            if (c < 3u) yp[c * ystride] = z;
+        }
     }
 }
 
@@ -180,6 +246,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
 // the GEMM
 // ---------------------------------------------------------------------------
 template <int MODE, bool RES>
+// 18 warps: five share one SM sub-partition (16384 registers), so at most 96 registers per thread
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const OzParams p,
                const int tiles_per_group, const int n_cb, const long long n_tiles) {
@@ -194,7 +261,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&tmem_full_bar, 1);
-        mbar_init(&tmem_empty_bar, 8);
+        mbar_init(&tmem_empty_bar, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -262,41 +329,58 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue: thread = output channel =====================
-        // 8 warps: two per TMEM lane quarter, each owning 32 of the tile's 64 columns (= rows of A).
-        // Phase A (holds TMEM): read the six diagonals, pack them EXACTLY into two int64 per output
+        // EPI_WARPS warps: four per TMEM lane quarter, each owning EPI_COLS of the tile's 64 columns
+        // (= rows of A).  Phase A (holds TMEM): read the six diagonals, pack them EXACTLY into two
+        // int64 per output
         //   hi = c0 2^16 + c1 2^8 + c2,  lo = c3 2^16 + c4 2^8 + c5   (|c_g| < 2^26),
         // round hi + lo 2^-24 ONCE to fp64 (the only rounding of the whole product) and release the
-        // accumulators so the next tile's MMAs start.  Phase B: scales, fused epilogue math, stores.
+        // accumulators so the next tile's MMAs start.  Phase B: scales, fused epilogue math, stores,
+        // in blocks of 8 columns: rows of A come in aligned groups of 8 that share one electron
+        // (NDp and rows-per-group are multiples of 8), so a block needs no per-column bookkeeping.
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                 // which 32 columns
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 32;
+        const int cg = (warp - 2) >> 2;                   // which EPI_COLS columns
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * EPI_COLS;
         uint32_t it = 0;
-        const double rs2 = 0.70710678118654752440;
         const double MAGIC = 6755399441055744.0;          // 2^52 + 2^51
+        int cur_cb = -1;
+        double sbn = 0.0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int cb = (int)(tile % n_cb);
             const long long rt = tile / n_cb;
             const long long grp = rt / tiles_per_group;
-            const long long q0 = (rt % tiles_per_group) * OZ_TN + half * 32;    // first row (in group) of this warp
+            const long long q0 = (rt % tiles_per_group) * OZ_TN + cg * EPI_COLS;   // first row (in group) of this warp
             const int n = cb * OZ_TM + q * 32 + lane;
             const bool nv = n < p.N;
-            const double sbn = nv ? p.sb[n] * (1.0 / 65536.0) : 0.0;
-            const long long prow0 = grp * p.gstride + p.goff + q0;              // physical row of column 0
+            const bool full = (cb + 1) * OZ_TM <= p.N;                             // warp-uniform
+            if (cb != cur_cb) { cur_cb = cb; sbn = nv ? p.sb[n] * (1.0 / 65536.0) : 0.0; }   // a CTA normally keeps its cb
+            const long long prow0 = grp * p.gstride + p.goff + q0;                 // physical row of column 0
+            const long long left = p.rpg - q0;
+            const int nvalid = left < 0 ? 0 : (left < EPI_COLS ? (int)left : EPI_COLS);   // warp-uniform
+            const double* sap = p.sa + prow0;                                      // scales of this warp's rows
+            if (MODE == OZ_JAC && RES && nv && nvalid == EPI_COLS) {
+                // pull the residual rows towards L2 while the MMAs of this tile run
+                const double* pr = p.R + prow0 * (long long)p.ldr + n;
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
+                    pr += p.ldr;
+                }
+            }
 
-            double zz[32];
+            double zz[EPI_COLS];
             mbar_wait(&tmem_full_bar, it & 1u);
             tc_fence_after();
             if (!(MODE == OZ_PLAIN && (p.dbg & 1))) {
 #pragma unroll
-                for (int c0 = 0; c0 < 32; c0 += 8) {
+                for (int c0 = 0; c0 < EPI_COLS; c0 += 8) {
                     int v[OZ_S][8];
 #pragma unroll
                     for (int g = 0; g < OZ_S; ++g) tmem_ld8(lane_addr + g * OZ_TN + c0, v[g]);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const long long hi = ((long long)v[0][j] << 16) + ((long long)v[1][j] << 8) + (long long)v[2][j];
-                        const long long lo = ((long long)v[3][j] << 16) + ((long long)v[4][j] << 8) + (long long)v[5][j];
+                        const long long hi = (long long)v[0][j] * 65536 + ((long long)v[1][j] * 256 + (long long)v[2][j]);
+                        const long long lo = (long long)v[3][j] * 65536 + ((long long)v[4][j] * 256 + (long long)v[5][j]);
                         const double dh = __longlong_as_double(hi + 0x4338000000000000LL) - MAGIC;
                         const double dl = __longlong_as_double(lo + 0x4338000000000000LL) - MAGIC;
                         zz[c0 + j] = fma(dl, 1.0 / 16777216.0, dh);     // one fp64 rounding of the exact integer sum
@@ -308,106 +392,68 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             if (lane == 0) mbar_arrive(&tmem_empty_bar);
             if (MODE == OZ_PLAIN && (p.dbg & 1)) continue;
 
-            // scales of this warp's 32 rows: one coalesced load, broadcast per column
-            const int nvalid = (int)((p.rpg - q0) < 32 ? (p.rpg - q0) : 32);          // warp-uniform, may be <= 0
-            const double sa_l = (lane < nvalid) ? p.sa[prow0 + lane] : 0.0;
-
-            // per-mode running state
-            long long cur_e = -1;
-            double sacc = 0.0, d1 = 0.0;
-            double Ex = 0.0, Ey = 0.0;
-            // JAC: (electron row e, direction d) of column 0, advanced incrementally
-            long long je = 0; int jd = 0;
-            if (MODE == OZ_JAC) { je = prow0 / p.NDp; jd = (int)(prow0 - je * p.NDp); }
-            int ois = 0, od = 0;
-            if (MODE == OZ_ORBJ) { ois = (int)(q0 / p.NDp); od = (int)(q0 - (long long)ois * p.NDp); }
-            double* cptr = (MODE == OZ_ORBJ) ? nullptr : p.C + prow0 * (long long)p.ldc + n;
-            const double* rptr = (MODE == OZ_JAC && RES) ? p.R + prow0 * (long long)p.ldr + n : nullptr;
             if (MODE == OZ_JAC) {
-                // blocks of 8 columns: issue the G / residual loads of the block first (independent of the
-                // stores of earlier columns), then the arithmetic and the stores
-                const double* __restrict__ Gp = p.G;
-                const double* __restrict__ Tp = p.T;
-                int jw = (int)(je / p.n_elec);
-                int ji = (int)(je - (long long)jw * p.n_elec);
+                // physical row = e * NDp + d  (e = walker * n_elec + electron); rows < 2^31 (checked by the launcher)
+                unsigned e = (unsigned)prow0 / (unsigned)p.NDp;
+                int d = (int)((unsigned)prow0 - e * (unsigned)p.NDp);
+                unsigned w = e / (unsigned)p.n_elec;
+                int ie = (int)(e - w * (unsigned)p.n_elec);
+                long long cur_e = -1;
+                double sacc = 0.0, d1 = 0.0;
 #pragma unroll
-                for (int j0 = 0; j0 < 32; j0 += 8) {
-                    double gv[8], rv[8];
-                    int dflag[8];                                   // 1: first column of a new electron row
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const bool ok = nv && (j0 + jj < nvalid);
-                        gv[jj] = ok ? Gp[((long long)jw * p.NDg + jd) * p.ldg + n] : 0.0;
-                        rv[jj] = (RES && ok) ? rptr[(long long)(j0 + jj) * p.ldr] : 0.0;
-                        dflag[jj] = (j0 + jj == 0) || (jd == 0);
-                        if (++jd == p.NDp) { jd = 0; if (++ji == p.n_elec) { ji = 0; ++jw; } }
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const int j = j0 + jj;
-                        const double z = zz[j] * (__shfl_sync(0xffffffffu, sa_l, j) * sbn);
-                        if (j < nvalid) {
-                            if (dflag[jj]) {
-                                if (cur_e >= 0) { if (nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc); ++cur_e; }
-                                else cur_e = je;
-                                sacc = 0.0;
-                                if (nv) { const double t = Tp[cur_e * (long long)p.ldt + n]; d1 = 1.0 - t * t; }
-                            }
-                            if (nv) {
-                                const double zj = z + gv[jj];
-                                sacc = fma(zj, zj, sacc);
-                                double o = d1 * zj;
-                                if (RES) o = (rv[jj] + o) * rs2;
-                                cptr[(long long)j * p.ldc] = o;
-                            }
+                for (int b = 0; b < EPI_COLS / 8; ++b) {
+                    if (8 * b < nvalid) {                                   // warp-uniform; blocks are all-or-nothing
+                        if ((long long)e != cur_e) {
+                            if (cur_e >= 0 && nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc);
+                            cur_e = e; sacc = 0.0;
+                            const double t = nv ? p.T[(long long)e * p.ldt + n] : 0.0;
+                            d1 = 1.0 - t * t;
                         }
+                        const double* gp = p.G + ((long long)w * p.NDg + d) * p.ldg + n;
+                        const double* rp = RES ? p.R + (prow0 + 8 * b) * (long long)p.ldr + n : nullptr;
+                        double* cp = p.C + (prow0 + 8 * b) * (long long)p.ldc + n;
+                        if (full) sacc = jac_block8<RES, true>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbn, d1, true, sacc);
+                        else sacc = jac_block8<RES, false>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbn, d1, nv, sacc);
                     }
+                    d += 8;
+                    if (d >= p.NDp) { d -= p.NDp; ++e; if (++ie == p.n_elec) { ie = 0; ++w; } }
                 }
+                if (cur_e >= 0 && nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc);
             } else if (MODE == OZ_PLAIN) {
+                double* cptr = p.C + prow0 * (long long)p.ldc + n;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const double z = zz[j] * (__shfl_sync(0xffffffffu, sa_l, j) * sbn);
-                    if (nv && j < nvalid) *cptr = z;
+                for (int j = 0; j < EPI_COLS; ++j) {
+                    if (nv && j < nvalid) *cptr = zz[j] * (__ldg(sap + j) * sbn);
                     cptr += p.ldc;
                 }
             } else {
                 // OZ_ORBJ: group = walker, row in group = is*NDp + d, channel n = 2*pp + (re|im), pp = k*n_s + o.
-                // All column-dependent offsets are warp-uniform and advanced incrementally.
                 const int pp = n >> 1, im = n & 1;
                 const int kdet = pp / p.n_s, oo = pp - kdet * p.n_s;
                 const int ND = 3 * p.n_elec;
                 const long long ns2 = 2LL * p.n_s * p.n_s;
-                double* dap = p.DA + 2 * ((((long long)grp * p.n_det + kdet) * p.NDp) * p.n_s * p.n_s + oo) + im;
-                long long coff = od * ns2 + 2LL * ois * p.n_s;
-                int own0 = 3 * (p.off_s + ois);
-                long long e = grp * p.n_elec + p.off_s + ois;
-                const double* ep = p.etab + e * 10LL * p.npar_max + 2 * pp;
-                double* yp = p.YOWN + 2 * (e * 3LL * p.npar_max + pp) + im;
-                bool newis = true;
+                int is = (int)((unsigned)q0 / (unsigned)p.NDp);
+                int d = (int)q0 - is * p.NDp;
+                double* dab = p.DA + 2 * ((((long long)grp * p.n_det + kdet) * p.NDp) * p.n_s * p.n_s + oo) + im;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const double z = zz[j] * (__shfl_sync(0xffffffffu, sa_l, j) * sbn);
-                    const double zp = __shfl_xor_sync(0xffffffffu, z, 1);
-                    if (j < nvalid && od < ND) {                        // warp-uniform
-                        if (newis) {
-                            newis = false;
-                            if (nv) { const double2 E = *reinterpret_cast<const double2*>(ep); Ex = E.x; Ey = E.y; }
-                        }
+                for (int b = 0; b < EPI_COLS / 8; ++b) {
+                    if (8 * b < nvalid) {                                   // warp-uniform
+                        const long long e = grp * p.n_elec + p.off_s + is;
+                        double Ex = 0.0, Ey = 0.0;
                         if (nv) {
-                            // (vr + i vi)(Ex + i Ey): re = vr Ex - vi Ey, im = vr Ey + vi Ex
-                            dap[coff] = im ? fma(zp, Ey, z * Ex) : fma(-zp, Ey, z * Ex);
-                            const unsigned c = (unsigned)(od - own0);
-                            if (c < 3u) yp[2LL * c * p.npar_max] = z;
+                            const double2 E = *reinterpret_cast<const double2*>(p.etab + e * 10LL * p.npar_max + 2 * pp);
+                            Ex = E.x; Ey = E.y;
                         }
+                        double* dp = dab + d * ns2 + 2LL * is * p.n_s;
+                        double* yp = p.YOWN + 2 * (e * 3LL * p.npar_max + pp) + im;
+                        const int c0 = d - 3 * (p.off_s + is);              // own-coordinate index of column 0
+                        if (full) orbj_block8<true>(zz + 8 * b, sap + 8 * b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, true);
+                        else orbj_block8<false>(zz + 8 * b, sap + 8 * b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, nv);
                     }
-                    ++od; coff += ns2;
-                    if (od == p.NDp) {
-                        od = 0; ++ois; coff = 2LL * ois * p.n_s; own0 += 3;
-                        ep += 10LL * p.npar_max; yp += 6LL * p.npar_max; newis = true;
-                    }
+                    d += 8;
+                    if (d >= p.NDp) { d -= p.NDp; ++is; }
                 }
             }
-            if (MODE == OZ_JAC && cur_e >= 0 && nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc);
         }
     }
     tc_fence_before();
@@ -506,6 +552,11 @@ int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t s
     DS_REQUIRE(p.K % OZ_BK == 0 && p.K >= OZ_BK, "oz_gemm: K must be a multiple of %d (K=%d)", OZ_BK, p.K);
     DS_REQUIRE((reinterpret_cast<uintptr_t>(p.Ad) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Wd) & 15) == 0,
                "oz_gemm: digit buffers must be 16-byte aligned");
+    if (mode == OZ_JAC || mode == OZ_ORBJ) {
+        DS_REQUIRE(p.NDp % 8 == 0 && p.rpg % 8 == 0 && p.goff % 8 == 0 && p.gstride % 8 == 0,
+                   "oz_gemm: Jacobian rows must come in aligned groups of 8 (NDp=%d rpg=%lld)", p.NDp, p.rpg);
+        DS_REQUIRE(p.rpg * (mode == OZ_JAC ? 1 : p.n_groups) < (1LL << 31), "oz_gemm: too many Jacobian rows in one launch");
+    }
     switch (mode) {
         case OZ_PLAIN: return launch<OZ_PLAIN, false>(p, stream);
         case OZ_JAC: return residual ? launch<OZ_JAC, true>(p, stream) : launch<OZ_JAC, false>(p, stream);

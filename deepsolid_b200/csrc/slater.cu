@@ -6,6 +6,7 @@
 //   lap psi/psi = sum_k w_k { sum_s [ tr(X lapM) - sum_d tr((X dM_d)^2) ] + sum_d (sum_s tr(X dM_d))^2 },
 //                 X = M^-1, w_k = D_k / psi
 #include "kernels.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -353,6 +354,260 @@ __global__ void __launch_bounds__(DET_THREADS) det_kernel(const DsSys sys, const
 }
 
 // ---------------------------------------------------------------------------
+// Determinant kernel of the Laplacian sweep, second version: one CTA per (walker, spin, determinant).
+//   * in-place Gauss-Jordan inverse X = M^-1 in shared memory (as det_kernel<true>)
+//   * directions are processed in groups of G: the G derivative matrices dM_d are staged with cp.async
+//     (no register round trip), every thread owns one 3x3 block position (rb, cb) of TWO directions
+//     (X operands loaded once for both: 9 LDS.128 per 72 DFMA), the products Y_d = X dM_d are written
+//     IN PLACE over the staged operands, and  sum_d tr(Y_d^2) = sum_{a,b} Y[a,b] Y[b,a]  is accumulated
+//     per thread from its register block and the transposed block read back from shared memory; only
+//     tr(Y_d) is reduced per direction (diagonal blocks).
+// blockDim.x >= (G/2) * nb^2 work items (nb = np/3), a multiple of 32, at most 512.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_s(void* smem_dst, const void* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(512, 1) det_lap_kernel(const DsSys sys, const SlaterBufs sb, int G) {
+    const DsDims& dm = sys.d;
+    const int D = dm.D, NDp = dm.NDp, ND = dm.ND;
+    const int k = blockIdx.x % D;
+    const int s = (blockIdx.x / D) % 2;
+    const long long w = blockIdx.x / (2 * D);
+    const int n = s ? dm.n_dn : dm.n_up;
+    const int np = ((n + 2) / 3) * 3;               // padded to the 3x3 register block
+    const int nb = np / 3;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+
+    extern __shared__ __align__(16) double smraw[];
+    cplx* Xs = reinterpret_cast<cplx*>(smraw);      // [np][np] rows = orbital (after inversion), cols = electron
+    cplx* colk = Xs + np * np;                      // [np]
+    cplx* buf = colk + np;                          // [G][np][np]  dM_d (rows = electron, cols = orbital), then Y_d
+    cplx* s_tau = buf + G * np * np;                // [G][nb] partial traces of the diagonal blocks
+    __shared__ int piv[128];
+    __shared__ int s_p;
+    __shared__ double s_red[2 * 16 + 4];
+
+    const cplx* mat = reinterpret_cast<const cplx*>(sb.MAT[s]) + (w * D + k) * (long long)n * n;
+    for (int t = tid; t < np * np; t += nthr) {
+        int r = t / np, c = t - r * np;
+        Xs[t] = (r < n && c < n) ? mat[r * n + c] : cplx{0.0, 0.0};
+    }
+    if (np != n)                                     // padding of the staged operands stays zero for the whole kernel
+        for (int t = tid; t < G * np * np; t += nthr) buf[t] = cplx{0.0, 0.0};
+    __syncthreads();
+
+    // first group of derivative matrices: in flight during the inversion
+    const cplx* da = reinterpret_cast<const cplx*>(sb.DA[s]) + (w * D + k) * (long long)NDp * n * n;
+    auto stage = [&](int d0, int g_cnt) {
+        if (np == n) {
+            const int tot = g_cnt * n * n;
+            const cplx* src = da + (long long)d0 * n * n;
+            for (int t = tid; t < tot; t += nthr) cp_async16_s(buf + t, src + t);
+        } else {
+            const int rows = g_cnt * n;              // one warp per matrix row
+            for (int rr = warp; rr < rows; rr += nwarp) {
+                const int g = rr / n, i = rr - g * n;
+                const cplx* src = da + ((long long)(d0 + g) * n + i) * n;
+                cplx* dst = buf + (g * np + i) * np;
+                for (int o = lane; o < n; o += 32) cp_async16_s(dst + o, src + o);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    stage(0, min(G, ND));
+
+    double logabs = 0.0;
+    cplx phase{1.0, 0.0};
+    for (int kk = 0; kk < n; ++kk) {
+        if (tid < 32) {
+            double best = -1.0;
+            int bi = kk;
+            for (int r = kk + tid; r < n; r += 32) {
+                double v = cabs1(Xs[r * np + kk]);
+                if (v > best) { best = v; bi = r; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, best, off);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (tid == 0) { s_p = bi; piv[kk] = bi; }
+        }
+        __syncthreads();
+        const int p = s_p;
+        if (p != kk) {
+            for (int c = tid; c < n; c += nthr) {
+                cplx a = Xs[kk * np + c];
+                Xs[kk * np + c] = Xs[p * np + c];
+                Xs[p * np + c] = a;
+            }
+            phase = cplx{-phase.re, -phase.im};
+        }
+        __syncthreads();
+        const cplx pv = Xs[kk * np + kk];
+        {
+            double a = hypot(pv.re, pv.im);
+            logabs += log(a);
+            phase = cmul(phase, cplx{pv.re / a, pv.im / a});
+        }
+        const cplx ipv = cinv(pv);
+        for (int r = tid; r < n; r += nthr) colk[r] = Xs[r * np + kk];
+        __syncthreads();
+        for (int c = tid; c < n; c += nthr) {
+            cplx a = (c == kk) ? cplx{1.0, 0.0} : Xs[kk * np + c];
+            Xs[kk * np + c] = cmul(a, ipv);
+        }
+        __syncthreads();
+        for (int t = tid; t < n * n; t += nthr) {
+            int r = t / n, c = t - r * n;
+            if (r == kk) continue;
+            cplx f = colk[r];
+            cplx a = (c == kk) ? cplx{0.0, 0.0} : Xs[r * np + c];
+            cplx b = Xs[kk * np + c];
+            a.re -= f.re * b.re - f.im * b.im;
+            a.im -= f.re * b.im + f.im * b.re;
+            Xs[r * np + c] = a;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double* ld = sb.LOGDET + ((w * 2 + s) * D + k) * 3;
+        ld[0] = logabs; ld[1] = phase.re; ld[2] = phase.im;
+    }
+    // undo the row pivoting: swap columns in reverse order
+    for (int kk = n - 1; kk >= 0; --kk) {
+        const int p = piv[kk];
+        if (p != kk) {
+            for (int r = tid; r < n; r += nthr) {
+                cplx a = Xs[r * np + kk];
+                Xs[r * np + kk] = Xs[r * np + p];
+                Xs[r * np + p] = a;
+            }
+        }
+        __syncthreads();
+    }
+    // now Xs[o][i] = (M^-1)[o,i]
+
+    auto block_sum2 = [&](double a, double b, double& oa, double& ob) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off);
+            b += __shfl_xor_sync(0xffffffffu, b, off);
+        }
+        __syncthreads();
+        if (lane == 0) { s_red[2 * warp] = a; s_red[2 * warp + 1] = b; }
+        __syncthreads();
+        oa = 0.0; ob = 0.0;
+        for (int q = 0; q < nwarp; ++q) { oa += s_red[2 * q]; ob += s_red[2 * q + 1]; }
+    };
+
+    // tr(X lapM) = sum_{i,o} X[o,i] lapM[i,o]
+    {
+        const cplx* lm = reinterpret_cast<const cplx*>(sb.LAPM[s]) + (w * D + k) * (long long)n * n;
+        cplx acc{0.0, 0.0};
+        for (int t = tid; t < n * n; t += nthr) {
+            int i = t / n, o = t - i * n;
+            cfma(acc, Xs[o * np + i], lm[t]);
+        }
+        double ra, rb;
+        block_sum2(acc.re, acc.im, ra, rb);
+        if (tid == 0) {
+            double* tl = sb.TRLAP + ((w * 2 + s) * D + k) * 2;
+            tl[0] = ra; tl[1] = rb;
+        }
+    }
+
+    // ---- direction groups ---------------------------------------------------
+    double* tau_out = sb.TAU + ((w * 2 + s) * D + k) * (long long)NDp * 2;
+    const int nb2 = nb * nb;
+    const int n_items = (G >> 1) * nb2;
+    const bool active = tid < n_items;
+    int pi = 0, rb = 0, cb = 0;
+    if (active) { pi = tid / nb2; int rem = tid - pi * nb2; rb = (rem / nb) * 3; cb = (rem - (rem / nb) * nb) * 3; }
+    const int g0 = 2 * pi;
+    const cplx* xa = Xs + rb * np;
+    cplx* b0 = buf + (g0 * np) * np + cb;            // dM_{g0}[i][cb..]
+    cplx* b1 = b0 + np * np;                         // dM_{g0+1}
+    cplx sq{0.0, 0.0};
+    for (int d0 = 0; d0 < ND; d0 += G) {
+        const int g_cnt = min(G, ND - d0);
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        cplx y0[3][3], y1[3][3];
+        if (active) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) { y0[a][b] = cplx{0.0, 0.0}; y1[a][b] = cplx{0.0, 0.0}; }
+#pragma unroll 3
+            for (int i = 0; i < n; ++i) {
+                cplx xv[3], dv0[3], dv1[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) xv[a] = xa[a * np + i];
+#pragma unroll
+                for (int b = 0; b < 3; ++b) { dv0[b] = b0[i * np + b]; dv1[b] = b1[i * np + b]; }
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) { cfma(y0[a][b], xv[a], dv0[b]); cfma(y1[a][b], xv[a], dv1[b]); }
+            }
+        }
+        __syncthreads();                             // every operand of this group has been read
+        if (active) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    b0[(rb + a) * np + b] = y0[a][b];
+                    b1[(rb + a) * np + b] = y1[a][b];
+                }
+            if (rb == cb) {
+                s_tau[g0 * nb + rb / 3] = cplx{y0[0][0].re + y0[1][1].re + y0[2][2].re, y0[0][0].im + y0[1][1].im + y0[2][2].im};
+                s_tau[(g0 + 1) * nb + rb / 3] = cplx{y1[0][0].re + y1[1][1].re + y1[2][2].re, y1[0][0].im + y1[1][1].im + y1[2][2].im};
+            }
+        }
+        __syncthreads();
+        if (active) {
+            // sum_{a,b in block} Y[rb+a, cb+b] Y[cb+b, rb+a]; the transposed block sits at rows cb.., columns rb..
+            const cplx* t0 = buf + (g0 * np + cb) * np + rb;
+            const cplx* t1 = t0 + np * np;
+            cplx q0{0.0, 0.0}, q1{0.0, 0.0};
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    cfma(q0, y0[a][b], t0[b * np + a]);
+                    cfma(q1, y1[a][b], t1[b * np + a]);
+                }
+            if (g0 < g_cnt) { sq.re += q0.re; sq.im += q0.im; }
+            if (g0 + 1 < g_cnt) { sq.re += q1.re; sq.im += q1.im; }
+        }
+        if (tid < g_cnt) {
+            cplx tr{0.0, 0.0};
+            for (int j = 0; j < nb; ++j) { cplx v = s_tau[tid * nb + j]; tr.re += v.re; tr.im += v.im; }
+            tau_out[2 * (d0 + tid)] = tr.re;
+            tau_out[2 * (d0 + tid) + 1] = tr.im;
+        }
+        if (d0 + G < ND) {
+            __syncthreads();                         // transposed blocks and s_tau consumed: the buffer may be refilled
+            stage(d0 + G, min(G, ND - d0 - G));
+        }
+    }
+    {
+        double ra, rb2;
+        block_sum2(sq.re, sq.im, ra, rb2);
+        if (tid == 0) {
+            double* ts = sb.TRSQ + ((w * 2 + s) * D + k) * 2;
+            ts[0] = ra; ts[1] = rb2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Combine determinants (logdet_matmul, network.py:395-427) and the kinetic energy.
 // One warp per walker.
 // ---------------------------------------------------------------------------
@@ -439,6 +694,30 @@ int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cuda
     DS_REQUIRE(nmax <= 128, "determinants larger than 128x128 are not supported (n_s=%d)", nmax);
     const int np = ((nmax + 2) / 3) * 3;
     const int nb = np / 3;
+    dim3 grid((unsigned)((long long)Wc * 2 * sys.d.D));
+    static const bool use_v1 = getenv("DS_DET_V1") && atoi(getenv("DS_DET_V1")) != 0;
+    if (lap && !use_v1) {
+        // det_lap_kernel: G directions per group, two per thread
+        const int nb2 = nb * nb;
+        int G = 2 * (256 / nb2 > 1 ? 256 / nb2 : 1);
+        auto smem_of = [&](int g) { return (size_t)(np * np + np + g * np * np + g * nb) * sizeof(cplx); };
+        while (G > 2 && smem_of(G) > 100 * 1024) G -= 2;
+        const int nd_even = (sys.d.ND + 1) & ~1;
+        if (G > nd_even) G = nd_even;
+        const int items = (G / 2) * nb2;
+        int threads = ((items > G ? items : G) + 31) & ~31;
+        const size_t smem = smem_of(G);
+        if (threads <= 512 && smem <= 226 * 1024) {
+            static size_t cfg = 0;
+            if (smem > cfg) {
+                DS_CUDA_CHECK(cudaFuncSetAttribute(det_lap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cfg = smem;
+            }
+            det_lap_kernel<<<grid, threads, smem, stream>>>(sys, sb, G);
+            DS_CUDA_CHECK(cudaGetLastError());
+            return 0;
+        }
+    }
     int G = 1;
     if (lap) {
         G = (DET_THREADS + nb * nb - 1) / (nb * nb);
@@ -448,7 +727,6 @@ int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cuda
     }
     size_t smem = (size_t)(np * np + np + (lap ? 2 * G * np * np : 0)) * sizeof(cplx);
     DS_REQUIRE(smem <= 226 * 1024, "determinant kernel needs %zu bytes of shared memory", smem);
-    dim3 grid((unsigned)((long long)Wc * 2 * sys.d.D));
     static size_t cfg_smem[2] = {0, 0};
     if (smem > cfg_smem[lap ? 1 : 0]) {
         if (lap) DS_CUDA_CHECK(cudaFuncSetAttribute(det_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -39,7 +39,96 @@ __global__ void __launch_bounds__(256) means_kernel(DsDims dm, int C, const doub
     }
 }
 
+// ---------------------------------------------------------------------------
+// Layer-0 Jacobian rows without a GEMM.  The layer-0 operand rows have only K0 = 4A+8 columns, and the
+// 4A own-feature columns of row (i, d) vanish unless d is a coordinate of electron i, so the
+// "GEMM" is 8 (or K0) FMAs per output and the kernel is a pure HBM stream of the output rows:
+//   z = A0J[(e,d),:] . B[:, n] + G[w, d, n];  S[e,n] = sum_d z^2;  J1[(e,d), n] = (1 - T[e,n]^2) z.
+// One CTA per electron e = (w, i); thread = channel n, its weight column in registers (KT = K0) or
+// read through L1 (KT = 0, any K0); the electron's operand rows are staged in shared memory.
+// ---------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(256) l0_jac_kernel(DsDims dm, const double* __restrict__ A0J,
+                                                     const double* __restrict__ B, const double* __restrict__ G, int ldg,
+                                                     const double* __restrict__ T, int ldt, double* __restrict__ S,
+                                                     double* __restrict__ OJ, int ldc) {
+    extern __shared__ __align__(16) double l0_sm[];          // [NDp][K0]
+    const int K0 = dm.K0, C0 = dm.C0, H = dm.H, NDp = dm.NDp;
+    const long long e = blockIdx.x;
+    const int w = (int)(e / dm.N), i = (int)(e - (long long)w * dm.N);
+    {
+        const double2* src = reinterpret_cast<const double2*>(A0J + e * (long long)NDp * K0);
+        double2* dst = reinterpret_cast<double2*>(l0_sm);
+        for (int t = threadIdx.x; t < NDp * K0 / 2; t += blockDim.x) dst[t] = src[t];
+    }
+    __syncthreads();
+    const double* g0 = G + (long long)w * dm.NDg * ldg;
+    double* o0 = OJ + e * (long long)NDp * ldc;
+    for (int n = threadIdx.x; n < H; n += blockDim.x) {
+        double wc[KT > 0 ? KT : 1];
+        if (KT > 0) {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) wc[k] = B[(long long)k * H + n];
+        }
+        const double t = T[e * (long long)ldt + n];
+        const double d1 = 1.0 - t * t;
+        double sacc = 0.0;
+        for (int db = 0; db < NDp; db += 4) {                // NDp is a multiple of 8
+            double z[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) z[u] = g0[(long long)(db + u) * ldg + n];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int d = db + u;
+                const double* a = l0_sm + d * K0;
+                const bool own = (d / 3) == i;               // warp-uniform
+                if (KT > 0) {
+                    if (own) {
+#pragma unroll
+                        for (int k = 0; k < KT - 8; ++k) z[u] = fma(a[k], wc[k], z[u]);
+                    }
+#pragma unroll
+                    for (int k = KT - 8; k < KT; ++k) z[u] = fma(a[k], wc[k], z[u]);
+                } else {
+                    for (int k = own ? 0 : C0; k < K0; ++k) z[u] = fma(a[k], B[(long long)k * H + n], z[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                sacc = fma(z[u], z[u], sacc);
+                o0[(long long)(db + u) * ldc + n] = d1 * z[u];
+            }
+        }
+        S[e * (long long)ldt + n] = sacc;
+    }
+}
+
 }  // namespace
+
+int ds_launch_l0_jac(const DsDims& dm, int Wc, const double* A0J, const double* B, const double* G, int ldg,
+                     const double* T, int ldt, double* S, double* OJ, int ldc, cudaStream_t stream) {
+    const size_t smem = (size_t)dm.NDp * dm.K0 * sizeof(double);
+    DS_REQUIRE(smem <= 200 * 1024, "layer-0 Jacobian kernel: operand rows of one electron need %zu bytes of shared memory", smem);
+    int threads = (dm.H + 31) & ~31;
+    if (threads > 256) threads = 256;
+    dim3 grid((unsigned)((long long)Wc * dm.N));
+    static size_t cfg[2] = {0, 0};
+    if (dm.K0 == 16) {
+        if (smem > 48 * 1024 && smem > cfg[0]) {
+            DS_CUDA_CHECK(cudaFuncSetAttribute(l0_jac_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cfg[0] = smem;
+        }
+        l0_jac_kernel<16><<<grid, threads, smem, stream>>>(dm, A0J, B, G, ldg, T, ldt, S, OJ, ldc);
+    } else {
+        if (smem > 48 * 1024 && smem > cfg[1]) {
+            DS_CUDA_CHECK(cudaFuncSetAttribute(l0_jac_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cfg[1] = smem;
+        }
+        l0_jac_kernel<0><<<grid, threads, smem, stream>>>(dm, A0J, B, G, ldg, T, ldt, S, OJ, ldc);
+    }
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
 
 int ds_launch_means(const DsDims& dm, int Wc, int C, const double* AJ, int ldj, const double* AV,
                     const double* AL, int ldv, double* GIN, int ldgin, bool jets, cudaStream_t stream) {
