@@ -81,6 +81,7 @@ struct ds_ctx {
     bool use_i8 = true;                 // Jacobian-sweep GEMMs on tcgen05 (false: fp64 DMMA kernels)
     bool i8_ok = false;                 // stream widths are multiples of the tcgen05 K block
     bool use_l0_kernel = true;          // layer-0 Jacobian rows by the streaming kernel (false: DMMA GEMM)
+    bool use_slice_means = true;        // digits + spin-channel means of a layer's Jacobian rows in one pass
     double* env_pi[2] = {};
     double* env_sigma[2] = {};
     double* klist[2] = {};
@@ -292,7 +293,15 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         double* OJ = Lo.J[outb(l)];
         const bool res = (C == H);
         if (lap) DS_CUDA_CHECK(cudaMemsetAsync(Lo.S, 0, (size_t)Wc * N * H * sizeof(double), st));
-        if (int rc = ds_launch_means(d, Wc, C, AJ, K, AV, AL, K, Lo.GIN, 2 * C, lap, st)) return rc;
+        const bool i8_layer = lap && c->use_i8 && c->i8_ok && l > 0;
+        const bool fused_means = i8_layer && c->use_slice_means;
+        if (fused_means) {
+            // digits of the Jacobian rows and their spin-channel means in one pass over the fp64 rows
+            if (int rc = ds_launch_slice_means(AJ, K, K, C, Wc, d.n_up, N, d.NDp, d.NDg, reinterpret_cast<signed char*>(Lo.AD),
+                                               Lo.SA, Lo.GIN, 2 * C, st)) return rc;
+            c->launches++;
+        }
+        if (int rc = ds_launch_means(d, Wc, C, AJ, K, AV, AL, K, Lo.GIN, 2 * C, lap, st, fused_means)) return rc;
         c->launches++;
         {   // shared spin-mean contribution, once per walker and direction
             GemmParams g{};
@@ -314,10 +323,13 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             v.A = AV; v.lda = K; v.M = (long long)Wc * N; v.C = OV; v.ldc = d.K1; v.R = AV; v.ldr = K;
             if (int rc = gemm(c, v, GEMM_VALUE, res, st)) return rc;
         }
-        if (lap && c->use_i8 && c->i8_ok && l > 0) {
+        if (i8_layer) {
             const long long rows = (long long)Wc * N * d.NDp;
             signed char* Ad = reinterpret_cast<signed char*>(Lo.AD);
-            if (int rc = ds_launch_slice_rows(AJ, K, rows, K, Ad, Lo.SA, st)) return rc;
+            if (!fused_means) {
+                if (int rc = ds_launch_slice_rows(AJ, K, rows, K, Ad, Lo.SA, st)) return rc;
+                c->launches++;
+            }
             ProfScope ps(c, st, true, 2.0 * (double)rows * H * K);     // the tcgen05 GEMM alone
             OzParams o{};
             o.Ad = Ad; o.sa = Lo.SA; o.rpg = rows; o.gstride = rows; o.goff = 0; o.n_groups = 1;
@@ -325,7 +337,7 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             o.C = OJ; o.ldc = d.K1; o.G = Lo.GOUT; o.ldg = H; o.n_elec = N; o.NDp = d.NDp; o.NDg = d.NDg;
             o.T = Lo.T; o.ldt = H; o.S = Lo.S; o.R = AJ; o.ldr = K;
             if (int rc = ds_launch_oz_gemm(o, OZ_JAC, res, st)) return rc;
-            c->launches += 2;
+            c->launches++;
         } else if (lap && l == 0 && !res && c->use_l0_kernel) {
             if (int rc = ds_launch_l0_jac(d, Wc, AJ, c->B_am[0], Lo.GOUT, H, Lo.T, H, Lo.S, OJ, d.K1, st)) return rc;
             c->launches++;
@@ -473,6 +485,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     c->device = device;
     if (const char* ev = getenv("DS_NO_I8")) c->use_i8 = atoi(ev) == 0;
     if (const char* ev = getenv("DS_L0_GEMM")) c->use_l0_kernel = atoi(ev) == 0;
+    if (const char* ev = getenv("DS_NO_SLICE_MEANS")) c->use_slice_means = atoi(ev) == 0;
     DsDims& d = c->sys.d;
     d.n_up = sd->n_up; d.n_dn = sd->n_dn; d.N = sd->n_up + sd->n_dn; d.A = sd->n_atoms_prim;
     d.H = nd->hidden_one; d.P = nd->hidden_two; d.D = nd->n_det; d.L = nd->n_layers;
@@ -827,6 +840,7 @@ extern "C" int ds_debug_set_int(ds_ctx* c, const char* key, int value) {
     if (!strcmp(key, "stop_layer")) { c->dbg_stop_layer = value; return 0; }
     if (!strcmp(key, "i8")) { c->use_i8 = value != 0; return 0; }
     if (!strcmp(key, "l0_kernel")) { c->use_l0_kernel = value != 0; return 0; }
+    if (!strcmp(key, "slice_means")) { c->use_slice_means = value != 0; return 0; }
     ds_set_error("unknown debug key %s", key);
     return -1;
 }

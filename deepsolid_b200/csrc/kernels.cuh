@@ -22,7 +22,8 @@ int ds_launch_features(const DsSys& sys, const FeatParams& fp, int Wc, bool jets
 // spin-channel means of the one-electron stream: rows of the shared-mean operand
 // GIN[w, d, s*C + c] = mean_{i in s} src[(w,i,d), c]; d = NDp -> value, NDp+1 -> Laplacian.
 int ds_launch_means(const DsDims& dm, int Wc, int C, const double* AJ, int ldj, const double* AV,
-                    const double* AL, int ldv, double* GIN, int ldgin, bool jets, cudaStream_t stream);
+                    const double* AL, int ldv, double* GIN, int ldgin, bool jets, cudaStream_t stream,
+                    bool skip_jacobian_rows = false);
 
 // layer-0 Jacobian rows (no GEMM): J1 = (1-T^2)(A0J.B + G), S = sum_d (A0J.B + G)^2
 int ds_launch_l0_jac(const DsDims& dm, int Wc, const double* A0J, const double* B, const double* G, int ldg,

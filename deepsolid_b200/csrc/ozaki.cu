@@ -124,30 +124,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 // 8 consecutive k per lane; a byte transpose (PRMT) turns them into one 8-byte word per slice, so a
 // warp stores 256 contiguous bytes per slice.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ A, int lda, long long rows, int K,
-                                                         signed char* __restrict__ Ad, double* __restrict__ sa) {
-    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= rows) return;
-    const int lane = threadIdx.x & 31;
-    const double* a = A + r * (long long)lda;
-    double v[2][8];
+// digits + scale of ONE row held by a warp as v[it][j] = A[r, it*256 + lane*8 + j] (zero beyond K)
+__device__ __forceinline__ void slice_row_warp(const double (&v)[2][8], int K, int lane, signed char* __restrict__ out,
+                                               double* __restrict__ sa_r) {
     unsigned mxh = 0u;                                // max over the row of the high words of |A|
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int c0 = it * 256 + lane * 8;
+    for (int it = 0; it < 2; ++it)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[it][j] = 0.0;
-        if (c0 < K) {
-            const double2* p = reinterpret_cast<const double2*>(a + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                double2 t = p[j];
-                v[it][2 * j] = t.x; v[it][2 * j + 1] = t.y;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) mxh = max(mxh, (unsigned)__double2hiint(v[it][j]) & 0x7fffffffu);
-        }
-    }
+        for (int j = 0; j < 8; ++j) mxh = max(mxh, (unsigned)__double2hiint(v[it][j]) & 0x7fffffffu);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mxh = max(mxh, __shfl_xor_sync(0xffffffffu, mxh, off));
     const bool bad = mxh >= 0x7ff00000u;              // inf or nan somewhere in the row
@@ -155,8 +139,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     if (e < -900) e = -900;
     // 2^(46-e) as an IEEE double (46-e in [-978, 946]: always a normal number)
     const double f = __hiloint2double((1023 + 8 * OZ_S - 2 - e) << 20, 0);
-    if (lane == 0) sa[r] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __hiloint2double((1023 + e - 6) << 20, 0);
-    signed char* out = Ad + r * (long long)OZ_S * K;
+    if (lane == 0) *sa_r = bad ? __longlong_as_double(0x7ff8000000000000LL) : __hiloint2double((1023 + e - 6) << 20, 0);
     const double MAGIC = 6755399441055744.0;          // 2^52 + 2^51
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
@@ -189,6 +172,82 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
 #pragma unroll
         for (int s = 0; s < OZ_S; ++s)
             *reinterpret_cast<uint2*>(out + (long long)s * K + c0) = make_uint2(w[s][0], w[s][1]);
+    }
+}
+
+__device__ __forceinline__ void load_row_warp(double (&v)[2][8], const double* __restrict__ a, int K, int lane) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int c0 = it * 256 + lane * 8;
+        if (c0 < K) {
+            const double2* p = reinterpret_cast<const double2*>(a + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double2 t = p[j];
+                v[it][2 * j] = t.x; v[it][2 * j + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[it][j] = 0.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ A, int lda, long long rows, int K,
+                                                         signed char* __restrict__ Ad, double* __restrict__ sa) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    double v[2][8];
+    load_row_warp(v, A + r * (long long)lda, K, lane);
+    slice_row_warp(v, K, lane, Ad + r * (long long)OZ_S * K, sa + r);
+}
+
+// Digits of the Jacobian rows of one-electron-stream layer l >= 1 AND the spin-channel means of the same
+// rows in ONE pass over the fp64 Jacobian: a warp owns (walker w, direction d) and walks the electrons
+// i = 0..N-1 (rows (w*N + i)*NDp + d), so the column sums over the electrons of a spin channel stay in
+// registers:  GIN[w, d, s*C + c] = mean_{i in s} J[(w,i,d), c],  c < C  (the own columns; network.py:322-330).
+__global__ void __launch_bounds__(256, 2) slice_means_kernel(const double* __restrict__ A, int lda, int K, int C,
+                                                          int n_walkers, int n_up, int n_elec, int NDp, int NDg,
+                                                          signed char* __restrict__ Ad, double* __restrict__ sa,
+                                                          double* __restrict__ GIN, int ldgin) {
+    const long long wd = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wd >= (long long)n_walkers * NDp) return;
+    const int lane = threadIdx.x & 31;
+    const int w = (int)(wd / NDp), d = (int)(wd - (long long)w * NDp);
+    double sum[2][8];
+    double* gout = GIN + ((long long)w * NDg + d) * ldgin;
+    double v[2][8], vn[2][8];
+    long long r = ((long long)w * n_elec) * NDp + d;
+    load_row_warp(vn, A + r * (long long)lda, K, lane);
+    for (int s = 0; s < 2; ++s) {
+        const int ibeg = s ? n_up : 0, iend = s ? n_elec : n_up;
+#pragma unroll
+        for (int it = 0; it < 2; ++it)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum[it][j] = 0.0;
+        for (int i = ibeg; i < iend; ++i, r += NDp) {
+#pragma unroll
+            for (int it = 0; it < 2; ++it)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[it][j] = vn[it][j];
+            if (i + 1 < n_elec) load_row_warp(vn, A + (r + NDp) * (long long)lda, K, lane);   // next row in flight
+#pragma unroll
+            for (int it = 0; it < 2; ++it)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sum[it][j] += v[it][j];
+            slice_row_warp(v, K, lane, Ad + r * (long long)OZ_S * K, sa + r);
+        }
+        const double inv = 1.0 / (double)(iend - ibeg);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int c0 = it * 256 + lane * 8;
+            if (c0 < C) {                             // C is a multiple of 8: a lane's 8 columns are all own or all pair-mean
+                double2* o = reinterpret_cast<double2*>(gout + s * C + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = make_double2(sum[it][2 * j] * inv, sum[it][2 * j + 1] * inv);
+            }
+        }
     }
 }
 
@@ -535,6 +594,19 @@ int ds_launch_slice_rows(const double* A, int lda, long long rows, int K, signed
     DS_REQUIRE(K % 8 == 0 && K <= 512 && lda % 2 == 0, "slice_rows: K must be a multiple of 8 and <= 512 (K=%d lda=%d)", K, lda);
     const int wpb = 8;
     slice_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(A, lda, rows, K, Ad, sa);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_slice_means(const double* A, int lda, int K, int C, int n_walkers, int n_up, int n_elec, int NDp, int NDg,
+                          signed char* Ad, double* sa, double* GIN, int ldgin, cudaStream_t stream) {
+    if (n_walkers <= 0) return 0;
+    DS_REQUIRE(K % 8 == 0 && K <= 512 && lda % 2 == 0 && C % 8 == 0 && C <= K && ldgin % 2 == 0,
+               "slice_means: K, C must be multiples of 8, C <= K <= 512 (K=%d C=%d lda=%d)", K, C, lda);
+    const long long warps = (long long)n_walkers * NDp;
+    const int wpb = 8;
+    slice_means_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(A, lda, K, C, n_walkers, n_up, n_elec,
+                                                                                     NDp, NDg, Ad, sa, GIN, ldgin);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

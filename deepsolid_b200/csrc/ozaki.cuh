@@ -56,6 +56,10 @@ struct OzParams {
 // digits + scales of `rows` rows of a row-major fp64 matrix (leading dimension lda, K columns)
 int ds_launch_slice_rows(const double* A, int lda, long long rows, int K, signed char* Ad, double* sa,
                          cudaStream_t stream);
+// the same digits for the Jacobian rows (w, i, d) of a layer, fused with the spin-channel means over i of
+// the first C columns:  GIN[(w*NDg + d)*ldgin + s*C + c]  (rows d < NDp only)
+int ds_launch_slice_means(const double* A, int lda, int K, int C, int n_walkers, int n_up, int n_elec, int NDp, int NDg,
+                          signed char* Ad, double* sa, double* GIN, int ldgin, cudaStream_t stream);
 // Bt[N][K] = B[K][N]^T
 int ds_launch_transpose(const double* B, int K, int N, double* Bt, cudaStream_t stream);
 int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t stream);

@@ -73,10 +73,17 @@ __global__ void __launch_bounds__(256) l0_jac_kernel(DsDims dm, const double* __
         const double t = T[e * (long long)ldt + n];
         const double d1 = 1.0 - t * t;
         double sacc = 0.0;
+        double zn[4];                                        // shared-mean rows of the next group, in flight
+#pragma unroll
+        for (int u = 0; u < 4; ++u) zn[u] = g0[(long long)u * ldg + n];
         for (int db = 0; db < NDp; db += 4) {                // NDp is a multiple of 8
             double z[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) z[u] = g0[(long long)(db + u) * ldg + n];
+            for (int u = 0; u < 4; ++u) z[u] = zn[u];
+            if (db + 4 < NDp) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) zn[u] = g0[(long long)(db + 4 + u) * ldg + n];
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int d = db + u;
@@ -131,10 +138,11 @@ int ds_launch_l0_jac(const DsDims& dm, int Wc, const double* A0J, const double* 
 }
 
 int ds_launch_means(const DsDims& dm, int Wc, int C, const double* AJ, int ldj, const double* AV,
-                    const double* AL, int ldv, double* GIN, int ldgin, bool jets, cudaStream_t stream) {
+                    const double* AL, int ldv, double* GIN, int ldgin, bool jets, cudaStream_t stream,
+                    bool skip_jacobian_rows) {
     int ntiles = dm.NDg / 8;
     int tile0 = 0;
-    if (!jets) { tile0 = dm.NDp / 8; ntiles = 1; }
+    if (!jets || skip_jacobian_rows) { tile0 = dm.NDp / 8; ntiles = 1; }     // only the value (/ Laplacian) rows
     dim3 grid(Wc, ntiles);
     means_kernel<<<grid, 256, 0, stream>>>(dm, C, AJ, ldj, AV, jets ? AL : nullptr, ldv, GIN, ldgin, tile0);
     DS_CUDA_CHECK(cudaGetLastError());
