@@ -283,6 +283,16 @@ def run_ours(args):
     except Exception:
         pass
     i8 = os.environ.get("DS_NO_I8", "0") in ("", "0")
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same chunk shape)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
+        if i8 and system == DEFAULT_SYSTEM:
+            traffic = {"oz_gemm_kernel<JAC>": tr["oz_gemm_kernel<1, 1>"]["dram_bytes_per_launch"],
+                       "oz_gemm_kernel<ORBJ>": tr["oz_gemm_kernel<2, 0>"]["dram_bytes_per_launch"],
+                       "source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, 85-walker chunk)"}
+    except Exception:
+        pass
     bf16_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
     peak_note = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks.get("bf16_tflops_sustained")
                  else ("MEASURED_PEAKS.json bf16_tflops" if peaks.get("bf16_tflops") else "fallback 1.59 PFLOP/s (MEASURED_PEAKS.json absent)"))
@@ -305,7 +315,7 @@ def run_ours(args):
             "hbm_gbs_peak": peaks.get("hbm_gbs"),
             "launches": prof["jac_launches"], "kernel_ms_per_step": prof["jac_ms"] / args.steps,
             "kernel_share_of_step": prof["jac_ms"] / ms,
-            "traffic": None,
+            "traffic": traffic,
             "survey_model_tflops": wm["F_EL"] * batch * args.steps / (ms / 1e3) / 1e12,
         }
     else:
