@@ -11,7 +11,13 @@ def world_size() -> int:
 
 
 def psum(t: torch.Tensor) -> torch.Tensor:
+    """Sum over ranks.  Host tensors (the host-buffer entry points return host statistics) are staged
+    through the current CUDA device when the process group is NCCL, which only reduces device memory."""
     if world_size() > 1:
+        if not t.is_cuda and td.get_backend() == "nccl":
+            d = t.to(torch.device("cuda", torch.cuda.current_device()))
+            td.all_reduce(d, op=td.ReduceOp.SUM)
+            return d.to(t.device)
         t = t.clone()
         td.all_reduce(t, op=td.ReduceOp.SUM)
     return t
