@@ -41,6 +41,8 @@ SIGNATURES = {
     "ds_set_workspace_limit": (C.c_int, [C.c_void_p, C.c_size_t]),
     "ds_set_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int]),
     "ds_logpsi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_logpsi_vjp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
     "ds_orbitals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ds_orbitals_size": (C.c_int64, [C.c_void_p]),
     "ds_local_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

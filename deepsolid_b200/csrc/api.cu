@@ -85,6 +85,19 @@ struct ds_ctx {
     double* env_pi[2] = {};
     double* env_sigma[2] = {};
     double* klist[2] = {};
+    // transposed weights and gradient accumulators of the parameter-gradient path (ds_logpsi_vjp)
+    double* B_amT[DS_MAX_LAYERS] = {};  // [H x (C + 2Pl)]
+    double* B_gT[DS_MAX_LAYERS] = {};   // [H x 2C]
+    double* WorbT[2] = {};              // [2 npar_s x H]
+    bool transposes_ready = false;
+    double* gB_am[DS_MAX_LAYERS] = {};
+    double* gB_g[DS_MAX_LAYERS] = {};
+    double* gbias1[DS_MAX_LAYERS] = {};
+    double* gWp[DS_MAX_LAYERS] = {};
+    double* gbp[DS_MAX_LAYERS] = {};
+    double* gWorb[2] = {};
+    double* genv_pi[2] = {};
+    double* genv_sigma[2] = {};
     // workspace
     Workspace ws;
     size_t ws_limit = size_t(8) << 30;  // bytes
@@ -183,20 +196,25 @@ struct Layout {
     double *MAT[2], *LAPM[2], *DA[2];
     double *LOGDET, *TAU, *TRSQ, *TRLAP;
     double *AD, *SA;        // int8 digits of the current Jacobian operand (as bytes) and its row scales
+    // parameter-gradient path: per-layer activations kept by the forward, cotangent buffers of the reverse sweep
+    bool grad;
+    double *Tl[DS_MAX_LAYERS], *GINV[DS_MAX_LAYERS];
+    double *XINV[2], *GYs[2], *GH[2], *GZ, *GZS, *GA, *GG, *GPM[DS_MAX_LAYERS];
 };
 
-void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap) {
+void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = false) {
     const DsDims& d = c->sys.d;
     const size_t W = (size_t)Wc, N = d.N;
     ws.reset();
-    L.lap = lap; L.Wc = Wc;
+    L.lap = lap; L.Wc = Wc; L.grad = grad;
     L.A0V = ws.take("A0V", W * N * d.K0);
     L.A0L = lap ? ws.take("A0L", W * N * d.K0) : nullptr;
     L.A0J = lap ? ws.take("A0J", W * N * d.NDp * d.K0) : nullptr;
     static const char* jn[] = {"J0", "J1", "J2", "J3"};
     static const char* vn[] = {"V0", "V1", "V2", "V3"};
     static const char* ln[] = {"L0", "L1", "L2", "L3"};
-    for (int b = 0; b < c->nbuf; ++b) {
+    const int nbuf = grad ? d.L : c->nbuf;          // the reverse sweep needs every layer's input
+    for (int b = 0; b < nbuf; ++b) {
         L.V[b] = ws.take(vn[b], W * N * d.K1);
         L.Lp[b] = lap ? ws.take(ln[b], W * N * d.K1) : nullptr;
         L.J[b] = lap ? ws.take(jn[b], W * N * d.NDp * d.K1) : nullptr;
@@ -228,12 +246,33 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap) {
     const bool i8 = lap && c->use_i8 && c->i8_ok;
     L.AD = i8 ? ws.take("AD", (W * N * d.NDp * OZ_S * d.K1 + 7) / 8) : nullptr;
     L.SA = i8 ? ws.take("SA", W * N * d.NDp) : nullptr;
+    if (grad) {
+        static const char* tn[] = {"T0", "T1", "T2", "T3"};
+        static const char* gn[] = {"GINV0", "GINV1", "GINV2", "GINV3"};
+        static const char* pn[] = {"GPM0", "GPM1", "GPM2", "GPM3"};
+        for (int l = 0; l < d.L; ++l) {
+            L.Tl[l] = ws.take(tn[l], W * N * d.H);
+            L.GINV[l] = ws.take(gn[l], W * 2 * (size_t)((l == 0) ? d.C0 : d.H));
+            L.GPM[l] = (l > 0) ? ws.take(pn[l], W * N * 2 * d.P) : nullptr;
+        }
+        for (int s = 0; s < 2; ++s) {
+            size_t ns = c->n_s[s];
+            L.XINV[s] = ws.take(s ? "XINV1" : "XINV0", W * d.D * ns * ns * 2);
+            L.GYs[s] = ws.take(s ? "GY1" : "GY0", W * ns * 2 * c->npar[s]);
+        }
+        L.GH[0] = ws.take("GH0", W * N * d.H);
+        L.GH[1] = ws.take("GH1", W * N * d.H);
+        L.GZ = ws.take("GZ", W * N * d.H);
+        L.GZS = ws.take("GZS", W * d.H);
+        L.GA = ws.take("GA", W * N * d.K1);
+        L.GG = ws.take("GG", W * 2 * d.H);
+    }
 }
 
-int plan_chunk(ds_ctx* c, long long batch, bool lap, int* Wc_out) {
+int plan_chunk(ds_ctx* c, long long batch, bool lap, int* Wc_out, bool grad = false) {
     Workspace probe;                      // base == nullptr: sizes only
     Layout L;
-    carve(c, probe, L, 1, lap);
+    carve(c, probe, L, 1, lap, grad);
     size_t per_walker = probe.used + 64;  // doubles (granule slack)
     size_t limit = c->ws_limit / sizeof(double);
     long long Wc = (long long)(limit / per_walker);
@@ -246,7 +285,7 @@ int plan_chunk(ds_ctx* c, long long batch, bool lap, int* Wc_out) {
     // keep the row counts of the Jacobian GEMM within int-friendly grid sizes
     Wc = std::min<long long>(Wc, 1 << 15);
     *Wc_out = (int)Wc;
-    carve(c, probe, L, (int)Wc, lap);
+    carve(c, probe, L, (int)Wc, lap, grad);
     size_t need = probe.used;
     if (need > c->ws.cap) {
         if (c->ws.base) { DS_CUDA_CHECK(cudaFree(c->ws.base)); c->ws.base = nullptr; c->ws.cap = 0; }
@@ -261,18 +300,23 @@ int plan_chunk(ds_ctx* c, long long batch, bool lap, int* Wc_out) {
 }
 
 // One chunk of walkers through the network.  lap=false: log psi only.
+int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int Wc, const double* cot_abs,
+               const double* cot_phase, cudaStream_t st);
+
 int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, double* phase, double* ke_re,
-              double* ke_im, double* mats_out, cudaStream_t st) {
+              double* ke_im, double* mats_out, cudaStream_t st, const double* cot_abs = nullptr,
+              const double* cot_phase = nullptr) {
     const DsSys& sys = c->sys;
     const DsDims& d = sys.d;
     Layout Lo;
-    carve(c, c->ws, Lo, Wc, lap);
+    const bool grad = cot_abs != nullptr;
+    carve(c, c->ws, Lo, Wc, lap, grad);
     c->last_regions = c->ws.regions;
     const int N = d.N, H = d.H, L = d.L;
 
     // buffer of the inputs of layer l >= 1 is (l-1); the last layer writes into buffer `outb(L-1)`
     auto inb = [&](int l) { return l - 1; };
-    auto outb = [&](int l) { return (l + 1 < L) ? l : ((L - 1 >= 2) ? 0 : 1); };
+    auto outb = [&](int l) { return (grad || l + 1 < L) ? l : ((L - 1 >= 2) ? 0 : 1); };
 
     FeatParams fp{};
     fp.X = X; fp.A0V = Lo.A0V; fp.A0L = Lo.A0L; fp.A0J = Lo.A0J; fp.RAE = Lo.RAE;
@@ -314,10 +358,14 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             }
             if (int rc = gemm(c, g, GEMM_PLAIN, false, st)) return rc;
         }
+        if (grad)   // value rows of the spin means of this layer: operand of the mean-block weight gradient
+            DS_CUDA_CHECK(cudaMemcpy2DAsync(Lo.GINV[l], (size_t)2 * C * sizeof(double), Lo.GIN + (size_t)d.NDp * 2 * C,
+                                            (size_t)d.NDg * 2 * C * sizeof(double), (size_t)2 * C * sizeof(double), Wc,
+                                            cudaMemcpyDeviceToDevice, st));
         GemmParams p{};
         p.B = c->B_am[l]; p.ldb = H; p.N = H; p.K = K; p.rpg = 0;
         p.G = Lo.GOUT; p.ldg = H; p.n_elec = N; p.NDp = d.NDp; p.NDg = d.NDg;
-        p.T = Lo.T; p.ldt = H; p.S = Lo.S; p.colbias = c->bias1[l];
+        p.T = grad ? Lo.Tl[l] : Lo.T; p.ldt = H; p.S = Lo.S; p.colbias = c->bias1[l];
         {
             GemmParams v = p;
             v.A = AV; v.lda = K; v.M = (long long)Wc * N; v.C = OV; v.ldc = d.K1; v.R = AV; v.ldr = K;
@@ -418,9 +466,80 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         }
         return 0;
     }
+    if (grad) {
+        FeatParams fpg = fp;
+        return grad_sweep(c, Lo, fpg, sb, Wc, cot_abs, cot_phase, st);
+    }
     if (int rc = ds_launch_det(sys, sb, Wc, lap, st)) return rc;
     c->launches++;
     if (int rc = ds_launch_combine(sys, sb, Wc, lap, log_abs, phase, ke_re, ke_im, st)) return rc;
+    c->launches++;
+    return 0;
+}
+
+// Reverse sweep of one chunk (forward activations are in the workspace): accumulates into the ctx gradient buffers.
+int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int Wc, const double* cot_abs,
+               const double* cot_phase, cudaStream_t st) {
+    const DsSys& sys = c->sys;
+    const DsDims& d = sys.d;
+    const int N = d.N, H = d.H, L = d.L, P = d.P;
+    sb.XINV[0] = Lo.XINV[0]; sb.XINV[1] = Lo.XINV[1];
+    if (int rc = ds_launch_det_inverse(sys, sb, Wc, st)) return rc;
+    c->launches++;
+    GradBufs gb{};
+    gb.cot_abs = cot_abs; gb.cot_phase = cot_phase;
+    for (int s = 0; s < 2; ++s) { gb.GY[s] = Lo.GYs[s]; gb.g_pi[s] = c->genv_pi[s]; gb.g_sigma[s] = c->genv_sigma[s]; }
+    if (int rc = ds_launch_orb_grad(sys, sb, gb, Wc, c->npar_max, st)) return rc;
+    c->launches++;
+    const double* hL = Lo.V[L - 1];                   // output of the last layer (own columns)
+    double* GHcur = Lo.GH[0];
+    double* GHnext = Lo.GH[1];
+    for (int s = 0; s < 2; ++s) {
+        const int ns = c->n_s[s], np2 = 2 * c->npar[s];
+        GemmParams t{};                               // gWorb[s] += hL_s^T . GY_s
+        t.A = hL; t.lda = d.K1; t.M = H; t.K = Wc * ns; t.rpg = ns; t.gstride = N; t.goff = c->off_s[s];
+        t.B = Lo.GYs[s]; t.ldb = np2; t.N = np2; t.C = c->gWorb[s]; t.ldc = np2; t.accumulate = 1;
+        if (int rc = gemm(c, t, GEMM_TN, false, st)) return rc;
+        GemmParams g{};                               // cotangent of h_L (rows of spin s) = GY_s . Worb_s^T
+        g.A = Lo.GYs[s]; g.lda = np2; g.M = (long long)Wc * ns; g.K = np2; g.no_amap = 1;
+        g.B = c->WorbT[s]; g.ldb = H; g.N = H;
+        g.C = GHcur; g.ldc = H; g.cmap = 1; g.rpg = ns; g.gstride = N; g.goff = c->off_s[s];
+        if (int rc = gemm(c, g, GEMM_PLAIN, false, st)) return rc;
+    }
+    for (int l = L - 1; l >= 0; --l) {
+        const int C = (l == 0) ? d.C0 : H;
+        const int K = (l == 0) ? d.K0 : d.K1;
+        const bool res = (C == H);
+        const double* Ain = (l == 0) ? Lo.A0V : Lo.V[l - 1];
+        gb.T = Lo.Tl[l]; gb.GH = GHcur; gb.GZ = Lo.GZ; gb.GZS = Lo.GZS; gb.g_bias = c->gbias1[l];
+        if (int rc = ds_launch_gz(d, gb, Wc, res, st)) return rc;
+        c->launches++;
+        GemmParams t{};                               // own + pair-mean rows of the weight gradient
+        t.A = Ain; t.lda = K; t.M = K; t.K = (long long)Wc * N; t.rpg = 0;
+        t.B = Lo.GZ; t.ldb = H; t.N = H; t.C = c->gB_am[l]; t.ldc = H; t.accumulate = 1;
+        if (int rc = gemm(c, t, GEMM_TN, false, st)) return rc;
+        GemmParams m{};                               // spin-mean rows
+        m.A = Lo.GINV[l]; m.lda = 2 * C; m.M = 2 * C; m.K = Wc; m.rpg = 0;
+        m.B = Lo.GZS; m.ldb = H; m.N = H; m.C = c->gB_g[l]; m.ldc = H; m.accumulate = 1;
+        if (int rc = gemm(c, m, GEMM_TN, false, st)) return rc;
+        if (l == 0) break;                            // the layer-0 inputs are parameter-free features
+        GemmParams a{};                               // GA = GZ . B_am^T
+        a.A = Lo.GZ; a.lda = H; a.M = (long long)Wc * N; a.K = H; a.rpg = 0;
+        a.B = c->B_amT[l]; a.ldb = K; a.N = K; a.C = Lo.GA; a.ldc = K;
+        if (int rc = gemm(c, a, GEMM_PLAIN, false, st)) return rc;
+        GemmParams q{};                               // GG = GZS . B_g^T
+        q.A = Lo.GZS; q.lda = H; q.M = Wc; q.K = H; q.rpg = 0;
+        q.B = c->B_gT[l]; q.ldb = 2 * C; q.N = 2 * C; q.C = Lo.GG; q.ldc = 2 * C;
+        if (int rc = gemm(c, q, GEMM_PLAIN, false, st)) return rc;
+        gb.GA = Lo.GA; gb.lda = K; gb.GG = Lo.GG; gb.ldgg = 2 * C; gb.GHin = GHnext; gb.GPM = Lo.GPM[l];
+        if (int rc = ds_launch_hin(d, gb, Wc, C, K, res, true, st)) return rc;
+        c->launches++;
+        std::swap(GHcur, GHnext);
+    }
+    for (int l = 1; l < L; ++l) gb.GPMl[l] = Lo.GPM[l];
+    for (int l = 0; l < L - 1; ++l) { gb.g_Wp[l] = c->gWp[l]; gb.g_bp[l] = c->gbp[l]; }
+    (void)P;
+    if (int rc = ds_launch_pair_grad(sys, fp, gb, Wc, st)) return rc;
     c->launches++;
     return 0;
 }
@@ -632,6 +751,7 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
         }
     }
     c->params_set = true;
+    c->transposes_ready = false;
     return 0;
 }
 
@@ -639,6 +759,108 @@ extern "C" int ds_logpsi(ds_ctx* c, const double* x, int64_t batch, double* log_
     DS_REQUIRE(c, "null context");
     Guard g(c->device);
     return run_batched(c, x, batch, false, log_abs, phase, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+namespace {
+// transposed weights and zeroed accumulators of the parameter-gradient path
+int prepare_grad(ds_ctx* c, cudaStream_t st) {
+    const DsDims& d = c->sys.d;
+    const int L = d.L, H = d.H, P = d.P;
+    auto need = [&](double** p, size_t n) -> int { if (!*p) return dev_alloc(c, p, n); return 0; };
+    for (int l = 0; l < L; ++l) {
+        const int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? 4 : P, K = C + 2 * Pl;
+        if (int rc = need(&c->B_amT[l], (size_t)K * H)) return rc;
+        if (int rc = need(&c->B_gT[l], (size_t)2 * C * H)) return rc;
+        if (int rc = need(&c->gB_am[l], (size_t)K * H)) return rc;
+        if (int rc = need(&c->gB_g[l], (size_t)2 * C * H)) return rc;
+        if (int rc = need(&c->gbias1[l], (size_t)H)) return rc;
+        DS_CUDA_CHECK(cudaMemsetAsync(c->gB_am[l], 0, (size_t)K * H * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->gB_g[l], 0, (size_t)2 * C * H * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->gbias1[l], 0, (size_t)H * sizeof(double), st));
+        if (!c->transposes_ready) {
+            if (int rc = ds_launch_transpose(c->B_am[l], K, H, c->B_amT[l], st)) return rc;
+            if (int rc = ds_launch_transpose(c->B_g[l], 2 * C, H, c->B_gT[l], st)) return rc;
+        }
+    }
+    for (int l = 0; l < L - 1; ++l) {
+        const int pin = (l == 0) ? 4 : P;
+        if (int rc = need(&c->gWp[l], (size_t)pin * P)) return rc;
+        if (int rc = need(&c->gbp[l], (size_t)P)) return rc;
+        DS_CUDA_CHECK(cudaMemsetAsync(c->gWp[l], 0, (size_t)pin * P * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->gbp[l], 0, (size_t)P * sizeof(double), st));
+    }
+    for (int s = 0; s < 2; ++s) {
+        const size_t np2 = 2 * (size_t)c->npar[s];
+        if (int rc = need(&c->WorbT[s], np2 * H)) return rc;
+        if (int rc = need(&c->gWorb[s], np2 * H)) return rc;
+        if (int rc = need(&c->genv_pi[s], (size_t)d.A * c->npar[s])) return rc;
+        if (int rc = need(&c->genv_sigma[s], (size_t)d.A * c->npar[s])) return rc;
+        DS_CUDA_CHECK(cudaMemsetAsync(c->gWorb[s], 0, np2 * H * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->genv_pi[s], 0, (size_t)d.A * c->npar[s] * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->genv_sigma[s], 0, (size_t)d.A * c->npar[s] * sizeof(double), st));
+        if (!c->transposes_ready)
+            if (int rc = ds_launch_transpose(c->Worb[s], H, (int)np2, c->WorbT[s], st)) return rc;
+    }
+    c->transposes_ready = true;
+    return 0;
+}
+}  // namespace
+
+// Vector-Jacobian product of (log|psi|, phase) with respect to the parameters, summed over the batch:
+//   grad_leaf = sum_w cot_abs[w] d log|psi_w| / d leaf + cot_phase[w] d phase_w / d leaf.
+// `grads`: n_leaves device pointers in the leaf order and sizes of ds_set_params; overwritten.
+extern "C" int ds_logpsi_vjp(ds_ctx* c, const double* x, int64_t batch, const double* cot_abs, const double* cot_phase,
+                             double* const* grads, const int64_t* sizes, int n_leaves, void* stream) {
+    DS_REQUIRE(c && c->params_set, "parameters have not been set (ds_set_params)");
+    DS_REQUIRE(grads && sizes, "null argument");
+    DS_REQUIRE(batch >= 0, "negative batch");
+    Guard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const DsDims& d = c->sys.d;
+    const int L = d.L, H = d.H, P = d.P;
+    const int expect = 2 * L + 2 * (L - 1) + 2 + 4;
+    DS_REQUIRE(n_leaves == expect, "expected %d gradient leaves for %d layers, got %d", expect, L, n_leaves);
+    if (int rc = prepare_grad(c, st)) return rc;
+    if (batch > 0) {
+        DS_REQUIRE(x && cot_abs && cot_phase, "null argument");
+        int Wc = 0;
+        if (int rc = plan_chunk(c, batch, false, &Wc, true)) return rc;
+        const int n3 = 3 * d.N;
+        for (long long w0 = 0; w0 < batch; w0 += Wc) {
+            int wc = (int)std::min<long long>(Wc, batch - w0);
+            if (int rc = run_chunk(c, x + w0 * n3, wc, false, nullptr, nullptr, nullptr, nullptr, nullptr, st,
+                                   cot_abs + w0, cot_phase + w0)) return rc;
+        }
+    }
+    // unpack into the leaf layout of the reference pytree
+    int li = 0;
+    for (int l = 0; l < L; ++l) {
+        const int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? 4 : P;
+        DS_REQUIRE(sizes[li] == (int64_t)(3 * C + 2 * Pl) * H && sizes[li + 1] == H, "gradient leaf %d has the wrong size", li);
+        double* w = grads[li++];
+        double* b = grads[li++];
+        DS_CUDA_CHECK(cudaMemcpyAsync(w, c->gB_am[l], (size_t)C * H * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        DS_CUDA_CHECK(cudaMemcpyAsync(w + (size_t)C * H, c->gB_g[l], (size_t)2 * C * H * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        DS_CUDA_CHECK(cudaMemcpyAsync(w + (size_t)3 * C * H, c->gB_am[l] + (size_t)C * H, (size_t)2 * Pl * H * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, st));
+        DS_CUDA_CHECK(cudaMemcpyAsync(b, c->gbias1[l], (size_t)H * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    for (int l = 0; l < L - 1; ++l) {
+        const int pin = (l == 0) ? 4 : P;
+        DS_REQUIRE(sizes[li] == (int64_t)pin * P && sizes[li + 1] == P, "gradient leaf %d has the wrong size", li);
+        DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->gWp[l], (size_t)pin * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->gbp[l], (size_t)P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    for (int s = 0; s < 2; ++s) {
+        DS_REQUIRE(sizes[li] == (int64_t)H * 2 * c->npar[s], "gradient leaf %d has the wrong size", li);
+        if (int rc = ds_launch_deinterleave(c->gWorb[s], grads[li++], H, c->npar[s], st)) return rc;
+    }
+    for (int s = 0; s < 2; ++s) {
+        DS_REQUIRE(sizes[li] == (int64_t)d.A * c->npar[s] && sizes[li + 1] == sizes[li], "gradient leaf %d has the wrong size", li);
+        DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->genv_pi[s], (size_t)d.A * c->npar[s] * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->genv_sigma[s], (size_t)d.A * c->npar[s] * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
 }
 
 extern "C" int64_t ds_orbitals_size(const ds_ctx* c) {

@@ -44,19 +44,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmParams 
     const int col0 = blockIdx.y * BN;
 
     // ---- global->shared assignment ---------------------------------------
+    constexpr bool TA = (MODE == GEMM_TN);
     const double* a_src[4];
     bool a_ok[4];
     int a_dst[4], a_col[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         int idx = tid + q * NTHREADS;
-        int r = idx >> 3, ch = idx & 7;
-        long long gr = row0 + r;
-        a_ok[q] = gr < p.M;
-        long long pr = a_ok[q] ? map_row(gr, p.rpg, p.gstride, p.goff) : 0;
-        a_src[q] = p.A + pr * (long long)p.lda + ch * 2;
-        a_dst[q] = r * AS_LD + ch * 2;
-        a_col[q] = ch * 2;
+        if (TA) {       // A^T tile [BK][BM+4]: 16 k-rows of 128 output rows m, two m per 16-byte copy
+            int kr = idx >> 6, ch = idx & 63;
+            long long m = row0 + ch * 2;
+            a_ok[q] = m < p.M;
+            a_src[q] = p.A + (a_ok[q] ? m : 0);
+            a_dst[q] = kr * BS_LD + ch * 2;
+            a_col[q] = kr;
+        } else {
+            int r = idx >> 3, ch = idx & 7;
+            long long gr = row0 + r;
+            a_ok[q] = gr < p.M;
+            long long pr = (a_ok[q] && !p.no_amap) ? map_row(gr, p.rpg, p.gstride, p.goff) : (a_ok[q] ? gr : 0);
+            a_src[q] = p.A + pr * (long long)p.lda + ch * 2;
+            a_dst[q] = r * AS_LD + ch * 2;
+            a_col[q] = ch * 2;
+        }
     }
     const double* b_src[4];
     bool b_ok[4];
@@ -75,8 +85,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmParams 
         double* as = As + stage * A_STAGE;
         double* bs = Bs + stage * B_STAGE;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            cp_async16(as + a_dst[q], a_src[q] + k0, a_ok[q] && (k0 + a_col[q] < p.K));
+        for (int q = 0; q < 4; ++q) {
+            if (TA) {
+                const int k = k0 + a_col[q];
+                const bool ok = a_ok[q] && k < p.K;
+                const long long pk = ok ? map_row(k, p.rpg, p.gstride, p.goff) : 0;
+                cp_async16(as + a_dst[q], a_src[q] + pk * (long long)p.lda, ok);
+            } else {
+                cp_async16(as + a_dst[q], a_src[q] + k0, a_ok[q] && (k0 + a_col[q] < p.K));
+            }
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             cp_async16(bs + b_dst[q], b_src[q] + (long long)k0 * p.ldb, b_ok[q] && (k0 + b_kr[q] < p.K));
@@ -94,7 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmParams 
         if (s < nk) load_stage(s, s * BK);
         cp_async_commit();
     }
-    const int a_frag = (wm * 64 + (lane >> 2)) * AS_LD + (lane & 3);
+    const int a_frag = TA ? (lane & 3) * BS_LD + wm * 64 + (lane >> 2) : (wm * 64 + (lane >> 2)) * AS_LD + (lane & 3);
     const int b_frag = (lane & 3) * BS_LD + wn * 32 + (lane >> 2);
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
@@ -110,7 +128,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmParams 
         for (int kk = 0; kk < BK; kk += 4) {
             double a[8], b[4];
 #pragma unroll
-            for (int mt = 0; mt < 8; ++mt) a[mt] = as[mt * 8 * AS_LD + kk];
+            for (int mt = 0; mt < 8; ++mt) a[mt] = TA ? as[kk * BS_LD + mt * 8] : as[mt * 8 * AS_LD + kk];
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) b[nt] = bs[kk * BS_LD + nt * 8];
 #pragma unroll
@@ -125,19 +143,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmParams 
     const double rs2 = 0.70710678118654752440;
     const int ncol_base = col0 + wn * 32 + (lane & 3) * 2;
 
-    if (MODE == GEMM_PLAIN) {
+    if (MODE == GEMM_PLAIN || MODE == GEMM_TN) {
 #pragma unroll
         for (int mt = 0; mt < 8; ++mt) {
             long long r = row0 + wm * 64 + mt * 8 + (lane >> 2);
             if (r >= p.M) continue;
-            long long cr = p.cmap ? map_row(r, p.rpg, p.gstride, p.goff) : r;
+            long long cr = (p.cmap && MODE == GEMM_PLAIN) ? map_row(r, p.rpg, p.gstride, p.goff) : r;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 int n = ncol_base + nt * 8;
                 if (n >= p.N) continue;
                 double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
                 if (p.colbias) { v0 += p.colbias[n]; v1 += p.colbias[n + 1]; }
-                *reinterpret_cast<double2*>(p.C + cr * (long long)p.ldc + n) = make_double2(v0, v1);
+                double2* dst = reinterpret_cast<double2*>(p.C + cr * (long long)p.ldc + n);
+                if (p.accumulate) { const double2 o = *dst; v0 += o.x; v1 += o.y; }
+                *dst = make_double2(v0, v1);
             }
         }
     } else if (MODE == GEMM_VALUE || MODE == GEMM_LAP) {
@@ -287,7 +307,7 @@ int launch(const GemmParams& p, cudaStream_t stream) {
 
 int ds_launch_gemm(const GemmParams& p, int mode, bool residual, cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
-    DS_REQUIRE((p.K % 2) == 0 && (p.N % 2) == 0 && (p.lda % 2) == 0 && (p.ldb % 2) == 0,
+    DS_REQUIRE((mode == GEMM_TN || (p.K % 2) == 0) && (p.N % 2) == 0 && (p.lda % 2) == 0 && (p.ldb % 2) == 0,
                "gemm: K, N, lda, ldb must be even (got K=%d N=%d lda=%d ldb=%d)", p.K, p.N, p.lda, p.ldb);
     switch (mode) {
         case GEMM_PLAIN: return launch<GEMM_PLAIN, false>(p, stream);
@@ -295,6 +315,9 @@ int ds_launch_gemm(const GemmParams& p, int mode, bool residual, cudaStream_t st
         case GEMM_JAC: return residual ? launch<GEMM_JAC, true>(p, stream) : launch<GEMM_JAC, false>(p, stream);
         case GEMM_LAP: return residual ? launch<GEMM_LAP, true>(p, stream) : launch<GEMM_LAP, false>(p, stream);
         case GEMM_ORBJ: return launch<GEMM_ORBJ, false>(p, stream);
+        case GEMM_TN:
+            DS_REQUIRE((p.M % 2) == 0, "gemm TN: M must be even (M=%lld)", p.M);
+            return launch<GEMM_TN, false>(p, stream);
     }
     ds_set_error("gemm: unknown mode %d", mode);
     return -1;

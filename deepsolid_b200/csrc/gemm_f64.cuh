@@ -10,8 +10,10 @@ enum GemmMode {
     GEMM_VALUE = 1,   // one-electron stream, value rows:    h' = res(tanh(A.B + G_val + b))
     GEMM_JAC = 2,     // Jacobian rows (w,i,d):               J' = res((1-t^2)(A.B + G_d)), S += (A.B+G_d)^2
     GEMM_LAP = 3,     // Laplacian rows:                      l' = res((1-t^2)(A.B+G_lap) - 2t(1-t^2) S)
-    GEMM_ORBJ = 4     // orbital layer Jacobian rows: complexify, scale by envelope*phase, scatter to
+    GEMM_ORBJ = 4,    // orbital layer Jacobian rows: complexify, scale by envelope*phase, scatter to
                       // per-determinant matrices; raw own-electron rows kept for the product rule
+    GEMM_TN = 5       // C (+)= A^T . B with A stored [K x M] row-major (weight gradients: reduction over rows);
+                      // the row mapping (rpg, gstride, goff) applies to the K index of A only
 };
 
 struct GemmParams {
@@ -22,6 +24,8 @@ struct GemmParams {
     long long rpg, gstride, goff;
     double* C; int ldc;          // output (logical->physical row mapping as for A when cmap != 0)
     int cmap;
+    int no_amap;                 // PLAIN: the row mapping applies to the rows of C only (A rows are compact)
+    int accumulate;              // PLAIN / TN: C += A.B instead of C = A.B
     const double* colbias;       // [N] or null
     // one-electron stream epilogues
     const double* G;             // GOUT [Wc*NDg x ldg]

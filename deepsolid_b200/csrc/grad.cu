@@ -1,0 +1,335 @@
+// Reverse sweep of (log|psi|, phase) with respect to the network parameters: the backward half of
+// DeepSolid's energy-gradient estimator (train.py:91-142: tangents_dot = mean(Re(clip_diff * conj(d log psi))),
+// i.e. a vector-Jacobian product of batch_network with per-walker cotangents a_w = Re clip_diff_w / B on
+// log|psi_w| and b_w = Im clip_diff_w / B on the phase).  The weight-gradient contractions themselves are fp64
+// DMMA GEMMs (gemm_f64.cu, GEMM_TN / GEMM_PLAIN); this file holds the element-wise and per-pair kernels.
+//
+//   psi = sum_k D_k,  D_k = prod_s det M_s^k,  d log psi = sum_k w_k sum_s tr(X_s^k dM_s^k),  w_k = D_k / psi
+//   dloss = Re[ conj(c) d log psi ],  c = a + i b      =>  cotangent of M_s^k[i,o]:  Gm = conj(c) w_k X_s^k[o,i]
+//   (dloss = Re sum Gm dM),   M[i,o] = Y[i,(k,o)] E_i[(k,o)],  Y = h.W_re + i h.W_im,  E = env * exp(i k_o.x_i).
+#include "kernels.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// Orbital layer: cotangents of the raw orbital outputs and the envelope parameter gradients.
+// grid = Wc*N (one CTA per electron), threads over p = k*n_s + o.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) orb_grad_kernel(const DsSys sys, const SlaterBufs sb, const GradBufs gb, int npar_max) {
+    const DsDims& dm = sys.d;
+    const long long e = blockIdx.x;
+    const int N = dm.N, A = dm.A, D = dm.D;
+    const long long w = e / N;
+    const int i = (int)(e % N);
+    const int s = (i < dm.n_up) ? 0 : 1;
+    const int ns = s ? dm.n_dn : dm.n_up;
+    const int is = s ? i - dm.n_up : i;
+    const int npar = ns * D;
+    __shared__ cplx wk_s[64];                       // conj(c) * w_k per determinant
+    if (threadIdx.x == 0) {
+        const double* ld = sb.LOGDET + w * 2 * D * 3;
+        double mx = -INFINITY;
+        for (int k = 0; k < D; ++k) mx = fmax(mx, ld[k * 3] + ld[(D + k) * 3]);
+        cplx tot{0.0, 0.0};
+        for (int k = 0; k < D; ++k) {
+            const double l = ld[k * 3] + ld[(D + k) * 3];
+            const cplx ph = cmul(cplx{ld[k * 3 + 1], ld[k * 3 + 2]}, cplx{ld[(D + k) * 3 + 1], ld[(D + k) * 3 + 2]});
+            const double m = exp(l - mx);
+            wk_s[k] = cplx{ph.re * m, ph.im * m};
+            tot.re += ph.re * m; tot.im += ph.im * m;
+        }
+        const cplx itot = cinv(tot);
+        const cplx cbar{gb.cot_abs[w], -gb.cot_phase[w]};
+        for (int k = 0; k < D; ++k) wk_s[k] = cmul(cbar, cmul(wk_s[k], itot));
+    }
+    __syncthreads();
+    const double* x = sb.X + w * 3 * N + 3 * i;
+    const double x0 = x[0], x1 = x[1], x2 = x[2];
+    const double* rae = sb.RAE + e * A * 5;
+    const double* pi_ = sb.env_pi[s];
+    const double* sg_ = sb.env_sigma[s];
+    const double* kl = sb.klist[s];
+    const cplx* E = reinterpret_cast<const cplx*>(sb.ETAB) + e * 5LL * npar_max;
+    const cplx* yv = reinterpret_cast<const cplx*>(sb.YV) + e * (long long)npar_max;
+    const cplx* xinv = reinterpret_cast<const cplx*>(sb.XINV[s]);
+    double* gy = gb.GY[s] + (w * ns + is) * 2LL * npar;
+    for (int p = threadIdx.x; p < npar; p += blockDim.x) {
+        const int k = p / ns, o = p - k * ns;
+        const cplx X = xinv[((w * D + k) * ns + o) * (long long)ns + is];
+        const cplx Gm = cmul(wk_s[k], X);
+        const cplx g = cmul(Gm, E[p]);              // cotangent of Y: dloss = Re(g dY) = g.re dYr - g.im dYi
+        gy[2 * p] = g.re;
+        gy[2 * p + 1] = -g.im;
+        double sn, cs;
+        sincos(kl[o * 3] * x0 + kl[o * 3 + 1] * x1 + kl[o * 3 + 2] * x2, &sn, &cs);
+        const cplx gyp = cmul(cmul(Gm, yv[p]), cplx{cs, sn});
+        const double genv = gyp.re;                  // cotangent of the (real) envelope value
+        for (int a = 0; a < A; ++a) {
+            const double r = rae[a * 5], sig = sg_[a * npar + p], pw = pi_[a * npar + p];
+            const double ex = exp(-fabs(r * sig));
+            atomicAdd(gb.g_pi[s] + a * npar + p, genv * ex);
+            atomicAdd(gb.g_sigma[s] + a * npar + p, -genv * pw * ex * r * ds_sign(r * sig));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// One-electron stream: cotangent of the pre-activations, their per-walker sums and the bias gradient.
+// grid = Wc, thread = channel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gz_kernel(DsDims dm, GradBufs gb, int residual) {
+    const int w = blockIdx.x, N = dm.N, H = dm.H;
+    const double rs2 = 0.70710678118654752440;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        double sum = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const long long o = ((long long)w * N + i) * H + c;
+            const double t = gb.T[o];
+            double g = gb.GH[o];
+            if (residual) g *= rs2;
+            const double gz = g * (1.0 - t * t);
+            gb.GZ[o] = gz;
+            sum += gz;
+        }
+        gb.GZS[(long long)w * H + c] = sum;
+        atomicAdd(gb.g_bias + c, sum);
+    }
+}
+
+// cotangent of the layer input: own columns of GZ.B_am^T, the share of the spin-channel means, the residual path;
+// the pair-mean columns are kept for the pair-stream sweep.  grid = Wc*N.
+__global__ void __launch_bounds__(256) hin_kernel(DsDims dm, GradBufs gb, int C, int residual, int want_pm) {
+    const long long e = blockIdx.x;
+    const int N = dm.N, H = dm.H, P = dm.P;
+    const long long w = e / N;
+    const int i = (int)(e % N);
+    const int s = (i < dm.n_up) ? 0 : 1;
+    const double invn = 1.0 / (double)(s ? dm.n_dn : dm.n_up);
+    const double rs2 = 0.70710678118654752440;
+    const double* ga = gb.GA + e * (long long)gb.lda;
+    const double* gg = gb.GG + w * (long long)gb.ldgg + s * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double v = ga[c] + gg[c] * invn;
+        if (residual) v += rs2 * gb.GH[e * H + c];
+        gb.GHin[e * C + c] = v;
+    }
+    if (want_pm)
+        for (int q = threadIdx.x; q < 2 * P; q += blockDim.x) gb.GPM[e * 2 * P + q] = ga[C + q];
+}
+
+// ---------------------------------------------------------------------------
+// Pair stream: forward values are recomputed per pair (they are never stored), then the reverse sweep.
+// grid = Wc*N (CTA = electron i, the second index of h_two[j,i]); warp = partner j; lane = channel.
+// Level 0 = the 4 input features, level l+1 = output of pair layer l.  GPM_l[e_i][s(j)*P + c] / n_s(j) is the
+// cotangent reaching h_two^l[j,i] through the pair means of one-electron layer l.
+// ---------------------------------------------------------------------------
+constexpr int PG_THREADS = 256;
+
+__global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, const FeatParams fp, const GradBufs gb) {
+    const DsDims& dm = sys.d;
+    const int N = dm.N, P = dm.P, L = dm.L;
+    const long long e = blockIdx.x;
+    const int w = (int)(e / N), i = (int)(e % N);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const double rs2 = 0.70710678118654752440;
+
+    extern __shared__ double sm[];
+    double* sx = sm;                             // [3N] wrapped positions
+    double* wsm = sx + 3 * N;                    // per pair layer: W [Pin x P], b [P], W^T [P x Pin]
+    double* red = wsm;                           // reduction scratch is carved after the weights (set below)
+    const double* x = fp.X + (long long)w * 3 * N;
+    for (int t = tid; t < N; t += blockDim.x) {
+        double xi[3] = {x[3 * t], x[3 * t + 1], x[3 * t + 2]}, o[3];
+        ds_wrap(sys.sim, xi, o);
+        sx[3 * t] = o[0]; sx[3 * t + 1] = o[1]; sx[3 * t + 2] = o[2];
+    }
+    int woff[DS_MAX_LAYERS];
+    {
+        int off = 0;
+        for (int l = 0; l < L - 1; ++l) {
+            const int pin = (l == 0) ? 4 : P;
+            woff[l] = off;
+            for (int t = tid; t < pin * P; t += blockDim.x) {
+                const double v = fp.Wp[l][t];
+                wsm[off + t] = v;
+                const int ci = t / P, co = t - ci * P;
+                wsm[off + pin * P + P + co * pin + ci] = v;        // transposed copy
+            }
+            for (int t = tid; t < P; t += blockDim.x) wsm[off + pin * P + t] = fp.bp[l][t];
+            off += 2 * pin * P + P;
+        }
+        red = wsm + off;                         // [nwarps][P+1] scratch rows
+    }
+    __syncthreads();
+
+    // per-lane gradient accumulators: column `lane` of every pair-layer weight and bias
+    double gW0[4], gW[DS_MAX_LAYERS - 2 > 0 ? DS_MAX_LAYERS - 2 : 1][32], gB[DS_MAX_LAYERS];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gW0[q] = 0.0;
+#pragma unroll
+    for (int l = 0; l < DS_MAX_LAYERS - 2; ++l)
+#pragma unroll
+        for (int c = 0; c < 32; ++c) gW[l][c] = 0.0;
+#pragma unroll
+    for (int l = 0; l < DS_MAX_LAYERS; ++l) gB[l] = 0.0;
+
+    const double inv_up = 1.0 / dm.n_up, inv_dn = 1.0 / dm.n_dn;
+    for (int j = warp; j < N; j += nwarps) {
+        const int sj = (j < dm.n_up) ? 0 : 1;
+        const double invn = sj ? inv_dn : inv_up;
+        double d[3];
+        for (int k = 0; k < 3; ++k) d[k] = sx[3 * j + k] - sx[3 * i + k] + (j == i ? 1.0 : 0.0);
+        Jet f[4];
+        ds_nu_distance<false>(sys.sim, d, f);
+        double cur[DS_MAX_LAYERS], tv[DS_MAX_LAYERS];       // level values and tanh outputs of this lane's channel
+        cur[0] = 0.0;
+        if (j != i && lane < 4) cur[0] = (lane == 0) ? f[0].v : (lane == 1) ? f[1].v : (lane == 2) ? f[2].v : f[3].v;
+#pragma unroll
+        for (int l = 0; l < DS_MAX_LAYERS - 1; ++l) {
+            if (l >= L - 1) break;
+            const int pin = (l == 0) ? 4 : P;
+            const double* W = wsm + woff[l];
+            double z = (lane < P) ? W[pin * P + lane] : 0.0;
+            for (int c = 0; c < pin; ++c) {
+                const double cv = __shfl_sync(0xffffffffu, cur[l], c);
+                if (lane < P) z = fma(cv, W[c * P + lane], z);
+            }
+            const double t = tanh(z);
+            tv[l + 1] = t;
+            double nv = (l >= 1) ? (cur[l] + t) * rs2 : t;
+            cur[l + 1] = (lane < P) ? nv : 0.0;
+        }
+        // reverse: cotangents of the levels
+        double g[DS_MAX_LAYERS];
+#pragma unroll
+        for (int l = 0; l < DS_MAX_LAYERS; ++l) g[l] = 0.0;
+        if (lane < P) {
+#pragma unroll
+            for (int lv = 1; lv < DS_MAX_LAYERS; ++lv)
+                if (lv < L && gb.GPMl[lv]) g[lv] = gb.GPMl[lv][e * 2 * P + sj * P + lane] * invn;
+        }
+#pragma unroll
+        for (int lv = DS_MAX_LAYERS - 1; lv >= 1; --lv) {
+            if (lv > L - 1) continue;
+            const int l = lv - 1;                            // pair layer that produced level lv
+            const int pin = (l == 0) ? 4 : P;
+            const bool res = (l >= 1);
+            const double gt = res ? g[lv] * rs2 : g[lv];
+            const double gz = (lane < P) ? gt * (1.0 - tv[lv] * tv[lv]) : 0.0;
+            gB[l] += gz;
+            if (l == 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) gW0[c] = fma(__shfl_sync(0xffffffffu, cur[0], c), gz, gW0[c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const double cv = __shfl_sync(0xffffffffu, cur[l], c);
+                    if (c < P) gW[l - 1][c] = fma(cv, gz, gW[l - 1][c]);
+                }
+                // cotangent of level l (it has parameters upstream): W.gz over the output channels + residual path
+                const double* WT = wsm + woff[l] + pin * P + P;      // [P_out][pin]
+                double acc = res ? g[lv] * rs2 : 0.0;
+                for (int c = 0; c < P; ++c) {
+                    const double gzc = __shfl_sync(0xffffffffu, gz, c);
+                    if (lane < pin) acc = fma(WT[c * pin + lane], gzc, acc);
+                }
+                g[l] += (lane < pin) ? acc : 0.0;
+            }
+        }
+    }
+
+    // cross-warp reduction, then one atomic per parameter and CTA
+    double* row = red + warp * 33;
+    auto reduce_and_add = [&](double v, double* dst, bool valid) {
+        __syncthreads();
+        row[lane] = v;
+        __syncthreads();
+        if (warp == 0) {
+            double s = 0.0;
+            for (int q = 0; q < nwarps; ++q) s += red[q * 33 + lane];
+            if (valid) atomicAdd(dst, s);
+        }
+    };
+    if (L > 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) reduce_and_add(gW0[c], gb.g_Wp[0] + c * P + lane, lane < P);
+        reduce_and_add(gB[0], gb.g_bp[0] + lane, lane < P);
+    }
+#pragma unroll
+    for (int l = 1; l < DS_MAX_LAYERS - 1; ++l) {
+        if (l >= L - 1) break;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (c < P) reduce_and_add(gW[l - 1][c], gb.g_Wp[l] + c * P + lane, lane < P);
+        reduce_and_add(gB[l], gb.g_bp[l] + lane, lane < P);
+    }
+}
+
+__global__ void copy2d_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int rows, int cols) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)rows * cols) return;
+    const int r = (int)(t / cols), c = (int)(t - (long long)r * cols);
+    dst[(long long)r * ldd + c] = src[(long long)r * lds + c];
+}
+
+// src [rows][2 np] with columns (re, im) interleaved  ->  dst [rows][2 np] = (re block | im block)   (network.py:543-545)
+__global__ void deinterleave_kernel(const double* __restrict__ src, double* __restrict__ dst, int rows, int np) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)rows * 2 * np) return;
+    const int r = (int)(t / (2 * np)), c = (int)(t - (long long)r * 2 * np);
+    const int p = c >> 1, im = c & 1;
+    dst[(long long)r * 2 * np + im * np + p] = src[t];
+}
+
+}  // namespace
+
+int ds_launch_orb_grad(const DsSys& sys, const SlaterBufs& sb, const GradBufs& gb, int Wc, int npar_max, cudaStream_t stream) {
+    DS_REQUIRE(sys.d.D <= 64, "orbital gradient kernel supports at most 64 determinants");
+    orb_grad_kernel<<<(unsigned)((long long)Wc * sys.d.N), 256, 0, stream>>>(sys, sb, gb, npar_max);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_gz(const DsDims& dm, const GradBufs& gb, int Wc, bool residual, cudaStream_t stream) {
+    gz_kernel<<<Wc, 256, 0, stream>>>(dm, gb, residual ? 1 : 0);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_hin(const DsDims& dm, const GradBufs& gb, int Wc, int C, int K, bool residual, bool want_pm, cudaStream_t stream) {
+    (void)K;
+    hin_kernel<<<(unsigned)((long long)Wc * dm.N), 256, 0, stream>>>(dm, gb, C, residual ? 1 : 0, want_pm ? 1 : 0);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& gb, int Wc, cudaStream_t stream) {
+    const DsDims& d = sys.d;
+    if (d.L < 2) return 0;
+    DS_REQUIRE(d.P <= 32, "pair-stream gradient kernel needs hidden_two <= 32");
+    size_t n = 3 * d.N;
+    for (int l = 0; l < d.L - 1; ++l) n += 2 * ((l == 0) ? 4 : d.P) * d.P + d.P;
+    n += (PG_THREADS / 32) * 33;
+    const size_t smem = n * sizeof(double);
+    if (smem > 48 * 1024)
+        DS_CUDA_CHECK(cudaFuncSetAttribute(pair_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pair_grad_kernel<<<(unsigned)((long long)Wc * d.N), PG_THREADS, smem, stream>>>(sys, fp, gb);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_copy2d(const double* src, int lds, double* dst, int ldd, int rows, int cols, cudaStream_t stream) {
+    const long long tot = (long long)rows * cols;
+    if (tot <= 0) return 0;
+    copy2d_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(src, lds, dst, ldd, rows, cols);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_deinterleave(const double* src, double* dst, int rows, int np, cudaStream_t stream) {
+    const long long tot = (long long)rows * 2 * np;
+    if (tot <= 0) return 0;
+    deinterleave_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(src, dst, rows, np);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

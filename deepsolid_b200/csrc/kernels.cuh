@@ -47,12 +47,45 @@ struct SlaterBufs {
     const double* env_pi[2];
     const double* env_sigma[2];     // [A][n_s*D]
     const double* klist[2];         // [n_s][3]
+    double* XINV[2];        // complex inverse matrices [(w*D+k)][o][i] (parameter-gradient path only, else null)
 };
 int ds_launch_etab(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max, bool jets, cudaStream_t stream);
 int ds_launch_orb_assemble(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max, bool jets, cudaStream_t stream);
 int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cudaStream_t stream);
 int ds_launch_combine(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, double* log_abs, double* phase,
                       double* ke_re, double* ke_im, cudaStream_t stream);
+// LOGDET and the inverse matrices XINV of every (walker, spin, determinant)
+int ds_launch_det_inverse(const DsSys& sys, const SlaterBufs& sb, int Wc, cudaStream_t stream);
+
+// grad.cu: reverse sweep of (log|psi|, phase) w.r.t. the parameters --------------------------------
+struct GradBufs {
+    // cotangents of the outputs, per walker (dloss = sum_w a_w dlog|psi_w| + b_w dphase_w)
+    const double* cot_abs; const double* cot_phase;
+    // orbital layer
+    double* GY[2];              // [Wc*n_s][2 npar_s] cotangent of the raw orbital outputs, columns (re, im) interleaved
+    double* g_pi[2];            // [A][npar_s]  accumulated
+    double* g_sigma[2];
+    // one-electron stream
+    const double* T;            // tanh values of the layer [Wc*N][H]
+    const double* GH;           // cotangent of the layer output [Wc*N][H]
+    double* GZ;                 // cotangent of the pre-activation [Wc*N][H]
+    double* GZS;                // per-walker sums of GZ [Wc][H]
+    double* g_bias;             // [H] accumulated
+    const double* GA; int lda;  // GZ . B_am^T [Wc*N][K]
+    const double* GG; int ldgg; // GZS . B_g^T [Wc][2C]
+    double* GHin;               // cotangent of the layer input (own columns) [Wc*N][C]
+    double* GPM;                // pair-mean cotangents of the layer [Wc*N][2P]
+    // pair stream
+    const double* GPMl[DS_MAX_LAYERS];          // cotangents of the pair means of level l (null for l = 0)
+    double* g_Wp[DS_MAX_LAYERS]; double* g_bp[DS_MAX_LAYERS];   // accumulated
+};
+int ds_launch_orb_grad(const DsSys& sys, const SlaterBufs& sb, const GradBufs& gb, int Wc, int npar_max, cudaStream_t stream);
+int ds_launch_gz(const DsDims& dm, const GradBufs& gb, int Wc, bool residual, cudaStream_t stream);
+int ds_launch_hin(const DsDims& dm, const GradBufs& gb, int Wc, int C, int K, bool residual, bool want_pm, cudaStream_t stream);
+int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& gb, int Wc, cudaStream_t stream);
+// dst[r, c] (+)= src[r, c] for a [rows x cols] block (leading dimensions lds, ldd); deinterleave: see grad.cu
+int ds_launch_copy2d(const double* src, int lds, double* dst, int ldd, int rows, int cols, cudaStream_t stream);
+int ds_launch_deinterleave(const double* src, double* dst, int rows, int np, cudaStream_t stream);
 
 // ewald.cu ------------------------------------------------------------------
 struct EwaldDev {

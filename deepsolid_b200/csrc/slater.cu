@@ -245,6 +245,14 @@ __global__ void __launch_bounds__(DET_THREADS) det_kernel(const DsSys sys, const
         __syncthreads();
     }
     // now Xs[o][i] = (M^-1)[o,i]
+    if (sb.XINV[s] != nullptr) {                     // parameter-gradient path: only the inverse is wanted
+        cplx* xo = reinterpret_cast<cplx*>(sb.XINV[s]) + (w * D + k) * (long long)n * n;
+        for (int t = tid; t < n * n; t += DET_THREADS) {
+            int o = t / n, i = t - o * n;
+            xo[t] = Xs[o * np + i];
+        }
+        return;
+    }
 
     const int lane = tid & 31, warp = tid >> 5;
     auto block_sum2 = [&](double a, double b, double& oa, double& ob) {
@@ -672,6 +680,8 @@ __global__ void __launch_bounds__(128) combine_kernel(const DsSys sys, const Sla
 
 }  // namespace
 
+static size_t g_det_smem[2] = {0, 0};     // largest dynamic shared memory configured for det_kernel<false/true>
+
 int ds_launch_etab(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max, bool jets, cudaStream_t stream) {
     dim3 grid((unsigned)((long long)Wc * sys.d.N));
     if (jets) etab_kernel<true><<<grid, 256, 0, stream>>>(sys, sb, npar_max);
@@ -727,14 +737,30 @@ int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cuda
     }
     size_t smem = (size_t)(np * np + np + (lap ? 2 * G * np * np : 0)) * sizeof(cplx);
     DS_REQUIRE(smem <= 226 * 1024, "determinant kernel needs %zu bytes of shared memory", smem);
-    static size_t cfg_smem[2] = {0, 0};
-    if (smem > cfg_smem[lap ? 1 : 0]) {
+    if (smem > g_det_smem[lap ? 1 : 0]) {
         if (lap) DS_CUDA_CHECK(cudaFuncSetAttribute(det_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else DS_CUDA_CHECK(cudaFuncSetAttribute(det_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg_smem[lap ? 1 : 0] = smem;
+        g_det_smem[lap ? 1 : 0] = smem;
     }
     if (lap) det_kernel<true><<<grid, DET_THREADS, smem, stream>>>(sys, sb, G);
     else det_kernel<false><<<grid, DET_THREADS, smem, stream>>>(sys, sb, G);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_det_inverse(const DsSys& sys, const SlaterBufs& sb, int Wc, cudaStream_t stream) {
+    const int nmax = sys.d.n_up > sys.d.n_dn ? sys.d.n_up : sys.d.n_dn;
+    DS_REQUIRE(nmax <= 128, "determinants larger than 128x128 are not supported (n_s=%d)", nmax);
+    DS_REQUIRE(sb.XINV[0] && sb.XINV[1], "det_inverse: output buffers missing");
+    const int np = ((nmax + 2) / 3) * 3;
+    const size_t smem = (size_t)(np * np + np) * sizeof(cplx);
+    DS_REQUIRE(smem <= 226 * 1024, "determinant kernel needs %zu bytes of shared memory", smem);
+    if (smem > g_det_smem[1]) {
+        DS_CUDA_CHECK(cudaFuncSetAttribute(det_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_det_smem[1] = smem;
+    }
+    dim3 grid((unsigned)((long long)Wc * 2 * sys.d.D));
+    det_kernel<true><<<grid, DET_THREADS, smem, stream>>>(sys, sb, 0);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

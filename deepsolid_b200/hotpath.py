@@ -41,6 +41,16 @@ def flatten_params(params) -> list:
     return leaves
 
 
+def unflatten_params(leaves, n_layers: int) -> dict:
+    """Inverse of flatten_params for the implemented option set (isotropic envelope, no orbital bias)."""
+    it = iter(leaves)
+    single = [{"w": next(it), "b": next(it)} for _ in range(n_layers)]
+    double = [{"w": next(it), "b": next(it)} for _ in range(n_layers - 1)]
+    orbital = [{"w": next(it)} for _ in range(2)]
+    envelope = [{"pi": next(it), "sigma": next(it)} for _ in range(2)]
+    return {"single": single, "double": double, "orbital": orbital, "envelope": envelope}
+
+
 class HotPath:
     def __init__(self, simulation_cell, klist, hidden_dims=((256, 32),) * 3, determinants: int = 8,
                  device: Optional[int] = None):
@@ -150,6 +160,27 @@ class HotPath:
             ph = torch.empty_like(la)
             _lib.check(self.lib.ds_logpsi_host(self.h, t.data_ptr(), B, la.data_ptr(), ph.data_ptr()))
         return (la[0], ph[0]) if one else (la, ph)
+
+    def logpsi_vjp(self, x, cot_abs, cot_phase):
+        """Parameter gradient pytree of sum_b cot_abs[b] log|psi_b| + cot_phase[b] angle(psi_b)
+        (the reverse sweep behind train.make_loss's custom JVP, train.py:129-137).  Device tensors in,
+        device tensors out, same pytree structure as the parameters last given to ``set_params``."""
+        t, one, on_dev = self._prep(x)
+        td = t if on_dev else t.to(self.tdev)
+        B = td.shape[0]
+        ca = torch.as_tensor(cot_abs, dtype=torch.float64).reshape(-1).to(self.tdev).contiguous()
+        cp = torch.as_tensor(cot_phase, dtype=torch.float64).reshape(-1).to(self.tdev).contiguous()
+        if ca.numel() != B or cp.numel() != B:
+            raise ValueError("cotangents must have one entry per walker")
+        if self._param_key is None:
+            raise ValueError("parameters have not been set")
+        outs = [torch.empty(tp.shape, dtype=torch.float64, device=self.tdev) for tp in self._keep_params]
+        n = len(outs)
+        ptrs = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        sizes = (C.c_int64 * n)(*[o.numel() for o in outs])
+        _lib.check(self.lib.ds_logpsi_vjp(self.h, td.data_ptr(), B, ca.data_ptr(), cp.data_ptr(), ptrs, sizes, n,
+                                          self._stream()))
+        return unflatten_params(outs, len(self.hidden_dims))
 
     def orbitals(self, x):
         t, one, on_dev = self._prep(x)

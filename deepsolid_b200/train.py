@@ -33,12 +33,40 @@ def reduce_energy_stats(stats6: torch.Tensor):
     return packed[0] / packed[3], packed[1] / packed[3], packed[2] / packed[3]
 
 
+def clip_difference(diff: torch.Tensor, clip_local_energy: float, clip_type: str) -> torch.Tensor:
+    """clip_diff of total_energy_jvp (train.py:101-127): `real` clips Re and Im separately around 0 by
+    clip * mean|.|, `complex` clips the radius around its median by clip * std; statistics are pmean'ed."""
+    if clip_local_energy <= 0.0:
+        return diff
+    if clip_type == "complex":
+        radius, phase = diff.abs(), torch.angle(diff)
+        radius_tv = _dist.pmean(radius.std(unbiased=False))
+        radius_mean = _dist.pmean(torch.quantile(radius, 0.5, interpolation="midpoint"))     # jnp.median
+        clip_radius = torch.maximum(torch.minimum(radius, radius_mean + radius_tv * clip_local_energy),
+                                    radius_mean - radius_tv * clip_local_energy)
+        return torch.polar(clip_radius, phase)
+    if clip_type == "real":
+        tv_re = _dist.pmean(diff.real.abs().mean())
+        tv_im = _dist.pmean(diff.imag.abs().mean())
+        re = torch.maximum(torch.minimum(diff.real, clip_local_energy * tv_re), -clip_local_energy * tv_re)
+        im = torch.maximum(torch.minimum(diff.imag, clip_local_energy * tv_im), -clip_local_energy * tv_im)
+        return torch.complex(re, im)
+    raise ValueError("Unrecognized clip type.")
+
+
 def make_loss(network, batch_network, simulation_cell, clip_local_energy=5.0, clip_type="real", mode="for",
               partition_number=3):
     """Returns ``total_energy(params, data) -> (loss, AuxiliaryLossData)`` (train.py:66-89).
-    The custom JVP (train.py:91-142) that turns it into a gradient estimator is not part
-    of this path yet."""
-    del clip_local_energy, clip_type, batch_network
+
+    The reference turns it into a gradient estimator with a custom JVP (train.py:91-142); a torch caller has no
+    tracer to hand a JVP rule to, so the same estimator is exposed as
+    ``total_energy.value_and_grad(params, data) -> ((loss, aux), grads)``:
+    ``grads = d/dparams mean(Re(clip_diff * conj(log psi)))`` with ``clip_diff`` held constant, computed by one
+    reverse sweep of the CUDA network (``ds_logpsi_vjp``); the cross-device pmean of the gradient is left to the
+    optimizer, as in the reference (kfac_ferminet_alpha optimizer.py:423)."""
+    del batch_network
+    if clip_type not in ("real", "complex"):
+        raise ValueError("Unrecognized clip type.")
     el_fun = hamiltonian.local_energy_seperate(network, simulation_cell=simulation_cell, mode=mode,
                                                partition_number=partition_number)
 
@@ -54,4 +82,15 @@ def make_loss(network, batch_network, simulation_cell, clip_local_energy=5.0, cl
         loss, imaginary, variance = reduce_energy_stats(stats)
         return loss, AuxiliaryLossData(variance=variance, local_energy=e_l, imaginary=imaginary, kinetic=ke, ewald=ew)
 
+    def value_and_grad(params, data):
+        loss, aux = total_energy(params, data)
+        diff = aux.local_energy - loss
+        clip_diff = clip_difference(diff, clip_local_energy, clip_type)
+        n = clip_diff.numel()
+        hp = el_fun.hotpath()
+        hp.set_params(params)
+        grads = hp.logpsi_vjp(data, clip_diff.real / n, clip_diff.imag / n)
+        return (loss, aux), grads
+
+    total_energy.value_and_grad = value_and_grad
     return total_energy

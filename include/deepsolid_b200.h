@@ -115,6 +115,15 @@ DS_API int ds_set_params(ds_ctx *ctx, const double *const *leaves, const int64_t
 DS_API int ds_logpsi(ds_ctx *ctx, const double *x_dev, int64_t batch,
               double *log_abs_dev, double *phase_dev, void *stream);
 
+/* Reverse-mode derivative of the batched network w.r.t. the parameters: what jax.jvp(batch_network, ...)
+ * contributes to the energy-gradient estimator of train.make_loss.total_energy_jvp (train.py:129-137),
+ *   tangents_dot = mean(Re(clip_diff * conj(d log psi)))  =  sum_b cot_abs[b] d log|psi_b| + cot_phase[b] d angle(psi_b)
+ * with cot_abs = Re(clip_diff)/batch, cot_phase = Im(clip_diff)/batch.  `grad_leaves` holds n_leaves DEVICE
+ * pointers in the leaf order and sizes of ds_set_params; every leaf is overwritten with its gradient. */
+DS_API int ds_logpsi_vjp(ds_ctx *ctx, const double *x_dev, int64_t batch, const double *cot_abs_dev,
+                  const double *cot_phase_dev, double *const *grad_leaves, const int64_t *leaf_sizes, int n_leaves,
+                  void *stream);
+
 /* method eval_mats (network.py:601-602): out = complex128 (re,im interleaved) of shape
  * (batch, 2 spins, n_det, n_s, n_s) with spin blocks concatenated (n_up block first). */
 DS_API int ds_orbitals(ds_ctx *ctx, const double *x_dev, int64_t batch, double *out_dev, void *stream);

@@ -561,3 +561,76 @@ def total_energy_stats(ke, ew):
 def batch_apply(apply, params, X):
     """process.py:116-118: the caller vmaps apply over the batch; a loop is the oracle."""
     return torch.stack([apply(params, x) for x in X])
+
+
+# ---------------------------------------------------------------------------
+# train.py:91-142 -- the energy-gradient estimator (custom JVP of total_energy), reverse mode via autograd
+# ---------------------------------------------------------------------------
+def _leaves(params):
+    out = []
+    for layer in params["single"]:
+        out += [layer["w"], layer["b"]]
+    for layer in params["double"]:
+        out += [layer["w"], layer["b"]]
+    for orb in params["orbital"]:
+        out += [orb["w"]]
+    for env in params["envelope"]:
+        out += [env["pi"], env["sigma"]]
+    return out
+
+
+def _clone_params(params, requires_grad=True):
+    def conv(v):
+        if isinstance(v, dict):
+            return {k: conv(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return [conv(x) for x in v]
+        return v.detach().clone().requires_grad_(requires_grad)
+    return conv(params)
+
+
+def logpsi_vjp(apply_phase_slog, params, X, cot_abs, cot_phase):
+    """Pytree of d/dparams sum_b cot_abs[b] log|psi_b| + cot_phase[b] angle(psi_b); `apply_phase_slog` is the
+    per-walker network with method_name='eval_phase_and_slogdet' (network.py:599-600)."""
+    P = _clone_params(params)
+    total = torch.zeros((), dtype=DT)
+    for b, x in enumerate(X):
+        sign, slog = apply_phase_slog(P, x)
+        total = total + cot_abs[b] * slog + cot_phase[b] * torch.angle(sign)
+    grads = torch.autograd.grad(total, _leaves(P), allow_unused=True)
+    it = iter([g if g is not None else torch.zeros_like(l) for g, l in zip(grads, _leaves(P))])
+    return {"single": [{"w": next(it), "b": next(it)} for _ in params["single"]],
+            "double": [{"w": next(it), "b": next(it)} for _ in params["double"]],
+            "orbital": [{"w": next(it)} for _ in params["orbital"]],
+            "envelope": [{"pi": next(it), "sigma": next(it)} for _ in params["envelope"]]}
+
+
+def clip_difference(diff, clip_local_energy=5.0, clip_type="real"):
+    """train.py:101-127 on one device."""
+    if clip_local_energy <= 0.0:
+        return diff
+    if clip_type == "complex":
+        radius, phase = diff.abs(), torch.angle(diff)
+        radius_tv = radius.std(unbiased=False)
+        radius_mean = torch.as_tensor(np.median(radius.numpy()))
+        clip_radius = torch.clip(radius, radius_mean - radius_tv * clip_local_energy,
+                                 radius_mean + radius_tv * clip_local_energy)
+        return clip_radius * torch.exp(1j * phase)
+    if clip_type == "real":
+        tv_re = diff.real.abs().mean()
+        tv_im = diff.imag.abs().mean()
+        return torch.complex(torch.clip(diff.real, -clip_local_energy * tv_re, clip_local_energy * tv_re),
+                             torch.clip(diff.imag, -clip_local_energy * tv_im, clip_local_energy * tv_im))
+    raise ValueError("Unrecognized clip type.")
+
+
+def total_energy_value_and_grad(apply_phase_slog, el_fun, params, X, clip_local_energy=5.0, clip_type="real"):
+    """(loss, e_l, grads) of train.make_loss: loss = Re mean e_l, grads = the pullback of
+    tangents_dot = mean(Re(clip_diff * conj(d log psi))) (train.py:129-137)."""
+    out = [el_fun(params, x) for x in X]
+    e_l = torch.stack([torch.as_tensor(complex(k) + float(e), dtype=torch.complex128) for k, e in out])
+    loss = e_l.mean().real
+    clip_diff = clip_difference(e_l - loss, clip_local_energy, clip_type)
+    n = len(X)
+    grads = logpsi_vjp(apply_phase_slog, params, X, clip_diff.real / n, clip_diff.imag / n)
+    return loss, e_l, grads
