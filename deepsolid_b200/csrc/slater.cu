@@ -616,6 +616,347 @@ __global__ void __launch_bounds__(512, 1) det_lap_kernel(const DsSys sys, const 
 }
 
 // ---------------------------------------------------------------------------
+// Determinant kernel of the Laplacian sweep, third version: the products Y_d = X dM_d on the fp64 tensor
+// path (mma.sync m8n8k4 f64 -> DMMA), one CTA per (walker, spin, determinant).
+//   * in-place Gauss-Jordan inverse X = M^-1 (complex, shared memory), then its real embedding
+//         Xe = [ Xr  -Xi ; Xi  Xr ]   (2n x 2n, padded to MT*8, leading dimension = 4 mod 16: conflict-free A fragments)
+//   * G directions per group are staged de-interleaved with 8-byte cp.async into
+//         Be = [ Re dM_g ; Im dM_g ]  (rows k = (re|im, electron i), columns (g, orbital o), ld = 4 mod 16)
+//     so that ONE real GEMM  Ye = Xe . Be  yields [ Re Y ; Im Y ] of all G directions; warp w owns the
+//     n-tiles {w, w+8} and all MT m-tiles (7 A-fragment + 2 B-fragment loads per 14 DMMAs at n = 27).
+//   * Y is written in place over Be; tr(Y_d) per direction and sum_d tr(Y_d^2) are read back from there.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8_s(void* smem_dst, const void* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int MT>
+__global__ void __launch_bounds__(256, 2) det_dmma_kernel(const DsSys sys, const SlaterBufs sb, int G, int LDB, int alias) {
+    const DsDims& dm = sys.d;
+    const int D = dm.D, NDp = dm.NDp, ND = dm.ND;
+    const int k = blockIdx.x % D;
+    const int s = (blockIdx.x / D) % 2;
+    const long long w = blockIdx.x / (2 * D);
+    const int n = s ? dm.n_dn : dm.n_up;
+    const int np = n;                               // no padding of the complex inverse
+    constexpr int MP = MT * 8;                      // rows of Xe / Be (>= 2n)
+    constexpr int LDX = MP + 4;                     // = 4 or 12 mod 16
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+
+    extern __shared__ __align__(16) double smraw[];
+    double* Xe = smraw;                             // [MP][LDX]
+    double* Be = Xe + MP * LDX;                     // [MP][LDB]
+    cplx* Xs = reinterpret_cast<cplx*>(alias ? Be : Be + MP * LDB);   // [n][n] complex inverse (aliases Be when tight)
+    cplx* colk = Xs + n * n;                        // [n]
+    __shared__ int piv[128];
+    __shared__ int s_p;
+    __shared__ double s_red[2 * 16 + 4];
+
+    const cplx* mat = reinterpret_cast<const cplx*>(sb.MAT[s]) + (w * D + k) * (long long)n * n;
+    for (int t = tid; t < n * n; t += nthr) Xs[t] = mat[t];
+    if (!alias)
+        for (int t = tid; t < MP * LDB; t += nthr) Be[t] = 0.0;
+    __syncthreads();
+
+    const double* da = sb.DA[s] + (w * D + k) * (long long)NDp * n * n * 2;     // complex (re, im) interleaved
+    // every thread owns up to JMAX fixed matrix elements (i, o) = idx / n, idx % n, idx = tid + j * nthr, of every
+    // direction: their operand-buffer offsets (straight and transposed) are computed once, not per group
+    constexpr int JMAX = 4;
+    const int nn = n * n;
+    int off_ab[JMAX];
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) {
+        const int idx = tid + j * nthr;
+        const int a = idx / n, b = idx - a * n;
+        off_ab[j] = a * LDB + b;
+    }
+    // trace elements: 4 x 8 lane tiles (a = 4 ta + lane/8, b = 8 tb + lane%8): the straight and the transposed
+    // read of a warp are both at most 2-way bank conflicted (ld = 4 mod 16 rules out conflict-free columns)
+    const int tiles_b = (n + 7) >> 3, n_tiles = ((n + 3) >> 2) * tiles_b;
+    int tr_ab[JMAX], tr_ba[JMAX];
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) {
+        const int tl = warp + j * nwarp;
+        const int ta = tl / tiles_b, tb = tl - ta * tiles_b;
+        const int a = 4 * ta + (lane >> 3), b = 8 * tb + (lane & 7);
+        const bool ok = tl < n_tiles && a < n && b < n;
+        tr_ab[j] = ok ? a * LDB + b : -1;
+        tr_ba[j] = b * LDB + a;
+    }
+    auto stage = [&](int d0, int g_cnt) {
+        for (int g = 0; g < g_cnt; ++g) {
+            const double* src = da + (long long)(d0 + g) * nn * 2;
+            double* dst = Be + g * n;
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+                const int idx = tid + j * nthr;
+                if (idx < nn) {
+                    cp_async8_s(dst + off_ab[j], src + 2 * idx);
+                    cp_async8_s(dst + n * LDB + off_ab[j], src + 2 * idx + 1);
+                }
+            }
+            for (int idx = tid + JMAX * nthr; idx < nn; idx += nthr) {      // matrices larger than JMAX * nthr elements
+                const int a = idx / n, b = idx - a * n;
+                cp_async8_s(dst + a * LDB + b, src + 2 * idx);
+                cp_async8_s(dst + (n + a) * LDB + b, src + 2 * idx + 1);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    if (!alias) stage(0, min(G, ND));
+
+    double logabs = 0.0;
+    cplx phase{1.0, 0.0};
+    for (int kk = 0; kk < n; ++kk) {
+        if (tid < 32) {
+            double best = -1.0;
+            int bi = kk;
+            for (int r = kk + tid; r < n; r += 32) {
+                double v = cabs1(Xs[r * np + kk]);
+                if (v > best) { best = v; bi = r; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, best, off);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (tid == 0) { s_p = bi; piv[kk] = bi; }
+        }
+        __syncthreads();
+        const int p = s_p;
+        if (p != kk) {
+            for (int c = tid; c < n; c += nthr) {
+                cplx a = Xs[kk * np + c];
+                Xs[kk * np + c] = Xs[p * np + c];
+                Xs[p * np + c] = a;
+            }
+            phase = cplx{-phase.re, -phase.im};
+        }
+        __syncthreads();
+        const cplx pv = Xs[kk * np + kk];
+        {
+            double a = hypot(pv.re, pv.im);
+            logabs += log(a);
+            phase = cmul(phase, cplx{pv.re / a, pv.im / a});
+        }
+        const cplx ipv = cinv(pv);
+        for (int r = tid; r < n; r += nthr) colk[r] = Xs[r * np + kk];
+        __syncthreads();
+        for (int c = tid; c < n; c += nthr) {
+            cplx a = (c == kk) ? cplx{1.0, 0.0} : Xs[kk * np + c];
+            Xs[kk * np + c] = cmul(a, ipv);
+        }
+        __syncthreads();
+        for (int t = tid; t < n * n; t += nthr) {
+            int r = t / n, c = t - r * n;
+            if (r == kk) continue;
+            cplx f = colk[r];
+            cplx a = (c == kk) ? cplx{0.0, 0.0} : Xs[r * np + c];
+            cplx b = Xs[kk * np + c];
+            a.re -= f.re * b.re - f.im * b.im;
+            a.im -= f.re * b.im + f.im * b.re;
+            Xs[r * np + c] = a;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double* ld = sb.LOGDET + ((w * 2 + s) * D + k) * 3;
+        ld[0] = logabs; ld[1] = phase.re; ld[2] = phase.im;
+    }
+    for (int kk = n - 1; kk >= 0; --kk) {            // undo the row pivoting: swap columns in reverse order
+        const int p = piv[kk];
+        if (p != kk) {
+            for (int r = tid; r < n; r += nthr) {
+                cplx a = Xs[r * np + kk];
+                Xs[r * np + kk] = Xs[r * np + p];
+                Xs[r * np + p] = a;
+            }
+        }
+        __syncthreads();
+    }
+    // now Xs[o][i] = (M^-1)[o,i]
+
+    auto block_sum2 = [&](double a, double b, double& oa, double& ob) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off);
+            b += __shfl_xor_sync(0xffffffffu, b, off);
+        }
+        __syncthreads();
+        if (lane == 0) { s_red[2 * warp] = a; s_red[2 * warp + 1] = b; }
+        __syncthreads();
+        oa = 0.0; ob = 0.0;
+        for (int q = 0; q < nwarp; ++q) { oa += s_red[2 * q]; ob += s_red[2 * q + 1]; }
+    };
+    {   // tr(X lapM) = sum_{i,o} X[o,i] lapM[i,o]
+        const cplx* lm = reinterpret_cast<const cplx*>(sb.LAPM[s]) + (w * D + k) * (long long)n * n;
+        cplx acc{0.0, 0.0};
+        for (int t = tid; t < n * n; t += nthr) {
+            int i = t / n, o = t - i * n;
+            cfma(acc, Xs[o * np + i], lm[t]);
+        }
+        double ra, rb;
+        block_sum2(acc.re, acc.im, ra, rb);
+        if (tid == 0) {
+            double* tl = sb.TRLAP + ((w * 2 + s) * D + k) * 2;
+            tl[0] = ra; tl[1] = rb;
+        }
+    }
+    // real embedding of the inverse
+    for (int t = tid; t < MP * LDX; t += nthr) {
+        const int r = t / LDX, c = t - r * LDX;
+        double v = 0.0;
+        if (r < 2 * n && c < 2 * n) {
+            const int o = (r < n) ? r : r - n, i = (c < n) ? c : c - n;
+            const cplx x = Xs[o * np + i];
+            v = ((r < n) == (c < n)) ? x.re : ((r < n) ? -x.im : x.im);
+        }
+        Xe[t] = v;
+    }
+    __syncthreads();
+    if (alias) {                                     // Xs is dead: its storage becomes the operand buffer
+        for (int t = tid; t < MP * LDB; t += nthr) Be[t] = 0.0;
+        __syncthreads();
+        stage(0, min(G, ND));
+    }
+
+    // ---- direction groups ---------------------------------------------------
+    double* tau_out = sb.TAU + ((w * 2 + s) * D + k) * (long long)NDp * 2;
+    const int ntiles = (G * n + 7) >> 3;             // n-tiles of 8 columns
+    const int gid = lane >> 2, tig = lane & 3;
+    const double* xa = Xe + gid * LDX + tig;         // A fragment: row gid, column tig of the 8x4 tile
+    double sq_re = 0.0, sq_im = 0.0;
+    for (int d0 = 0; d0 < ND; d0 += G) {
+        const int g_cnt = min(G, ND - d0);
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        double acc[MT][2][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
+        const int nt0 = warp, nt1 = warp + nwarp;
+        const bool has0 = nt0 < ntiles, has1 = nt1 < ntiles;
+        if (has0) {
+            const double* xb0 = Be + tig * LDB + nt0 * 8 + gid;       // B fragment: row tig, column gid of the 4x8 tile
+            const double* xb1 = Be + tig * LDB + nt1 * 8 + gid;
+#pragma unroll 2
+            for (int k0 = 0; k0 < MP; k0 += 4) {
+                double a[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) a[mt] = xa[mt * 8 * LDX + k0];
+                const double b0 = xb0[k0 * LDB];
+                const double b1 = has1 ? xb1[k0 * LDB] : 0.0;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    dmma884(acc[mt][0][0], acc[mt][0][1], a[mt], b0);
+                    if (has1) dmma884(acc[mt][1][0], acc[mt][1][1], a[mt], b1);
+                }
+            }
+        }
+        __syncthreads();                             // every operand of this group has been read
+        if (has0) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                double* y0 = Be + (mt * 8 + gid) * LDB + nt0 * 8 + 2 * tig;
+                *reinterpret_cast<double2*>(y0) = make_double2(acc[mt][0][0], acc[mt][0][1]);
+                if (has1) {
+                    double* y1 = Be + (mt * 8 + gid) * LDB + nt1 * 8 + 2 * tig;
+                    *reinterpret_cast<double2*>(y1) = make_double2(acc[mt][1][0], acc[mt][1][1]);
+                }
+            }
+        }
+        __syncthreads();
+        // sum_{a,b} Y[a,b] Y[b,a] of the valid directions (complex), the thread's fixed elements (a, b)
+        for (int g = 0; g < g_cnt; ++g) {
+            const double* col = Be + g * n;
+            const double* coli = col + n * LDB;
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+                if (tr_ab[j] >= 0) {
+                    const double yr = col[tr_ab[j]], yi = coli[tr_ab[j]];
+                    const double zr = col[tr_ba[j]], zi = coli[tr_ba[j]];
+                    sq_re = fma(yr, zr, sq_re); sq_re = fma(-yi, zi, sq_re);
+                    sq_im = fma(yr, zi, sq_im); sq_im = fma(yi, zr, sq_im);
+                }
+            }
+            for (int tl = warp + JMAX * nwarp; tl < n_tiles; tl += nwarp) {      // matrices with more than JMAX * nwarp tiles
+                const int ta = tl / tiles_b, tb = tl - ta * tiles_b;
+                const int a = 4 * ta + (lane >> 3), b = 8 * tb + (lane & 7);
+                if (a < n && b < n) {
+                    const double yr = col[a * LDB + b], yi = coli[a * LDB + b];
+                    const double zr = col[b * LDB + a], zi = coli[b * LDB + a];
+                    sq_re = fma(yr, zr, sq_re); sq_re = fma(-yi, zi, sq_re);
+                    sq_im = fma(yr, zi, sq_im); sq_im = fma(yi, zr, sq_im);
+                }
+            }
+        }
+        // tr(Y_g): warp g
+        for (int g = warp; g < g_cnt; g += nwarp) {
+            double tr = 0.0, ti = 0.0;
+            for (int o = lane; o < n; o += 32) { tr += Be[o * LDB + g * n + o]; ti += Be[(n + o) * LDB + g * n + o]; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                tr += __shfl_xor_sync(0xffffffffu, tr, off);
+                ti += __shfl_xor_sync(0xffffffffu, ti, off);
+            }
+            if (lane == 0) { tau_out[2 * (d0 + g)] = tr; tau_out[2 * (d0 + g) + 1] = ti; }
+        }
+        if (d0 + G < ND) {
+            __syncthreads();                         // Y consumed: the buffer may be refilled
+            stage(d0 + G, min(G, ND - d0 - G));
+        }
+    }
+    {
+        double ra, rb2;
+        block_sum2(sq_re, sq_im, ra, rb2);
+        if (tid == 0) {
+            double* ts = sb.TRSQ + ((w * 2 + s) * D + k) * 2;
+            ts[0] = ra; ts[1] = rb2;
+        }
+    }
+}
+
+template <int MT>
+int launch_det_dmma(const DsSys& sys, const SlaterBufs& sb, int Wc, int nmax, cudaStream_t stream, bool* done) {
+    *done = false;
+    constexpr int MP = MT * 8, LDX = MP + 4;
+    // directions per group: at most 16 n-tiles (two per warp), operand buffer small enough for two CTAs per SM
+    int G = (16 * 8) / nmax;
+    if (G < 1) return 0;
+    if (G > sys.d.ND) G = sys.d.ND;
+    auto ldb_of = [&](int g) { int npad = (g * nmax + 7) & ~7; return npad + ((4 - (npad & 15)) & 15); };    // = 4 mod 16
+    auto smem_of = [&](int g, bool alias) {
+        size_t xs = (size_t)(nmax * nmax + nmax) * sizeof(cplx);
+        size_t be = (size_t)MP * ldb_of(g) * sizeof(double);
+        return (size_t)MP * LDX * sizeof(double) + (alias ? (be > xs ? be : xs) : be + xs);
+    };
+    while (G > 1 && smem_of(G, false) > 112 * 1024) --G;
+    bool alias = false;
+    if (smem_of(G, false) > 112 * 1024) alias = true;
+    const size_t smem = smem_of(G, alias);
+    if (smem > 226 * 1024) return 0;
+    static size_t cfg = 0;
+    if (smem > cfg) {
+        DS_CUDA_CHECK(cudaFuncSetAttribute(det_dmma_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg = smem;
+    }
+    dim3 grid((unsigned)((long long)Wc * 2 * sys.d.D));
+    det_dmma_kernel<MT><<<grid, 256, smem, stream>>>(sys, sb, G, ldb_of(G), alias ? 1 : 0);
+    DS_CUDA_CHECK(cudaGetLastError());
+    *done = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Combine determinants (logdet_matmul, network.py:395-427) and the kinetic energy.
 // One warp per walker.
 // ---------------------------------------------------------------------------
@@ -706,6 +1047,29 @@ int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cuda
     const int nb = np / 3;
     dim3 grid((unsigned)((long long)Wc * 2 * sys.d.D));
     static const bool use_v1 = getenv("DS_DET_V1") && atoi(getenv("DS_DET_V1")) != 0;
+    static const bool use_v2 = getenv("DS_DET_V2") && atoi(getenv("DS_DET_V2")) != 0;
+    if (lap && !use_v1 && !use_v2) {
+        // fp64 tensor-path kernel: MT = m-tiles of the real embedding (2 n_s rows, padded to 8)
+        const int mt = (2 * nmax + 7) / 8;
+        bool done = false;
+        int rc = 0;
+        switch (mt) {
+            case 1: rc = launch_det_dmma<1>(sys, sb, Wc, nmax, stream, &done); break;
+            case 2: rc = launch_det_dmma<2>(sys, sb, Wc, nmax, stream, &done); break;
+            case 3: rc = launch_det_dmma<3>(sys, sb, Wc, nmax, stream, &done); break;
+            case 4: rc = launch_det_dmma<4>(sys, sb, Wc, nmax, stream, &done); break;
+            case 5: case 6: rc = launch_det_dmma<6>(sys, sb, Wc, nmax, stream, &done); break;
+            case 7: rc = launch_det_dmma<7>(sys, sb, Wc, nmax, stream, &done); break;
+            case 8: rc = launch_det_dmma<8>(sys, sb, Wc, nmax, stream, &done); break;
+            case 9: case 10: rc = launch_det_dmma<10>(sys, sb, Wc, nmax, stream, &done); break;
+            case 11: case 12: rc = launch_det_dmma<12>(sys, sb, Wc, nmax, stream, &done); break;
+            case 13: case 14: rc = launch_det_dmma<14>(sys, sb, Wc, nmax, stream, &done); break;
+            case 15: case 16: rc = launch_det_dmma<16>(sys, sb, Wc, nmax, stream, &done); break;
+            default: break;
+        }
+        if (rc) return rc;
+        if (done) return 0;
+    }
     if (lap && !use_v1) {
         // det_lap_kernel: G directions per group, two per thread
         const int nb2 = nb * nb;
