@@ -43,6 +43,10 @@ SIGNATURES = {
     "ds_logpsi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_logpsi_vjp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                 C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
+    "ds_logpsi_grad_x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+    "ds_mcmc_step_one_electron": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_uint64,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_orbitals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ds_orbitals_size": (C.c_int64, [C.c_void_p]),
     "ds_local_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

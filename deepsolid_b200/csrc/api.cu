@@ -110,6 +110,9 @@ struct ds_ctx {
     cudaEvent_t tot_a = nullptr, tot_b = nullptr;
     double tot_ms = 0.0;
     int dbg_stop_layer = -1;
+    // optional outputs of the sweep: d log|psi| / dx and d phase / dx of the current chunk (ds_logpsi_grad_x)
+    double* gx_abs = nullptr;
+    double* gx_phase = nullptr;
     // layout of the last local-energy chunk (for ds_debug_buffer)
     std::vector<Region> last_regions;
 };
@@ -472,7 +475,8 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
     }
     if (int rc = ds_launch_det(sys, sb, Wc, lap, st)) return rc;
     c->launches++;
-    if (int rc = ds_launch_combine(sys, sb, Wc, lap, log_abs, phase, ke_re, ke_im, st)) return rc;
+    if (int rc = ds_launch_combine(sys, sb, Wc, lap, log_abs, phase, ke_re, ke_im, st, lap ? c->gx_abs : nullptr,
+                                   lap ? c->gx_phase : nullptr)) return rc;
     c->launches++;
     return 0;
 }
@@ -554,14 +558,19 @@ int run_batched(ds_ctx* c, const double* X, long long batch, bool lap, double* l
     if (int rc = plan_chunk(c, batch, lap, &Wc)) return rc;
     const int n3 = 3 * c->sys.d.N;
     const size_t mat_per = (size_t)c->sys.d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
-    for (long long w0 = 0; w0 < batch; w0 += Wc) {
+    double* const gxa = c->gx_abs;
+    double* const gxp = c->gx_phase;
+    int rc = 0;
+    for (long long w0 = 0; w0 < batch && !rc; w0 += Wc) {
         int wc = (int)std::min<long long>(Wc, batch - w0);
-        int rc = run_chunk(c, X + w0 * n3, wc, lap, log_abs ? log_abs + w0 : nullptr, phase ? phase + w0 : nullptr,
-                           ke_re ? ke_re + w0 : nullptr, ke_im ? ke_im + w0 : nullptr,
-                           mats_out ? mats_out + w0 * mat_per : nullptr, st);
-        if (rc) return rc;
+        c->gx_abs = gxa ? gxa + w0 * n3 : nullptr;
+        c->gx_phase = gxp ? gxp + w0 * n3 : nullptr;
+        rc = run_chunk(c, X + w0 * n3, wc, lap, log_abs ? log_abs + w0 : nullptr, phase ? phase + w0 : nullptr,
+                       ke_re ? ke_re + w0 : nullptr, ke_im ? ke_im + w0 : nullptr,
+                       mats_out ? mats_out + w0 * mat_per : nullptr, st);
     }
-    return 0;
+    c->gx_abs = gxa; c->gx_phase = gxp;
+    return rc;
 }
 
 int ensure(ds_ctx* c, DevBuf& b, size_t n) {
@@ -863,6 +872,20 @@ extern "C" int ds_logpsi_vjp(ds_ctx* c, const double* x, int64_t batch, const do
     return 0;
 }
 
+// log|psi|, phase and their gradients with respect to the electron coordinates (what
+// jax.value_and_grad(slog_network, argnums=1) gives importance_update, qmc.py:101-118); the gradients come out of
+// the forward-Laplacian sweep (first-derivative half: d log psi / d x_d = sum_k w_k sum_s tr(X dM_d)).
+extern "C" int ds_logpsi_grad_x(ds_ctx* c, const double* x, int64_t batch, double* log_abs, double* phase,
+                                double* grad_abs, double* grad_phase, void* stream) {
+    DS_REQUIRE(c, "null context");
+    DS_REQUIRE(grad_abs || grad_phase, "no gradient output requested");
+    Guard g(c->device);
+    c->gx_abs = grad_abs; c->gx_phase = grad_phase;
+    int rc = run_batched(c, x, batch, true, log_abs, phase, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    c->gx_abs = nullptr; c->gx_phase = nullptr;
+    return rc;
+}
+
 extern "C" int64_t ds_orbitals_size(const ds_ctx* c) {
     if (!c) return -1;
     return (int64_t)c->sys.d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
@@ -917,8 +940,25 @@ extern "C" int ds_local_energy(ds_ctx* c, const double* x, int64_t batch, int mo
     return 0;
 }
 
+static int mcmc_impl(ds_ctx* c, double* x, int64_t batch, int steps, double width, uint64_t seed, const double* xi,
+                     const double* u, uint8_t* accept, double* n_accept, void* stream, bool one_electron);
+
 extern "C" int ds_mcmc_step(ds_ctx* c, double* x, int64_t batch, int steps, double width, uint64_t seed,
                             const double* xi, const double* u, uint8_t* accept, double* n_accept, void* stream) {
+    return mcmc_impl(c, x, batch, steps, width, seed, xi, u, accept, n_accept, stream, false);
+}
+
+// qmc.mh_one_electron_update (qmc.py:227-287) driven as make_mcmc_step does (qmc.py:355-358): steps * N
+// single-electron moves, move i displaces electron i % N; xi has shape (steps*N, batch, 3), u and the accept
+// masks (steps*N, batch).
+extern "C" int ds_mcmc_step_one_electron(ds_ctx* c, double* x, int64_t batch, int steps, double width, uint64_t seed,
+                                         const double* xi, const double* u, uint8_t* accept, double* n_accept,
+                                         void* stream) {
+    return mcmc_impl(c, x, batch, steps, width, seed, xi, u, accept, n_accept, stream, true);
+}
+
+static int mcmc_impl(ds_ctx* c, double* x, int64_t batch, int steps, double width, uint64_t seed, const double* xi,
+                     const double* u, uint8_t* accept, double* n_accept, void* stream, bool one_electron) {
     DS_REQUIRE(c && n_accept, "null argument");
     DS_REQUIRE(steps >= 0, "negative number of MCMC steps");
     DS_REQUIRE(x || batch == 0, "null walker pointer");
@@ -934,9 +974,13 @@ extern "C" int ds_mcmc_step(ds_ctx* c, double* x, int64_t batch, int steps, doub
     if (int rc = run_batched(c, x, batch, false, c->mc_lp.p, nullptr, nullptr, nullptr, nullptr, st)) return rc;
     if (int rc = ds_launch_scale(c->mc_lp.p, c->mc_lp.p, 2.0, batch, st)) return rc;
     c->launches++;
-    for (int s = 0; s < steps; ++s) {
+    const int n_el = c->sys.d.N;
+    const long long nsteps = one_electron ? (long long)steps * n_el : steps;
+    const size_t xi_stride = one_electron ? (size_t)batch * 3 : (size_t)batch * n3;
+    for (long long s = 0; s < nsteps; ++s) {
         if (int rc = ds_launch_propose(c->sys.sim, x, c->mc_x2.p, batch, n3, width,
-                                       xi ? xi + (size_t)s * batch * n3 : nullptr, seed, (unsigned long long)s, st)) return rc;
+                                       xi ? xi + (size_t)s * xi_stride : nullptr, seed, (unsigned long long)s, st,
+                                       one_electron ? (int)(s % n_el) : -1)) return rc;
         if (int rc = run_batched(c, c->mc_x2.p, batch, false, c->mc_lp2.p, nullptr, nullptr, nullptr, nullptr, st)) return rc;
         if (int rc = ds_launch_scale(c->mc_lp2.p, c->mc_lp2.p, 2.0, batch, st)) return rc;
         if (int rc = ds_launch_accept(x, c->mc_x2.p, c->mc_lp.p, c->mc_lp2.p, batch, n3,

@@ -53,7 +53,8 @@ int ds_launch_etab(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max,
 int ds_launch_orb_assemble(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max, bool jets, cudaStream_t stream);
 int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cudaStream_t stream);
 int ds_launch_combine(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, double* log_abs, double* phase,
-                      double* ke_re, double* ke_im, cudaStream_t stream);
+                      double* ke_re, double* ke_im, cudaStream_t stream, double* gx_abs = nullptr,
+                      double* gx_phase = nullptr);
 // LOGDET and the inverse matrices XINV of every (walker, spin, determinant)
 int ds_launch_det_inverse(const DsSys& sys, const SlaterBufs& sb, int Wc, cudaStream_t stream);
 
@@ -107,7 +108,7 @@ int ds_launch_ewald(const EwaldDev& ew, const double* X, long long batch, double
 // mcmc.cu -------------------------------------------------------------------
 int ds_launch_propose(const DsLattice& sim, const double* x, double* x2, long long batch, int n3, double width,
                       const double* xi_or_null, unsigned long long seed, unsigned long long step,
-                      cudaStream_t stream);
+                      cudaStream_t stream, int only_electron = -1);
 int ds_launch_accept(double* x, const double* x2, double* lp, const double* lp2, long long batch, int n3,
                      const double* u_or_null, unsigned long long seed, unsigned long long step,
                      unsigned char* mask_or_null, double* n_accept, cudaStream_t stream);

@@ -26,25 +26,34 @@ __device__ __forceinline__ void philox_uniform2(unsigned long long seed, unsigne
     u2 = ((double)c[2] + 0.5) * (1.0 / 4294967296.0);
 }
 
+// only_electron < 0: all-electron move (mh_update, qmc.py:192); otherwise only that electron of every walker is
+// displaced (mh_one_electron_update, qmc.py:270-273; noise xi then has shape (batch, 3)) while every electron
+// is re-wrapped, as distance.enforce_pbc does to the whole configuration.
 __global__ void __launch_bounds__(256) propose_kernel(const DsLattice sim, const double* __restrict__ x,
                                                       double* __restrict__ x2, long long n_elec_total, int n3,
                                                       double width, const double* __restrict__ xi,
-                                                      unsigned long long seed, unsigned long long step) {
+                                                      unsigned long long seed, unsigned long long step, int only_electron) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // electron index over the batch
     if (t >= n_elec_total) return;
+    const int n_el = n3 / 3;
+    const long long b = t / n_el;
+    const bool moved = only_electron < 0 || (int)(t - b * n_el) == only_electron;
     double p[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const long long idx = 3 * t + c;
-        double z;
-        if (xi) {
-            z = xi[idx];
-        } else {
-            double u1, u2;
-            philox_uniform2(seed, 2 * step, (unsigned long long)idx, u1, u2);
-            z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        const long long nidx = only_electron < 0 ? idx : 3 * b + c;           // index into the noise array
+        double z = 0.0;
+        if (moved) {
+            if (xi) {
+                z = xi[nidx];
+            } else {
+                double u1, u2;
+                philox_uniform2(seed, 2 * step, (unsigned long long)nidx, u1, u2);
+                z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+            }
         }
-        p[c] = __dadd_rn(x[idx], __dmul_rn(width, z));      // x1 + stddev * N(0,1), no FMA contraction
+        p[c] = moved ? __dadd_rn(x[idx], __dmul_rn(width, z)) : x[idx];      // x1 + stddev * N(0,1), no FMA contraction
     }
     double o[3];
     ds_wrap(sim, p, o);                                     // distance.enforce_pbc: divmod(frac, 1)
@@ -115,10 +124,11 @@ __global__ void __launch_bounds__(256) stats_kernel(const double* __restrict__ k
 
 int ds_launch_propose(const DsLattice& sim, const double* x, double* x2, long long batch, int n3, double width,
                       const double* xi_or_null, unsigned long long seed, unsigned long long step,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int only_electron) {
     long long ne = batch * (n3 / 3);
     if (ne <= 0) return 0;
-    propose_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, stream>>>(sim, x, x2, ne, n3, width, xi_or_null, seed, step);
+    propose_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, stream>>>(sim, x, x2, ne, n3, width, xi_or_null, seed, step,
+                                                                  only_electron);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -962,7 +962,8 @@ int launch_det_dmma(const DsSys& sys, const SlaterBufs& sb, int Wc, int nmax, cu
 // ---------------------------------------------------------------------------
 template <bool LAP>
 __global__ void __launch_bounds__(128) combine_kernel(const DsSys sys, const SlaterBufs sb, int Wc, double* log_abs,
-                                                      double* phase, double* ke_re, double* ke_im) {
+                                                      double* phase, double* ke_re, double* ke_im, double* gx_abs,
+                                                      double* gx_phase) {
     const DsDims& dm = sys.d;
     const int D = dm.D, NDp = dm.NDp, ND = dm.ND;
     const int lane = threadIdx.x & 31;
@@ -988,6 +989,23 @@ __global__ void __launch_bounds__(128) combine_kernel(const DsSys sys, const Sla
     }
     if (!LAP) return;
     const cplx itot = cinv(tot);
+    if (gx_abs != nullptr || gx_phase != nullptr) {
+        // d log psi / d x_d = sum_k w_k sum_s tr(X dM_d): real part = grad log|psi|, imaginary part = grad of the phase
+        for (int d = lane; d < ND; d += 32) {
+            cplx gsum{0.0, 0.0};
+            for (int k = 0; k < D; ++k) {
+                double l = ld[k * 3] + ld[(D + k) * 3];
+                cplx ph = cmul(cplx{ld[k * 3 + 1], ld[k * 3 + 2]}, cplx{ld[(D + k) * 3 + 1], ld[(D + k) * 3 + 2]});
+                double m = exp(l - mx);
+                cplx wk = cmul(cplx{ph.re * m, ph.im * m}, itot);
+                const double* t0 = sb.TAU + ((w * 2 + 0) * D + k) * (long long)NDp * 2;
+                const double* t1 = sb.TAU + ((w * 2 + 1) * D + k) * (long long)NDp * 2;
+                cfma(gsum, wk, cplx{t0[2 * d] + t1[2 * d], t0[2 * d + 1] + t1[2 * d + 1]});
+            }
+            if (gx_abs) gx_abs[w * ND + d] = gsum.re;
+            if (gx_phase) gx_phase[w * ND + d] = gsum.im;
+        }
+    }
     cplx ke{0.0, 0.0};
     for (int k = 0; k < D; ++k) {
         double l = ld[k * 3] + ld[(D + k) * 3];
@@ -1014,8 +1032,8 @@ __global__ void __launch_bounds__(128) combine_kernel(const DsSys sys, const Sla
         cfma(ke, wk, per);
     }
     if (lane == 0) {
-        ke_re[w] = -0.5 * ke.re;
-        ke_im[w] = -0.5 * ke.im;
+        if (ke_re) ke_re[w] = -0.5 * ke.re;
+        if (ke_im) ke_im[w] = -0.5 * ke.im;
     }
 }
 
@@ -1130,10 +1148,10 @@ int ds_launch_det_inverse(const DsSys& sys, const SlaterBufs& sb, int Wc, cudaSt
 }
 
 int ds_launch_combine(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, double* log_abs, double* phase,
-                      double* ke_re, double* ke_im, cudaStream_t stream) {
+                      double* ke_re, double* ke_im, cudaStream_t stream, double* gx_abs, double* gx_phase) {
     dim3 grid((unsigned)((Wc + 3) / 4));
-    if (lap) combine_kernel<true><<<grid, 128, 0, stream>>>(sys, sb, Wc, log_abs, phase, ke_re, ke_im);
-    else combine_kernel<false><<<grid, 128, 0, stream>>>(sys, sb, Wc, log_abs, phase, ke_re, ke_im);
+    if (lap) combine_kernel<true><<<grid, 128, 0, stream>>>(sys, sb, Wc, log_abs, phase, ke_re, ke_im, gx_abs, gx_phase);
+    else combine_kernel<false><<<grid, 128, 0, stream>>>(sys, sb, Wc, log_abs, phase, ke_re, ke_im, nullptr, nullptr);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -182,6 +182,23 @@ class HotPath:
                                           self._stream()))
         return unflatten_params(outs, len(self.hidden_dims))
 
+    def logpsi_grad_x(self, x, want_phase_grad: bool = False):
+        """(log|psi|, phase, d log|psi|/dx [, d phase/dx]) on the device: jax.value_and_grad of the slog network
+        w.r.t. the walker (qmc.py:325), from the first-derivative half of the forward-Laplacian sweep."""
+        t, one, on_dev = self._prep(x)
+        td = t if on_dev else t.to(self.tdev)
+        B = td.shape[0]
+        la = torch.empty(B, dtype=torch.float64, device=self.tdev)
+        ph = torch.empty_like(la)
+        ga = torch.empty(B, 3 * self.nelec, dtype=torch.float64, device=self.tdev)
+        gp = torch.empty_like(ga) if want_phase_grad else None
+        _lib.check(self.lib.ds_logpsi_grad_x(self.h, td.data_ptr(), B, la.data_ptr(), ph.data_ptr(), ga.data_ptr(),
+                                             gp.data_ptr() if gp is not None else None, self._stream()))
+        out = (la, ph, ga) + ((gp,) if want_phase_grad else ())
+        if not on_dev:
+            out = tuple(o.cpu() for o in out)
+        return tuple(o[0] for o in out) if one else out
+
     def orbitals(self, x):
         t, one, on_dev = self._prep(x)
         B = t.shape[0]
@@ -229,12 +246,33 @@ class HotPath:
             res = tuple(r.cpu() for r in res)
         return tuple(r[0] for r in res) if one else res
 
-    def mcmc(self, data, steps: int, width: float, seed: int = 0, xi=None, u=None, return_masks: bool = False):
-        """In-place-free Metropolis sweep: returns (new_data, n_accept tensor[1], masks or None)."""
+    def mcmc(self, data, steps: int, width: float, seed: int = 0, xi=None, u=None, return_masks: bool = False,
+             one_electron: bool = False):
+        """In-place-free Metropolis sweep: returns (new_data, n_accept tensor[1], masks or None).
+        ``one_electron``: steps * N single-electron moves (qmc.py:227-287, 355-358); noise shapes are then
+        xi (steps*N, batch, 3), u (steps*N, batch)."""
         t, one, on_dev = self._prep(data)
         if one:
             raise ValueError("mcmc_step needs batched walkers (batch, 3N)")
         B = t.shape[0]
+        if one_electron:
+            ns = steps * self.nelec
+            x = t.clone() if on_dev else t.to(self.tdev)
+            nacc = torch.zeros(1, dtype=torch.float64, device=self.tdev)
+            masks = torch.empty(ns, B, dtype=torch.uint8, device=self.tdev) if return_masks else None
+            xi_d = xi.to(self.tdev, torch.float64).contiguous() if xi is not None else None
+            u_d = u.to(self.tdev, torch.float64).contiguous() if u is not None else None
+            if xi_d is not None and tuple(xi_d.shape) != (ns, B, 3):
+                raise ValueError("xi must have shape (steps*N, batch, 3) for one-electron moves")
+            if u_d is not None and tuple(u_d.shape) != (ns, B):
+                raise ValueError("u must have shape (steps*N, batch) for one-electron moves")
+            _lib.check(self.lib.ds_mcmc_step_one_electron(
+                self.h, x.data_ptr(), B, int(steps), float(width), int(seed) & (2 ** 64 - 1),
+                xi_d.data_ptr() if xi_d is not None else None, u_d.data_ptr() if u_d is not None else None,
+                masks.data_ptr() if masks is not None else None, nacc.data_ptr(), self._stream()))
+            if not on_dev:
+                return x.cpu(), nacc.cpu(), (masks.cpu() if masks is not None else None)
+            return x, nacc, masks
         if on_dev:
             x = t.clone()
             nacc = torch.zeros(1, dtype=torch.float64, device=self.tdev)

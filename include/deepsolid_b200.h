@@ -124,6 +124,12 @@ DS_API int ds_logpsi_vjp(ds_ctx *ctx, const double *x_dev, int64_t batch, const 
                   const double *cot_phase_dev, double *const *grad_leaves, const int64_t *leaf_sizes, int n_leaves,
                   void *stream);
 
+/* jax.value_and_grad(slog_network, argnums=1), batched (the `func` importance_update receives, qmc.py:325,101-118):
+ * log|psi|, phase and d log|psi| / dx, d phase / dx of shape (batch, 3N).  Any output but one gradient may be NULL.
+ * The gradients are the first-derivative half of the forward-Laplacian sweep (same cost as ds_local_energy). */
+DS_API int ds_logpsi_grad_x(ds_ctx *ctx, const double *x_dev, int64_t batch, double *log_abs_dev, double *phase_dev,
+                     double *grad_abs_dev, double *grad_phase_dev, void *stream);
+
 /* method eval_mats (network.py:601-602): out = complex128 (re,im interleaved) of shape
  * (batch, 2 spins, n_det, n_s, n_s) with spin blocks concatenated (n_up block first). */
 DS_API int ds_orbitals(ds_ctx *ctx, const double *x_dev, int64_t batch, double *out_dev, void *stream);
@@ -161,6 +167,13 @@ DS_API int ds_energy_stats(ds_ctx *ctx, const double *ke_re_dev, const double *k
 DS_API int ds_logpsi_host(ds_ctx *ctx, const double *x_host, int64_t batch, double *log_abs_host, double *phase_host);
 DS_API int ds_local_energy_host(ds_ctx *ctx, const double *x_host, int64_t batch, int mode, int partition_number,
                          double *ke_re_host, double *ke_im_host, double *ewald_host);
+/* qmc.mh_one_electron_update (qmc.py:227-287) as driven by make_mcmc_step(one_electron_moves=True)
+ * (qmc.py:355-358): steps * N single-electron moves, move i displaces electron i % N and re-wraps the walker.
+ * xi_dev: optional gaussians (steps*N, batch, 3); u_dev, accept_dev: (steps*N, batch). */
+DS_API int ds_mcmc_step_one_electron(ds_ctx *ctx, double *x_dev, int64_t batch, int steps, double width, uint64_t seed,
+                              const double *xi_dev, const double *u_dev, uint8_t *accept_dev, double *n_accept_dev,
+                              void *stream);
+
 DS_API int ds_mcmc_step_host(ds_ctx *ctx, double *x_host, int64_t batch, int steps, double width, uint64_t seed,
                       const double *xi_host, const double *u_host, uint8_t *accept_host, double *n_accept_host);
 

@@ -634,3 +634,86 @@ def total_energy_value_and_grad(apply_phase_slog, el_fun, params, X, clip_local_
     n = len(X)
     grads = logpsi_vjp(apply_phase_slog, params, X, clip_diff.real / n, clip_diff.imag / n)
     return loss, e_l, grads
+
+
+# ---------------------------------------------------------------------------
+# qmc.py:63-150, 227-287 -- one-electron moves and importance sampling (caller-supplied noise)
+# ---------------------------------------------------------------------------
+def limdrift(g, cutoff=1.0):
+    """qmc.py:63-82."""
+    shape = g.shape
+    g3 = g.reshape(-1, 3)
+    tot = torch.linalg.norm(g3, dim=-1)
+    normalize = torch.clip(tot, min=cutoff, max=float(tot.max()) if tot.numel() else cutoff)
+    return (cutoff * g3 / normalize[:, None]).reshape(shape)
+
+
+def mh_one_electron_update(params, f_batch, x1, lp_1, num_accepts, latvec, stddev, xi3, u, i):
+    """qmc.py:227-287: move electron i % N of every walker by stddev * xi3 (B,3), re-wrap the configuration."""
+    n = x1.shape[0]
+    x = x1.reshape(n, -1, 3)
+    ii = i % x.shape[1]
+    x2 = x.clone()
+    x2[:, ii] = x2[:, ii] + stddev * xi3
+    x2, _ = enforce_pbc_batch(latvec, x2.reshape(n, -1))
+    lp_2 = 2.0 * f_batch(params, x2)
+    cond = (lp_2 - lp_1) > torch.log(u)
+    return torch.where(cond[..., None], x2, x1), torch.where(cond, lp_2, lp_1), num_accepts + cond.sum().to(DT), cond
+
+
+def make_mcmc_step_one_electron(batch_slog_network, batch_per_device, latvec, steps=10):
+    """qmc.py:355-358 with one_electron_moves=True; noise = (xi[steps*N,B,3], u[steps*N,B])."""
+    def mcmc_step(params, data, noise, width):
+        xi, u = noise
+        nelec = data.shape[-1] // 3
+        nsteps = nelec * steps
+        logprob = 2.0 * batch_slog_network(params, data)
+        n_acc = torch.zeros((), dtype=DT)
+        masks = []
+        for s in range(nsteps):
+            data, logprob, n_acc, cond = mh_one_electron_update(params, batch_slog_network, data, logprob, n_acc,
+                                                                latvec, width, xi[s], u[s], s)
+            masks.append(cond)
+        return data, n_acc / (nsteps * batch_per_device), torch.stack(masks)
+    return mcmc_step
+
+
+def value_and_grad_x(slog_apply, params, X):
+    """jax.vmap(jax.value_and_grad(slog_network, argnums=1)) (qmc.py:325)."""
+    vals, grads = [], []
+    for x in X:
+        xr = x.detach().clone().requires_grad_(True)
+        v = slog_apply(params, xr)
+        g, = torch.autograd.grad(v, xr)
+        vals.append(v.detach()); grads.append(g)
+    return torch.stack(vals), torch.stack(grads)
+
+
+def make_mcmc_step_importance(slog_apply, batch_per_device, latvec, steps=10):
+    """importance_update (qmc.py:83-150, atoms=None) driven by make_mcmc_step; noise = (xi[steps,B,3N], u[steps,B]).
+    The reference recomputes grad(x1) every step; it equals the stored gradient of the accepted configuration."""
+    def mcmc_step(params, data, noise, width):
+        xi, u = noise
+        x1 = data
+        lpsi, _ = value_and_grad_x(slog_apply, params, x1)
+        lp_1 = 2.0 * lpsi
+        n_acc = torch.zeros((), dtype=DT)
+        masks = []
+        for s in range(steps):
+            _, grad = value_and_grad_x(slog_apply, params, x1)
+            grad = limdrift(grad)
+            gauss = width * xi[s]
+            x2 = x1 + gauss + width ** 2 * grad
+            x2, _ = enforce_pbc_batch(latvec, x2)
+            lpsi_2, new_grad = value_and_grad_x(slog_apply, params, x2)
+            new_grad = limdrift(new_grad)
+            forward = (gauss ** 2).sum(-1)
+            backward = ((gauss + width ** 2 * (grad + new_grad)) ** 2).sum(-1)
+            lp_2 = 2.0 * lpsi_2 + (forward - backward) / (2.0 * width ** 2)
+            cond = (lp_2 - lp_1) > torch.log(u[s])
+            x1 = torch.where(cond[..., None], x2, x1)
+            lp_1 = torch.where(cond, lp_2, lp_1)
+            n_acc = n_acc + cond.sum()
+            masks.append(cond)
+        return x1, n_acc / (steps * batch_per_device), torch.stack(masks)
+    return mcmc_step
