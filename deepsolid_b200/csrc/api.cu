@@ -607,6 +607,10 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     DS_REQUIRE(nd->hidden_one >= 2 && nd->hidden_one % 2 == 0, "one-electron stream width must be even");
     DS_REQUIRE(nd->n_det >= 1, "need at least one determinant");
     DS_REQUIRE(sd->dist_kind >= 0 && sd->dist_kind <= 2, "dist_kind must be 0, 1 or 2");
+    DS_REQUIRE(nd->distance_type == 0 || nd->distance_type == 1, "Unrecognized distance function.");
+    DS_REQUIRE(((nd->distance_type == 1) ? 7 : 4) * (sd->n_atoms_prim + 2) <= 32,
+               "layer-0 operand rows wider than 32 columns are not supported (%d primitive-cell atoms with this distance_type)",
+               sd->n_atoms_prim);
     DS_REQUIRE(sd->n_g >= 0 && sd->n_atoms_sim > 0, "bad Ewald table sizes");
     DS_CUDA_CHECK(cudaSetDevice(device));
     ds_ctx* c = new ds_ctx();
@@ -618,7 +622,8 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     d.n_up = sd->n_up; d.n_dn = sd->n_dn; d.N = sd->n_up + sd->n_dn; d.A = sd->n_atoms_prim;
     d.H = nd->hidden_one; d.P = nd->hidden_two; d.D = nd->n_det; d.L = nd->n_layers;
     d.ND = 3 * d.N; d.NDp = (d.ND + 7) / 8 * 8; d.NDg = d.NDp + 8;
-    d.C0 = 4 * d.A; d.K0 = d.C0 + 8; d.K1 = d.H + 2 * d.P;
+    d.dist_type = nd->distance_type; d.F = (nd->distance_type == 1) ? 7 : 4;
+    d.C0 = d.F * d.A; d.K0 = d.C0 + 2 * d.F; d.K1 = d.H + 2 * d.P;
     fill_lattice(c->sys.prim, sd->prim_latvec, sd->prim_AV, sd->prim_BV);
     fill_lattice(c->sys.sim, sd->sim_latvec, sd->sim_AV, sd->sim_BV);
     memcpy(c->sys.atoms, sd->prim_atoms, sizeof(double) * 3 * d.A);
@@ -679,12 +684,12 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
     // expected sizes
     std::vector<int64_t> want;
     for (int l = 0; l < L; ++l) {
-        int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? 4 : P;
+        int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? d.F : P;
         want.push_back((int64_t)(3 * C + 2 * Pl) * H);
         want.push_back(H);
     }
     for (int l = 0; l < L - 1; ++l) {
-        want.push_back((int64_t)((l == 0) ? 4 : P) * P);
+        want.push_back((int64_t)((l == 0) ? d.F : P) * P);
         want.push_back(P);
     }
     for (int s = 0; s < 2; ++s) want.push_back((int64_t)H * 2 * c->npar[s]);
@@ -706,7 +711,7 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
     };
     int li = 0;
     for (int l = 0; l < L; ++l) {
-        const int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? 4 : P;
+        const int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? d.F : P;
         const std::vector<double>& W = h[li++];
         const std::vector<double>& b = h[li++];
         std::vector<double> am((size_t)(C + 2 * Pl) * H), gg((size_t)2 * C * H);
@@ -777,7 +782,7 @@ int prepare_grad(ds_ctx* c, cudaStream_t st) {
     const int L = d.L, H = d.H, P = d.P;
     auto need = [&](double** p, size_t n) -> int { if (!*p) return dev_alloc(c, p, n); return 0; };
     for (int l = 0; l < L; ++l) {
-        const int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? 4 : P, K = C + 2 * Pl;
+        const int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? d.F : P, K = C + 2 * Pl;
         if (int rc = need(&c->B_amT[l], (size_t)K * H)) return rc;
         if (int rc = need(&c->B_gT[l], (size_t)2 * C * H)) return rc;
         if (int rc = need(&c->gB_am[l], (size_t)K * H)) return rc;
@@ -792,7 +797,7 @@ int prepare_grad(ds_ctx* c, cudaStream_t st) {
         }
     }
     for (int l = 0; l < L - 1; ++l) {
-        const int pin = (l == 0) ? 4 : P;
+        const int pin = (l == 0) ? d.F : P;
         if (int rc = need(&c->gWp[l], (size_t)pin * P)) return rc;
         if (int rc = need(&c->gbp[l], (size_t)P)) return rc;
         DS_CUDA_CHECK(cudaMemsetAsync(c->gWp[l], 0, (size_t)pin * P * sizeof(double), st));
@@ -844,7 +849,7 @@ extern "C" int ds_logpsi_vjp(ds_ctx* c, const double* x, int64_t batch, const do
     // unpack into the leaf layout of the reference pytree
     int li = 0;
     for (int l = 0; l < L; ++l) {
-        const int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? 4 : P;
+        const int C = (l == 0) ? d.C0 : H, Pl = (l == 0) ? d.F : P;
         DS_REQUIRE(sizes[li] == (int64_t)(3 * C + 2 * Pl) * H && sizes[li + 1] == H, "gradient leaf %d has the wrong size", li);
         double* w = grads[li++];
         double* b = grads[li++];
@@ -855,7 +860,7 @@ extern "C" int ds_logpsi_vjp(ds_ctx* c, const double* x, int64_t batch, const do
         DS_CUDA_CHECK(cudaMemcpyAsync(b, c->gbias1[l], (size_t)H * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     for (int l = 0; l < L - 1; ++l) {
-        const int pin = (l == 0) ? 4 : P;
+        const int pin = (l == 0) ? d.F : P;
         DS_REQUIRE(sizes[li] == (int64_t)pin * P && sizes[li + 1] == P, "gradient leaf %d has the wrong size", li);
         DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->gWp[l], (size_t)pin * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
         DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->gbp[l], (size_t)P * sizeof(double), cudaMemcpyDeviceToDevice, st));

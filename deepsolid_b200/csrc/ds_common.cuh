@@ -25,7 +25,9 @@ struct DsDims {
     int A;                  // atoms in the primitive cell (network features)
     int H, P, D, L;         // stream widths, determinants, layers
     int ND, NDp, NDg;       // 3N, padded to a multiple of 8, NDp+8 (rows of the shared-mean matrix)
-    int C0, K0;             // 4A, 4A+8 (layer-0 one-electron inputs, own + pair-mean)
+    int F;                  // features per electron-atom / electron-electron pair: 4 ('nu') or 7 ('tri')
+    int dist_type;          // 0 = nu_distance (network.py:189-224), 1 = tri_distance (network.py:227-246)
+    int C0, K0;             // F*A, F*A + 2F (layer-0 one-electron inputs, own + pair-mean)
     int K1;                 // H + 2P  (own + pair-mean columns of layers >= 1)
 };
 
@@ -146,6 +148,61 @@ __host__ __device__ __forceinline__ void ds_nu_distance(const DsLattice& L, cons
     if (JETS) out[0] = jet_chain(sd2, sd, 0.5 / sd, -0.25 / (sd * sd * sd));
     else out[0] = jet_const(sd);
     out[1] = rel[0]; out[2] = rel[1]; out[3] = rel[2];
+}
+
+// network.tri_distance (network.py:227-246): w = d.BV^T, rel = [sum_l sin(w_l) AV_l, sum_l cos(w_l) AV_l] (6),
+// sd^2 = sum_{lm} (AV_l.AV_m) [ (1-cos w_l)(1-cos w_m) + sin w_l sin w_m ].  out[0] = sd, out[1..6] = rel.
+template <bool JETS>
+__host__ __device__ __forceinline__ void ds_tri_distance(const DsLattice& L, const double d[3], Jet out[7]) {
+    Jet sj[3], cj[3];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const double w = d[0] * L.BV[l * 3 + 0] + d[1] * L.BV[l * 3 + 1] + d[2] * L.BV[l * 3 + 2];
+        double sn, cs;
+        sincos(w, &sn, &cs);
+        if (JETS) {
+            Jet wj{w, L.BV[l * 3 + 0], L.BV[l * 3 + 1], L.BV[l * 3 + 2], 0.0};
+            sj[l] = jet_chain(wj, sn, cs, -sn);
+            cj[l] = jet_chain(wj, cs, -sn, -cs);
+        } else {
+            sj[l] = jet_const(sn);
+            cj[l] = jet_const(cs);
+        }
+    }
+    Jet sd2 = jet_const(0.0);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) out[1 + j] = jet_const(0.0);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        Jet oml = jet_const(1.0);
+        jet_axpy(oml, -1.0, cj[l]);                                  // 1 - cos w_l
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            Jet omm = jet_const(1.0);
+            jet_axpy(omm, -1.0, cj[m]);
+            if (JETS) {
+                jet_axpy(sd2, L.metric[l * 3 + m], jet_mul(oml, omm));
+                jet_axpy(sd2, L.metric[l * 3 + m], jet_mul(sj[l], sj[m]));
+            } else {
+                sd2.v += L.metric[l * 3 + m] * (oml.v * omm.v + sj[l].v * sj[m].v);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (JETS) { jet_axpy(out[1 + j], L.AV[l * 3 + j], sj[l]); jet_axpy(out[4 + j], L.AV[l * 3 + j], cj[l]); }
+            else { out[1 + j].v += L.AV[l * 3 + j] * sj[l].v; out[4 + j].v += L.AV[l * 3 + j] * cj[l].v; }
+        }
+    }
+    const double sd = sqrt(sd2.v);
+    if (JETS) out[0] = jet_chain(sd2, sd, 0.5 / sd, -0.25 / (sd * sd * sd));
+    else out[0] = jet_const(sd);
+}
+
+// distance features of one displacement: returns nothing, fills out[0..F-1] (F = 4 or 7)
+template <bool JETS>
+__host__ __device__ __forceinline__ void ds_distance(int dist_type, const DsLattice& L, const double d[3], Jet out[7]) {
+    if (dist_type == 1) ds_tri_distance<JETS>(L, d, out);
+    else ds_nu_distance<JETS>(L, d, out);
 }
 
 // ---------------------------------------------------------------------------

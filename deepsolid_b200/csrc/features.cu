@@ -14,15 +14,22 @@ namespace {
 
 constexpr int FEAT_THREADS = 256;
 
-__device__ __forceinline__ Jet pick4(const Jet f[4], int q) {
-    return (q == 0) ? f[0] : (q == 1) ? f[1] : (q == 2) ? f[2] : f[3];
+template <int FT>
+__device__ __forceinline__ Jet pick4(const Jet (&f)[FT], int q) {    // f[q] without a dynamically indexed register array
+    Jet r = f[0];
+#pragma unroll
+    for (int t = 1; t < FT; ++t)
+        if (q == t) r = f[t];
+    return r;
 }
 
-template <bool JETS>
+// FT = features per pair: 4 (nu_distance) or 7 (tri_distance)
+template <bool JETS, int FT>
 __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const DsSys sys, const FeatParams fp) {
     const DsDims& dm = sys.d;
     const int N = dm.N, A = dm.A, P = dm.P, L = dm.L, C0 = dm.C0, K0 = dm.K0, K1 = dm.K1, H = dm.H;
     const int NDp = dm.NDp, ND = dm.ND;
+    constexpr int F = FT;
     const long long e = blockIdx.x;             // w*N + i
     const int w = (int)(e / N), i = (int)(e % N);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -42,7 +49,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
     {   // stage pair-stream weights
         int off = 0;
         for (int l = 0; l < L - 1; ++l) {
-            int pin = (l == 0) ? 4 : P;
+            int pin = (l == 0) ? F : P;
             for (int t = tid; t < pin * P; t += blockDim.x) wsm[off + t] = fp.Wp[l][t];
             for (int t = tid; t < P; t += blockDim.x) wsm[off + pin * P + t] = fp.bp[l][t];
             off += pin * P + P;
@@ -55,17 +62,18 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
         double xi[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]}, px[3], d[3];
         ds_wrap(sys.prim, xi, px);
         for (int k = 0; k < 3; ++k) d[k] = px[k] - sys.atoms[3 * tid + k];
-        Jet f[4];
-        ds_nu_distance<JETS>(sys.prim, d, f);
+        Jet f[FT];
+        if (FT == 7) ds_tri_distance<JETS>(sys.prim, d, f);
+        else ds_nu_distance<JETS>(sys.prim, d, f);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            fp.A0V[e * K0 + tid * 4 + q] = f[q].v;
+        for (int q = 0; q < FT; ++q) {
+            fp.A0V[e * K0 + tid * F + q] = f[q].v;
             if (JETS) {
-                fp.A0L[e * K0 + tid * 4 + q] = f[q].l;
+                fp.A0L[e * K0 + tid * F + q] = f[q].l;
                 long long r = e * NDp + 3 * i;
-                fp.A0J[(r + 0) * K0 + tid * 4 + q] = f[q].g0;
-                fp.A0J[(r + 1) * K0 + tid * 4 + q] = f[q].g1;
-                fp.A0J[(r + 2) * K0 + tid * 4 + q] = f[q].g2;
+                fp.A0J[(r + 0) * K0 + tid * F + q] = f[q].g0;
+                fp.A0J[(r + 1) * K0 + tid * F + q] = f[q].g1;
+                fp.A0J[(r + 2) * K0 + tid * F + q] = f[q].g2;
             }
         }
         double* ra = fp.RAE + (e * A + tid) * 5;
@@ -87,20 +95,21 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
     for (int j = jbeg + warp; j < jend; j += nwarps) {
         double d[3];
         for (int k = 0; k < 3; ++k) d[k] = sx[3 * j + k] - sx[3 * i + k] + (j == i ? 1.0 : 0.0);
-        Jet f[4];
-        ds_nu_distance<JETS>(sys.sim, d, f);
+        Jet f[FT];
+        if (FT == 7) ds_tri_distance<JETS>(sys.sim, d, f);
+        else ds_nu_distance<JETS>(sys.sim, d, f);
         if (j == i) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) f[q] = jet_const(0.0);
+            for (int q = 0; q < FT; ++q) f[q] = jet_const(0.0);
         }
         Jet cur = jet_const(0.0);
-        if (lane < 4) cur = pick4(f, lane);
+        if (lane < F) cur = pick4(f, lane);
         const long long rj = e * NDp + 3 * j;      // Jacobian rows of directions (j, c)
         int woff = 0;
 #pragma unroll
         for (int l = 0; l < DS_MAX_LAYERS; ++l) {
             if (l >= L) break;
-            const int Pl = (l == 0) ? 4 : P;
+            const int Pl = (l == 0) ? F : P;
             // accumulate spin-channel sums of level l
             if (lane < Pl) {
                 acc[l][0] += cur.v;
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
                     if (lane < K0) {
                         double v0 = 0.0, v1 = 0.0, v2 = 0.0;
                         if (lane >= C0) {
-                            int s = (lane - C0) >> 2, q = (lane - C0) & 3;
+                            int s = (lane - C0) / F, q = (lane - C0) - s * F;
                             Jet fq = pick4(f, q);
                             if (s == sj) { v0 = fq.g0 * invn; v1 = fq.g1 * invn; v2 = fq.g2 * invn; }
                         }
@@ -174,7 +183,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
 #pragma unroll
     for (int l = 0; l < DS_MAX_LAYERS; ++l) {
         if (l >= L) break;
-        const int Pl = (l == 0) ? 4 : P;
+        const int Pl = (l == 0) ? F : P;
         for (int t = tid; t < 64; t += blockDim.x) {
             const int lane_c = t & 31, s = t >> 5;
             if (lane_c >= Pl) continue;
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
             const double invn = s ? inv_dn : inv_up;
             const long long r = e * NDp + 3 * i;
             if (l == 0) {
-                long long col = C0 + s * 4 + lane_c;
+                long long col = C0 + s * F + lane_c;
                 fp.A0V[e * K0 + col] = sv[0] * invn;
                 if (JETS) {
                     fp.A0L[e * K0 + col] = 2.0 * sv[4 * 32] * invn;
@@ -220,16 +229,19 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
 
 size_t ds_features_smem(const DsDims& d) {
     size_t n = 3 * d.N + 2 * d.L * 5 * 32;
-    for (int l = 0; l < d.L - 1; ++l) n += ((l == 0) ? 4 : d.P) * d.P + d.P;
+    for (int l = 0; l < d.L - 1; ++l) n += ((l == 0) ? d.F : d.P) * d.P + d.P;
     return n * sizeof(double);
 }
 
 int ds_launch_features(const DsSys& sys, const FeatParams& fp, int Wc, bool jets, cudaStream_t stream) {
     size_t smem = ds_features_smem(sys.d);
     dim3 grid((unsigned)((long long)Wc * sys.d.N));
+    const bool tri = sys.d.F == 7;
     if (smem > 48 * 1024) {
-        DS_CUDA_CHECK(cudaFuncSetAttribute(features_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DS_CUDA_CHECK(cudaFuncSetAttribute(features_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DS_CUDA_CHECK(cudaFuncSetAttribute(features_pair_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DS_CUDA_CHECK(cudaFuncSetAttribute(features_pair_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DS_CUDA_CHECK(cudaFuncSetAttribute(features_pair_kernel<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DS_CUDA_CHECK(cudaFuncSetAttribute(features_pair_kernel<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     // warps per CTA: a warp owns one partner j at a time, one spin channel after the other; 4 or 8 warps
     // (whole warps per SM sub-partition, 128 registers each), whichever wastes fewer warp-rounds
@@ -241,8 +253,13 @@ int ds_launch_features(const DsSys& sys, const FeatParams& fp, int Wc, bool jets
         if (eff > best_eff + 1e-9) { best_eff = eff; best_w = w; }
     }
     const int threads = jets ? 32 * best_w : FEAT_THREADS;
-    if (jets) features_pair_kernel<true><<<grid, threads, smem, stream>>>(sys, fp);
-    else features_pair_kernel<false><<<grid, threads, smem, stream>>>(sys, fp);
+    if (jets) {
+        if (tri) features_pair_kernel<true, 7><<<grid, threads, smem, stream>>>(sys, fp);
+        else features_pair_kernel<true, 4><<<grid, threads, smem, stream>>>(sys, fp);
+    } else {
+        if (tri) features_pair_kernel<false, 7><<<grid, threads, smem, stream>>>(sys, fp);
+        else features_pair_kernel<false, 4><<<grid, threads, smem, stream>>>(sys, fp);
+    }
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

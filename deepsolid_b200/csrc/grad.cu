@@ -127,7 +127,7 @@ constexpr int PG_THREADS = 256;
 
 __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, const FeatParams fp, const GradBufs gb) {
     const DsDims& dm = sys.d;
-    const int N = dm.N, P = dm.P, L = dm.L;
+    const int N = dm.N, P = dm.P, L = dm.L, F = dm.F;
     const long long e = blockIdx.x;
     const int w = (int)(e / N), i = (int)(e % N);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
     {
         int off = 0;
         for (int l = 0; l < L - 1; ++l) {
-            const int pin = (l == 0) ? 4 : P;
+            const int pin = (l == 0) ? F : P;
             woff[l] = off;
             for (int t = tid; t < pin * P; t += blockDim.x) {
                 const double v = fp.Wp[l][t];
@@ -163,9 +163,9 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
     __syncthreads();
 
     // per-lane gradient accumulators: column `lane` of every pair-layer weight and bias
-    double gW0[4], gW[DS_MAX_LAYERS - 2 > 0 ? DS_MAX_LAYERS - 2 : 1][32], gB[DS_MAX_LAYERS];
+    double gW0[7], gW[DS_MAX_LAYERS - 2 > 0 ? DS_MAX_LAYERS - 2 : 1][32], gB[DS_MAX_LAYERS];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) gW0[q] = 0.0;
+    for (int q = 0; q < 7; ++q) gW0[q] = 0.0;
 #pragma unroll
     for (int l = 0; l < DS_MAX_LAYERS - 2; ++l)
 #pragma unroll
@@ -179,15 +179,17 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
         const double invn = sj ? inv_dn : inv_up;
         double d[3];
         for (int k = 0; k < 3; ++k) d[k] = sx[3 * j + k] - sx[3 * i + k] + (j == i ? 1.0 : 0.0);
-        Jet f[4];
-        ds_nu_distance<false>(sys.sim, d, f);
+        Jet f[7];
+        ds_distance<false>(dm.dist_type, sys.sim, d, f);
         double cur[DS_MAX_LAYERS], tv[DS_MAX_LAYERS];       // level values and tanh outputs of this lane's channel
         cur[0] = 0.0;
-        if (j != i && lane < 4) cur[0] = (lane == 0) ? f[0].v : (lane == 1) ? f[1].v : (lane == 2) ? f[2].v : f[3].v;
+        if (j != i && lane < F)
+            cur[0] = (lane == 0) ? f[0].v : (lane == 1) ? f[1].v : (lane == 2) ? f[2].v : (lane == 3) ? f[3].v
+                   : (lane == 4) ? f[4].v : (lane == 5) ? f[5].v : f[6].v;
 #pragma unroll
         for (int l = 0; l < DS_MAX_LAYERS - 1; ++l) {
             if (l >= L - 1) break;
-            const int pin = (l == 0) ? 4 : P;
+            const int pin = (l == 0) ? F : P;
             const double* W = wsm + woff[l];
             double z = (lane < P) ? W[pin * P + lane] : 0.0;
             for (int c = 0; c < pin; ++c) {
@@ -212,14 +214,14 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
         for (int lv = DS_MAX_LAYERS - 1; lv >= 1; --lv) {
             if (lv > L - 1) continue;
             const int l = lv - 1;                            // pair layer that produced level lv
-            const int pin = (l == 0) ? 4 : P;
+            const int pin = (l == 0) ? F : P;
             const bool res = (l >= 1);
             const double gt = res ? g[lv] * rs2 : g[lv];
             const double gz = (lane < P) ? gt * (1.0 - tv[lv] * tv[lv]) : 0.0;
             gB[l] += gz;
             if (l == 0) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) gW0[c] = fma(__shfl_sync(0xffffffffu, cur[0], c), gz, gW0[c]);
+                for (int c = 0; c < 7; ++c) gW0[c] = fma(__shfl_sync(0xffffffffu, cur[0], c), gz, gW0[c]);      // cur[0] = 0 beyond F
             } else {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -252,7 +254,8 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
     };
     if (L > 1) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) reduce_and_add(gW0[c], gb.g_Wp[0] + c * P + lane, lane < P);
+        for (int c = 0; c < 7; ++c)
+            if (c < F) reduce_and_add(gW0[c], gb.g_Wp[0] + c * P + lane, lane < P);
         reduce_and_add(gB[0], gb.g_bp[0] + lane, lane < P);
     }
 #pragma unroll
@@ -308,7 +311,7 @@ int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& 
     if (d.L < 2) return 0;
     DS_REQUIRE(d.P <= 32, "pair-stream gradient kernel needs hidden_two <= 32");
     size_t n = 3 * d.N;
-    for (int l = 0; l < d.L - 1; ++l) n += 2 * ((l == 0) ? 4 : d.P) * d.P + d.P;
+    for (int l = 0; l < d.L - 1; ++l) n += 2 * ((l == 0) ? d.F : d.P) * d.P + d.P;
     n += (PG_THREADS / 32) * 33;
     const size_t smem = n * sizeof(double);
     if (smem > 48 * 1024)

@@ -53,7 +53,7 @@ def unflatten_params(leaves, n_layers: int) -> dict:
 
 class HotPath:
     def __init__(self, simulation_cell, klist, hidden_dims=((256, 32),) * 3, determinants: int = 8,
-                 device: Optional[int] = None):
+                 device: Optional[int] = None, distance_type: str = "nu"):
         if not torch.cuda.is_available():
             raise RuntimeError("deepsolid_b200 needs a CUDA device: the local-energy hot path has no CPU fallback")
         self.lib = _lib.load()
@@ -66,6 +66,9 @@ class HotPath:
             raise ValueError("the CUDA hot path needs equal widths in every layer of hidden_dims")
         self.hidden_dims = hidden_dims
         self.determinants = int(determinants)
+        if distance_type not in ("nu", "tri"):
+            raise ValueError("Unrecognized distance function.")
+        self.distance_type = distance_type
         self.n_up, self.n_dn = simulation_cell.nelec
         self.nelec = self.n_up + self.n_dn
         tb = build_ewald_tables(simulation_cell)
@@ -91,7 +94,7 @@ class HotPath:
             ion_exp_re=_ptr(keep[15]), ion_exp_im=_ptr(keep[16]),
             ee_const=float(tb.ee_const(ne)), ei_const=float(tb.ei_const(ne)), ii_total=float(tb.ii_total))
         nd = _lib.NetDesc(n_layers=len(hidden_dims), hidden_one=hidden_dims[0][0], hidden_two=hidden_dims[0][1],
-                          n_det=self.determinants)
+                          n_det=self.determinants, distance_type=1 if distance_type == "tri" else 0)
         h = C.c_void_p()
         _lib.check(self.lib.ds_ctx_create(C.byref(sd), C.byref(nd), self.device, C.byref(h)))
         self.h = h

@@ -81,8 +81,8 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
                          device: Optional[int] = None, hotpath: Optional[HotPath] = None):
     """network.py:609-667.  The signature defaults are the reference's; the CUDA path
     implements the configuration the reference actually runs (base_config.py:129-139):
-    envelope_type='isotropic', full_det=False, use_last_layer=False, bias_orbitals=False,
-    distance_type='nu'.  Anything else raises ValueError at construction."""
+    envelope_type='isotropic', full_det=False, use_last_layer=False, bias_orbitals=False, with either
+    distance_type ('nu' or 'tri').  Anything else raises ValueError at construction."""
     if method_name not in _METHODS:
         raise ValueError("Method name is not in class dir.")
     if distance_type not in ("nu", "tri"):
@@ -96,12 +96,10 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
         unsupported.append("use_last_layer=True")
     if bias_orbitals:
         unsupported.append("bias_orbitals=True")
-    if distance_type != "nu":
-        unsupported.append(f"distance_type={distance_type!r}")
     if unsupported:
         raise ValueError("not implemented in the CUDA hot path: " + ", ".join(unsupported) +
                          " (the reference's tested defaults are isotropic / full_det=False / "
-                         "use_last_layer=False / bias_orbitals=False / nu)")
+                         "use_last_layer=False / bias_orbitals=False)")
     if simulation_cell is None or klist is None:
         raise ValueError("simulation_cell and klist are required")
 
@@ -110,7 +108,7 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
     def _hp() -> HotPath:
         if state["hp"] is None:
             state["hp"] = HotPath(simulation_cell, klist, hidden_dims=hidden_dims, determinants=determinants,
-                                  device=device)
+                                  device=device, distance_type=distance_type)
         return state["hp"]
 
     def init(key, data=None):

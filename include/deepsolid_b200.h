@@ -79,14 +79,15 @@ typedef struct ds_system_desc {
     double ee_const, ei_const, ii_total;   /* ewaldsum.py:109-113,188-190              */
 } ds_system_desc;
 
-/* Network hyper-parameters (base_config.py:129-139).  Only the reference's tested
- * defaults for the structural switches are implemented: envelope_type='isotropic',
- * full_det=False, use_last_layer=False, bias_orbitals=False, distance_type='nu'. */
+/* Network hyper-parameters (base_config.py:129-139).  Of the structural switches the
+ * reference's tested defaults are implemented (envelope_type='isotropic', full_det=False,
+ * use_last_layer=False, bias_orbitals=False) plus both distance functions. */
 typedef struct ds_net_desc {
-    int32_t n_layers;     /* len(hidden_dims)            (3)   */
-    int32_t hidden_one;   /* one-electron stream width   (256) */
-    int32_t hidden_two;   /* two-electron stream width   (32)  */
-    int32_t n_det;        /* determinants                (8)   */
+    int32_t n_layers;      /* len(hidden_dims)            (3)   */
+    int32_t hidden_one;    /* one-electron stream width   (256) */
+    int32_t hidden_two;    /* two-electron stream width   (32)  */
+    int32_t n_det;         /* determinants                (8)   */
+    int32_t distance_type; /* 0 = 'nu' (network.py:189-224, 4 features per pair), 1 = 'tri' (network.py:227-246, 7) */
 } ds_net_desc;
 
 DS_API const char *ds_last_error(void);

@@ -1,0 +1,80 @@
+"""Secondary structural variants on the same kernels: the `tri` distance features
+(network.py:227-246; 7 features per electron-atom / electron-electron pair).  Same tolerances as the default path."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import angle_diff
+from deepsolid_b200 import cell as C
+from oracle import deepsolid_oracle as O
+
+
+def _setup(name):
+    sc = C.build_system(name)
+    kl = C.make_klist(sc)
+    pn = O.init_params(np.random.default_rng(888), sc.original_cell.natm, sc.nelec, distance_type="tri")
+    return sc, kl, O.params_to_torch(pn)
+
+
+def test_oracle_tri_features_are_periodic_and_shaped():
+    sc, kl, P = _setup("graphene8")
+    assert P["single"][0]["w"].shape[0] == 3 * 7 * sc.original_cell.natm + 2 * 7
+    assert P["double"][0]["w"].shape[0] == 7
+    f = O.make_solid_fermi_net(kl, sc, distance_type="tri", method_name="eval_slogdet")
+    x = torch.as_tensor(C.init_walkers(sc, 1, seed=3))[0]
+    shift = torch.as_tensor(sc.lattice_vectors())[0].repeat(sum(sc.nelec))
+    assert abs(float(f(P, x)) - float(f(P, x + shift))) < 1e-10          # periodic under a supercell lattice vector
+
+
+def test_unknown_distance_raises():
+    from deepsolid_b200 import network
+    sc, kl, P = _setup("h4")
+    with pytest.raises(ValueError):
+        network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc,
+                                     determinants=8, distance_type="cubic")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["h4", "graphene8", "lih_prim"])
+def test_gpu_tri_distance_matches_oracle(name):
+    from deepsolid_b200 import network, hamiltonian, qmc
+    sc, kl, P = _setup(name)
+    dev = torch.device("cuda", 0)
+    kw = dict(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc, determinants=8, distance_type="tri")
+    ld = network.make_solid_fermi_net(method_name="eval_logdet", **kw)
+    hp = ld.apply.hotpath()
+    sl = network.make_solid_fermi_net(method_name="eval_slogdet", hotpath=hp, **kw)
+    nw = 3
+    X = torch.as_tensor(C.init_walkers(sc, nw, seed=17))
+    f_ld = O.make_solid_fermi_net(kl, sc, distance_type="tri", method_name="eval_logdet")
+    f_ps = O.make_solid_fermi_net(kl, sc, distance_type="tri", method_name="eval_phase_and_slogdet")
+    f_sl = O.make_solid_fermi_net(kl, sc, distance_type="tri", method_name="eval_slogdet")
+    v = ld.apply(P, X.to(dev)).cpu()
+    vo = torch.stack([f_ld(P, x) for x in X])
+    assert float((v.real - vo.real).abs().max()) < 1e-10
+    assert float(angle_diff(v.imag, vo.imag).max()) < 1e-10
+    el = hamiltonian.local_energy_seperate(ld.apply, sc, mode="for")
+    ke, ew = el(P, X.to(dev))
+    elo = O.local_energy_seperate(f_ld, sc, mode="dim_batch")
+    for b in range(nw):
+        ko, eo = elo(P, X[b])
+        assert abs(complex(ko) - complex(ke[b].cpu())) < 1e-8
+        assert abs(float(eo) - float(ew[b])) < 1e-9
+    # parameter gradient
+    rng = np.random.default_rng(1)
+    ca, cp = torch.as_tensor(rng.standard_normal(nw)), torch.as_tensor(rng.standard_normal(nw))
+    g = hp.logpsi_vjp(X.to(dev), ca, cp)
+    go = O.logpsi_vjp(f_ps, P, X, ca, cp)
+    for a, b in zip(O._leaves(g), O._leaves(go)):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert float((a.cpu() - b).abs().max()) < 1e-9 * max(1.0, float(b.abs().max()))
+    # Metropolis accept masks
+    B, steps = 4, 3
+    Xm = torch.as_tensor(C.init_walkers(sc, B, seed=5))
+    gen = torch.Generator().manual_seed(2)
+    xi = torch.randn(steps, B, Xm.shape[1], dtype=torch.float64, generator=gen)
+    u = torch.rand(steps, B, dtype=torch.float64, generator=gen)
+    lat = torch.as_tensor(sc.lattice_vectors())
+    xn, pm, masks = qmc.make_mcmc_step(sl.apply, B, lat, steps=steps)(P, Xm.to(dev), (xi, u), 0.3, return_masks=True)
+    xo, po, mo = O.make_mcmc_step(lambda p, x: O.batch_apply(f_sl, p, x), B, lat, steps=steps)(P, Xm, (xi, u), 0.3)
+    assert torch.equal(masks.cpu().bool(), mo)
