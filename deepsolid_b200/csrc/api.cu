@@ -76,6 +76,9 @@ struct ds_ctx {
     // int8 digits of the transposed weights for the tcgen05 path (ozaki.cuh): [N][OZ_S][K] + scales [N]
     signed char* Wd_am[DS_MAX_LAYERS] = {};
     double* sb_am[DS_MAX_LAYERS] = {};
+    signed char* Wd_g[DS_MAX_LAYERS] = {};   // spin-mean block B_g (layers >= 1, K = 2H)
+    double* sb_g[DS_MAX_LAYERS] = {};
+    bool use_i8_means = true;                // shared-mean GEMM GOUT = GIN.B_g on the int8 path as well
     signed char* Wd_orb[2] = {};
     double* sb_orb[2] = {};
     bool use_i8 = true;                 // Jacobian-sweep GEMMs on tcgen05 (false: fp64 DMMA kernels)
@@ -199,6 +202,7 @@ struct Layout {
     double *MAT[2], *LAPM[2], *DA[2];
     double *LOGDET, *TAU, *TRSQ, *TRLAP;
     double *AD, *SA;        // int8 digits of the current Jacobian operand (as bytes) and its row scales
+    double *GD, *GS;        // digits and scales of the spin-mean rows GIN (shared-mean GEMM on the int8 path)
     // parameter-gradient path: per-layer activations kept by the forward, cotangent buffers of the reverse sweep
     bool grad;
     double *Tl[DS_MAX_LAYERS], *GINV[DS_MAX_LAYERS];
@@ -249,6 +253,8 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
     const bool i8 = lap && c->use_i8 && c->i8_ok;
     L.AD = i8 ? ws.take("AD", (W * N * d.NDp * OZ_S * d.K1 + 7) / 8) : nullptr;
     L.SA = i8 ? ws.take("SA", W * N * d.NDp) : nullptr;
+    L.GD = i8 ? ws.take("GD", (W * d.NDg * OZ_S * 2 * d.H + 7) / 8) : nullptr;
+    L.GS = i8 ? ws.take("GS", W * d.NDg) : nullptr;
     if (grad) {
         static const char* tn[] = {"T0", "T1", "T2", "T3"};
         static const char* gn[] = {"GINV0", "GINV1", "GINV2", "GINV3"};
@@ -359,7 +365,18 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
                 g.A = Lo.GIN + (size_t)d.NDp * 2 * C; g.lda = d.NDg * 2 * C; g.M = Wc;
                 g.C = Lo.GOUT + (size_t)d.NDp * H; g.ldc = d.NDg * H;
             }
-            if (int rc = gemm(c, g, GEMM_PLAIN, false, st)) return rc;
+            if (lap && i8_layer && c->use_i8_means && c->Wd_g[l]) {
+                // the same contraction as exact int8 slices (K = 2H): digits of the mean rows, then the tcgen05 GEMM;
+                // AD/SA are free here (the layer's own digits are only formed after this point when not fused) --
+                // with the fused digit+means pass they are already in use, so the mean digits go to a separate area
+                const long long rows = (long long)Wc * d.NDg;
+                if (int rc = ds_launch_slice_rows(Lo.GIN, 2 * C, rows, 2 * C, reinterpret_cast<signed char*>(Lo.GD), Lo.GS, st)) return rc;
+                OzParams z{};
+                z.Ad = reinterpret_cast<signed char*>(Lo.GD); z.sa = Lo.GS; z.rpg = rows; z.gstride = rows; z.goff = 0; z.n_groups = 1;
+                z.Wd = c->Wd_g[l]; z.sb = c->sb_g[l]; z.N = H; z.K = 2 * C; z.C = Lo.GOUT; z.ldc = H;
+                if (int rc = ds_launch_oz_gemm(z, OZ_PLAIN, false, st)) return rc;
+                c->launches += 2;
+            } else if (int rc = gemm(c, g, GEMM_PLAIN, false, st)) return rc;
         }
         if (grad)   // value rows of the spin means of this layer: operand of the mean-block weight gradient
             DS_CUDA_CHECK(cudaMemcpy2DAsync(Lo.GINV[l], (size_t)2 * C * sizeof(double), Lo.GIN + (size_t)d.NDp * 2 * C,
@@ -618,6 +635,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     if (const char* ev = getenv("DS_NO_I8")) c->use_i8 = atoi(ev) == 0;
     if (const char* ev = getenv("DS_L0_GEMM")) c->use_l0_kernel = atoi(ev) == 0;
     if (const char* ev = getenv("DS_NO_SLICE_MEANS")) c->use_slice_means = atoi(ev) == 0;
+    if (const char* ev = getenv("DS_NO_I8_MEANS")) c->use_i8_means = atoi(ev) == 0;
     DsDims& d = c->sys.d;
     d.n_up = sd->n_up; d.n_dn = sd->n_dn; d.N = sd->n_up + sd->n_dn; d.A = sd->n_atoms_prim;
     d.H = nd->hidden_one; d.P = nd->hidden_two; d.D = nd->n_det; d.L = nd->n_layers;
@@ -760,6 +778,9 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
         if (c->i8_ok) {
             for (int l = 1; l < L; ++l)
                 if (int rc = digits(c->B_am[l], d.K1, H, &c->Wd_am[l], &c->sb_am[l])) return rc;
+            if (2 * H <= 512 && (2 * H) % OZ_BK == 0)
+                for (int l = 1; l < L; ++l)
+                    if (int rc = digits(c->B_g[l], 2 * H, H, &c->Wd_g[l], &c->sb_g[l])) return rc;
             for (int s = 0; s < 2; ++s)
                 if (int rc = digits(c->Worb[s], H, 2 * c->npar[s], &c->Wd_orb[s], &c->sb_orb[s])) return rc;
         }
