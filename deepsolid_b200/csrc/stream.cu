@@ -6,6 +6,7 @@
 //   GOUT[w,d,:] = GIN[w,d,:] . W[C:3C]   with   GIN[w,d,s*C+c] = mean_{i in s} J[(w,i,d), c].
 // Rows d = NDp / NDp+1 of GIN carry the value / Laplacian means.
 #include "kernels.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -110,6 +111,71 @@ __global__ void __launch_bounds__(256) l0_jac_kernel(DsDims dm, const double* __
     }
 }
 
+// Two channels (n, n + H/2) per thread for the common K0 = 16 case: the operand row of a direction is read from
+// shared memory once for both, which halves the per-output instruction count of this instruction-bound stream.
+__global__ void __launch_bounds__(128) l0_jac2_kernel(DsDims dm, const double* __restrict__ A0J,
+                                                      const double* __restrict__ B, const double* __restrict__ G, int ldg,
+                                                      const double* __restrict__ T, int ldt, double* __restrict__ S,
+                                                      double* __restrict__ OJ, int ldc) {
+    constexpr int KT = 16;
+    extern __shared__ __align__(16) double l0_sm[];          // [NDp][16]
+    const int H = dm.H, NDp = dm.NDp, H2 = dm.H >> 1;
+    const long long e = blockIdx.x;
+    const int w = (int)(e / dm.N), i = (int)(e - (long long)w * dm.N);
+    {
+        const double2* src = reinterpret_cast<const double2*>(A0J + e * (long long)NDp * KT);
+        double2* dst = reinterpret_cast<double2*>(l0_sm);
+        for (int t = threadIdx.x; t < NDp * KT / 2; t += blockDim.x) dst[t] = src[t];
+    }
+    __syncthreads();
+    const double* g0 = G + (long long)w * dm.NDg * ldg;
+    double* o0 = OJ + e * (long long)NDp * ldc;
+    for (int n = threadIdx.x; n < H2; n += blockDim.x) {
+        const int n1 = n + H2;
+        double wa[KT], wb[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { wa[k] = B[(long long)k * H + n]; wb[k] = B[(long long)k * H + n1]; }
+        const double ta = T[e * (long long)ldt + n], tb = T[e * (long long)ldt + n1];
+        const double da = 1.0 - ta * ta, db_ = 1.0 - tb * tb;
+        double sa = 0.0, sb = 0.0;
+        double zna[4], znb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { zna[u] = g0[(long long)u * ldg + n]; znb[u] = g0[(long long)u * ldg + n1]; }
+        for (int d0 = 0; d0 < NDp; d0 += 4) {
+            double za[4], zb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { za[u] = zna[u]; zb[u] = znb[u]; }
+            if (d0 + 4 < NDp) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    zna[u] = g0[(long long)(d0 + 4 + u) * ldg + n];
+                    znb[u] = g0[(long long)(d0 + 4 + u) * ldg + n1];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int d = d0 + u;
+                const double* a = l0_sm + d * KT;
+                if ((d / 3) == i) {                          // warp-uniform: own-feature columns only for own directions
+#pragma unroll
+                    for (int k = 0; k < KT - 8; ++k) { const double av = a[k]; za[u] = fma(av, wa[k], za[u]); zb[u] = fma(av, wb[k], zb[u]); }
+                }
+#pragma unroll
+                for (int k = KT - 8; k < KT; ++k) { const double av = a[k]; za[u] = fma(av, wa[k], za[u]); zb[u] = fma(av, wb[k], zb[u]); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                sa = fma(za[u], za[u], sa);
+                sb = fma(zb[u], zb[u], sb);
+                o0[(long long)(d0 + u) * ldc + n] = da * za[u];
+                o0[(long long)(d0 + u) * ldc + n1] = db_ * zb[u];
+            }
+        }
+        S[e * (long long)ldt + n] = sa;
+        S[e * (long long)ldt + n1] = sb;
+    }
+}
+
 }  // namespace
 
 int ds_launch_l0_jac(const DsDims& dm, int Wc, const double* A0J, const double* B, const double* G, int ldg,
@@ -120,7 +186,17 @@ int ds_launch_l0_jac(const DsDims& dm, int Wc, const double* A0J, const double* 
     if (threads > 256) threads = 256;
     dim3 grid((unsigned)((long long)Wc * dm.N));
     static size_t cfg[2] = {0, 0};
-    if (dm.K0 == 16) {
+    static const bool one_ch = getenv("DS_L0_ONE") && atoi(getenv("DS_L0_ONE")) != 0;
+    if (dm.K0 == 16 && dm.C0 == 8 && (dm.H & 63) == 0 && !one_ch) {
+        static size_t cfg2 = 0;
+        if (smem > 48 * 1024 && smem > cfg2) {
+            DS_CUDA_CHECK(cudaFuncSetAttribute(l0_jac2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cfg2 = smem;
+        }
+        int t2 = dm.H / 2;
+        if (t2 > 128) t2 = 128;
+        l0_jac2_kernel<<<grid, t2, smem, stream>>>(dm, A0J, B, G, ldg, T, ldt, S, OJ, ldc);
+    } else if (dm.K0 == 16) {
         if (smem > 48 * 1024 && smem > cfg[0]) {
             DS_CUDA_CHECK(cudaFuncSetAttribute(l0_jac_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             cfg[0] = smem;
