@@ -293,6 +293,17 @@ def run_ours(args):
                        "source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, 85-walker chunk)"}
     except Exception:
         pass
+    # DRAM traffic of the WHOLE local-energy pass (every kernel) from the committed ncu launch list
+    hbm = None
+    try:
+        hb = json.load(open(os.path.join(ROOT, "profiles", "r1_hbm.json")))
+        if i8 and system == DEFAULT_SYSTEM:
+            gbs = hb["dram_bytes_per_walker"] * batch * args.steps / (ms / 1e3) / 1e9
+            hbm = {"achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                   "dram_bytes_per_walker": hb["dram_bytes_per_walker"],
+                   "source": "profiles/r1_hbm.json (ncu dram__bytes_read+write summed over every kernel of the pass) / step time"}
+    except Exception:
+        pass
     bf16_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
     peak_note = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks.get("bf16_tflops_sustained")
                  else ("MEASURED_PEAKS.json bf16_tflops" if peaks.get("bf16_tflops") else "fallback 1.59 PFLOP/s (MEASURED_PEAKS.json absent)"))
@@ -312,7 +323,7 @@ def run_ours(args):
             "int8_tops_executed": (jac_tf * oz_products) if jac_tf else None, "int8_tops_peak": i8_peak,
             "fp64_dmma_peak_tflops": fp64_peak,
             "frac_of_fp64_dmma_peak": (jac_tf / fp64_peak) if (jac_tf and fp64_peak) else None,
-            "hbm_gbs_peak": peaks.get("hbm_gbs"),
+            "hbm_gbs_peak": peaks.get("hbm_gbs"), "hbm": hbm,
             "launches": prof["jac_launches"], "kernel_ms_per_step": prof["jac_ms"] / args.steps,
             "kernel_share_of_step": prof["jac_ms"] / ms,
             "traffic": traffic,

@@ -30,7 +30,7 @@ class SystemDesc(C.Structure):
 
 class NetDesc(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("hidden_one", C.c_int32), ("hidden_two", C.c_int32), ("n_det", C.c_int32),
-                ("distance_type", C.c_int32)]
+                ("distance_type", C.c_int32), ("envelope_type", C.c_int32)]
 
 
 #: name -> (restype, argtypes); must list every DS_API symbol of the header
@@ -48,6 +48,8 @@ SIGNATURES = {
                                    C.c_void_p]),
     "ds_mcmc_step_one_electron": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_uint64,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_orbitals_vjp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p),
+                                  C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
     "ds_orbitals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ds_orbitals_size": (C.c_int64, [C.c_void_p]),
     "ds_local_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -116,6 +116,7 @@ struct ds_ctx {
     // optional outputs of the sweep: d log|psi| / dx and d phase / dx of the current chunk (ds_logpsi_grad_x)
     double* gx_abs = nullptr;
     double* gx_phase = nullptr;
+    const double* cot_mats = nullptr;       // cotangent of the orbital matrices of the current chunk (ds_orbitals_vjp)
     // layout of the last local-energy chunk (for ds_debug_buffer)
     std::vector<Region> last_regions;
 };
@@ -231,7 +232,7 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
     const size_t cmax = (size_t)std::max(d.C0, d.H);
     L.GIN = ws.take("GIN", W * d.NDg * 2 * cmax);
     L.GOUT = ws.take("GOUT", W * d.NDg * d.H);
-    L.RAE = ws.take("RAE", W * N * d.A * 5);
+    L.RAE = ws.take("RAE", W * N * d.A * DS_RAE_STRIDE);
     const size_t npm = c->npar_max;
     L.ETAB = ws.take("ETAB", W * N * 5 * npm * 2);
     L.YV = ws.take("YV", W * N * npm * 2);
@@ -504,10 +505,15 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
     const DsSys& sys = c->sys;
     const DsDims& d = sys.d;
     const int N = d.N, H = d.H, L = d.L, P = d.P;
-    sb.XINV[0] = Lo.XINV[0]; sb.XINV[1] = Lo.XINV[1];
-    if (int rc = ds_launch_det_inverse(sys, sb, Wc, st)) return rc;
-    c->launches++;
     GradBufs gb{};
+    if (c->cot_mats) {      // eval_mats cotangent: no determinant involved
+        gb.cot_mats = c->cot_mats;
+        gb.cot_mats_stride = (long long)d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
+    } else {
+        sb.XINV[0] = Lo.XINV[0]; sb.XINV[1] = Lo.XINV[1];
+        if (int rc = ds_launch_det_inverse(sys, sb, Wc, st)) return rc;
+        c->launches++;
+    }
     gb.cot_abs = cot_abs; gb.cot_phase = cot_phase;
     for (int s = 0; s < 2; ++s) { gb.GY[s] = Lo.GYs[s]; gb.g_pi[s] = c->genv_pi[s]; gb.g_sigma[s] = c->genv_sigma[s]; }
     if (int rc = ds_launch_orb_grad(sys, sb, gb, Wc, c->npar_max, st)) return rc;
@@ -625,6 +631,9 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     DS_REQUIRE(nd->n_det >= 1, "need at least one determinant");
     DS_REQUIRE(sd->dist_kind >= 0 && sd->dist_kind <= 2, "dist_kind must be 0, 1 or 2");
     DS_REQUIRE(nd->distance_type == 0 || nd->distance_type == 1, "Unrecognized distance function.");
+    DS_REQUIRE(nd->envelope_type >= 0 && nd->envelope_type <= 2, "envelope_type must be 0 (isotropic), 1 (diagonal) or 2 (full)");
+    DS_REQUIRE(nd->envelope_type == 0 || nd->distance_type == 0,
+               "diagonal / full envelopes act on 3-component relative vectors: they need distance_type='nu'");
     DS_REQUIRE(((nd->distance_type == 1) ? 7 : 4) * (sd->n_atoms_prim + 2) <= 32,
                "layer-0 operand rows wider than 32 columns are not supported (%d primitive-cell atoms with this distance_type)",
                sd->n_atoms_prim);
@@ -641,6 +650,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     d.H = nd->hidden_one; d.P = nd->hidden_two; d.D = nd->n_det; d.L = nd->n_layers;
     d.ND = 3 * d.N; d.NDp = (d.ND + 7) / 8 * 8; d.NDg = d.NDp + 8;
     d.dist_type = nd->distance_type; d.F = (nd->distance_type == 1) ? 7 : 4;
+    d.env_type = nd->envelope_type;
     d.C0 = d.F * d.A; d.K0 = d.C0 + 2 * d.F; d.K1 = d.H + 2 * d.P;
     fill_lattice(c->sys.prim, sd->prim_latvec, sd->prim_AV, sd->prim_BV);
     fill_lattice(c->sys.sim, sd->sim_latvec, sd->sim_AV, sd->sim_BV);
@@ -711,10 +721,11 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
         want.push_back(P);
     }
     for (int s = 0; s < 2; ++s) want.push_back((int64_t)H * 2 * c->npar[s]);
-    for (int s = 0; s < 2; ++s) { want.push_back((int64_t)d.A * c->npar[s]); want.push_back((int64_t)d.A * c->npar[s]); }
+    const int64_t sig_mult = (d.env_type == 0) ? 1 : (d.env_type == 1 ? 3 : 9);
+    for (int s = 0; s < 2; ++s) { want.push_back((int64_t)d.A * c->npar[s]); want.push_back(sig_mult * d.A * c->npar[s]); }
     for (int i = 0; i < n_leaves; ++i)
         DS_REQUIRE(sizes[i] == want[i], "parameter leaf %d has %lld elements, expected %lld "
-                   "(only envelope_type='isotropic', full_det=False, use_last_layer=False, bias_orbitals=False are implemented)",
+                   "(full_det=False, use_last_layer=False, bias_orbitals=False are implemented; envelope sizes follow envelope_type)",
                    i, (long long)sizes[i], (long long)want[i]);
     // stage every leaf on the host (pointers may be host or device memory)
     std::vector<std::vector<double>> h(n_leaves);
@@ -829,10 +840,11 @@ int prepare_grad(ds_ctx* c, cudaStream_t st) {
         if (int rc = need(&c->WorbT[s], np2 * H)) return rc;
         if (int rc = need(&c->gWorb[s], np2 * H)) return rc;
         if (int rc = need(&c->genv_pi[s], (size_t)d.A * c->npar[s])) return rc;
-        if (int rc = need(&c->genv_sigma[s], (size_t)d.A * c->npar[s])) return rc;
+        const size_t sig_mult = (d.env_type == 0) ? 1 : (d.env_type == 1 ? 3 : 9);
+        if (int rc = need(&c->genv_sigma[s], sig_mult * d.A * c->npar[s])) return rc;
         DS_CUDA_CHECK(cudaMemsetAsync(c->gWorb[s], 0, np2 * H * sizeof(double), st));
         DS_CUDA_CHECK(cudaMemsetAsync(c->genv_pi[s], 0, (size_t)d.A * c->npar[s] * sizeof(double), st));
-        DS_CUDA_CHECK(cudaMemsetAsync(c->genv_sigma[s], 0, (size_t)d.A * c->npar[s] * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->genv_sigma[s], 0, sig_mult * d.A * c->npar[s] * sizeof(double), st));
         if (!c->transposes_ready)
             if (int rc = ds_launch_transpose(c->Worb[s], H, (int)np2, c->WorbT[s], st)) return rc;
     }
@@ -844,8 +856,25 @@ int prepare_grad(ds_ctx* c, cudaStream_t st) {
 // Vector-Jacobian product of (log|psi|, phase) with respect to the parameters, summed over the batch:
 //   grad_leaf = sum_w cot_abs[w] d log|psi_w| / d leaf + cot_phase[w] d phase_w / d leaf.
 // `grads`: n_leaves device pointers in the leaf order and sizes of ds_set_params; overwritten.
+static int vjp_impl(ds_ctx* c, const double* x, int64_t batch, const double* cot_abs, const double* cot_phase,
+                    const double* cot_mats, double* const* grads, const int64_t* sizes, int n_leaves, void* stream);
+
 extern "C" int ds_logpsi_vjp(ds_ctx* c, const double* x, int64_t batch, const double* cot_abs, const double* cot_phase,
                              double* const* grads, const int64_t* sizes, int n_leaves, void* stream) {
+    DS_REQUIRE(batch == 0 || (cot_abs && cot_phase), "null argument");
+    return vjp_impl(c, x, batch, cot_abs, cot_phase, nullptr, grads, sizes, n_leaves, stream);
+}
+
+// Pullback through method eval_mats (network.py:601-602; the pretraining loss of pretrain.py:70-89 differentiates the
+// orbital matrices): cot_mats has the layout of ds_orbitals, grads = d/dparams sum cot_re Re(M) + cot_im Im(M).
+extern "C" int ds_orbitals_vjp(ds_ctx* c, const double* x, int64_t batch, const double* cot_mats, double* const* grads,
+                               const int64_t* sizes, int n_leaves, void* stream) {
+    DS_REQUIRE(batch == 0 || cot_mats, "null argument");
+    return vjp_impl(c, x, batch, nullptr, nullptr, cot_mats, grads, sizes, n_leaves, stream);
+}
+
+static int vjp_impl(ds_ctx* c, const double* x, int64_t batch, const double* cot_abs, const double* cot_phase,
+                    const double* cot_mats, double* const* grads, const int64_t* sizes, int n_leaves, void* stream) {
     DS_REQUIRE(c && c->params_set, "parameters have not been set (ds_set_params)");
     DS_REQUIRE(grads && sizes, "null argument");
     DS_REQUIRE(batch >= 0, "negative batch");
@@ -857,15 +886,21 @@ extern "C" int ds_logpsi_vjp(ds_ctx* c, const double* x, int64_t batch, const do
     DS_REQUIRE(n_leaves == expect, "expected %d gradient leaves for %d layers, got %d", expect, L, n_leaves);
     if (int rc = prepare_grad(c, st)) return rc;
     if (batch > 0) {
-        DS_REQUIRE(x && cot_abs && cot_phase, "null argument");
+        DS_REQUIRE(x, "null argument");
         int Wc = 0;
         if (int rc = plan_chunk(c, batch, false, &Wc, true)) return rc;
         const int n3 = 3 * d.N;
-        for (long long w0 = 0; w0 < batch; w0 += Wc) {
+        const long long mstride = (long long)d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
+        static const double dummy = 0.0;           // grad mode of run_chunk is keyed on a non-null cotangent pointer
+        int rc = 0;
+        for (long long w0 = 0; w0 < batch && !rc; w0 += Wc) {
             int wc = (int)std::min<long long>(Wc, batch - w0);
-            if (int rc = run_chunk(c, x + w0 * n3, wc, false, nullptr, nullptr, nullptr, nullptr, nullptr, st,
-                                   cot_abs + w0, cot_phase + w0)) return rc;
+            c->cot_mats = cot_mats ? cot_mats + w0 * mstride : nullptr;
+            rc = run_chunk(c, x + w0 * n3, wc, false, nullptr, nullptr, nullptr, nullptr, nullptr, st,
+                           cot_mats ? &dummy : cot_abs + w0, cot_mats ? &dummy : cot_phase + w0);
         }
+        c->cot_mats = nullptr;
+        if (rc) return rc;
     }
     // unpack into the leaf layout of the reference pytree
     int li = 0;
@@ -891,9 +926,10 @@ extern "C" int ds_logpsi_vjp(ds_ctx* c, const double* x, int64_t batch, const do
         if (int rc = ds_launch_deinterleave(c->gWorb[s], grads[li++], H, c->npar[s], st)) return rc;
     }
     for (int s = 0; s < 2; ++s) {
-        DS_REQUIRE(sizes[li] == (int64_t)d.A * c->npar[s] && sizes[li + 1] == sizes[li], "gradient leaf %d has the wrong size", li);
+        const int64_t sig_mult = (d.env_type == 0) ? 1 : (d.env_type == 1 ? 3 : 9);
+        DS_REQUIRE(sizes[li] == (int64_t)d.A * c->npar[s] && sizes[li + 1] == sig_mult * sizes[li], "gradient leaf %d has the wrong size", li);
         DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->genv_pi[s], (size_t)d.A * c->npar[s] * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->genv_sigma[s], (size_t)d.A * c->npar[s] * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->genv_sigma[s], (size_t)sig_mult * d.A * c->npar[s] * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     return 0;
 }

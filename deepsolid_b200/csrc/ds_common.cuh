@@ -7,6 +7,7 @@
 
 #define DS_PI 3.14159265358979323846
 #define DS_MAX_ATOMS_PRIM 16
+#define DS_RAE_STRIDE 20   // per (electron, atom): jets (v, g0, g1, g2, lap) of the distance and of the 3 relative-vector components
 
 // ---------------------------------------------------------------------------
 // Static description of the system + network, passed by value to kernels.
@@ -27,6 +28,7 @@ struct DsDims {
     int ND, NDp, NDg;       // 3N, padded to a multiple of 8, NDp+8 (rows of the shared-mean matrix)
     int F;                  // features per electron-atom / electron-electron pair: 4 ('nu') or 7 ('tri')
     int dist_type;          // 0 = nu_distance (network.py:189-224), 1 = tri_distance (network.py:227-246)
+    int env_type;           // 0 = isotropic, 1 = diagonal, 2 = full envelope (network.py:335-364)
     int C0, K0;             // F*A, F*A + 2F (layer-0 one-electron inputs, own + pair-mean)
     int K1;                 // H + 2P  (own + pair-mean columns of layers >= 1)
 };
@@ -79,6 +81,30 @@ __host__ __device__ __forceinline__ Jet jet_tanh(const Jet& z) {
 }
 
 __host__ __device__ __forceinline__ double ds_sign(double w) { return (w > 0.0) - (w < 0.0); }
+
+// Envelope value jet of one (electron, atom, parameter) term exp(-|S.rel|) for the anisotropic envelopes
+// (network.py:340-364): y_m = sum_k S[k][m] rel_k, r = |y|; `rel` = jets of the 3 relative-vector components.
+// diag: S[k][m] = delta_km sigma_m.  Also returns y and r for the parameter gradient.
+__host__ __device__ __forceinline__ Jet ds_aniso_env(const Jet rel[3], const double S[9], bool diag, double y_out[3], double* r_out) {
+    Jet q = jet_const(0.0);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        Jet y = jet_const(0.0);
+        if (diag) {
+            y = jet_scale(rel[m], S[m * 3 + m]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) jet_axpy(y, S[k * 3 + m], rel[k]);
+        }
+        y_out[m] = y.v;
+        q = jet_add(q, jet_mul(y, y));
+    }
+    const double r = sqrt(q.v);
+    *r_out = r;
+    const Jet rj = jet_chain(q, r, 0.5 / r, -0.25 / (r * r * r));
+    const double ex = exp(-r);
+    return jet_chain(rj, ex, -ex, ex);
+}
 
 // network.enforce_pbc (network.py:42-57): wrap a position into the cell.
 __host__ __device__ __forceinline__ void ds_wrap(const DsLattice& L, const double x[3], double out[3]) {

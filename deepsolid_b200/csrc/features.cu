@@ -76,8 +76,11 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
                 fp.A0J[(r + 2) * K0 + tid * F + q] = f[q].g2;
             }
         }
-        double* ra = fp.RAE + (e * A + tid) * 5;
-        ra[0] = f[0].v; ra[1] = f[0].g0; ra[2] = f[0].g1; ra[3] = f[0].g2; ra[4] = f[0].l;
+        double* ra = fp.RAE + (e * A + tid) * DS_RAE_STRIDE;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {               // distance, then the relative vector (its first 3 components)
+            ra[5 * q] = f[q].v; ra[5 * q + 1] = f[q].g0; ra[5 * q + 2] = f[q].g1; ra[5 * q + 3] = f[q].g2; ra[5 * q + 4] = f[q].l;
+        }
     }
 
     // ---- pairs (j, i) ---------------------------------------------------------

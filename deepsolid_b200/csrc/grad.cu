@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(256) orb_grad_kernel(const DsSys sys, const Sl
     const int is = s ? i - dm.n_up : i;
     const int npar = ns * D;
     __shared__ cplx wk_s[64];                       // conj(c) * w_k per determinant
-    if (threadIdx.x == 0) {
+    const bool direct = gb.cot_mats != nullptr;     // cotangent of the matrices given by the caller (eval_mats)
+    if (threadIdx.x == 0 && !direct) {
         const double* ld = sb.LOGDET + w * 2 * D * 3;
         double mx = -INFINITY;
         for (int k = 0; k < D; ++k) mx = fmax(mx, ld[k * 3] + ld[(D + k) * 3]);
@@ -45,7 +46,8 @@ __global__ void __launch_bounds__(256) orb_grad_kernel(const DsSys sys, const Sl
     __syncthreads();
     const double* x = sb.X + w * 3 * N + 3 * i;
     const double x0 = x[0], x1 = x[1], x2 = x[2];
-    const double* rae = sb.RAE + e * A * 5;
+    const double* rae = sb.RAE + e * A * DS_RAE_STRIDE;
+    const int env_type = dm.env_type;
     const double* pi_ = sb.env_pi[s];
     const double* sg_ = sb.env_sigma[s];
     const double* kl = sb.klist[s];
@@ -55,8 +57,16 @@ __global__ void __launch_bounds__(256) orb_grad_kernel(const DsSys sys, const Sl
     double* gy = gb.GY[s] + (w * ns + is) * 2LL * npar;
     for (int p = threadIdx.x; p < npar; p += blockDim.x) {
         const int k = p / ns, o = p - k * ns;
-        const cplx X = xinv[((w * D + k) * ns + o) * (long long)ns + is];
-        const cplx Gm = cmul(wk_s[k], X);
+        cplx Gm;
+        if (direct) {
+            // ds_orbitals layout: per walker [spin0: D n0 n0][spin1: D n1 n1] complex, element (k, i_s, o)
+            const long long soff = s ? (long long)D * dm.n_up * dm.n_up : 0;
+            const double* cm = gb.cot_mats + w * gb.cot_mats_stride + 2 * (soff + ((long long)k * ns + is) * ns + o);
+            Gm = cplx{cm[0], -cm[1]};               // dloss = Re(conj(cot) dM)
+        } else {
+            const cplx X = xinv[((w * D + k) * ns + o) * (long long)ns + is];
+            Gm = cmul(wk_s[k], X);
+        }
         const cplx g = cmul(Gm, E[p]);              // cotangent of Y: dloss = Re(g dY) = g.re dYr - g.im dYi
         gy[2 * p] = g.re;
         gy[2 * p + 1] = -g.im;
@@ -65,10 +75,43 @@ __global__ void __launch_bounds__(256) orb_grad_kernel(const DsSys sys, const Sl
         const cplx gyp = cmul(cmul(Gm, yv[p]), cplx{cs, sn});
         const double genv = gyp.re;                  // cotangent of the (real) envelope value
         for (int a = 0; a < A; ++a) {
-            const double r = rae[a * 5], sig = sg_[a * npar + p], pw = pi_[a * npar + p];
-            const double ex = exp(-fabs(r * sig));
-            atomicAdd(gb.g_pi[s] + a * npar + p, genv * ex);
-            atomicAdd(gb.g_sigma[s] + a * npar + p, -genv * pw * ex * r * ds_sign(r * sig));
+            const double* ra = rae + a * DS_RAE_STRIDE;
+            const double pw = pi_[a * npar + p];
+            if (env_type == 0) {
+                const double r = ra[0], sig = sg_[a * npar + p];
+                const double ex = exp(-fabs(r * sig));
+                atomicAdd(gb.g_pi[s] + a * npar + p, genv * ex);
+                atomicAdd(gb.g_sigma[s] + a * npar + p, -genv * pw * ex * r * ds_sign(r * sig));
+            } else {
+                double S[9];
+                if (env_type == 1) {
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) S[m * 3 + m] = sg_[((long long)a * 3 + m) * npar + p];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) S[k * 3 + m] = sg_[(((long long)k * 3 + m) * A + a) * npar + p];
+                }
+                Jet rel[3];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) rel[m] = jet_const(ra[5 * (1 + m)]);
+                double yv[3], rr;
+                const Jet en = ds_aniso_env(rel, S, env_type == 1, yv, &rr);
+                atomicAdd(gb.g_pi[s] + a * npar + p, genv * en.v);
+                // d exp(-r) / d S[k][m] = -exp(-r) y_m rel_k / r
+                const double c = -genv * pw * en.v / rr;
+                if (env_type == 1) {
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) atomicAdd(gb.g_sigma[s] + ((long long)a * 3 + m) * npar + p, c * yv[m] * rel[m].v);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int m = 0; m < 3; ++m)
+                            atomicAdd(gb.g_sigma[s] + (((long long)k * 3 + m) * A + a) * npar + p, c * yv[m] * rel[k].v);
+                }
+            }
         }
     }
 }

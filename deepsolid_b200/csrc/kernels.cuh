@@ -12,7 +12,7 @@ struct FeatParams {
     double* AV[DS_MAX_LAYERS];       // value rows of layer l >= 1 (ld K1); pair-mean columns written here
     double* AL[DS_MAX_LAYERS];       // Laplacian rows
     double* AJ[DS_MAX_LAYERS];       // Jacobian rows
-    double* RAE;                     // [(w*N+i)*A + a][5] jet of the electron-atom distance
+    double* RAE;                     // [(w*N+i)*A + a][DS_RAE_STRIDE] jets of the electron-atom distance and relative vector
     const double* Wp[DS_MAX_LAYERS]; // pair-stream weights [in x P]
     const double* bp[DS_MAX_LAYERS]; // pair-stream biases [P]
 };
@@ -62,6 +62,9 @@ int ds_launch_det_inverse(const DsSys& sys, const SlaterBufs& sb, int Wc, cudaSt
 struct GradBufs {
     // cotangents of the outputs, per walker (dloss = sum_w a_w dlog|psi_w| + b_w dphase_w)
     const double* cot_abs; const double* cot_phase;
+    // alternatively the cotangent of the orbital matrices themselves (eval_mats, pretraining): complex (re, im)
+    // interleaved in the layout of ds_orbitals, dloss = sum cot_re dRe(M) + cot_im dIm(M); null otherwise
+    const double* cot_mats; long long cot_mats_stride;
     // orbital layer
     double* GY[2];              // [Wc*n_s][2 npar_s] cotangent of the raw orbital outputs, columns (re, im) interleaved
     double* g_pi[2];            // [A][npar_s]  accumulated

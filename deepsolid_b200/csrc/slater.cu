@@ -24,24 +24,51 @@ __global__ void __launch_bounds__(256) etab_kernel(const DsSys sys, const Slater
     const int npar = ns * D;
     const double* x = sb.X + (long long)w * 3 * N + 3 * i;
     const double x0 = x[0], x1 = x[1], x2 = x[2];
-    const double* rae = sb.RAE + e * A * 5;
+    const double* rae = sb.RAE + e * A * DS_RAE_STRIDE;
     const double* pi_ = sb.env_pi[s];
+    const int env_type = dm.env_type;
     const double* sg_ = sb.env_sigma[s];
     const double* kl = sb.klist[s];
     double* out = sb.ETAB + e * 5LL * npar_max * 2;
     for (int p = threadIdx.x; p < npar; p += blockDim.x) {
         double ev = 0.0, eg0 = 0.0, eg1 = 0.0, eg2 = 0.0, el = 0.0;
         for (int a = 0; a < A; ++a) {
-            const double r = rae[a * 5], sig = sg_[a * npar + p], pw = pi_[a * npar + p];
-            const double asig = fabs(sig);
-            const double ex = exp(-fabs(r * sig)) * pw;
-            ev += ex;
-            if (JETS) {
-                const double g0 = rae[a * 5 + 1], g1 = rae[a * 5 + 2], g2 = rae[a * 5 + 3], l = rae[a * 5 + 4];
-                const double sr = ds_sign(r);      // r >= 0; keeps d|r sigma|/dr = sign(r sigma) sigma exact
-                const double d1 = -asig * sr * ex;
-                eg0 += d1 * g0; eg1 += d1 * g1; eg2 += d1 * g2;
-                el += d1 * l + sig * sig * ex * (g0 * g0 + g1 * g1 + g2 * g2);
+            const double* ra = rae + a * DS_RAE_STRIDE;
+            const double pw = pi_[a * npar + p];
+            if (env_type == 0) {
+                const double r = ra[0], sig = sg_[a * npar + p];
+                const double asig = fabs(sig);
+                const double ex = exp(-fabs(r * sig)) * pw;
+                ev += ex;
+                if (JETS) {
+                    const double g0 = ra[1], g1 = ra[2], g2 = ra[3], l = ra[4];
+                    const double sr = ds_sign(r);      // r >= 0; keeps d|r sigma|/dr = sign(r sigma) sigma exact
+                    const double d1 = -asig * sr * ex;
+                    eg0 += d1 * g0; eg1 += d1 * g1; eg2 += d1 * g2;
+                    el += d1 * l + sig * sig * ex * (g0 * g0 + g1 * g1 + g2 * g2);
+                }
+            } else {
+                // diagonal: sigma [A][3][npar]; full: sigma [3][3][A][npar]   (network.py:146-152)
+                double S[9];
+                if (env_type == 1) {
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) S[m * 3 + m] = sg_[((long long)a * 3 + m) * npar + p];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) S[k * 3 + m] = sg_[(((long long)k * 3 + m) * A + a) * npar + p];
+                }
+                Jet rel[3];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const double* rj = ra + 5 * (1 + m);
+                    rel[m] = Jet{rj[0], JETS ? rj[1] : 0.0, JETS ? rj[2] : 0.0, JETS ? rj[3] : 0.0, JETS ? rj[4] : 0.0};
+                }
+                double yv[3], rr;
+                const Jet en = ds_aniso_env(rel, S, env_type == 1, yv, &rr);
+                ev += pw * en.v;
+                if (JETS) { eg0 += pw * en.g0; eg1 += pw * en.g1; eg2 += pw * en.g2; el += pw * en.l; }
             }
         }
         const int o = p % ns;

@@ -53,7 +53,7 @@ def unflatten_params(leaves, n_layers: int) -> dict:
 
 class HotPath:
     def __init__(self, simulation_cell, klist, hidden_dims=((256, 32),) * 3, determinants: int = 8,
-                 device: Optional[int] = None, distance_type: str = "nu"):
+                 device: Optional[int] = None, distance_type: str = "nu", envelope_type: str = "isotropic"):
         if not torch.cuda.is_available():
             raise RuntimeError("deepsolid_b200 needs a CUDA device: the local-energy hot path has no CPU fallback")
         self.lib = _lib.load()
@@ -69,6 +69,12 @@ class HotPath:
         if distance_type not in ("nu", "tri"):
             raise ValueError("Unrecognized distance function.")
         self.distance_type = distance_type
+        envs = {"isotropic": 0, "diagonal": 1, "full": 2}
+        if envelope_type not in envs:
+            raise ValueError(f"envelope_type={envelope_type!r} is not implemented in the CUDA hot path")
+        if envelope_type != "isotropic" and distance_type != "nu":
+            raise ValueError("diagonal / full envelopes need distance_type='nu' (3-component relative vectors)")
+        self.envelope_type = envelope_type
         self.n_up, self.n_dn = simulation_cell.nelec
         self.nelec = self.n_up + self.n_dn
         tb = build_ewald_tables(simulation_cell)
@@ -94,7 +100,8 @@ class HotPath:
             ion_exp_re=_ptr(keep[15]), ion_exp_im=_ptr(keep[16]),
             ee_const=float(tb.ee_const(ne)), ei_const=float(tb.ei_const(ne)), ii_total=float(tb.ii_total))
         nd = _lib.NetDesc(n_layers=len(hidden_dims), hidden_one=hidden_dims[0][0], hidden_two=hidden_dims[0][1],
-                          n_det=self.determinants, distance_type=1 if distance_type == "tri" else 0)
+                          n_det=self.determinants, distance_type=1 if distance_type == "tri" else 0,
+                          envelope_type=envs[envelope_type])
         h = C.c_void_p()
         _lib.check(self.lib.ds_ctx_create(C.byref(sd), C.byref(nd), self.device, C.byref(h)))
         self.h = h
@@ -183,6 +190,30 @@ class HotPath:
         sizes = (C.c_int64 * n)(*[o.numel() for o in outs])
         _lib.check(self.lib.ds_logpsi_vjp(self.h, td.data_ptr(), B, ca.data_ptr(), cp.data_ptr(), ptrs, sizes, n,
                                           self._stream()))
+        return unflatten_params(outs, len(self.hidden_dims))
+
+    def orbitals_vjp(self, x, cot_mats):
+        """Parameter gradient pytree of sum Re(conj(cot) * M) over the orbital matrices of ``orbitals(x)``
+        (eval_mats, network.py:601-602; pretrain.py:70-89).  ``cot_mats``: list of two complex tensors
+        (B, D, n_s, n_s), the cotangents of the spin-up / spin-down matrices."""
+        t, one, on_dev = self._prep(x)
+        td = t if on_dev else t.to(self.tdev)
+        B = td.shape[0]
+        D = self.determinants
+        parts = []
+        for cm, ns in zip(cot_mats, (self.n_up, self.n_dn)):
+            cm = torch.as_tensor(cm).to(self.tdev).to(torch.complex128).reshape(B, D * ns * ns)
+            parts.append(torch.view_as_real(cm).reshape(B, -1))
+        cot = torch.cat(parts, dim=1).contiguous()
+        if cot.shape[1] != int(self.lib.ds_orbitals_size(self.h)):
+            raise ValueError("cotangent does not have the shape of the orbital matrices")
+        if self._param_key is None:
+            raise ValueError("parameters have not been set")
+        outs = [torch.empty(tp.shape, dtype=torch.float64, device=self.tdev) for tp in self._keep_params]
+        n = len(outs)
+        ptrs = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        sizes = (C.c_int64 * n)(*[o.numel() for o in outs])
+        _lib.check(self.lib.ds_orbitals_vjp(self.h, td.data_ptr(), B, cot.data_ptr(), ptrs, sizes, n, self._stream()))
         return unflatten_params(outs, len(self.hidden_dims))
 
     def logpsi_grad_x(self, x, want_phase_grad: bool = False):

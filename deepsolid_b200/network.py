@@ -88,7 +88,7 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
     if distance_type not in ("nu", "tri"):
         raise ValueError("Unrecognized distance function.")
     unsupported = []
-    if envelope_type != "isotropic":
+    if envelope_type not in ("isotropic", "diagonal", "full"):
         unsupported.append(f"envelope_type={envelope_type!r}")
     if full_det:
         unsupported.append("full_det=True")
@@ -108,7 +108,7 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
     def _hp() -> HotPath:
         if state["hp"] is None:
             state["hp"] = HotPath(simulation_cell, klist, hidden_dims=hidden_dims, determinants=determinants,
-                                  device=device, distance_type=distance_type)
+                                  device=device, distance_type=distance_type, envelope_type=envelope_type)
         return state["hp"]
 
     def init(key, data=None):

@@ -80,14 +80,15 @@ typedef struct ds_system_desc {
 } ds_system_desc;
 
 /* Network hyper-parameters (base_config.py:129-139).  Of the structural switches the
- * reference's tested defaults are implemented (envelope_type='isotropic', full_det=False,
- * use_last_layer=False, bias_orbitals=False) plus both distance functions. */
+ * reference's tested defaults are implemented (full_det=False, use_last_layer=False,
+ * bias_orbitals=False) with every envelope_type and both distance functions. */
 typedef struct ds_net_desc {
     int32_t n_layers;      /* len(hidden_dims)            (3)   */
     int32_t hidden_one;    /* one-electron stream width   (256) */
     int32_t hidden_two;    /* two-electron stream width   (32)  */
     int32_t n_det;         /* determinants                (8)   */
     int32_t distance_type; /* 0 = 'nu' (network.py:189-224, 4 features per pair), 1 = 'tri' (network.py:227-246, 7) */
+    int32_t envelope_type; /* 0 = isotropic, 1 = diagonal (sigma [A][3][n_s*D]), 2 = full (sigma [3][3][A][n_s*D]); network.py:335-364 */
 } ds_net_desc;
 
 DS_API const char *ds_last_error(void);
@@ -124,6 +125,12 @@ DS_API int ds_logpsi(ds_ctx *ctx, const double *x_dev, int64_t batch,
 DS_API int ds_logpsi_vjp(ds_ctx *ctx, const double *x_dev, int64_t batch, const double *cot_abs_dev,
                   const double *cot_phase_dev, double *const *grad_leaves, const int64_t *leaf_sizes, int n_leaves,
                   void *stream);
+
+/* Pullback through method eval_mats (network.py:601-602), what jax.grad of the pretraining loss
+ * (pretrain.py:70-89) needs: cot_mats_dev has the layout of ds_orbitals' output,
+ * grad_leaf = d/dleaf sum cot_re Re(M) + cot_im Im(M); leaves as in ds_logpsi_vjp. */
+DS_API int ds_orbitals_vjp(ds_ctx *ctx, const double *x_dev, int64_t batch, const double *cot_mats_dev,
+                    double *const *grad_leaves, const int64_t *leaf_sizes, int n_leaves, void *stream);
 
 /* jax.value_and_grad(slog_network, argnums=1), batched (the `func` importance_update receives, qmc.py:325,101-118):
  * log|psi|, phase and d log|psi| / dx, d phase / dx of shape (batch, 3N).  Any output but one gradient may be NULL.

@@ -78,3 +78,56 @@ def test_gpu_tri_distance_matches_oracle(name):
     xn, pm, masks = qmc.make_mcmc_step(sl.apply, B, lat, steps=steps)(P, Xm.to(dev), (xi, u), 0.3, return_masks=True)
     xo, po, mo = O.make_mcmc_step(lambda p, x: O.batch_apply(f_sl, p, x), B, lat, steps=steps)(P, Xm, (xi, u), 0.3)
     assert torch.equal(masks.cpu().bool(), mo)
+
+
+# ---------------------------------------------------------------------------
+# diagonal / full envelopes (network.py:340-364)
+# ---------------------------------------------------------------------------
+def _env_setup(name, envelope_type):
+    sc = C.build_system(name)
+    kl = C.make_klist(sc)
+    rng = np.random.default_rng(888)
+    pn = O.init_params(rng, sc.original_cell.natm, sc.nelec, envelope_type=envelope_type)
+    for env in pn["envelope"]:          # the initial values (ones / identity) would hide index mistakes
+        env["sigma"] = env["sigma"] * (0.6 + 0.8 * rng.random(env["sigma"].shape)) + 0.15 * rng.standard_normal(env["sigma"].shape)
+        env["pi"] = env["pi"] * (0.5 + rng.random(env["pi"].shape))
+    return sc, kl, O.params_to_torch(pn)
+
+
+def test_envelope_needs_nu_distance():
+    from deepsolid_b200 import network
+    sc, kl, P = _env_setup("h4", "diagonal")
+    with pytest.raises(ValueError):
+        network.make_solid_fermi_net(envelope_type="cubic", full_det=False, klist=kl, simulation_cell=sc, determinants=8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("envelope_type", ["diagonal", "full"])
+@pytest.mark.parametrize("name", ["h4", "graphene8"])
+def test_gpu_anisotropic_envelopes_match_oracle(name, envelope_type):
+    from deepsolid_b200 import network, hamiltonian
+    sc, kl, P = _env_setup(name, envelope_type)
+    dev = torch.device("cuda", 0)
+    kw = dict(envelope_type=envelope_type, full_det=False, klist=kl, simulation_cell=sc, determinants=8)
+    ld = network.make_solid_fermi_net(method_name="eval_logdet", **kw)
+    hp = ld.apply.hotpath()
+    nw = 3
+    X = torch.as_tensor(C.init_walkers(sc, nw, seed=23))
+    f_ld = O.make_solid_fermi_net(kl, sc, envelope_type=envelope_type, method_name="eval_logdet")
+    f_ps = O.make_solid_fermi_net(kl, sc, envelope_type=envelope_type, method_name="eval_phase_and_slogdet")
+    v = ld.apply(P, X.to(dev)).cpu()
+    vo = torch.stack([f_ld(P, x) for x in X])
+    assert float((v.real - vo.real).abs().max()) < 1e-10
+    assert float(angle_diff(v.imag, vo.imag).max()) < 1e-10
+    ke, ew = hamiltonian.local_energy_seperate(ld.apply, sc, mode="for")(P, X.to(dev))
+    elo = O.local_energy_seperate(f_ld, sc, mode="dim_batch")
+    for b in range(nw):
+        ko, eo = elo(P, X[b])
+        assert abs(complex(ko) - complex(ke[b].cpu())) < 1e-8
+    rng = np.random.default_rng(4)
+    ca, cp = torch.as_tensor(rng.standard_normal(nw)), torch.as_tensor(rng.standard_normal(nw))
+    g = hp.logpsi_vjp(X.to(dev), ca, cp)
+    go = O.logpsi_vjp(f_ps, P, X, ca, cp)
+    for a, b in zip(O._leaves(g), O._leaves(go)):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert float((a.cpu() - b).abs().max()) < 1e-9 * max(1.0, float(b.abs().max()))
