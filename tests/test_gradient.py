@@ -143,3 +143,35 @@ def test_gpu_value_and_grad_matches_oracle():
             assert _rel_err(a.cpu(), b) < 1e-7
     with pytest.raises(ValueError):
         train.make_loss(net.apply, None, sc, clip_type="polar")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["h4", "graphene8"])
+def test_gpu_orbitals_vjp_matches_oracle(name):
+    """eval_mats pullback (network.py:601-602; pretrain.py:70-89): gradient of sum Re(conj(cot) M)."""
+    from deepsolid_b200 import network
+    sc, kl, pn, P = system(name)
+    dev = torch.device("cuda", 0)
+    net = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc,
+                                       determinants=8, method_name="eval_mats")
+    hp = net.apply.hotpath()
+    hp.set_params(P)
+    nw = 3
+    X = torch.as_tensor(C.init_walkers(sc, nw, seed=31))
+    mats = net.apply(P, X.to(dev))
+    gen = torch.Generator().manual_seed(3)
+    cots = [torch.complex(torch.randn(m.shape, dtype=torch.float64, generator=gen),
+                          torch.randn(m.shape, dtype=torch.float64, generator=gen)) for m in mats]
+    g = hp.orbitals_vjp(X.to(dev), cots)
+    f = O.make_solid_fermi_net(kl, sc, method_name="eval_mats")
+    Pc = O._clone_params(P)
+    total = torch.zeros((), dtype=torch.float64)
+    for b, x in enumerate(X):
+        ms = f(Pc, x)
+        for m, c in zip(ms, cots):
+            assert float((m.detach() - mats[[id(q) for q in cots].index(id(c))][b].cpu()).abs().max()) < 1e-10
+            total = total + (c[b].real * m.real + c[b].imag * m.imag).sum()
+    go = torch.autograd.grad(total, O._leaves(Pc), allow_unused=True)
+    for a, b in zip(_flat(g), go):
+        b = torch.zeros_like(a.cpu()) if b is None else b
+        assert _rel_err(a.cpu(), b) < 1e-9 or float(b.abs().max()) == 0.0 and float(a.abs().max()) == 0.0
