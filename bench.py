@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--mcmc", action="store_true", help="also time the Metropolis step (extras)")
+    ap.add_argument("--grad", action="store_true", help="also time energy + parameter gradient (value_and_grad; extras)")
     ap.add_argument("--equil", type=int, default=2, help="Metropolis calls (20 moves each) used to equilibrate walkers")
     return ap.parse_args()
 
@@ -271,6 +272,13 @@ def run_ours(args):
         ms_m = timed(step_mcmc, max(1, args.steps // 2), 1)
         extras["mcmc_moves_per_sec"] = world * batch * 20 * max(1, args.steps // 2) / (ms_m / 1e3)
 
+    if args.grad:
+        def step_grad():
+            (loss_g, aux_g), grads = total_energy.value_and_grad(P, Xd)
+            keep["gnorm"] = grads["single"][1]["w"]
+        ms_g = timed(step_grad, max(1, args.steps // 2), 1)
+        extras["value_and_grad_walkers_per_sec"] = world * batch * max(1, args.steps // 2) / (ms_g / 1e3)
+        extras["grad_single1_w_norm"] = float(keep["gnorm"].norm())
     if rank != 0:
         if world > 1:
             td.destroy_process_group()

@@ -73,6 +73,9 @@ struct ds_ctx {
     double* Wp[DS_MAX_LAYERS] = {};     // pair-stream weights
     double* bp[DS_MAX_LAYERS] = {};
     double* Worb[2] = {};               // [H x 2 npar_s], columns interleaved (re, im)
+    double* borb[2] = {};               // [2 npar_s] orbital bias (bias_orbitals=True), interleaved like Worb; else null
+    double* gborb[2] = {};
+    bool bias_orb = false;
     // int8 digits of the transposed weights for the tcgen05 path (ozaki.cuh): [N][OZ_S][K] + scales [N]
     signed char* Wd_am[DS_MAX_LAYERS] = {};
     double* sb_am[DS_MAX_LAYERS] = {};
@@ -448,7 +451,9 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         o.rpg = ns; o.gstride = N; o.goff = c->off_s[s];
         o.M = (long long)Wc * ns;
         o.A = hV; o.C = Lo.YV;
+        o.colbias = c->bias_orb ? c->borb[s] : nullptr;     // the bias enters the value only (network.py:538-541)
         if (int rc = gemm(c, o, GEMM_PLAIN, false, st)) return rc;
+        o.colbias = nullptr;
         if (lap) {
             o.A = hL; o.C = Lo.YL;
             if (int rc = gemm(c, o, GEMM_PLAIN, false, st)) return rc;
@@ -527,6 +532,10 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
         t.A = hL; t.lda = d.K1; t.M = H; t.K = Wc * ns; t.rpg = ns; t.gstride = N; t.goff = c->off_s[s];
         t.B = Lo.GYs[s]; t.ldb = np2; t.N = np2; t.C = c->gWorb[s]; t.ldc = np2; t.accumulate = 1;
         if (int rc = gemm(c, t, GEMM_TN, false, st)) return rc;
+        if (c->bias_orb) {
+            if (int rc = ds_launch_colsum_add(Lo.GYs[s], np2, Wc * ns, np2, c->gborb[s], st)) return rc;
+            c->launches++;
+        }
         GemmParams g{};                               // cotangent of h_L (rows of spin s) = GY_s . Worb_s^T
         g.A = Lo.GYs[s]; g.lda = np2; g.M = (long long)Wc * ns; g.K = np2; g.no_amap = 1;
         g.B = c->WorbT[s]; g.ldb = H; g.N = H;
@@ -651,6 +660,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     d.ND = 3 * d.N; d.NDp = (d.ND + 7) / 8 * 8; d.NDg = d.NDp + 8;
     d.dist_type = nd->distance_type; d.F = (nd->distance_type == 1) ? 7 : 4;
     d.env_type = nd->envelope_type;
+    c->bias_orb = nd->bias_orbitals != 0;
     d.C0 = d.F * d.A; d.K0 = d.C0 + 2 * d.F; d.K1 = d.H + 2 * d.P;
     fill_lattice(c->sys.prim, sd->prim_latvec, sd->prim_AV, sd->prim_BV);
     fill_lattice(c->sys.sim, sd->sim_latvec, sd->sim_AV, sd->sim_BV);
@@ -707,7 +717,7 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
     Guard g(c->device);
     const DsDims& d = c->sys.d;
     const int L = d.L, H = d.H, P = d.P;
-    const int expect = 2 * L + 2 * (L - 1) + 2 + 4;
+    const int expect = 2 * L + 2 * (L - 1) + (c->bias_orb ? 4 : 2) + 4;
     DS_REQUIRE(n_leaves == expect, "expected %d parameter leaves for %d layers, got %d", expect, L, n_leaves);
     // expected sizes
     std::vector<int64_t> want;
@@ -720,12 +730,15 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
         want.push_back((int64_t)((l == 0) ? d.F : P) * P);
         want.push_back(P);
     }
-    for (int s = 0; s < 2; ++s) want.push_back((int64_t)H * 2 * c->npar[s]);
+    for (int s = 0; s < 2; ++s) {
+        want.push_back((int64_t)H * 2 * c->npar[s]);
+        if (c->bias_orb) want.push_back((int64_t)2 * c->npar[s]);
+    }
     const int64_t sig_mult = (d.env_type == 0) ? 1 : (d.env_type == 1 ? 3 : 9);
     for (int s = 0; s < 2; ++s) { want.push_back((int64_t)d.A * c->npar[s]); want.push_back(sig_mult * d.A * c->npar[s]); }
     for (int i = 0; i < n_leaves; ++i)
         DS_REQUIRE(sizes[i] == want[i], "parameter leaf %d has %lld elements, expected %lld "
-                   "(full_det=False, use_last_layer=False, bias_orbitals=False are implemented; envelope sizes follow envelope_type)",
+                   "(full_det=False, use_last_layer=False are implemented; envelope / orbital-bias leaves follow the net descriptor)",
                    i, (long long)sizes[i], (long long)want[i]);
     // stage every leaf on the host (pointers may be host or device memory)
     std::vector<std::vector<double>> h(n_leaves);
@@ -765,6 +778,12 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
                 wi[(size_t)r * 2 * np + 2 * p + 1] = W[(size_t)r * 2 * np + np + p];
             }
         if (int rc = put(&c->Worb[s], wi)) return rc;
+        if (c->bias_orb) {
+            const std::vector<double>& bv = h[li++];
+            std::vector<double> bi((size_t)2 * np);
+            for (int p = 0; p < np; ++p) { bi[2 * p] = bv[p]; bi[2 * p + 1] = bv[np + p]; }
+            if (int rc = put(&c->borb[s], bi)) return rc;
+        }
     }
     for (int s = 0; s < 2; ++s) {
         if (int rc = put(&c->env_pi[s], h[li++])) return rc;
@@ -839,6 +858,10 @@ int prepare_grad(ds_ctx* c, cudaStream_t st) {
         const size_t np2 = 2 * (size_t)c->npar[s];
         if (int rc = need(&c->WorbT[s], np2 * H)) return rc;
         if (int rc = need(&c->gWorb[s], np2 * H)) return rc;
+        if (c->bias_orb) {
+            if (int rc = need(&c->gborb[s], np2)) return rc;
+            DS_CUDA_CHECK(cudaMemsetAsync(c->gborb[s], 0, np2 * sizeof(double), st));
+        }
         if (int rc = need(&c->genv_pi[s], (size_t)d.A * c->npar[s])) return rc;
         const size_t sig_mult = (d.env_type == 0) ? 1 : (d.env_type == 1 ? 3 : 9);
         if (int rc = need(&c->genv_sigma[s], sig_mult * d.A * c->npar[s])) return rc;
@@ -882,7 +905,7 @@ static int vjp_impl(ds_ctx* c, const double* x, int64_t batch, const double* cot
     cudaStream_t st = (cudaStream_t)stream;
     const DsDims& d = c->sys.d;
     const int L = d.L, H = d.H, P = d.P;
-    const int expect = 2 * L + 2 * (L - 1) + 2 + 4;
+    const int expect = 2 * L + 2 * (L - 1) + (c->bias_orb ? 4 : 2) + 4;
     DS_REQUIRE(n_leaves == expect, "expected %d gradient leaves for %d layers, got %d", expect, L, n_leaves);
     if (int rc = prepare_grad(c, st)) return rc;
     if (batch > 0) {
@@ -924,6 +947,10 @@ static int vjp_impl(ds_ctx* c, const double* x, int64_t batch, const double* cot
     for (int s = 0; s < 2; ++s) {
         DS_REQUIRE(sizes[li] == (int64_t)H * 2 * c->npar[s], "gradient leaf %d has the wrong size", li);
         if (int rc = ds_launch_deinterleave(c->gWorb[s], grads[li++], H, c->npar[s], st)) return rc;
+        if (c->bias_orb) {
+            DS_REQUIRE(sizes[li] == (int64_t)2 * c->npar[s], "gradient leaf %d has the wrong size", li);
+            if (int rc = ds_launch_deinterleave(c->gborb[s], grads[li++], 1, c->npar[s], st)) return rc;
+        }
     }
     for (int s = 0; s < 2; ++s) {
         const int64_t sig_mult = (d.env_type == 0) ? 1 : (d.env_type == 1 ? 3 : 9);

@@ -311,6 +311,15 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
     }
 }
 
+// dst[c] += sum_r src[r, c]
+__global__ void colsum_add_kernel(const double* __restrict__ src, int lds, int rows, int cols, double* __restrict__ dst) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += src[(long long)r * lds + c];
+    dst[c] += s;
+}
+
 __global__ void copy2d_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int rows, int cols) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)rows * cols) return;
@@ -360,6 +369,13 @@ int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& 
     if (smem > 48 * 1024)
         DS_CUDA_CHECK(cudaFuncSetAttribute(pair_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pair_grad_kernel<<<(unsigned)((long long)Wc * d.N), PG_THREADS, smem, stream>>>(sys, fp, gb);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_colsum_add(const double* src, int lds, int rows, int cols, double* dst, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    colsum_add_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(src, lds, rows, cols, dst);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -89,6 +89,7 @@ int ds_launch_hin(const DsDims& dm, const GradBufs& gb, int Wc, int C, int K, bo
 int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& gb, int Wc, cudaStream_t stream);
 // dst[r, c] (+)= src[r, c] for a [rows x cols] block (leading dimensions lds, ldd); deinterleave: see grad.cu
 int ds_launch_copy2d(const double* src, int lds, double* dst, int ldd, int rows, int cols, cudaStream_t stream);
+int ds_launch_colsum_add(const double* src, int lds, int rows, int cols, double* dst, cudaStream_t stream);
 int ds_launch_deinterleave(const double* src, double* dst, int rows, int np, cudaStream_t stream);
 
 // ewald.cu ------------------------------------------------------------------

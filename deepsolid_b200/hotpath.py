@@ -33,27 +33,28 @@ def flatten_params(params) -> list:
     for layer in params["double"]:
         leaves += [layer["w"], layer["b"]]
     for orb in params["orbital"]:
-        if "b" in orb:
-            raise ValueError("bias_orbitals=True is not implemented in the CUDA hot path")
         leaves.append(orb["w"])
+        if "b" in orb:
+            leaves.append(orb["b"])
     for env in params["envelope"]:
         leaves += [env["pi"], env["sigma"]]
     return leaves
 
 
-def unflatten_params(leaves, n_layers: int) -> dict:
-    """Inverse of flatten_params for the implemented option set (isotropic envelope, no orbital bias)."""
+def unflatten_params(leaves, n_layers: int, bias_orbitals: bool = False) -> dict:
+    """Inverse of flatten_params."""
     it = iter(leaves)
     single = [{"w": next(it), "b": next(it)} for _ in range(n_layers)]
     double = [{"w": next(it), "b": next(it)} for _ in range(n_layers - 1)]
-    orbital = [{"w": next(it)} for _ in range(2)]
+    orbital = [({"w": next(it), "b": next(it)} if bias_orbitals else {"w": next(it)}) for _ in range(2)]
     envelope = [{"pi": next(it), "sigma": next(it)} for _ in range(2)]
     return {"single": single, "double": double, "orbital": orbital, "envelope": envelope}
 
 
 class HotPath:
     def __init__(self, simulation_cell, klist, hidden_dims=((256, 32),) * 3, determinants: int = 8,
-                 device: Optional[int] = None, distance_type: str = "nu", envelope_type: str = "isotropic"):
+                 device: Optional[int] = None, distance_type: str = "nu", envelope_type: str = "isotropic",
+                 bias_orbitals: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("deepsolid_b200 needs a CUDA device: the local-energy hot path has no CPU fallback")
         self.lib = _lib.load()
@@ -75,6 +76,7 @@ class HotPath:
         if envelope_type != "isotropic" and distance_type != "nu":
             raise ValueError("diagonal / full envelopes need distance_type='nu' (3-component relative vectors)")
         self.envelope_type = envelope_type
+        self.bias_orbitals = bool(bias_orbitals)
         self.n_up, self.n_dn = simulation_cell.nelec
         self.nelec = self.n_up + self.n_dn
         tb = build_ewald_tables(simulation_cell)
@@ -101,7 +103,7 @@ class HotPath:
             ee_const=float(tb.ee_const(ne)), ei_const=float(tb.ei_const(ne)), ii_total=float(tb.ii_total))
         nd = _lib.NetDesc(n_layers=len(hidden_dims), hidden_one=hidden_dims[0][0], hidden_two=hidden_dims[0][1],
                           n_det=self.determinants, distance_type=1 if distance_type == "tri" else 0,
-                          envelope_type=envs[envelope_type])
+                          envelope_type=envs[envelope_type], bias_orbitals=1 if bias_orbitals else 0)
         h = C.c_void_p()
         _lib.check(self.lib.ds_ctx_create(C.byref(sd), C.byref(nd), self.device, C.byref(h)))
         self.h = h
@@ -190,7 +192,7 @@ class HotPath:
         sizes = (C.c_int64 * n)(*[o.numel() for o in outs])
         _lib.check(self.lib.ds_logpsi_vjp(self.h, td.data_ptr(), B, ca.data_ptr(), cp.data_ptr(), ptrs, sizes, n,
                                           self._stream()))
-        return unflatten_params(outs, len(self.hidden_dims))
+        return unflatten_params(outs, len(self.hidden_dims), self.bias_orbitals)
 
     def orbitals_vjp(self, x, cot_mats):
         """Parameter gradient pytree of sum Re(conj(cot) * M) over the orbital matrices of ``orbitals(x)``
@@ -214,7 +216,7 @@ class HotPath:
         ptrs = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
         sizes = (C.c_int64 * n)(*[o.numel() for o in outs])
         _lib.check(self.lib.ds_orbitals_vjp(self.h, td.data_ptr(), B, cot.data_ptr(), ptrs, sizes, n, self._stream()))
-        return unflatten_params(outs, len(self.hidden_dims))
+        return unflatten_params(outs, len(self.hidden_dims), self.bias_orbitals)
 
     def logpsi_grad_x(self, x, want_phase_grad: bool = False):
         """(log|psi|, phase, d log|psi|/dx [, d phase/dx]) on the device: jax.value_and_grad of the slog network

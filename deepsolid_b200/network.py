@@ -94,8 +94,6 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
         unsupported.append("full_det=True")
     if use_last_layer:
         unsupported.append("use_last_layer=True")
-    if bias_orbitals:
-        unsupported.append("bias_orbitals=True")
     if unsupported:
         raise ValueError("not implemented in the CUDA hot path: " + ", ".join(unsupported) +
                          " (the reference's tested defaults are isotropic / full_det=False / "
@@ -108,7 +106,8 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
     def _hp() -> HotPath:
         if state["hp"] is None:
             state["hp"] = HotPath(simulation_cell, klist, hidden_dims=hidden_dims, determinants=determinants,
-                                  device=device, distance_type=distance_type, envelope_type=envelope_type)
+                                  device=device, distance_type=distance_type, envelope_type=envelope_type,
+                                  bias_orbitals=bias_orbitals)
         return state["hp"]
 
     def init(key, data=None):

@@ -80,8 +80,8 @@ typedef struct ds_system_desc {
 } ds_system_desc;
 
 /* Network hyper-parameters (base_config.py:129-139).  Of the structural switches the
- * reference's tested defaults are implemented (full_det=False, use_last_layer=False,
- * bias_orbitals=False) with every envelope_type and both distance functions. */
+ * reference's tested defaults are implemented (full_det=False, use_last_layer=False)
+ * with every envelope_type, both distance functions and optional orbital biases. */
 typedef struct ds_net_desc {
     int32_t n_layers;      /* len(hidden_dims)            (3)   */
     int32_t hidden_one;    /* one-electron stream width   (256) */
@@ -89,6 +89,7 @@ typedef struct ds_net_desc {
     int32_t n_det;         /* determinants                (8)   */
     int32_t distance_type; /* 0 = 'nu' (network.py:189-224, 4 features per pair), 1 = 'tri' (network.py:227-246, 7) */
     int32_t envelope_type; /* 0 = isotropic, 1 = diagonal (sigma [A][3][n_s*D]), 2 = full (sigma [3][3][A][n_s*D]); network.py:335-364 */
+    int32_t bias_orbitals; /* 1: every orbital[s] has a bias leaf b (2*n_s*D,) right after its w (network.py:177-179) */
 } ds_net_desc;
 
 DS_API const char *ds_last_error(void);
@@ -105,7 +106,7 @@ DS_API int ds_set_workspace_limit(ds_ctx *ctx, size_t bytes);
  * this order (L = n_layers):
  *   single[0].w, single[0].b, ..., single[L-1].w, single[L-1].b,
  *   double[0].w, double[0].b, ..., double[L-2].w, double[L-2].b,
- *   orbital[0].w, orbital[1].w,
+ *   orbital[0].w, [orbital[0].b,] orbital[1].w, [orbital[1].b,]      (b only with bias_orbitals)
  *   envelope[0].pi, envelope[0].sigma, envelope[1].pi, envelope[1].sigma
  * Every leaf is row-major fp64; pointers may be host or device memory; the data is
  * copied (and re-laid-out) so the caller may free or mutate it afterwards. */

@@ -131,3 +131,47 @@ def test_gpu_anisotropic_envelopes_match_oracle(name, envelope_type):
     for a, b in zip(O._leaves(g), O._leaves(go)):
         assert tuple(a.shape) == tuple(b.shape)
         assert float((a.cpu() - b).abs().max()) < 1e-9 * max(1.0, float(b.abs().max()))
+
+
+# ---------------------------------------------------------------------------
+# bias_orbitals=True (network.py:177-179, 538-541)
+# ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["h4", "graphene8"])
+def test_gpu_orbital_bias_matches_oracle(name):
+    from deepsolid_b200 import network, hamiltonian
+    sc = C.build_system(name)
+    kl = C.make_klist(sc)
+    pn = O.init_params(np.random.default_rng(888), sc.original_cell.natm, sc.nelec, bias_orbitals=True)
+    P = O.params_to_torch(pn)
+    assert "b" in P["orbital"][0]
+    dev = torch.device("cuda", 0)
+    kw = dict(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc, determinants=8, bias_orbitals=True)
+    ld = network.make_solid_fermi_net(method_name="eval_logdet", **kw)
+    hp = ld.apply.hotpath()
+    nw = 3
+    X = torch.as_tensor(C.init_walkers(sc, nw, seed=29))
+    f_ld = O.make_solid_fermi_net(kl, sc, bias_orbitals=True, method_name="eval_logdet")
+    f_ps = O.make_solid_fermi_net(kl, sc, bias_orbitals=True, method_name="eval_phase_and_slogdet")
+    v = ld.apply(P, X.to(dev)).cpu()
+    vo = torch.stack([f_ld(P, x) for x in X])
+    assert float((v.real - vo.real).abs().max()) < 1e-10
+    assert float(angle_diff(v.imag, vo.imag).max()) < 1e-10
+    ke, ew = hamiltonian.local_energy_seperate(ld.apply, sc, mode="for")(P, X.to(dev))
+    elo = O.local_energy_seperate(f_ld, sc, mode="dim_batch")
+    for b in range(nw):
+        ko, eo = elo(P, X[b])
+        assert abs(complex(ko) - complex(ke[b].cpu())) < 1e-8
+    rng = np.random.default_rng(6)
+    ca, cp = torch.as_tensor(rng.standard_normal(nw)), torch.as_tensor(rng.standard_normal(nw))
+    g = hp.logpsi_vjp(X.to(dev), ca, cp)
+    Pc = O._clone_params(P)
+    total = torch.zeros((), dtype=torch.float64)
+    for b, x in enumerate(X):
+        sign, slog = f_ps(Pc, x)
+        total = total + ca[b] * slog + cp[b] * torch.angle(sign)
+    from deepsolid_b200.hotpath import flatten_params
+    go = torch.autograd.grad(total, flatten_params(Pc))
+    for a, b in zip(flatten_params(g), go):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert float((a.cpu() - b).abs().max()) < 1e-9 * max(1.0, float(b.abs().max()))
