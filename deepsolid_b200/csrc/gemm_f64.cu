@@ -106,10 +106,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmParams 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    const int nk = (p.K + BK - 1) / BK;
+    // split-K (GEMM_TN only: tiny outputs, reductions over hundreds of thousands of rows): gridDim.z CTAs share one
+    // output tile, each reduces a contiguous range of K blocks and adds its partial tile atomically
+    const int nk_all = (p.K + BK - 1) / BK;
+    int kb0 = 0, nk = nk_all;
+    if (TA && gridDim.z > 1) {
+        const int per = (nk_all + gridDim.z - 1) / gridDim.z;
+        kb0 = blockIdx.z * per;
+        nk = nk_all - kb0 < per ? nk_all - kb0 : per;
+        if (nk <= 0) return;
+    }
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) load_stage(s, s * BK);
+        if (s < nk) load_stage(s, (kb0 + s) * BK);
         cp_async_commit();
     }
     const int a_frag = TA ? (lane & 3) * BS_LD + wm * 64 + (lane >> 2) : (wm * 64 + (lane >> 2)) * AS_LD + (lane & 3);
@@ -119,7 +128,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmParams 
         __syncthreads();
         {
             int nx = kt + STAGES - 1;
-            if (nx < nk) load_stage(nx % STAGES, nx * BK);
+            if (nx < nk) load_stage(nx % STAGES, (kb0 + nx) * BK);
             cp_async_commit();
         }
         const double* as = As + (kt % STAGES) * A_STAGE + a_frag;
@@ -156,6 +165,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmParams 
                 double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
                 if (p.colbias) { v0 += p.colbias[n]; v1 += p.colbias[n + 1]; }
                 double2* dst = reinterpret_cast<double2*>(p.C + cr * (long long)p.ldc + n);
+                if (TA && gridDim.z > 1) {
+                    atomicAdd(&dst->x, v0);
+                    atomicAdd(&dst->y, v1);
+                    continue;
+                }
                 if (p.accumulate) { const double2 o = *dst; v0 += o.x; v1 += o.y; }
                 *dst = make_double2(v0, v1);
             }
@@ -298,6 +312,15 @@ int launch(const GemmParams& p, cudaStream_t stream) {
         configured = true;
     }
     dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN));
+    if (MODE == GEMM_TN && p.accumulate && !p.colbias) {
+        // enough CTAs for two waves of the machine, at least 8 K blocks each
+        const long long tiles = (long long)grid.x * grid.y;
+        const int nkb = (p.K + BK - 1) / BK;
+        long long z = (2 * 148 + tiles - 1) / tiles;
+        if (z > nkb / 8) z = nkb / 8;
+        if (z < 1) z = 1;
+        grid.z = (unsigned)z;
+    }
     gemm_f64_kernel<MODE, RES><<<grid, NTHREADS, SMEM_BYTES, stream>>>(p);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -168,11 +168,10 @@ __global__ void __launch_bounds__(256) hin_kernel(DsDims dm, GradBufs gb, int C,
 // ---------------------------------------------------------------------------
 constexpr int PG_THREADS = 256;
 
-__global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, const FeatParams fp, const GradBufs gb) {
+__global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, const FeatParams fp, const GradBufs gb,
+                                                               long long n_e) {
     const DsDims& dm = sys.d;
     const int N = dm.N, P = dm.P, L = dm.L, F = dm.F;
-    const long long e = blockIdx.x;
-    const int w = (int)(e / N), i = (int)(e % N);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const double rs2 = 0.70710678118654752440;
 
@@ -180,12 +179,6 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
     double* sx = sm;                             // [3N] wrapped positions
     double* wsm = sx + 3 * N;                    // per pair layer: W [Pin x P], b [P], W^T [P x Pin]
     double* red = wsm;                           // reduction scratch is carved after the weights (set below)
-    const double* x = fp.X + (long long)w * 3 * N;
-    for (int t = tid; t < N; t += blockDim.x) {
-        double xi[3] = {x[3 * t], x[3 * t + 1], x[3 * t + 2]}, o[3];
-        ds_wrap(sys.sim, xi, o);
-        sx[3 * t] = o[0]; sx[3 * t + 1] = o[1]; sx[3 * t + 2] = o[2];
-    }
     int woff[DS_MAX_LAYERS];
     {
         int off = 0;
@@ -217,6 +210,22 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
     for (int l = 0; l < DS_MAX_LAYERS; ++l) gB[l] = 0.0;
 
     const double inv_up = 1.0 / dm.n_up, inv_dn = 1.0 / dm.n_dn;
+    // persistent CTAs: every CTA walks over many electrons and adds its parameter-gradient partials once at the end
+    // (one atomic per parameter and CTA instead of per electron)
+    int w_cur = -1;
+    for (long long e = blockIdx.x; e < n_e; e += gridDim.x) {
+    const int w = (int)(e / N), i = (int)(e % N);
+    if (w != w_cur) {                            // CTA-uniform
+        __syncthreads();
+        const double* x = fp.X + (long long)w * 3 * N;
+        for (int t = tid; t < N; t += blockDim.x) {
+            double xi[3] = {x[3 * t], x[3 * t + 1], x[3 * t + 2]}, o[3];
+            ds_wrap(sys.sim, xi, o);
+            sx[3 * t] = o[0]; sx[3 * t + 1] = o[1]; sx[3 * t + 2] = o[2];
+        }
+        __syncthreads();
+        w_cur = w;
+    }
     for (int j = warp; j < N; j += nwarps) {
         const int sj = (j < dm.n_up) ? 0 : 1;
         const double invn = sj ? inv_dn : inv_up;
@@ -282,6 +291,8 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
             }
         }
     }
+
+    }   // electrons of this CTA
 
     // cross-warp reduction, then one atomic per parameter and CTA
     double* row = red + warp * 33;
@@ -368,7 +379,9 @@ int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& 
     const size_t smem = n * sizeof(double);
     if (smem > 48 * 1024)
         DS_CUDA_CHECK(cudaFuncSetAttribute(pair_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pair_grad_kernel<<<(unsigned)((long long)Wc * d.N), PG_THREADS, smem, stream>>>(sys, fp, gb);
+    const long long n_e = (long long)Wc * d.N;
+    const int grid = (int)(n_e < 4 * 148 ? n_e : 4 * 148);
+    pair_grad_kernel<<<grid, PG_THREADS, smem, stream>>>(sys, fp, gb, n_e);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,20 @@
+"""Launch list of one parameter-gradient pass (ds_logpsi_vjp) at the benchmark configuration (profiling helper)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from deepsolid_b200 import cell as C, network
+from oracle import deepsolid_oracle as O
+sc = C.build_system("graphite54"); kl = C.make_klist(sc)
+P = O.params_to_torch(O.init_params(np.random.default_rng(888), sc.original_cell.natm, sc.nelec))
+net = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc, determinants=8,
+                                   method_name="eval_logdet")
+hp = net.apply.hotpath(); hp.set_params(P)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+X = torch.as_tensor(C.init_walkers(sc, B, seed=1)).cuda()
+ca = torch.randn(B, dtype=torch.float64); cp = torch.randn(B, dtype=torch.float64)
+for _ in range(2):
+    g = hp.logpsi_vjp(X, ca, cp)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); g = hp.logpsi_vjp(X, ca, cp); e1.record(); torch.cuda.synchronize()
+print(f"vjp of {B} walkers: {e0.elapsed_time(e1):.2f} ms")
