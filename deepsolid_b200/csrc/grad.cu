@@ -168,8 +168,10 @@ __global__ void __launch_bounds__(256) hin_kernel(DsDims dm, GradBufs gb, int C,
 // ---------------------------------------------------------------------------
 constexpr int PG_THREADS = 256;
 
-__global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, const FeatParams fp, const GradBufs gb,
-                                                               long long n_e) {
+// NPL = number of P x P pair layers (= L - 2): sizes the per-lane weight-gradient accumulators
+template <int NPL>
+__global__ void __launch_bounds__(PG_THREADS, NPL <= 1 ? 2 : 1) pair_grad_kernel(const DsSys sys, const FeatParams fp,
+                                                                                 const GradBufs gb, long long n_e) {
     const DsDims& dm = sys.d;
     const int N = dm.N, P = dm.P, L = dm.L, F = dm.F;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -199,11 +201,11 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
     __syncthreads();
 
     // per-lane gradient accumulators: column `lane` of every pair-layer weight and bias
-    double gW0[7], gW[DS_MAX_LAYERS - 2 > 0 ? DS_MAX_LAYERS - 2 : 1][32], gB[DS_MAX_LAYERS];
+    double gW0[7], gW[NPL > 0 ? NPL : 1][32], gB[DS_MAX_LAYERS];
 #pragma unroll
     for (int q = 0; q < 7; ++q) gW0[q] = 0.0;
 #pragma unroll
-    for (int l = 0; l < DS_MAX_LAYERS - 2; ++l)
+    for (int l = 0; l < (NPL > 0 ? NPL : 1); ++l)
 #pragma unroll
         for (int c = 0; c < 32; ++c) gW[l][c] = 0.0;
 #pragma unroll
@@ -274,11 +276,11 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
             if (l == 0) {
 #pragma unroll
                 for (int c = 0; c < 7; ++c) gW0[c] = fma(__shfl_sync(0xffffffffu, cur[0], c), gz, gW0[c]);      // cur[0] = 0 beyond F
-            } else {
+            } else if (l - 1 < NPL) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     const double cv = __shfl_sync(0xffffffffu, cur[l], c);
-                    if (c < P) gW[l - 1][c] = fma(cv, gz, gW[l - 1][c]);
+                    if (c < P) gW[l - 1 < NPL ? l - 1 : 0][c] = fma(cv, gz, gW[l - 1 < NPL ? l - 1 : 0][c]);
                 }
                 // cotangent of level l (it has parameters upstream): W.gz over the output channels + residual path
                 const double* WT = wsm + woff[l] + pin * P + P;      // [P_out][pin]
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(PG_THREADS) pair_grad_kernel(const DsSys sys, 
         reduce_and_add(gB[0], gb.g_bp[0] + lane, lane < P);
     }
 #pragma unroll
-    for (int l = 1; l < DS_MAX_LAYERS - 1; ++l) {
+    for (int l = 1; l <= NPL; ++l) {
         if (l >= L - 1) break;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
@@ -377,11 +379,19 @@ int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& 
     for (int l = 0; l < d.L - 1; ++l) n += 2 * ((l == 0) ? d.F : d.P) * d.P + d.P;
     n += (PG_THREADS / 32) * 33;
     const size_t smem = n * sizeof(double);
-    if (smem > 48 * 1024)
-        DS_CUDA_CHECK(cudaFuncSetAttribute(pair_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long n_e = (long long)Wc * d.N;
+    const int npl = d.L - 2;
     const int grid = (int)(n_e < 4 * 148 ? n_e : 4 * 148);
-    pair_grad_kernel<<<grid, PG_THREADS, smem, stream>>>(sys, fp, gb, n_e);
+#define DS_PG_LAUNCH(NPL_)                                                                                              \
+    do {                                                                                                                \
+        if (smem > 48 * 1024)                                                                                           \
+            DS_CUDA_CHECK(cudaFuncSetAttribute(pair_grad_kernel<NPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        pair_grad_kernel<NPL_><<<grid, PG_THREADS, smem, stream>>>(sys, fp, gb, n_e);                                     \
+    } while (0)
+    if (npl <= 0) DS_PG_LAUNCH(0);
+    else if (npl == 1) DS_PG_LAUNCH(1);
+    else DS_PG_LAUNCH(2);
+#undef DS_PG_LAUNCH
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

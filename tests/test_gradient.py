@@ -70,7 +70,7 @@ def _rel_err(a, b):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,nw", [("h4", 5), ("lih_prim", 4), ("graphene8", 3), ("h10", 3)])
+@pytest.mark.parametrize("name,nw", [("h4", 5), ("lih_prim", 4), ("graphene8", 3), ("h10", 3), ("graphite54", 2)])
 def test_gpu_logpsi_vjp_matches_oracle(name, nw):
     from deepsolid_b200 import network
     sc, kl, pn, P = system(name)
