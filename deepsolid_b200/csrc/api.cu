@@ -126,6 +126,15 @@ struct ds_ctx {
 
 namespace {
 
+// Slater matrix blocks: two n_s x n_s matrices per determinant, or one N x N matrix with full_det
+inline int nblk_of(const ds_ctx* c) { return ds_nblk(c->sys.d); }
+inline size_t blk_n(const ds_ctx* c, int b) { return (size_t)ds_blk_n(c->sys.d, b); }
+inline size_t mats_per_walker(const ds_ctx* c) {
+    size_t t = 0;
+    for (int b = 0; b < nblk_of(c); ++b) t += (size_t)c->sys.d.D * blk_n(c, b) * blk_n(c, b) * 2;
+    return t;
+}
+
 template <typename T>
 int dev_alloc(ds_ctx* c, T** out, size_t count) {
     void* p = nullptr;
@@ -245,7 +254,9 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
     static const char* lmn[] = {"LAPM0", "LAPM1"};
     static const char* dn[] = {"DA0", "DA1"};
     for (int s = 0; s < 2; ++s) {
-        size_t ns = c->n_s[s];
+        L.MAT[s] = L.LAPM[s] = L.DA[s] = nullptr;
+        if (s >= nblk_of(c)) continue;
+        size_t ns = blk_n(c, s);
         L.MAT[s] = ws.take(mn[s], W * d.D * ns * ns * 2);
         L.LAPM[s] = lap ? ws.take(lmn[s], W * d.D * ns * ns * 2) : nullptr;
         L.DA[s] = lap ? ws.take(dn[s], W * d.D * d.NDp * ns * ns * 2) : nullptr;
@@ -270,7 +281,7 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
         }
         for (int s = 0; s < 2; ++s) {
             size_t ns = c->n_s[s];
-            L.XINV[s] = ws.take(s ? "XINV1" : "XINV0", W * d.D * ns * ns * 2);
+            L.XINV[s] = (s < nblk_of(c)) ? ws.take(s ? "XINV1" : "XINV0", W * d.D * blk_n(c, s) * blk_n(c, s) * 2) : nullptr;
             L.GYs[s] = ws.take(s ? "GY1" : "GY0", W * ns * 2 * c->npar[s]);
         }
         L.GH[0] = ws.take("GH0", W * N * d.H);
@@ -466,7 +477,8 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             z.n_groups = Wc;
             z.Wd = c->Wd_orb[s]; z.sb = c->sb_orb[s]; z.N = 2 * c->npar[s]; z.K = H;
             z.n_elec = N; z.NDp = d.NDp; z.etab = Lo.ETAB; z.npar_max = c->npar_max;
-            z.n_s = ns; z.off_s = c->off_s[s]; z.n_det = d.D; z.DA = Lo.DA[s]; z.YOWN = Lo.YOWN;
+            z.n_s = ns; z.off_s = c->off_s[s]; z.n_det = d.D; z.DA = Lo.DA[d.full_det ? 0 : s]; z.YOWN = Lo.YOWN;
+            z.n_orb = ds_norb(d, s); z.n_rows_mat = ds_blk_n(d, d.full_det ? 0 : s); z.row0 = d.full_det ? c->off_s[s] : 0;
             if (int rc = ds_launch_oz_gemm(z, OZ_ORBJ, false, st)) return rc;
             c->launches++;
         } else if (lap) {
@@ -475,7 +487,8 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             j.rpg = (long long)ns * d.NDp; j.gstride = (long long)N * d.NDp; j.goff = (long long)c->off_s[s] * d.NDp;
             j.M = (long long)Wc * ns * d.NDp;
             j.n_elec = N; j.NDp = d.NDp; j.etab = Lo.ETAB; j.npar_max = c->npar_max;
-            j.n_s = ns; j.off_s = c->off_s[s]; j.n_det = d.D; j.DA = Lo.DA[s]; j.YOWN = Lo.YOWN;
+            j.n_s = ns; j.off_s = c->off_s[s]; j.n_det = d.D; j.DA = Lo.DA[d.full_det ? 0 : s]; j.YOWN = Lo.YOWN;
+            j.n_orb = ds_norb(d, s); j.n_rows_mat = ds_blk_n(d, d.full_det ? 0 : s); j.row0 = d.full_det ? c->off_s[s] : 0;
             if (int rc = gemm(c, j, GEMM_ORBJ, false, st, /*profile*/ true)) return rc;
         }
     }
@@ -483,9 +496,9 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
     c->launches++;
     if (mats_out) {
         size_t off = 0;
-        for (int s = 0; s < 2; ++s) {
-            size_t per = (size_t)d.D * c->n_s[s] * c->n_s[s] * 2;
-            size_t tot = (size_t)d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
+        for (int s = 0; s < nblk_of(c); ++s) {
+            size_t per = (size_t)d.D * blk_n(c, s) * blk_n(c, s) * 2;
+            size_t tot = mats_per_walker(c);
             DS_CUDA_CHECK(cudaMemcpy2DAsync(mats_out + off, tot * sizeof(double), Lo.MAT[s], per * sizeof(double),
                                             per * sizeof(double), Wc, cudaMemcpyDeviceToDevice, st));
             off += per;
@@ -513,7 +526,7 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
     GradBufs gb{};
     if (c->cot_mats) {      // eval_mats cotangent: no determinant involved
         gb.cot_mats = c->cot_mats;
-        gb.cot_mats_stride = (long long)d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
+        gb.cot_mats_stride = (long long)mats_per_walker(c);
     } else {
         sb.XINV[0] = Lo.XINV[0]; sb.XINV[1] = Lo.XINV[1];
         if (int rc = ds_launch_det_inverse(sys, sb, Wc, st)) return rc;
@@ -589,7 +602,7 @@ int run_batched(ds_ctx* c, const double* X, long long batch, bool lap, double* l
     int Wc = 0;
     if (int rc = plan_chunk(c, batch, lap, &Wc)) return rc;
     const int n3 = 3 * c->sys.d.N;
-    const size_t mat_per = (size_t)c->sys.d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
+    const size_t mat_per = mats_per_walker(c);
     double* const gxa = c->gx_abs;
     double* const gxp = c->gx_phase;
     int rc = 0;
@@ -661,12 +674,13 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     d.dist_type = nd->distance_type; d.F = (nd->distance_type == 1) ? 7 : 4;
     d.env_type = nd->envelope_type;
     c->bias_orb = nd->bias_orbitals != 0;
+    d.full_det = nd->full_det != 0;
     d.C0 = d.F * d.A; d.K0 = d.C0 + 2 * d.F; d.K1 = d.H + 2 * d.P;
     fill_lattice(c->sys.prim, sd->prim_latvec, sd->prim_AV, sd->prim_BV);
     fill_lattice(c->sys.sim, sd->sim_latvec, sd->sim_AV, sd->sim_BV);
     memcpy(c->sys.atoms, sd->prim_atoms, sizeof(double) * 3 * d.A);
     c->n_s[0] = d.n_up; c->n_s[1] = d.n_dn; c->off_s[0] = 0; c->off_s[1] = d.n_up;
-    c->npar[0] = d.n_up * d.D; c->npar[1] = d.n_dn * d.D; c->npar_max = std::max(c->npar[0], c->npar[1]);
+    c->npar[0] = ds_norb(d, 0) * d.D; c->npar[1] = ds_norb(d, 1) * d.D; c->npar_max = std::max(c->npar[0], c->npar[1]);
     c->nbuf = std::max(2, d.L - 1);
 
     EwaldDev& ew = c->ew;
@@ -684,8 +698,16 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     rc |= upload(c, &tmp, sd->gweight, (size_t)sd->n_g); ew.gweight = tmp;
     rc |= upload(c, &tmp, sd->ion_exp_re, (size_t)sd->n_g); ew.ion_re = tmp;
     rc |= upload(c, &tmp, sd->ion_exp_im, (size_t)sd->n_g); ew.ion_im = tmp;
-    rc |= upload(c, &c->klist[0], sd->klist_up, 3 * (size_t)d.n_up);
-    rc |= upload(c, &c->klist[1], sd->klist_dn, 3 * (size_t)d.n_dn);
+    if (d.full_det) {       // every channel carries all N orbitals: k-points of both channels concatenated (network.py:453)
+        std::vector<double> kcat(3 * (size_t)d.N);
+        memcpy(kcat.data(), sd->klist_up, 3 * (size_t)d.n_up * sizeof(double));
+        memcpy(kcat.data() + 3 * (size_t)d.n_up, sd->klist_dn, 3 * (size_t)d.n_dn * sizeof(double));
+        rc |= upload(c, &c->klist[0], kcat.data(), kcat.size());
+        rc |= upload(c, &c->klist[1], kcat.data(), kcat.size());
+    } else {
+        rc |= upload(c, &c->klist[0], sd->klist_up, 3 * (size_t)d.n_up);
+        rc |= upload(c, &c->klist[1], sd->klist_dn, 3 * (size_t)d.n_dn);
+    }
     if (rc) { ds_ctx_destroy(c); return DS_ERR_CUDA; }
     *out = c;
     return 0;
@@ -913,7 +935,7 @@ static int vjp_impl(ds_ctx* c, const double* x, int64_t batch, const double* cot
         int Wc = 0;
         if (int rc = plan_chunk(c, batch, false, &Wc, true)) return rc;
         const int n3 = 3 * d.N;
-        const long long mstride = (long long)d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
+        const long long mstride = (long long)mats_per_walker(c);
         static const double dummy = 0.0;           // grad mode of run_chunk is keyed on a non-null cotangent pointer
         int rc = 0;
         for (long long w0 = 0; w0 < batch && !rc; w0 += Wc) {
@@ -977,7 +999,7 @@ extern "C" int ds_logpsi_grad_x(ds_ctx* c, const double* x, int64_t batch, doubl
 
 extern "C" int64_t ds_orbitals_size(const ds_ctx* c) {
     if (!c) return -1;
-    return (int64_t)c->sys.d.D * (c->n_s[0] * c->n_s[0] + c->n_s[1] * c->n_s[1]) * 2;
+    return (int64_t)mats_per_walker(c);
 }
 
 extern "C" int ds_orbitals(ds_ctx* c, const double* x, int64_t batch, double* out, void* stream) {

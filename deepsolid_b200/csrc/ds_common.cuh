@@ -29,9 +29,16 @@ struct DsDims {
     int F;                  // features per electron-atom / electron-electron pair: 4 ('nu') or 7 ('tri')
     int dist_type;          // 0 = nu_distance (network.py:189-224), 1 = tri_distance (network.py:227-246)
     int env_type;           // 0 = isotropic, 1 = diagonal, 2 = full envelope (network.py:335-364)
+    int full_det;           // 1: every spin channel produces N orbitals and ONE N x N determinant per k is taken
+                            //    (network.py:552-559); 0: one n_s x n_s determinant per spin channel
     int C0, K0;             // F*A, F*A + 2F (layer-0 one-electron inputs, own + pair-mean)
     int K1;                 // H + 2P  (own + pair-mean columns of layers >= 1)
 };
+
+// orbitals per spin channel, and the Slater matrix an electron row goes to: block index, its size, the row index
+__host__ __device__ __forceinline__ int ds_norb(const DsDims& d, int s) { return d.full_det ? d.N : (s ? d.n_dn : d.n_up); }
+__host__ __device__ __forceinline__ int ds_nblk(const DsDims& d) { return d.full_det ? 1 : 2; }
+__host__ __device__ __forceinline__ int ds_blk_n(const DsDims& d, int blk) { return d.full_det ? d.N : (blk ? d.n_dn : d.n_up); }
 
 struct DsSys {
     DsDims d;

@@ -287,11 +287,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(const GemmParams 
                 int n = ncol_base + nt * 8;
                 if (n >= p.N) continue;
                 int pp = n >> 1;
-                int k = pp / p.n_s, o = pp - k * p.n_s;
+                int k = pp / p.n_orb, o = pp - k * p.n_orb;
                 double vr = acc[mt][nt][0], vi = acc[mt][nt][1];
                 double2 E = *reinterpret_cast<const double2*>(et + 2 * pp);
                 double outr = vr * E.x - vi * E.y, outi = vr * E.y + vi * E.x;
-                long long di = (((w * p.n_det + k) * p.NDp + d) * p.n_s + is) * (long long)p.n_s + o;
+                long long di = (((w * p.n_det + k) * p.NDp + d) * p.n_rows_mat + p.row0 + is) * (long long)p.n_orb + o;
                 *reinterpret_cast<double2*>(p.DA + 2 * di) = make_double2(outr, outi);
                 if (own) {
                     int c = d - 3 * (d / 3);

@@ -39,6 +39,7 @@ struct GemmParams {
     const double* etab;          // complex E value table [(w*N+i) * (5*npar_max) + p] (re,im)
     int npar_max;                // stride unit of etab / yown
     int n_s, off_s, n_det;
+    int n_orb, n_rows_mat, row0;   // orbitals per determinant (matrix columns), matrix rows, row of this channel's first electron
     double* DA;                  // complex [((w*D+k)*NDp+d)*n_s*n_s + i_s*n_s + o]
     double* YOWN;                // raw complex own rows [((w*N+i)*3+c)*npar_max + p]
 };

@@ -22,8 +22,12 @@ __global__ void __launch_bounds__(256) orb_grad_kernel(const DsSys sys, const Sl
     const long long w = e / N;
     const int i = (int)(e % N);
     const int s = (i < dm.n_up) ? 0 : 1;
-    const int ns = s ? dm.n_dn : dm.n_up;
-    const int is = s ? i - dm.n_up : i;
+    const int ne_s = s ? dm.n_dn : dm.n_up;         // electrons of this spin channel (rows of GY)
+    const int is_loc = s ? i - dm.n_up : i;
+    const int ns = ds_norb(dm, s);                  // orbitals per determinant = matrix columns
+    const int blk = dm.full_det ? 0 : s;
+    const int nrow = ds_blk_n(dm, blk);
+    const int is = dm.full_det ? i : is_loc;        // row of this electron in its matrix
     const int npar = ns * D;
     __shared__ cplx wk_s[64];                       // conj(c) * w_k per determinant
     const bool direct = gb.cot_mats != nullptr;     // cotangent of the matrices given by the caller (eval_mats)
@@ -53,18 +57,18 @@ __global__ void __launch_bounds__(256) orb_grad_kernel(const DsSys sys, const Sl
     const double* kl = sb.klist[s];
     const cplx* E = reinterpret_cast<const cplx*>(sb.ETAB) + e * 5LL * npar_max;
     const cplx* yv = reinterpret_cast<const cplx*>(sb.YV) + e * (long long)npar_max;
-    const cplx* xinv = reinterpret_cast<const cplx*>(sb.XINV[s]);
-    double* gy = gb.GY[s] + (w * ns + is) * 2LL * npar;
+    const cplx* xinv = reinterpret_cast<const cplx*>(sb.XINV[blk]);
+    double* gy = gb.GY[s] + (w * ne_s + is_loc) * 2LL * npar;
     for (int p = threadIdx.x; p < npar; p += blockDim.x) {
         const int k = p / ns, o = p - k * ns;
         cplx Gm;
         if (direct) {
             // ds_orbitals layout: per walker [spin0: D n0 n0][spin1: D n1 n1] complex, element (k, i_s, o)
-            const long long soff = s ? (long long)D * dm.n_up * dm.n_up : 0;
-            const double* cm = gb.cot_mats + w * gb.cot_mats_stride + 2 * (soff + ((long long)k * ns + is) * ns + o);
+            const long long soff = (s && !dm.full_det) ? (long long)D * dm.n_up * dm.n_up : 0;
+            const double* cm = gb.cot_mats + w * gb.cot_mats_stride + 2 * (soff + ((long long)k * nrow + is) * ns + o);
             Gm = cplx{cm[0], -cm[1]};               // dloss = Re(conj(cot) dM)
         } else {
-            const cplx X = xinv[((w * D + k) * ns + o) * (long long)ns + is];
+            const cplx X = xinv[((w * D + k) * nrow + o) * (long long)nrow + is];
             Gm = cmul(wk_s[k], X);
         }
         const cplx g = cmul(Gm, E[p]);              // cotangent of Y: dloss = Re(g dY) = g.re dYr - g.im dYi

@@ -488,12 +488,12 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             } else {
                 // OZ_ORBJ: group = walker, row in group = is*NDp + d, channel n = 2*pp + (re|im), pp = k*n_s + o.
                 const int pp = n >> 1, im = n & 1;
-                const int kdet = pp / p.n_s, oo = pp - kdet * p.n_s;
+                const int kdet = pp / p.n_orb, oo = pp - kdet * p.n_orb;
                 const int ND = 3 * p.n_elec;
-                const long long ns2 = 2LL * p.n_s * p.n_s;
+                const long long ns2 = 2LL * p.n_rows_mat * p.n_orb;
                 int is = (int)((unsigned)q0 / (unsigned)p.NDp);
                 int d = (int)q0 - is * p.NDp;
-                double* dab = p.DA + 2 * ((((long long)grp * p.n_det + kdet) * p.NDp) * p.n_s * p.n_s + oo) + im;
+                double* dab = p.DA + 2 * ((((long long)grp * p.n_det + kdet) * p.NDp) * p.n_rows_mat * p.n_orb + oo) + im;
 #pragma unroll
                 for (int b = 0; b < EPI_COLS / 8; ++b) {
                     if (8 * b < nvalid) {                                   // warp-uniform
@@ -503,7 +503,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             const double2 E = *reinterpret_cast<const double2*>(p.etab + e * 10LL * p.npar_max + 2 * pp);
                             Ex = E.x; Ey = E.y;
                         }
-                        double* dp = dab + d * ns2 + 2LL * is * p.n_s;
+                        double* dp = dab + d * ns2 + 2LL * (p.row0 + is) * p.n_orb;
                         double* yp = p.YOWN + 2 * (e * 3LL * p.npar_max + pp) + im;
                         const int c0 = d - 3 * (p.off_s + is);              // own-coordinate index of column 0
                         if (full) orbj_block8<true>(zz + 8 * b, sap + 8 * b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, true);

@@ -49,6 +49,7 @@ struct OzParams {
     const double* R; int ldr;
     const double* etab; int npar_max;
     int n_s, off_s, n_det;
+    int n_orb, n_rows_mat, row0;   // orbitals per determinant (matrix columns), matrix rows, row of this channel's first electron
     double* DA; double* YOWN;
     int dbg;                 // probe only: 1 = epilogue skips TMEM reads/stores, 2 = no MMA issue, 4 = no TMA
 };

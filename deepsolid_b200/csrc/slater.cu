@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) etab_kernel(const DsSys sys, const Slater
     const int N = dm.N, A = dm.A, D = dm.D;
     const int w = (int)(e / N), i = (int)(e % N);
     const int s = (i < dm.n_up) ? 0 : 1;
-    const int ns = s ? dm.n_dn : dm.n_up;
+    const int ns = ds_norb(dm, s);              // orbitals of this spin channel
     const int npar = ns * D;
     const double* x = sb.X + (long long)w * 3 * N + 3 * i;
     const double x0 = x[0], x1 = x[1], x2 = x[2];
@@ -112,21 +112,23 @@ __global__ void __launch_bounds__(256) assemble_kernel(const DsSys sys, const Sl
     const long long w = e / N;
     const int i = (int)(e % N);
     const int s = (i < dm.n_up) ? 0 : 1;
-    const int ns = s ? dm.n_dn : dm.n_up;
-    const int is = s ? i - dm.n_up : i;
+    const int ns = ds_norb(dm, s);                              // orbitals = columns of the matrix
+    const int blk = dm.full_det ? 0 : s;
+    const int nrow = ds_blk_n(dm, blk);                         // rows of the matrix
+    const int is = dm.full_det ? i : (s ? i - dm.n_up : i);     // row of this electron
     const int npar = ns * D;
     const cplx* E = reinterpret_cast<const cplx*>(sb.ETAB) + e * 5LL * npar_max;
     const cplx* yv = reinterpret_cast<const cplx*>(sb.YV) + e * (long long)npar_max;
     const cplx* yl = reinterpret_cast<const cplx*>(sb.YL) + e * (long long)npar_max;
     const cplx* yo = reinterpret_cast<const cplx*>(sb.YOWN) + e * 3LL * npar_max;
-    cplx* mat = reinterpret_cast<cplx*>(sb.MAT[s]);
-    cplx* lapm = reinterpret_cast<cplx*>(sb.LAPM[s]);
-    cplx* da = reinterpret_cast<cplx*>(sb.DA[s]);
+    cplx* mat = reinterpret_cast<cplx*>(sb.MAT[blk]);
+    cplx* lapm = reinterpret_cast<cplx*>(sb.LAPM[blk]);
+    cplx* da = reinterpret_cast<cplx*>(sb.DA[blk]);
     for (int p = threadIdx.x; p < npar; p += blockDim.x) {
         const int k = p / ns, o = p - k * ns;
         const cplx O = yv[p];
         const cplx E0 = E[p];
-        const long long mi = ((w * D + k) * ns + is) * ns + o;
+        const long long mi = ((w * D + k) * nrow + is) * ns + o;
         mat[mi] = cmul(O, E0);
         if (JETS) {
             cplx l = cmul(yl[p], E0);
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const DsSys sys, const Sl
                 const cplx oj = yo[(long long)c * npar_max + p];
                 l.re += 2.0 * (oj.re * Ec.re - oj.im * Ec.im);
                 l.im += 2.0 * (oj.re * Ec.im + oj.im * Ec.re);
-                const long long di = (((w * D + k) * NDp + 3 * i + c) * ns + is) * (long long)ns + o;
+                const long long di = (((w * D + k) * NDp + 3 * i + c) * nrow + is) * (long long)ns + o;
                 cplx cur = da[di];
                 cfma(cur, O, Ec);
                 da[di] = cur;
@@ -161,9 +163,21 @@ __global__ void __launch_bounds__(DET_THREADS) det_kernel(const DsSys sys, const
     const DsDims& dm = sys.d;
     const int D = dm.D, NDp = dm.NDp, ND = dm.ND;
     const int k = blockIdx.x % D;
-    const int s = (blockIdx.x / D) % 2;
-    const long long w = blockIdx.x / (2 * D);
-    const int n = s ? dm.n_dn : dm.n_up;
+    const int nblk = ds_nblk(dm);
+    const int s = (blockIdx.x / D) % nblk;          // matrix block: spin channel, or the single full determinant
+    const long long w = blockIdx.x / (nblk * D);
+    const int n = ds_blk_n(dm, s);
+    if (dm.full_det) {                               // the second slot of the per-spin results stays neutral
+        const long long slot1 = (w * 2 + 1) * D + k;
+        if (threadIdx.x == 0) {
+            double* ld1 = sb.LOGDET + slot1 * 3;
+            ld1[0] = 0.0; ld1[1] = 1.0; ld1[2] = 0.0;
+            if (sb.TRSQ) { sb.TRSQ[slot1 * 2] = 0.0; sb.TRSQ[slot1 * 2 + 1] = 0.0; }
+            if (sb.TRLAP) { sb.TRLAP[slot1 * 2] = 0.0; sb.TRLAP[slot1 * 2 + 1] = 0.0; }
+        }
+        if (sb.TAU)
+            for (int t = threadIdx.x; t < 2 * dm.NDp; t += blockDim.x) sb.TAU[slot1 * 2 * dm.NDp + t] = 0.0;
+    }
     const int np = ((n + 2) / 3) * 3;               // padded to the 3x3 register block
     const int tid = threadIdx.x;
 
@@ -408,9 +422,21 @@ __global__ void __launch_bounds__(512, 1) det_lap_kernel(const DsSys sys, const 
     const DsDims& dm = sys.d;
     const int D = dm.D, NDp = dm.NDp, ND = dm.ND;
     const int k = blockIdx.x % D;
-    const int s = (blockIdx.x / D) % 2;
-    const long long w = blockIdx.x / (2 * D);
-    const int n = s ? dm.n_dn : dm.n_up;
+    const int nblk = ds_nblk(dm);
+    const int s = (blockIdx.x / D) % nblk;          // matrix block: spin channel, or the single full determinant
+    const long long w = blockIdx.x / (nblk * D);
+    const int n = ds_blk_n(dm, s);
+    if (dm.full_det) {                               // the second slot of the per-spin results stays neutral
+        const long long slot1 = (w * 2 + 1) * D + k;
+        if (threadIdx.x == 0) {
+            double* ld1 = sb.LOGDET + slot1 * 3;
+            ld1[0] = 0.0; ld1[1] = 1.0; ld1[2] = 0.0;
+            if (sb.TRSQ) { sb.TRSQ[slot1 * 2] = 0.0; sb.TRSQ[slot1 * 2 + 1] = 0.0; }
+            if (sb.TRLAP) { sb.TRLAP[slot1 * 2] = 0.0; sb.TRLAP[slot1 * 2 + 1] = 0.0; }
+        }
+        if (sb.TAU)
+            for (int t = threadIdx.x; t < 2 * dm.NDp; t += blockDim.x) sb.TAU[slot1 * 2 * dm.NDp + t] = 0.0;
+    }
     const int np = ((n + 2) / 3) * 3;               // padded to the 3x3 register block
     const int nb = np / 3;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -668,9 +694,21 @@ __global__ void __launch_bounds__(256, 2) det_dmma_kernel(const DsSys sys, const
     const DsDims& dm = sys.d;
     const int D = dm.D, NDp = dm.NDp, ND = dm.ND;
     const int k = blockIdx.x % D;
-    const int s = (blockIdx.x / D) % 2;
-    const long long w = blockIdx.x / (2 * D);
-    const int n = s ? dm.n_dn : dm.n_up;
+    const int nblk = ds_nblk(dm);
+    const int s = (blockIdx.x / D) % nblk;          // matrix block: spin channel, or the single full determinant
+    const long long w = blockIdx.x / (nblk * D);
+    const int n = ds_blk_n(dm, s);
+    if (dm.full_det) {                               // the second slot of the per-spin results stays neutral
+        const long long slot1 = (w * 2 + 1) * D + k;
+        if (threadIdx.x == 0) {
+            double* ld1 = sb.LOGDET + slot1 * 3;
+            ld1[0] = 0.0; ld1[1] = 1.0; ld1[2] = 0.0;
+            if (sb.TRSQ) { sb.TRSQ[slot1 * 2] = 0.0; sb.TRSQ[slot1 * 2 + 1] = 0.0; }
+            if (sb.TRLAP) { sb.TRLAP[slot1 * 2] = 0.0; sb.TRLAP[slot1 * 2 + 1] = 0.0; }
+        }
+        if (sb.TAU)
+            for (int t = threadIdx.x; t < 2 * dm.NDp; t += blockDim.x) sb.TAU[slot1 * 2 * dm.NDp + t] = 0.0;
+    }
     const int np = n;                               // no padding of the complex inverse
     constexpr int MP = MT * 8;                      // rows of Xe / Be (>= 2n)
     constexpr int LDX = MP + 4;                     // = 4 or 12 mod 16
@@ -976,7 +1014,7 @@ int launch_det_dmma(const DsSys& sys, const SlaterBufs& sb, int Wc, int nmax, cu
         DS_CUDA_CHECK(cudaFuncSetAttribute(det_dmma_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg = smem;
     }
-    dim3 grid((unsigned)((long long)Wc * 2 * sys.d.D));
+    dim3 grid((unsigned)((long long)Wc * ds_nblk(sys.d) * sys.d.D));
     det_dmma_kernel<MT><<<grid, 256, smem, stream>>>(sys, sb, G, ldb_of(G), alias ? 1 : 0);
     DS_CUDA_CHECK(cudaGetLastError());
     *done = true;
@@ -1086,11 +1124,11 @@ int ds_launch_orb_assemble(const DsSys& sys, const SlaterBufs& sb, int Wc, int n
 }
 
 int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cudaStream_t stream) {
-    const int nmax = sys.d.n_up > sys.d.n_dn ? sys.d.n_up : sys.d.n_dn;
+    const int nmax = sys.d.full_det ? sys.d.N : (sys.d.n_up > sys.d.n_dn ? sys.d.n_up : sys.d.n_dn);
     DS_REQUIRE(nmax <= 128, "determinants larger than 128x128 are not supported (n_s=%d)", nmax);
     const int np = ((nmax + 2) / 3) * 3;
     const int nb = np / 3;
-    dim3 grid((unsigned)((long long)Wc * 2 * sys.d.D));
+    dim3 grid((unsigned)((long long)Wc * ds_nblk(sys.d) * sys.d.D));
     static const bool use_v1 = getenv("DS_DET_V1") && atoi(getenv("DS_DET_V1")) != 0;
     static const bool use_v2 = getenv("DS_DET_V2") && atoi(getenv("DS_DET_V2")) != 0;
     if (lap && !use_v1 && !use_v2) {
@@ -1158,9 +1196,9 @@ int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cuda
 }
 
 int ds_launch_det_inverse(const DsSys& sys, const SlaterBufs& sb, int Wc, cudaStream_t stream) {
-    const int nmax = sys.d.n_up > sys.d.n_dn ? sys.d.n_up : sys.d.n_dn;
+    const int nmax = sys.d.full_det ? sys.d.N : (sys.d.n_up > sys.d.n_dn ? sys.d.n_up : sys.d.n_dn);
     DS_REQUIRE(nmax <= 128, "determinants larger than 128x128 are not supported (n_s=%d)", nmax);
-    DS_REQUIRE(sb.XINV[0] && sb.XINV[1], "det_inverse: output buffers missing");
+    DS_REQUIRE(sb.XINV[0] && (sys.d.full_det || sb.XINV[1]), "det_inverse: output buffers missing");
     const int np = ((nmax + 2) / 3) * 3;
     const size_t smem = (size_t)(np * np + np) * sizeof(cplx);
     DS_REQUIRE(smem <= 226 * 1024, "determinant kernel needs %zu bytes of shared memory", smem);
@@ -1168,7 +1206,7 @@ int ds_launch_det_inverse(const DsSys& sys, const SlaterBufs& sb, int Wc, cudaSt
         DS_CUDA_CHECK(cudaFuncSetAttribute(det_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_det_smem[1] = smem;
     }
-    dim3 grid((unsigned)((long long)Wc * 2 * sys.d.D));
+    dim3 grid((unsigned)((long long)Wc * ds_nblk(sys.d) * sys.d.D));
     det_kernel<true><<<grid, DET_THREADS, smem, stream>>>(sys, sb, 0);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -54,7 +54,7 @@ def unflatten_params(leaves, n_layers: int, bias_orbitals: bool = False) -> dict
 class HotPath:
     def __init__(self, simulation_cell, klist, hidden_dims=((256, 32),) * 3, determinants: int = 8,
                  device: Optional[int] = None, distance_type: str = "nu", envelope_type: str = "isotropic",
-                 bias_orbitals: bool = False):
+                 bias_orbitals: bool = False, full_det: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("deepsolid_b200 needs a CUDA device: the local-energy hot path has no CPU fallback")
         self.lib = _lib.load()
@@ -77,6 +77,7 @@ class HotPath:
             raise ValueError("diagonal / full envelopes need distance_type='nu' (3-component relative vectors)")
         self.envelope_type = envelope_type
         self.bias_orbitals = bool(bias_orbitals)
+        self.full_det = bool(full_det)
         self.n_up, self.n_dn = simulation_cell.nelec
         self.nelec = self.n_up + self.n_dn
         tb = build_ewald_tables(simulation_cell)
@@ -103,7 +104,8 @@ class HotPath:
             ee_const=float(tb.ee_const(ne)), ei_const=float(tb.ei_const(ne)), ii_total=float(tb.ii_total))
         nd = _lib.NetDesc(n_layers=len(hidden_dims), hidden_one=hidden_dims[0][0], hidden_two=hidden_dims[0][1],
                           n_det=self.determinants, distance_type=1 if distance_type == "tri" else 0,
-                          envelope_type=envs[envelope_type], bias_orbitals=1 if bias_orbitals else 0)
+                          envelope_type=envs[envelope_type], bias_orbitals=1 if bias_orbitals else 0,
+                          full_det=1 if full_det else 0)
         h = C.c_void_p()
         _lib.check(self.lib.ds_ctx_create(C.byref(sd), C.byref(nd), self.device, C.byref(h)))
         self.h = h
@@ -203,7 +205,7 @@ class HotPath:
         B = td.shape[0]
         D = self.determinants
         parts = []
-        for cm, ns in zip(cot_mats, (self.n_up, self.n_dn)):
+        for cm, ns in zip(cot_mats, ((self.nelec,) if self.full_det else (self.n_up, self.n_dn))):
             cm = torch.as_tensor(cm).to(self.tdev).to(torch.complex128).reshape(B, D * ns * ns)
             parts.append(torch.view_as_real(cm).reshape(B, -1))
         cot = torch.cat(parts, dim=1).contiguous()
@@ -244,7 +246,7 @@ class HotPath:
         _lib.check(self.lib.ds_orbitals(self.h, td.data_ptr(), B, out.data_ptr(), self._stream()))
         D = self.determinants
         mats, o = [], 0
-        for ns in (self.n_up, self.n_dn):
+        for ns in ((self.nelec,) if self.full_det else (self.n_up, self.n_dn)):
             n = D * ns * ns * 2
             m = torch.view_as_complex(out[:, o:o + n].reshape(B, D, ns, ns, 2).contiguous())
             mats.append(m if on_dev else m.cpu())

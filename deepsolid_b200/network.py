@@ -90,14 +90,11 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
     unsupported = []
     if envelope_type not in ("isotropic", "diagonal", "full"):
         unsupported.append(f"envelope_type={envelope_type!r}")
-    if full_det:
-        unsupported.append("full_det=True")
     if use_last_layer:
         unsupported.append("use_last_layer=True")
     if unsupported:
         raise ValueError("not implemented in the CUDA hot path: " + ", ".join(unsupported) +
-                         " (the reference's tested defaults are isotropic / full_det=False / "
-                         "use_last_layer=False / bias_orbitals=False)")
+                         " (use_last_layer=True is the one structural option without a CUDA path)")
     if simulation_cell is None or klist is None:
         raise ValueError("simulation_cell and klist are required")
 
@@ -107,7 +104,7 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
         if state["hp"] is None:
             state["hp"] = HotPath(simulation_cell, klist, hidden_dims=hidden_dims, determinants=determinants,
                                   device=device, distance_type=distance_type, envelope_type=envelope_type,
-                                  bias_orbitals=bias_orbitals)
+                                  bias_orbitals=bias_orbitals, full_det=full_det)
         return state["hp"]
 
     def init(key, data=None):

@@ -80,8 +80,8 @@ typedef struct ds_system_desc {
 } ds_system_desc;
 
 /* Network hyper-parameters (base_config.py:129-139).  Of the structural switches the
- * reference's tested defaults are implemented (full_det=False, use_last_layer=False)
- * with every envelope_type, both distance functions and optional orbital biases. */
+ * only use_last_layer=True is not implemented: every envelope_type, both distance functions, optional
+ * orbital biases, per-spin or full determinants. */
 typedef struct ds_net_desc {
     int32_t n_layers;      /* len(hidden_dims)            (3)   */
     int32_t hidden_one;    /* one-electron stream width   (256) */
@@ -90,6 +90,8 @@ typedef struct ds_net_desc {
     int32_t distance_type; /* 0 = 'nu' (network.py:189-224, 4 features per pair), 1 = 'tri' (network.py:227-246, 7) */
     int32_t envelope_type; /* 0 = isotropic, 1 = diagonal (sigma [A][3][n_s*D]), 2 = full (sigma [3][3][A][n_s*D]); network.py:335-364 */
     int32_t bias_orbitals; /* 1: every orbital[s] has a bias leaf b (2*n_s*D,) right after its w (network.py:177-179) */
+    int32_t full_det;      /* 1: every spin channel makes N orbitals per determinant and ONE (N x N) determinant per k is
+                            * taken (network.py:552-559): orbital w (H, 2*N*D), envelope (A, N*D), ds_orbitals -> (D, N, N) */
 } ds_net_desc;
 
 DS_API const char *ds_last_error(void);

@@ -62,7 +62,10 @@ def test_constructor_errors_match_reference():
     with pytest.raises(ValueError, match="distance"):
         network.make_solid_fermi_net(klist=kl, simulation_cell=sc, distance_type="l2", envelope_type="isotropic", full_det=False)
     with pytest.raises(ValueError, match="not implemented"):
-        network.make_solid_fermi_net(klist=kl, simulation_cell=sc)             # reference defaults full/full_det
+        network.make_solid_fermi_net(klist=kl, simulation_cell=sc, use_last_layer=True)
+    with pytest.raises(ValueError, match="not implemented"):
+        network.make_solid_fermi_net(klist=kl, simulation_cell=sc, envelope_type="output")
+    network.make_solid_fermi_net(klist=kl, simulation_cell=sc)                  # reference defaults (full / full_det) construct
     net = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc, determinants=8)
     with pytest.raises(ValueError, match="laplacian"):
         hamiltonian.local_energy_seperate(net.apply, sc, mode="nope")

@@ -175,3 +175,49 @@ def test_gpu_orbital_bias_matches_oracle(name):
     for a, b in zip(flatten_params(g), go):
         assert tuple(a.shape) == tuple(b.shape)
         assert float((a.cpu() - b).abs().max()) < 1e-9 * max(1.0, float(b.abs().max()))
+
+
+# ---------------------------------------------------------------------------
+# full_det=True (network.py:552-559): one N x N determinant per k instead of one per spin channel
+# ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["h4", "graphene8", "lih_prim"])
+def test_gpu_full_det_matches_oracle(name):
+    from deepsolid_b200 import network, hamiltonian
+    from deepsolid_b200.hotpath import flatten_params
+    sc = C.build_system(name)
+    kl = C.make_klist(sc)
+    N = sum(sc.nelec)
+    pn = O.init_params(np.random.default_rng(888), sc.original_cell.natm, sc.nelec, full_det=True)
+    P = O.params_to_torch(pn)
+    assert P["orbital"][0]["w"].shape[1] == 2 * N * 8
+    dev = torch.device("cuda", 0)
+    kw = dict(envelope_type="isotropic", full_det=True, klist=kl, simulation_cell=sc, determinants=8)
+    ld = network.make_solid_fermi_net(method_name="eval_logdet", **kw)
+    hp = ld.apply.hotpath()
+    mt = network.make_solid_fermi_net(method_name="eval_mats", hotpath=hp, **kw)
+    nw = 3
+    X = torch.as_tensor(C.init_walkers(sc, nw, seed=37))
+    f_ld = O.make_solid_fermi_net(kl, sc, full_det=True, method_name="eval_logdet")
+    f_ps = O.make_solid_fermi_net(kl, sc, full_det=True, method_name="eval_phase_and_slogdet")
+    f_mt = O.make_solid_fermi_net(kl, sc, full_det=True, method_name="eval_mats")
+    mats = mt.apply(P, X.to(dev))
+    assert len(mats) == 1 and tuple(mats[0].shape) == (nw, 8, N, N)
+    for b in range(nw):
+        assert float((mats[0][b].cpu() - f_mt(P, X[b])[0]).abs().max()) < 1e-10
+    v = ld.apply(P, X.to(dev)).cpu()
+    vo = torch.stack([f_ld(P, x) for x in X])
+    assert float((v.real - vo.real).abs().max()) < 1e-10
+    assert float(angle_diff(v.imag, vo.imag).max()) < 1e-10
+    ke, ew = hamiltonian.local_energy_seperate(ld.apply, sc, mode="for")(P, X.to(dev))
+    elo = O.local_energy_seperate(f_ld, sc, mode="dim_batch")
+    for b in range(nw):
+        ko, eo = elo(P, X[b])
+        assert abs(complex(ko) - complex(ke[b].cpu())) < 1e-8
+    rng = np.random.default_rng(8)
+    ca, cp = torch.as_tensor(rng.standard_normal(nw)), torch.as_tensor(rng.standard_normal(nw))
+    g = hp.logpsi_vjp(X.to(dev), ca, cp)
+    go = O.logpsi_vjp(f_ps, P, X, ca, cp)
+    for a, b in zip(flatten_params(g), flatten_params(go)):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert float((a.cpu() - b).abs().max()) < 1e-9 * max(1.0, float(b.abs().max()))
