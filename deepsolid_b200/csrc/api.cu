@@ -106,7 +106,7 @@ struct ds_ctx {
     double* genv_sigma[2] = {};
     // workspace
     Workspace ws;
-    size_t ws_limit = size_t(8) << 30;  // bytes
+    size_t ws_limit = size_t(24) << 30; // bytes: ~270 walkers per chunk at 54 electrons (fewer, longer launches)
     // mcmc scratch
     DevBuf mc_x2, mc_lp, mc_lp2, host_stage;
     // instrumentation
@@ -667,6 +667,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     if (const char* ev = getenv("DS_L0_GEMM")) c->use_l0_kernel = atoi(ev) == 0;
     if (const char* ev = getenv("DS_NO_SLICE_MEANS")) c->use_slice_means = atoi(ev) == 0;
     if (const char* ev = getenv("DS_NO_I8_MEANS")) c->use_i8_means = atoi(ev) == 0;
+    if (const char* ev = getenv("DS_WS_GIB")) { double g = atof(ev); if (g >= 0.25) c->ws_limit = (size_t)(g * 1073741824.0); }
     DsDims& d = c->sys.d;
     d.n_up = sd->n_up; d.n_dn = sd->n_dn; d.N = sd->n_up + sd->n_dn; d.A = sd->n_atoms_prim;
     d.H = nd->hidden_one; d.P = nd->hidden_two; d.D = nd->n_det; d.L = nd->n_layers;
