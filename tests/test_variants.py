@@ -221,3 +221,60 @@ def test_gpu_full_det_matches_oracle(name):
     for a, b in zip(flatten_params(g), flatten_params(go)):
         assert tuple(a.shape) == tuple(b.shape)
         assert float((a.cpu() - b).abs().max()) < 1e-9 * max(1.0, float(b.abs().max()))
+
+
+# ---------------------------------------------------------------------------
+# spin-polarised occupations (n_up != n_dn): different matrix sizes per spin channel everywhere
+# ---------------------------------------------------------------------------
+def _polarised(name, nelec):
+    sc = C.build_system(name)
+    assert sum(nelec) == sum(sc.nelec)
+    sc.nelec = tuple(nelec)
+    kl = C.make_klist(sc)
+    pn = O.init_params(np.random.default_rng(888), sc.original_cell.natm, sc.nelec)
+    return sc, kl, O.params_to_torch(pn)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,nelec,full_det", [("h4", (3, 1), False), ("graphene8", (5, 3), False), ("graphene8", (3, 5), False),
+                                                 ("h4", (1, 3), True)])
+def test_gpu_spin_polarised_matches_oracle(name, nelec, full_det):
+    from deepsolid_b200 import network, hamiltonian, qmc
+    from deepsolid_b200.hotpath import flatten_params
+    sc, kl, P = _polarised(name, nelec)
+    if full_det:
+        P = O.params_to_torch(O.init_params(np.random.default_rng(888), sc.original_cell.natm, sc.nelec, full_det=True))
+    dev = torch.device("cuda", 0)
+    kw = dict(envelope_type="isotropic", full_det=full_det, klist=kl, simulation_cell=sc, determinants=8)
+    ld = network.make_solid_fermi_net(method_name="eval_logdet", **kw)
+    hp = ld.apply.hotpath()
+    sl = network.make_solid_fermi_net(method_name="eval_slogdet", hotpath=hp, **kw)
+    nw = 5
+    X = torch.as_tensor(C.init_walkers(sc, nw, seed=41))
+    f_ld = O.make_solid_fermi_net(kl, sc, full_det=full_det, method_name="eval_logdet")
+    f_ps = O.make_solid_fermi_net(kl, sc, full_det=full_det, method_name="eval_phase_and_slogdet")
+    f_sl = O.make_solid_fermi_net(kl, sc, full_det=full_det, method_name="eval_slogdet")
+    v = ld.apply(P, X.to(dev)).cpu()
+    vo = torch.stack([f_ld(P, x) for x in X])
+    assert float((v.real - vo.real).abs().max()) < 1e-10
+    assert float(angle_diff(v.imag, vo.imag).max()) < 1e-10
+    ke, ew = hamiltonian.local_energy_seperate(ld.apply, sc, mode="for")(P, X.to(dev))
+    elo = O.local_energy_seperate(f_ld, sc, mode="dim_batch")
+    for b in range(nw):
+        ko, eo = elo(P, X[b])
+        assert abs(complex(ko) - complex(ke[b].cpu())) < 1e-8
+        assert abs(float(eo) - float(ew[b])) < 1e-9
+    rng = np.random.default_rng(12)
+    ca, cp = torch.as_tensor(rng.standard_normal(nw)), torch.as_tensor(rng.standard_normal(nw))
+    g = hp.logpsi_vjp(X.to(dev), ca, cp)
+    go = O.logpsi_vjp(f_ps, P, X, ca, cp)
+    for a, b in zip(flatten_params(g), flatten_params(go)):
+        assert float((a.cpu() - b).abs().max()) < 1e-9 * max(1.0, float(b.abs().max()))
+    B, steps = 4, 2
+    gen = torch.Generator().manual_seed(6)
+    xi = torch.randn(steps, B, X.shape[1], dtype=torch.float64, generator=gen)
+    u = torch.rand(steps, B, dtype=torch.float64, generator=gen)
+    lat = torch.as_tensor(sc.lattice_vectors())
+    xn, pm, masks = qmc.make_mcmc_step(sl.apply, B, lat, steps=steps)(P, X[:B].to(dev), (xi, u), 0.3, return_masks=True)
+    xo, po, mo = O.make_mcmc_step(lambda p, x: O.batch_apply(f_sl, p, x), B, lat, steps=steps)(P, X[:B], (xi, u), 0.3)
+    assert torch.equal(masks.cpu().bool(), mo)
