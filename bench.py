@@ -74,27 +74,20 @@ def make_inputs(system, batch, seed=666):
     return cell, klist, X
 
 
-def oracle_params(cell):
-    from oracle import deepsolid_oracle as O      # parameters only (numpy RNG, seed 888)
-    return O.init_params(np.random.default_rng(888), cell.original_cell.natm, cell.nelec)
-
-
-def torch_params(pn):
-    def conv(v):
-        if isinstance(v, dict):
-            return {k: conv(x) for k, x in v.items()}
-        if isinstance(v, list):
-            return [conv(x) for x in v]
-        return torch.as_tensor(np.asarray(v, dtype=np.float64))
-    return conv(pn)
+def make_params(cell):
+    """Random-init parameters of the named architecture (product-side init, numpy Generator seed 888; the draw
+    order is the reference's, network.py:135-184)."""
+    from deepsolid_b200 import network
+    return network.init_solid_fermi_net_params(888, atoms=cell.original_cell.atom_coords(), spins=cell.nelec,
+                                               envelope_type="isotropic", full_det=False, determinants=8)
 
 
 # ---------------------------------------------------------------------------
-def cpu_oracle_rate(cell, klist, pn, X, n_walkers, threads):
-    """Local energies/s of the oracle (reference algorithm) on `threads` host threads."""
+def cpu_oracle_rate(cell, klist, P, X, n_walkers, threads):
+    """Local energies/s of the oracle (reference algorithm) on `threads` host threads.  The oracle is imported
+    here only: it is the CPU baseline / checker, never part of the measured GPU path."""
     from oracle import deepsolid_oracle as O
     torch.set_num_threads(threads)
-    P = O.params_to_torch(pn)
     f = O.make_solid_fermi_net(klist, cell, method_name="eval_logdet")
     el = O.local_energy_seperate(f, cell, mode="dim_batch")
     Xs = torch.as_tensor(X[:n_walkers])
@@ -188,8 +181,7 @@ def run_ours(args):
     batch = args.batch or C.SYSTEMS[system][1]
     mode, pn = C.SYSTEMS[system][2], C.SYSTEMS[system][3]
     cell, klist, X = make_inputs(system, batch, seed=666 + rank)        # every rank its own walkers
-    pnum = oracle_params(cell)
-    P = torch_params(pnum)
+    P = make_params(cell)
     net = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=klist,
                                        simulation_cell=cell, determinants=8, method_name="eval_logdet", device=local)
     slog = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=klist,
@@ -371,7 +363,7 @@ def run_ours(args):
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         nsamp = args.cpu_sample or max(1, min(8, int(20.0 / max(0.02, 1.5e-3 * cell.nelectron ** 2))))
-        rate, dt, out = cpu_oracle_rate(cell, klist, pnum, Xh.numpy(), nsamp, threads)
+        rate, dt, out = cpu_oracle_rate(cell, klist, P, Xh.numpy(), nsamp, threads)
         # the same walkers through the GPU: report the agreement next to the rate
         ke_g, ew_g = net.apply.hotpath().local_energy(Xd[:nsamp])
         d = max(abs(complex(k) + float(e) - complex(kg) - float(eg)) for (k, e), kg, eg in
@@ -392,7 +384,7 @@ def run_reference(args):
     system = args.system
     batch = args.batch or C.SYSTEMS[system][1]
     cell, klist, X = make_inputs(system, batch)
-    pnum = oracle_params(cell)
+    pnum = make_params(cell)
     threads = os.cpu_count() or 1
     nsamp = args.cpu_sample or max(1, min(4, int(10.0 / max(0.02, 1.5e-3 * cell.nelectron ** 2))))
     rates = []

@@ -3,9 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from deepsolid_b200 import cell as C, network
-from oracle import deepsolid_oracle as O
 sc = C.build_system("graphite54"); kl = C.make_klist(sc)
-P = O.params_to_torch(O.init_params(np.random.default_rng(888), sc.original_cell.natm, sc.nelec))
+P = network.init_solid_fermi_net_params(888, atoms=sc.original_cell.atom_coords(), spins=sc.nelec)
 net = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc, determinants=8,
                                    method_name="eval_logdet")
 hp = net.apply.hotpath(); hp.set_params(P)
