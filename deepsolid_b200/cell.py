@@ -240,6 +240,8 @@ def rock_salt(S: int = 3, L_ang: float = 4.0, Zx: float = 3.0, Zy: float = 1.0) 
 SYSTEMS = {
     "h10": (lambda: hydrogen_chain(5, 2.0), 256, "for", 3),
     "li24": (lambda: bcc_lithium((2, 2, 1)), 4096, "for", 3),
+    # the literal read_poscar.py tiling S = 2I of config/poscar/bcc_li.vasp (SURVEY section 8d, config 2 note)
+    "li48": (lambda: bcc_lithium((2, 2, 2)), 4096, "for", 3),
     "graphite54": (lambda: graphene((3, 3, 1)), 4096, "for", 3),
     "diamond64": (lambda: diamond(2), 4096, "partition", 3),
     "lih108": (lambda: rock_salt(3), 2048, "for", 3),
