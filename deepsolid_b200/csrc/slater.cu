@@ -742,18 +742,25 @@ __global__ void __launch_bounds__(256, 2) det_dmma_kernel(const DsSys sys, const
         const int a = idx / n, b = idx - a * n;
         off_ab[j] = a * LDB + b;
     }
-    // trace elements: 4 x 8 lane tiles (a = 4 ta + lane/8, b = 8 tb + lane%8): the straight and the transposed
-    // read of a warp are both at most 2-way bank conflicted (ld = 4 mod 16 rules out conflict-free columns)
-    const int tiles_b = (n + 7) >> 3, n_tiles = ((n + 3) >> 2) * tiles_b;
+    // trace elements: sum_{a,b} Y[a,b] Y[b,a] = sum_a Y[a,a]^2 + 2 sum_{a<b} Y[a,b] Y[b,a]: every thread owns up to
+    // JMAX fixed pairs (a <= b) of the upper triangle (linear index idx = tid + j * nthr, row-major over the triangle)
+    const int n_tri = n * (n + 1) / 2;
     int tr_ab[JMAX], tr_ba[JMAX];
+    double tr_w[JMAX];
 #pragma unroll
     for (int j = 0; j < JMAX; ++j) {
-        const int tl = warp + j * nwarp;
-        const int ta = tl / tiles_b, tb = tl - ta * tiles_b;
-        const int a = 4 * ta + (lane >> 3), b = 8 * tb + (lane & 7);
-        const bool ok = tl < n_tiles && a < n && b < n;
-        tr_ab[j] = ok ? a * LDB + b : -1;
-        tr_ba[j] = b * LDB + a;
+        const int idx = tid + j * nthr;
+        tr_ab[j] = -1; tr_ba[j] = 0; tr_w[j] = 0.0;
+        if (idx < n_tri) {
+            // row a holds n - a entries (b = a .. n-1); first index of row a: a n - a (a - 1) / 2
+            int a = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * idx)) * 0.5);
+            while (a > 0 && a * n - a * (a - 1) / 2 > idx) --a;
+            while ((a + 1) * n - (a + 1) * a / 2 <= idx) ++a;
+            const int b = a + (idx - (a * n - a * (a - 1) / 2));
+            tr_ab[j] = a * LDB + b;
+            tr_ba[j] = b * LDB + a;
+            tr_w[j] = (a == b) ? 1.0 : 2.0;
+        }
     }
     auto stage = [&](int d0, int g_cnt) {
         for (int g = 0; g < g_cnt; ++g) {
@@ -940,28 +947,29 @@ __global__ void __launch_bounds__(256, 2) det_dmma_kernel(const DsSys sys, const
             }
         }
         __syncthreads();
-        // sum_{a,b} Y[a,b] Y[b,a] of the valid directions (complex), the thread's fixed elements (a, b)
+        // sum_{a,b} Y[a,b] Y[b,a] of the valid directions (complex), the thread's fixed pairs (a <= b)
         for (int g = 0; g < g_cnt; ++g) {
             const double* col = Be + g * n;
             const double* coli = col + n * LDB;
 #pragma unroll
             for (int j = 0; j < JMAX; ++j) {
                 if (tr_ab[j] >= 0) {
-                    const double yr = col[tr_ab[j]], yi = coli[tr_ab[j]];
+                    const double yr = col[tr_ab[j]] * tr_w[j], yi = coli[tr_ab[j]] * tr_w[j];
                     const double zr = col[tr_ba[j]], zi = coli[tr_ba[j]];
                     sq_re = fma(yr, zr, sq_re); sq_re = fma(-yi, zi, sq_re);
                     sq_im = fma(yr, zi, sq_im); sq_im = fma(yi, zr, sq_im);
                 }
             }
-            for (int tl = warp + JMAX * nwarp; tl < n_tiles; tl += nwarp) {      // matrices with more than JMAX * nwarp tiles
-                const int ta = tl / tiles_b, tb = tl - ta * tiles_b;
-                const int a = 4 * ta + (lane >> 3), b = 8 * tb + (lane & 7);
-                if (a < n && b < n) {
-                    const double yr = col[a * LDB + b], yi = coli[a * LDB + b];
-                    const double zr = col[b * LDB + a], zi = coli[b * LDB + a];
-                    sq_re = fma(yr, zr, sq_re); sq_re = fma(-yi, zi, sq_re);
-                    sq_im = fma(yr, zi, sq_im); sq_im = fma(yi, zr, sq_im);
-                }
+            for (int idx = tid + JMAX * nthr; idx < n_tri; idx += nthr) {       // triangles larger than JMAX * nthr pairs
+                int a = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * idx)) * 0.5);
+                while (a > 0 && a * n - a * (a - 1) / 2 > idx) --a;
+                while ((a + 1) * n - (a + 1) * a / 2 <= idx) ++a;
+                const int b = a + (idx - (a * n - a * (a - 1) / 2));
+                const double wgt = (a == b) ? 1.0 : 2.0;
+                const double yr = col[a * LDB + b] * wgt, yi = coli[a * LDB + b] * wgt;
+                const double zr = col[b * LDB + a], zi = coli[b * LDB + a];
+                sq_re = fma(yr, zr, sq_re); sq_re = fma(-yi, zi, sq_re);
+                sq_im = fma(yr, zi, sq_im); sq_im = fma(yi, zr, sq_im);
             }
         }
         // tr(Y_g): warp g
