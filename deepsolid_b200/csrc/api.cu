@@ -82,6 +82,7 @@ struct ds_ctx {
     signed char* Wd_g[DS_MAX_LAYERS] = {};   // spin-mean block B_g (layers >= 1, K = 2H)
     double* sb_g[DS_MAX_LAYERS] = {};
     bool use_i8_means = true;                // shared-mean GEMM GOUT = GIN.B_g on the int8 path as well
+    bool use_i8_value = true;                // value / Laplacian rows of layers >= 1 on the int8 path as well
     signed char* Wd_orb[2] = {};
     double* sb_orb[2] = {};
     bool use_i8 = true;                 // Jacobian-sweep GEMMs on tcgen05 (false: fp64 DMMA kernels)
@@ -216,6 +217,7 @@ struct Layout {
     double *LOGDET, *TAU, *TRSQ, *TRLAP;
     double *AD, *SA;        // int8 digits of the current Jacobian operand (as bytes) and its row scales
     double *GD, *GS;        // digits and scales of the spin-mean rows GIN (shared-mean GEMM on the int8 path)
+    double *VD, *VS;        // digits and scales of the value / Laplacian rows of the current layer (per electron)
     // parameter-gradient path: per-layer activations kept by the forward, cotangent buffers of the reverse sweep
     bool grad;
     double *Tl[DS_MAX_LAYERS], *GINV[DS_MAX_LAYERS];
@@ -270,6 +272,9 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
     L.SA = i8 ? ws.take("SA", W * N * d.NDp) : nullptr;
     L.GD = i8 ? ws.take("GD", (W * d.NDg * OZ_S * 2 * d.H + 7) / 8) : nullptr;
     L.GS = i8 ? ws.take("GS", W * d.NDg) : nullptr;
+    const bool i8v = c->use_i8 && c->i8_ok && c->use_i8_value;
+    L.VD = i8v ? ws.take("VD", (W * N * OZ_S * d.K1 + 7) / 8) : nullptr;
+    L.VS = i8v ? ws.take("VS", W * N) : nullptr;
     if (grad) {
         static const char* tn[] = {"T0", "T1", "T2", "T3"};
         static const char* gn[] = {"GINV0", "GINV1", "GINV2", "GINV3"};
@@ -401,7 +406,23 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         p.B = c->B_am[l]; p.ldb = H; p.N = H; p.K = K; p.rpg = 0;
         p.G = Lo.GOUT; p.ldg = H; p.n_elec = N; p.NDp = d.NDp; p.NDg = d.NDg;
         p.T = grad ? Lo.Tl[l] : Lo.T; p.ldt = H; p.S = Lo.S; p.colbias = c->bias1[l];
-        {
+        const bool i8_rows = Lo.VD && l > 0 && c->use_i8 && c->i8_ok;      // value / Laplacian rows on tcgen05 too
+        auto oz_rows = [&](const double* Arows, double* Out, int mode) -> int {
+            const long long rows = (long long)Wc * N;
+            signed char* Vd = reinterpret_cast<signed char*>(Lo.VD);
+            if (int rc = ds_launch_slice_rows(Arows, K, rows, K, Vd, Lo.VS, st)) return rc;
+            OzParams o{};
+            o.Ad = Vd; o.sa = Lo.VS; o.rpg = rows; o.gstride = rows; o.goff = 0; o.n_groups = 1;
+            o.Wd = c->Wd_am[l]; o.sb = c->sb_am[l]; o.N = H; o.K = K;
+            o.C = Out; o.ldc = d.K1; o.G = Lo.GOUT; o.ldg = H; o.n_elec = N; o.NDp = d.NDp; o.NDg = d.NDg;
+            o.T = p.T; o.Tout = p.T; o.ldt = H; o.S = Lo.S; o.R = Arows; o.ldr = K; o.colbias = c->bias1[l];
+            if (int rc = ds_launch_oz_gemm(o, mode, res, st)) return rc;
+            c->launches += 2;
+            return 0;
+        };
+        if (i8_rows) {
+            if (int rc = oz_rows(AV, OV, OZ_VALUE)) return rc;
+        } else {
             GemmParams v = p;
             v.A = AV; v.lda = K; v.M = (long long)Wc * N; v.C = OV; v.ldc = d.K1; v.R = AV; v.ldr = K;
             if (int rc = gemm(c, v, GEMM_VALUE, res, st)) return rc;
@@ -429,7 +450,9 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             j.A = AJ; j.lda = K; j.M = (long long)Wc * N * d.NDp; j.C = OJ; j.ldc = d.K1; j.R = AJ; j.ldr = K;
             if (int rc = gemm(c, j, GEMM_JAC, res, st, /*profile*/ l > 0)) return rc;
         }
-        if (lap) {
+        if (lap && i8_rows) {
+            if (int rc = oz_rows(AL, OL, OZ_LAP)) return rc;
+        } else if (lap) {
             GemmParams q = p;
             q.A = AL; q.lda = K; q.M = (long long)Wc * N; q.C = OL; q.ldc = d.K1; q.R = AL; q.ldr = K;
             if (int rc = gemm(c, q, GEMM_LAP, res, st)) return rc;
@@ -667,6 +690,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     if (const char* ev = getenv("DS_L0_GEMM")) c->use_l0_kernel = atoi(ev) == 0;
     if (const char* ev = getenv("DS_NO_SLICE_MEANS")) c->use_slice_means = atoi(ev) == 0;
     if (const char* ev = getenv("DS_NO_I8_MEANS")) c->use_i8_means = atoi(ev) == 0;
+    if (const char* ev = getenv("DS_NO_I8_VALUE")) c->use_i8_value = atoi(ev) == 0;
     if (const char* ev = getenv("DS_WS_GIB")) { double g = atof(ev); if (g >= 0.25) c->ws_limit = (size_t)(g * 1073741824.0); }
     DsDims& d = c->sys.d;
     d.n_up = sd->n_up; d.n_dn = sd->n_dn; d.N = sd->n_up + sd->n_dn; d.A = sd->n_atoms_prim;

@@ -478,6 +478,32 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     if (d >= p.NDp) { d -= p.NDp; ++e; if (++ie == p.n_elec) { ie = 0; ++w; } }
                 }
                 if (cur_e >= 0 && nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc);
+            } else if (MODE == OZ_VALUE || MODE == OZ_LAP) {
+                // rows are electrons e = prow0 + j (value or Laplacian row of each); walker = e / n_elec
+                unsigned w = (unsigned)prow0 / (unsigned)p.n_elec;
+                int ie = (int)((unsigned)prow0 - w * (unsigned)p.n_elec);
+                const double rs2v = 0.70710678118654752440;
+                const double bias = (MODE == OZ_VALUE && nv) ? p.colbias[n] : 0.0;
+                const int grow = p.NDp + (MODE == OZ_VALUE ? 0 : 1);
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) {
+                    if (j < nvalid && nv) {
+                        const long long e = prow0 + j;
+                        const double z = fma(zz[j], __ldg(sap + j) * sbn, p.G[((long long)w * p.NDg + grow) * p.ldg + n]);
+                        double o;
+                        if (MODE == OZ_VALUE) {
+                            o = tanh(z + bias);
+                            p.Tout[e * p.ldt + n] = o;
+                        } else {
+                            const double t = p.T[e * p.ldt + n], sv = p.S[e * p.ldt + n];
+                            const double d1 = 1.0 - t * t;
+                            o = d1 * z - 2.0 * t * d1 * sv;
+                        }
+                        if (RES) o = (p.R[e * (long long)p.ldr + n] + o) * rs2v;
+                        p.C[e * (long long)p.ldc + n] = o;
+                    }
+                    if (++ie == p.n_elec) { ie = 0; ++w; }
+                }
             } else if (MODE == OZ_PLAIN) {
                 double* cptr = p.C + prow0 * (long long)p.ldc + n;
 #pragma unroll
@@ -624,6 +650,8 @@ int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t s
     DS_REQUIRE(p.K % OZ_BK == 0 && p.K >= OZ_BK, "oz_gemm: K must be a multiple of %d (K=%d)", OZ_BK, p.K);
     DS_REQUIRE((reinterpret_cast<uintptr_t>(p.Ad) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Wd) & 15) == 0,
                "oz_gemm: digit buffers must be 16-byte aligned");
+    if (mode == OZ_VALUE || mode == OZ_LAP)
+        DS_REQUIRE(p.n_groups == 1 && p.rpg < (1LL << 31), "oz_gemm: value / Laplacian rows come as one group");
     if (mode == OZ_JAC || mode == OZ_ORBJ) {
         DS_REQUIRE(p.NDp % 8 == 0 && p.rpg % 8 == 0 && p.goff % 8 == 0 && p.gstride % 8 == 0,
                    "oz_gemm: Jacobian rows must come in aligned groups of 8 (NDp=%d rpg=%lld)", p.NDp, p.rpg);
@@ -633,6 +661,8 @@ int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t s
         case OZ_PLAIN: return launch<OZ_PLAIN, false>(p, stream);
         case OZ_JAC: return residual ? launch<OZ_JAC, true>(p, stream) : launch<OZ_JAC, false>(p, stream);
         case OZ_ORBJ: return launch<OZ_ORBJ, false>(p, stream);
+        case OZ_VALUE: return residual ? launch<OZ_VALUE, true>(p, stream) : launch<OZ_VALUE, false>(p, stream);
+        case OZ_LAP: return residual ? launch<OZ_LAP, true>(p, stream) : launch<OZ_LAP, false>(p, stream);
     }
     ds_set_error("oz_gemm: unknown mode %d", mode);
     return -1;

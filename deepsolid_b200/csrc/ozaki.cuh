@@ -28,7 +28,9 @@
 enum OzMode {
     OZ_PLAIN = 0,   // C[r, n] = Z
     OZ_JAC = 1,     // one-electron stream Jacobian rows (see gemm_f64.cuh GEMM_JAC)
-    OZ_ORBJ = 2     // orbital-layer Jacobian rows (see gemm_f64.cuh GEMM_ORBJ)
+    OZ_ORBJ = 2,    // orbital-layer Jacobian rows (see gemm_f64.cuh GEMM_ORBJ)
+    OZ_VALUE = 3,   // one-electron stream value rows:     h' = res(tanh(Z + G_val + b)), tanh values kept in Tout
+    OZ_LAP = 4      // one-electron stream Laplacian rows: l' = res((1-t^2)(Z + G_lap) - 2t(1-t^2) S)
 };
 
 struct OzParams {
@@ -45,6 +47,8 @@ struct OzParams {
     const double* G; int ldg;
     int n_elec, NDp, NDg;
     const double* T; int ldt;
+    double* Tout;            // OZ_VALUE: tanh values written here (same leading dimension ldt)
+    const double* colbias;   // OZ_VALUE: layer bias [N]
     double* S;
     const double* R; int ldr;
     const double* etab; int npar_max;
