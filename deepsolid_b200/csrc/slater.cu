@@ -1030,6 +1030,93 @@ int launch_det_dmma(const DsSys& sys, const SlaterBufs& sb, int Wc, int nmax, cu
 }
 
 // ---------------------------------------------------------------------------
+// Value-only log-determinants (the Metropolis inner loop): ONE WARP per matrix, lane r holds row r in registers,
+// complex LU with partial pivoting done with warp shuffles and no shared memory / block barriers.  Pivoting is
+// implicit (rows never move: the pivot row of step k is the not-yet-used lane with the largest |a[k]|, the same
+// choice as the row-swapping LU of det_kernel), the permutation parity is recovered from the pivot order.
+// NMAX >= n is the compile-time row length (8, 16 or 32).
+// ---------------------------------------------------------------------------
+template <int NMAX>
+__global__ void __launch_bounds__(256) det_warp_kernel(const DsSys sys, const SlaterBufs sb, long long n_mats) {
+    const DsDims& dm = sys.d;
+    const int D = dm.D;
+    const int lane = threadIdx.x & 31;
+    const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= n_mats) return;
+    const int nblk = ds_nblk(dm);
+    const int k = (int)(m % D);
+    const int s = (int)((m / D) % nblk);
+    const long long w = m / ((long long)nblk * D);
+    const int n = ds_blk_n(dm, s);
+    const cplx* mat = reinterpret_cast<const cplx*>(sb.MAT[s]) + (w * D + k) * (long long)n * n;
+    double ar[NMAX], ai[NMAX];
+#pragma unroll
+    for (int c = 0; c < NMAX; ++c) {
+        cplx v{0.0, 0.0};
+        if (lane < n && c < n) v = mat[lane * n + c];
+        ar[c] = v.re; ai[c] = v.im;
+    }
+    double logabs = 0.0;
+    cplx phase{1.0, 0.0};
+    bool done = lane >= n;                       // rows already used as pivots (and the padding lanes)
+    int my_step = -1;                            // step at which this row was the pivot
+    for (int kk = 0; kk < n; ++kk) {
+        // a[kk] of this lane (register array indexed by a runtime kk: select through the unrolled scan)
+        double pr = 0.0, pi = 0.0;
+#pragma unroll
+        for (int c = 0; c < NMAX; ++c)
+            if (c == kk) { pr = ar[c]; pi = ai[c]; }
+        double best = done ? -1.0 : fabs(pr) + fabs(pi);
+        int bi = lane;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        const int p = bi;                        // warp-uniform pivot row
+        const double pvr = __shfl_sync(0xffffffffu, pr, p), pvi = __shfl_sync(0xffffffffu, pi, p);
+        {
+            const double a = hypot(pvr, pvi);
+            logabs += log(a);
+            phase = cmul(phase, cplx{pvr / a, pvi / a});
+        }
+        if (lane == p) { done = true; my_step = kk; }
+        const cplx ipv = cinv(cplx{pvr, pvi});
+        const cplx f = done ? cplx{0.0, 0.0} : cmul(cplx{pr, pi}, ipv);      // multiplier of the active rows
+#pragma unroll
+        for (int c = 0; c < NMAX; ++c) {
+            if (c > kk && c < n) {               // warp-uniform
+                const double br = __shfl_sync(0xffffffffu, ar[c], p), bim = __shfl_sync(0xffffffffu, ai[c], p);
+                ar[c] -= f.re * br - f.im * bim;
+                ai[c] -= f.re * bim + f.im * br;
+            }
+        }
+    }
+    // parity of the permutation step -> row: sign = (-1)^(n - #cycles)
+    unsigned visited = 0u;
+    int cycles = 0;
+    for (int r0 = 0; r0 < n; ++r0) {
+        if (visited & (1u << r0)) continue;
+        ++cycles;
+        int r = r0;
+        while (!(visited & (1u << r))) {
+            visited |= 1u << r;
+            r = __shfl_sync(0xffffffffu, my_step, r);     // row r was the pivot of step my_step[r]: next element of the cycle
+        }
+    }
+    if (((n - cycles) & 1) != 0) phase = cplx{-phase.re, -phase.im};
+    if (lane == 0) {
+        double* ld = sb.LOGDET + ((w * 2 + s) * D + k) * 3;
+        ld[0] = logabs; ld[1] = phase.re; ld[2] = phase.im;
+        if (dm.full_det) {
+            double* ld1 = sb.LOGDET + ((w * 2 + 1) * D + k) * 3;
+            ld1[0] = 0.0; ld1[1] = 1.0; ld1[2] = 0.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Combine determinants (logdet_matmul, network.py:395-427) and the kinetic energy.
 // One warp per walker.
 // ---------------------------------------------------------------------------
@@ -1182,6 +1269,16 @@ int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cuda
             DS_CUDA_CHECK(cudaGetLastError());
             return 0;
         }
+    }
+    static const bool cta_lu = getenv("DS_DET_CTA_LU") && atoi(getenv("DS_DET_CTA_LU")) != 0;
+    if (!lap && nmax <= 32 && !cta_lu) {        // value-only: warp-per-matrix LU
+        const long long n_mats = (long long)Wc * ds_nblk(sys.d) * sys.d.D;
+        const unsigned blocks = (unsigned)((n_mats + 7) / 8);
+        if (nmax <= 8) det_warp_kernel<8><<<blocks, 256, 0, stream>>>(sys, sb, n_mats);
+        else if (nmax <= 16) det_warp_kernel<16><<<blocks, 256, 0, stream>>>(sys, sb, n_mats);
+        else det_warp_kernel<32><<<blocks, 256, 0, stream>>>(sys, sb, n_mats);
+        DS_CUDA_CHECK(cudaGetLastError());
+        return 0;
     }
     int G = 1;
     if (lap) {
