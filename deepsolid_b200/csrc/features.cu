@@ -9,6 +9,7 @@
 // channel of the pair stream.  Outputs are written straight into the operand
 // matrices of the one-electron-stream GEMMs (own + pair-mean columns).
 #include "kernels.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -228,6 +229,196 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
     }
 }
 
+// ---------------------------------------------------------------------------
+// Value-only variant (log psi of a Metropolis proposal, the forward of the gradient pass): LANE = pair.
+// A warp owns (walker w, electron i, spin channel s) and its lanes the partners j of that channel, so the distance
+// features are computed once per pair (not once per lane), the pair-layer products are plain register FMAs against
+// weights broadcast from shared memory (no shuffles), and the sum over partners is one shared-memory transpose per
+// level.  P <= 32 channels live in registers (z[], cur[]).
+// ---------------------------------------------------------------------------
+constexpr int FV_WARPS = 4;
+constexpr int FV_NB = 4;          // output channels per step of the rolled channel loop (independent FMA chains)
+
+// shared-memory doubles of the staged pair weights: per layer W^T [32][pin_pad] + b [32]
+__host__ __device__ inline int fv_pin_pad(int pin) { return (pin + 1) & ~1; }
+
+template <int FT>
+__global__ void __launch_bounds__(FV_WARPS * 32, 4) features_value_kernel(const DsSys sys, const FeatParams fp, long long n_items) {
+    const DsDims& dm = sys.d;
+    const int N = dm.N, A = dm.A, P = dm.P, L = dm.L, C0 = dm.C0, K0 = dm.K0, K1 = dm.K1, H = dm.H;
+    constexpr int F = FT;
+    constexpr int FP = (FT + 1) & ~1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double rs2 = 0.70710678118654752440;
+
+    extern __shared__ __align__(16) double fv_sm[];
+    // layer 0: Wt [32][FP], b [32]; layers l >= 1: Wt [32][32], b [32]   (output channels >= P zero)
+    double* w0 = fv_sm;
+    double* w1 = w0 + 32 * FP + 32;
+    constexpr int W1_STRIDE = 32 * 32 + 32;
+    for (int t = tid; t < 32 * FP; t += blockDim.x) {
+        const int co = t / FP, ci = t - co * FP;
+        w0[t] = (co < P && ci < F && L > 1) ? fp.Wp[0][ci * P + co] : 0.0;
+    }
+    for (int t = tid; t < 32; t += blockDim.x) w0[32 * FP + t] = (t < P && L > 1) ? fp.bp[0][t] : 0.0;
+    for (int l = 1; l < L - 1; ++l) {
+        double* wl = w1 + (l - 1) * W1_STRIDE;
+        for (int t = tid; t < 32 * 32; t += blockDim.x) {
+            const int co = t >> 5, ci = t & 31;
+            wl[t] = (co < P && ci < P) ? fp.Wp[l][ci * P + co] : 0.0;
+        }
+        for (int t = tid; t < 32; t += blockDim.x) wl[32 * 32 + t] = (t < P) ? fp.bp[l][t] : 0.0;
+    }
+    double* tr = w1 + (L > 2 ? L - 2 : 0) * W1_STRIDE + warp * (32 * 33);      // per-warp scratch [32 lanes][33]
+    double* my = tr + lane * 33;
+    __syncthreads();
+
+    for (long long item = (long long)blockIdx.x * FV_WARPS + warp; item < n_items; item += (long long)gridDim.x * FV_WARPS) {
+        const int s = (int)(item & 1);
+        const long long e = item >> 1;                   // w * N + i
+        const int w = (int)(e / N), i = (int)(e - (long long)w * N);
+        const int jbeg = s ? dm.n_up : 0, jend = s ? N : dm.n_up;
+        const double invn = (jend > jbeg) ? 1.0 / (double)(jend - jbeg) : 0.0;
+        const double* x = fp.X + (long long)w * 3 * N;
+        double xi3[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]}, wi[3];
+        ds_wrap(sys.sim, xi3, wi);
+
+        // electron-atom features of electron i (primitive cell): done once, by the spin-up item of the electron
+        if (s == 0 && lane < A) {
+            double px[3], d[3];
+            ds_wrap(sys.prim, xi3, px);
+            for (int q = 0; q < 3; ++q) d[q] = px[q] - sys.atoms[3 * lane + q];
+            Jet f[FT];
+            if (FT == 7) ds_tri_distance<false>(sys.prim, d, f);
+            else ds_nu_distance<false>(sys.prim, d, f);
+#pragma unroll
+            for (int q = 0; q < FT; ++q) fp.A0V[e * K0 + lane * F + q] = f[q].v;
+            double* ra = fp.RAE + (e * A + lane) * DS_RAE_STRIDE;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { ra[5 * q] = f[q].v; ra[5 * q + 1] = 0.0; ra[5 * q + 2] = 0.0; ra[5 * q + 3] = 0.0; ra[5 * q + 4] = 0.0; }
+        }
+
+        double colsum[DS_MAX_LAYERS];                    // lane c: sum over partners of channel c, per level
+#pragma unroll
+        for (int l = 0; l < DS_MAX_LAYERS; ++l) colsum[l] = 0.0;
+
+        for (int j0 = jbeg; j0 < jend; j0 += 32) {
+            const int j = j0 + lane;
+            const bool valid = j < jend;
+            const double vmask = valid ? 1.0 : 0.0;
+            double f[FP];
+            {
+                double xj3[3] = {0.0, 0.0, 0.0}, wj[3], d[3];
+                if (valid) { xj3[0] = x[3 * j]; xj3[1] = x[3 * j + 1]; xj3[2] = x[3 * j + 2]; }
+                ds_wrap(sys.sim, xj3, wj);
+                for (int q = 0; q < 3; ++q) d[q] = wj[q] - wi[q] + ((valid && j == i) ? 1.0 : 0.0);
+                Jet fj[FT];
+                if (FT == 7) ds_tri_distance<false>(sys.sim, d, fj);
+                else ds_nu_distance<false>(sys.sim, d, fj);
+#pragma unroll
+                for (int q = 0; q < FT; ++q) f[q] = (valid && j != i) ? fj[q].v : 0.0;
+                if (FP > FT) f[FP - 1] = 0.0;
+            }
+            // level 0: sum over partners of the F features
+#pragma unroll
+            for (int q = 0; q < FT; ++q) my[q] = f[q];
+            __syncwarp();
+            double bsum = 0.0;                           // this block's column sum at the current level
+            if (lane < F) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int r = 0; r < 32; r += 4) {
+                    s0 += tr[r * 33 + lane]; s1 += tr[(r + 1) * 33 + lane]; s2 += tr[(r + 2) * 33 + lane]; s3 += tr[(r + 3) * 33 + lane];
+                }
+                bsum = (s0 + s1) + (s2 + s3);
+                colsum[0] += bsum;
+            }
+            __syncwarp();
+            if (L <= 1) continue;
+
+            // pair layer 0: t = tanh(f . W0 + b0), raw values to the scratch row
+            {
+                const double* bb = w0 + 32 * FP;
+#pragma unroll 1
+                for (int n = 0; n < 32; n += FV_NB) {
+                    double z[FV_NB];
+#pragma unroll
+                    for (int u = 0; u < FV_NB; ++u) z[u] = bb[n + u];
+#pragma unroll
+                    for (int c = 0; c < FP; c += 2) {
+#pragma unroll
+                        for (int u = 0; u < FV_NB; ++u) {
+                            const double2 w2 = *reinterpret_cast<const double2*>(w0 + (n + u) * FP + c);
+                            z[u] = fma(f[c], w2.x, z[u]); z[u] = fma(f[c + 1], w2.y, z[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < FV_NB; ++u) my[n + u] = tanh(z[u]) * vmask;    // lanes past the channel end contribute 0
+                }
+            }
+            double cur[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) cur[c] = my[c];
+            __syncwarp();
+            {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int r = 0; r < 32; r += 4) {
+                    s0 += tr[r * 33 + lane]; s1 += tr[(r + 1) * 33 + lane]; s2 += tr[(r + 2) * 33 + lane]; s3 += tr[(r + 3) * 33 + lane];
+                }
+                bsum = (s0 + s1) + (s2 + s3);
+            }
+            __syncwarp();
+            colsum[1] += bsum;
+
+            // pair layers l >= 1 (square, residual): cur <- (cur + tanh(cur . Wl + bl)) / sqrt 2
+#pragma unroll 1
+            for (int l = 1; l < L - 1; ++l) {
+                const double* wl = w1 + (l - 1) * W1_STRIDE;
+                const double* bb = wl + 32 * 32;
+#pragma unroll 1
+                for (int n = 0; n < 32; n += FV_NB) {
+                    double z[FV_NB];
+#pragma unroll
+                    for (int u = 0; u < FV_NB; ++u) z[u] = bb[n + u];
+#pragma unroll
+                    for (int c = 0; c < 32; c += 2) {
+#pragma unroll
+                        for (int u = 0; u < FV_NB; ++u) {
+                            const double2 w2 = *reinterpret_cast<const double2*>(wl + (n + u) * 32 + c);
+                            z[u] = fma(cur[c], w2.x, z[u]); z[u] = fma(cur[c + 1], w2.y, z[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < FV_NB; ++u) my[n + u] = tanh(z[u]) * vmask;
+                }
+                __syncwarp();
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int r = 0; r < 32; r += 4) {
+                    s0 += tr[r * 33 + lane]; s1 += tr[(r + 1) * 33 + lane]; s2 += tr[(r + 2) * 33 + lane]; s3 += tr[(r + 3) * 33 + lane];
+                }
+                bsum = (bsum + ((s0 + s1) + (s2 + s3))) * rs2;       // column sum of the residual update
+#pragma unroll
+                for (int c = 0; c < 32; ++c) cur[c] = (cur[c] + my[c]) * rs2;
+                __syncwarp();
+                if (l + 1 < DS_MAX_LAYERS) {
+                    // colsum[] is indexed by a runtime level here: spelled out to keep it in registers
+#pragma unroll
+                    for (int q = 2; q < DS_MAX_LAYERS; ++q) if (q == l + 1) colsum[q] += bsum;
+                }
+            }
+        }
+        // means of this spin channel -> pair-mean columns of the one-electron operands
+        if (lane < F) fp.A0V[e * K0 + C0 + s * F + lane] = colsum[0] * invn;
+#pragma unroll
+        for (int l = 1; l < DS_MAX_LAYERS; ++l) {
+            if (l >= L) break;
+            if (lane < P) fp.AV[l][e * K1 + H + s * P + lane] = colsum[l] * invn;
+        }
+    }
+}
+
 }  // namespace
 
 size_t ds_features_smem(const DsDims& d) {
@@ -256,6 +447,25 @@ int ds_launch_features(const DsSys& sys, const FeatParams& fp, int Wc, bool jets
         if (eff > best_eff + 1e-9) { best_eff = eff; best_w = w; }
     }
     const int threads = jets ? 32 * best_w : FEAT_THREADS;
+    static const bool old_value = getenv("DS_FEAT_OLD") && atoi(getenv("DS_FEAT_OLD")) != 0;
+    if (!jets && sys.d.P <= 32 && !old_value) {
+        // lane-per-pair value kernel
+        const int fpad = fv_pin_pad(sys.d.F);
+        size_t n = (size_t)FV_WARPS * 32 * 33 + 32 * fpad + 32 + (size_t)(sys.d.L > 2 ? sys.d.L - 2 : 0) * (32 * 32 + 32);
+        const size_t sm2 = n * sizeof(double);
+        const long long n_items = 2LL * Wc * sys.d.N;
+        long long blocks = (n_items + FV_WARPS - 1) / FV_WARPS;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (tri) {
+            DS_CUDA_CHECK(cudaFuncSetAttribute(features_value_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            features_value_kernel<7><<<(unsigned)blocks, FV_WARPS * 32, sm2, stream>>>(sys, fp, n_items);
+        } else {
+            DS_CUDA_CHECK(cudaFuncSetAttribute(features_value_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            features_value_kernel<4><<<(unsigned)blocks, FV_WARPS * 32, sm2, stream>>>(sys, fp, n_items);
+        }
+        DS_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     if (jets) {
         if (tri) features_pair_kernel<true, 7><<<grid, threads, smem, stream>>>(sys, fp);
         else features_pair_kernel<true, 4><<<grid, threads, smem, stream>>>(sys, fp);
