@@ -121,6 +121,19 @@ struct ds_ctx {
     double* gx_abs = nullptr;
     double* gx_phase = nullptr;
     const double* cot_mats = nullptr;       // cotangent of the orbital matrices of the current chunk (ds_orbitals_vjp)
+    // Kronecker-factor statistics (ds_kfac_factors): raw accumulators, allocated on first use
+    bool fact_on = false;
+    double* fA1[DS_MAX_LAYERS] = {};        // [(3C+2Pl+2)^2] Gram matrix of the one-electron layer inputs (x, 1, 0)
+    double* fG1[DS_MAX_LAYERS] = {};        // [H^2] Gram matrix of the pre-activation cotangents, both passes
+    double* fAo[2] = {};                    // [(H+2)^2]
+    double* fGo[2] = {};                    // [(2 npar_s)^2], (re, im) interleaved
+    double* fAp[DS_MAX_LAYERS] = {};        // [32*32] pair layers
+    double* fAps[DS_MAX_LAYERS] = {};       // [32]
+    double* fGp[DS_MAX_LAYERS] = {};        // [32*32]
+    double* fenv_pi[2][2] = {};             // [pass][spin] gradients of sum_w log|psi_w| (pass 0) / sum_w phase_w (pass 1)
+    double* fenv_sigma[2][2] = {};
+    double* fones = nullptr;                // [fones_n] ones then [fones_n] zeros: unit cotangents
+    size_t fones_n = 0;
     // layout of the last local-energy chunk (for ds_debug_buffer)
     std::vector<Region> last_regions;
 };
@@ -222,6 +235,7 @@ struct Layout {
     bool grad;
     double *Tl[DS_MAX_LAYERS], *GINV[DS_MAX_LAYERS];
     double *XINV[2], *GYs[2], *GH[2], *GZ, *GZS, *GA, *GG, *GPM[DS_MAX_LAYERS];
+    double *XF;             // factor statistics: explicit rows of a layer's input
 };
 
 void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = false) {
@@ -295,6 +309,7 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
         L.GZS = ws.take("GZS", W * d.H);
         L.GA = ws.take("GA", W * N * d.K1);
         L.GG = ws.take("GG", W * 2 * d.H);
+        L.XF = c->fact_on ? ws.take("XF", W * N * (3 * cmax + 2 * (size_t)std::max(d.P, d.F) + 2)) : nullptr;
     }
 }
 
@@ -330,7 +345,8 @@ int plan_chunk(ds_ctx* c, long long batch, bool lap, int* Wc_out, bool grad = fa
 
 // One chunk of walkers through the network.  lap=false: log psi only.
 int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int Wc, const double* cot_abs,
-               const double* cot_phase, cudaStream_t st);
+               const double* cot_phase, cudaStream_t st, int fact_pass = -1);
+int fact_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int Wc, cudaStream_t st);
 
 int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, double* phase, double* ke_re,
               double* ke_im, double* mats_out, cudaStream_t st, const double* cot_abs = nullptr,
@@ -530,6 +546,7 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
     }
     if (grad) {
         FeatParams fpg = fp;
+        if (c->fact_on) return fact_sweep(c, Lo, fpg, sb, Wc, st);
         return grad_sweep(c, Lo, fpg, sb, Wc, cot_abs, cot_phase, st);
     }
     if (int rc = ds_launch_det(sys, sb, Wc, lap, st)) return rc;
@@ -541,8 +558,11 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
 }
 
 // Reverse sweep of one chunk (forward activations are in the workspace): accumulates into the ctx gradient buffers.
+// fact_pass >= 0: the sweep feeds the Kronecker-factor statistics instead of the parameter gradients (pass 0: unit
+// cotangent on log|psi|, pass 1: on the phase): Gram matrices of the cotangents of every tagged layer output.
 int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int Wc, const double* cot_abs,
-               const double* cot_phase, cudaStream_t st) {
+               const double* cot_phase, cudaStream_t st, int fact_pass) {
+    const bool fact = fact_pass >= 0;
     const DsSys& sys = c->sys;
     const DsDims& d = sys.d;
     const int N = d.N, H = d.H, L = d.L, P = d.P;
@@ -556,7 +576,11 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
         c->launches++;
     }
     gb.cot_abs = cot_abs; gb.cot_phase = cot_phase;
-    for (int s = 0; s < 2; ++s) { gb.GY[s] = Lo.GYs[s]; gb.g_pi[s] = c->genv_pi[s]; gb.g_sigma[s] = c->genv_sigma[s]; }
+    for (int s = 0; s < 2; ++s) {
+        gb.GY[s] = Lo.GYs[s];
+        gb.g_pi[s] = fact ? c->fenv_pi[fact_pass][s] : c->genv_pi[s];
+        gb.g_sigma[s] = fact ? c->fenv_sigma[fact_pass][s] : c->genv_sigma[s];
+    }
     if (int rc = ds_launch_orb_grad(sys, sb, gb, Wc, c->npar_max, st)) return rc;
     c->launches++;
     const double* hL = Lo.V[L - 1];                   // output of the last layer (own columns)
@@ -567,8 +591,12 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
         GemmParams t{};                               // gWorb[s] += hL_s^T . GY_s
         t.A = hL; t.lda = d.K1; t.M = H; t.K = Wc * ns; t.rpg = ns; t.gstride = N; t.goff = c->off_s[s];
         t.B = Lo.GYs[s]; t.ldb = np2; t.N = np2; t.C = c->gWorb[s]; t.ldc = np2; t.accumulate = 1;
-        if (int rc = gemm(c, t, GEMM_TN, false, st)) return rc;
-        if (c->bias_orb) {
+        if (fact) {                                   // fGo[s] += GY_s^T . GY_s
+            t.A = Lo.GYs[s]; t.lda = np2; t.M = np2; t.rpg = 0; t.C = c->fGo[s];
+        }
+        if (ns > 0)
+            if (int rc = gemm(c, t, GEMM_TN, false, st)) return rc;
+        if (c->bias_orb && !fact) {
             if (int rc = ds_launch_colsum_add(Lo.GYs[s], np2, Wc * ns, np2, c->gborb[s], st)) return rc;
             c->launches++;
         }
@@ -589,11 +617,16 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
         GemmParams t{};                               // own + pair-mean rows of the weight gradient
         t.A = Ain; t.lda = K; t.M = K; t.K = (long long)Wc * N; t.rpg = 0;
         t.B = Lo.GZ; t.ldb = H; t.N = H; t.C = c->gB_am[l]; t.ldc = H; t.accumulate = 1;
+        if (fact) {                                   // fG1[l] += GZ^T . GZ
+            t.A = Lo.GZ; t.lda = H; t.M = H; t.C = c->fG1[l];
+        }
         if (int rc = gemm(c, t, GEMM_TN, false, st)) return rc;
-        GemmParams m{};                               // spin-mean rows
-        m.A = Lo.GINV[l]; m.lda = 2 * C; m.M = 2 * C; m.K = Wc; m.rpg = 0;
-        m.B = Lo.GZS; m.ldb = H; m.N = H; m.C = c->gB_g[l]; m.ldc = H; m.accumulate = 1;
-        if (int rc = gemm(c, m, GEMM_TN, false, st)) return rc;
+        if (!fact) {
+            GemmParams m{};                           // spin-mean rows
+            m.A = Lo.GINV[l]; m.lda = 2 * C; m.M = 2 * C; m.K = Wc; m.rpg = 0;
+            m.B = Lo.GZS; m.ldb = H; m.N = H; m.C = c->gB_g[l]; m.ldc = H; m.accumulate = 1;
+            if (int rc = gemm(c, m, GEMM_TN, false, st)) return rc;
+        }
         if (l == 0) break;                            // the layer-0 inputs are parameter-free features
         GemmParams a{};                               // GA = GZ . B_am^T
         a.A = Lo.GZ; a.lda = H; a.M = (long long)Wc * N; a.K = H; a.rpg = 0;
@@ -609,11 +642,49 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
         std::swap(GHcur, GHnext);
     }
     for (int l = 1; l < L; ++l) gb.GPMl[l] = Lo.GPM[l];
-    for (int l = 0; l < L - 1; ++l) { gb.g_Wp[l] = c->gWp[l]; gb.g_bp[l] = c->gbp[l]; }
+    for (int l = 0; l < L - 1; ++l) { gb.g_Wp[l] = c->gWp[l]; gb.g_bp[l] = c->gbp[l]; gb.fact_G[l] = c->fGp[l]; }
     (void)P;
-    if (int rc = ds_launch_pair_grad(sys, fp, gb, Wc, st)) return rc;
+    if (int rc = ds_launch_pair_grad(sys, fp, gb, Wc, st, fact ? 2 : 0)) return rc;
     c->launches++;
     return 0;
+}
+
+// Kronecker-factor statistics of one chunk: Gram matrices of every tagged layer's inputs, then two reverse sweeps
+// (unit cotangent on log|psi|, then on the phase) for the Gram matrices of the output cotangents.
+int fact_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int Wc, cudaStream_t st) {
+    const DsDims& d = c->sys.d;
+    const int N = d.N, H = d.H, L = d.L;
+    for (int l = 0; l < L; ++l) {
+        const int C = (l == 0) ? d.C0 : H;
+        const int K = (l == 0) ? d.K0 : d.K1;
+        const int ldx = 2 * C + K + 2;
+        const double* Ain = (l == 0) ? Lo.A0V : Lo.V[l - 1];
+        if (int rc = ds_launch_layer_input_rows(Ain, K, Lo.GINV[l], C, N, (long long)Wc * N, Lo.XF, st)) return rc;
+        c->launches++;
+        GemmParams t{};
+        t.A = Lo.XF; t.lda = ldx; t.M = ldx; t.K = (long long)Wc * N; t.rpg = 0;
+        t.B = Lo.XF; t.ldb = ldx; t.N = ldx; t.C = c->fA1[l]; t.ldc = ldx; t.accumulate = 1;
+        if (int rc = gemm(c, t, GEMM_TN, false, st)) return rc;
+    }
+    for (int s = 0; s < 2; ++s) {
+        const int ns = c->n_s[s];
+        if (ns == 0) continue;
+        if (int rc = ds_launch_spin_rows(Lo.V[L - 1], d.K1, H, N, c->off_s[s], ns, Wc, Lo.XF, st)) return rc;
+        c->launches++;
+        GemmParams t{};
+        t.A = Lo.XF; t.lda = H + 2; t.M = H + 2; t.K = (long long)Wc * ns; t.rpg = 0;
+        t.B = Lo.XF; t.ldb = H + 2; t.N = H + 2; t.C = c->fAo[s]; t.ldc = H + 2; t.accumulate = 1;
+        if (int rc = gemm(c, t, GEMM_TN, false, st)) return rc;
+    }
+    {
+        GradBufs gb{};
+        for (int l = 0; l < L - 1; ++l) { gb.fact_A[l] = c->fAp[l]; gb.fact_As[l] = c->fAps[l]; }
+        if (int rc = ds_launch_pair_grad(c->sys, fp, gb, Wc, st, 1)) return rc;
+        c->launches++;
+    }
+    DS_REQUIRE((size_t)Wc <= c->fones_n, "unit cotangent buffer too small");
+    if (int rc = grad_sweep(c, Lo, fp, sb, Wc, c->fones, c->fones + c->fones_n, st, 0)) return rc;
+    return grad_sweep(c, Lo, fp, sb, Wc, c->fones + c->fones_n, c->fones, st, 1);
 }
 
 int run_batched(ds_ctx* c, const double* X, long long batch, bool lap, double* log_abs, double* phase,
@@ -1004,6 +1075,122 @@ static int vjp_impl(ds_ctx* c, const double* x, int64_t batch, const double* cot
         DS_REQUIRE(sizes[li] == (int64_t)d.A * c->npar[s] && sizes[li + 1] == sig_mult * sizes[li], "gradient leaf %d has the wrong size", li);
         DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->genv_pi[s], (size_t)d.A * c->npar[s] * sizeof(double), cudaMemcpyDeviceToDevice, st));
         DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->genv_sigma[s], (size_t)sig_mult * d.A * c->npar[s] * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+// Kronecker-factor statistics of the tagged dense layers, as the reference's KFAC estimator extracts them from
+// total_energy_jvp (train.py:128-133 registers conj(log psi) as a normal predictive distribution; estimation mode
+// fisher_exact, process.py:221, estimator.py:284-320): for every register_repeated_dense layer (network.py:443 - the
+// one-electron layers, the pair layers, the orbital projections) the sums over all rows r (walker x electron / pair) of
+//     a_out[layer] = sum_r (x_r, 1)(x_r, 1)^T                        [(in+1)^2]  (curvature_blocks.py:262-281)
+//     g_out[layer] = sum_r ga_r ga_r^T + gp_r gp_r^T                 [out^2]
+// with ga / gp the cotangents of the layer output y = x w + b for d(sum_w log|psi_w|) and d(sum_w phase_w).  The
+// reference's dy = sqrt(2) (ga - i gp) (variance 0.5, loss_functions.py:593-597, vjp_rc.py), so its output factor is
+// 2 g_out / rows; normalisation, EMA and the cross-device mean are the host's (deepsolid_b200/kfac.py).
+// Layer order: single[0..L-1], double[0..L-2], orbital[spin 0, 1] (orbital output columns: re block | im block).
+// env_abs / env_phase: gradients of sum_w log|psi_w| and sum_w phase_w with respect to (pi_0, sigma_0, pi_1, sigma_1)
+// (the untagged envelope parameters get a NaiveDiagonal block, curvature_blocks.py:111-133).
+extern "C" int ds_kfac_factors(ds_ctx* c, const double* x, int64_t batch, double* const* a_out, const int64_t* a_sizes,
+                               double* const* g_out, const int64_t* g_sizes, int n_layers, double* const* env_abs,
+                               double* const* env_phase, const int64_t* env_sizes, int n_env, void* stream) {
+    DS_REQUIRE(c && c->params_set, "parameters have not been set (ds_set_params)");
+    DS_REQUIRE(a_out && a_sizes && g_out && g_sizes && env_abs && env_phase && env_sizes, "null argument");
+    DS_REQUIRE(batch >= 0, "negative batch");
+    Guard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const DsDims& d = c->sys.d;
+    const int L = d.L, H = d.H, P = d.P, N = d.N;
+    DS_REQUIRE(n_layers == 2 * L - 1 + 2, "expected %d tagged layers, got %d", 2 * L + 1, n_layers);
+    DS_REQUIRE(n_env == 4, "expected 4 envelope leaves, got %d", n_env);
+    if (int rc = prepare_grad(c, st)) return rc;
+    auto need = [&](double** p, size_t n) -> int { if (!*p) { if (int rc = dev_alloc(c, p, n)) return rc; } return 0; };
+    const size_t sig_mult = (d.env_type == 0) ? 1 : (d.env_type == 1 ? 3 : 9);
+    for (int l = 0; l < L; ++l) {
+        const int C = (l == 0) ? d.C0 : H, K = (l == 0) ? d.K0 : d.K1;
+        const size_t ldx = 2 * C + K + 2;
+        if (int rc = need(&c->fA1[l], ldx * ldx)) return rc;
+        if (int rc = need(&c->fG1[l], (size_t)H * H)) return rc;
+        DS_CUDA_CHECK(cudaMemsetAsync(c->fA1[l], 0, ldx * ldx * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->fG1[l], 0, (size_t)H * H * sizeof(double), st));
+    }
+    for (int l = 0; l < L - 1; ++l) {
+        if (int rc = need(&c->fAp[l], 32 * 32)) return rc;
+        if (int rc = need(&c->fAps[l], 32)) return rc;
+        if (int rc = need(&c->fGp[l], 32 * 32)) return rc;
+        DS_CUDA_CHECK(cudaMemsetAsync(c->fAp[l], 0, 32 * 32 * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->fAps[l], 0, 32 * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->fGp[l], 0, 32 * 32 * sizeof(double), st));
+    }
+    for (int s = 0; s < 2; ++s) {
+        const size_t np2 = 2 * (size_t)c->npar[s];
+        if (int rc = need(&c->fAo[s], (size_t)(H + 2) * (H + 2))) return rc;
+        if (int rc = need(&c->fGo[s], std::max<size_t>(np2 * np2, 1))) return rc;
+        DS_CUDA_CHECK(cudaMemsetAsync(c->fAo[s], 0, (size_t)(H + 2) * (H + 2) * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->fGo[s], 0, np2 * np2 * sizeof(double), st));
+        for (int ps = 0; ps < 2; ++ps) {
+            const size_t npi = std::max<size_t>((size_t)d.A * c->npar[s], 1);
+            if (int rc = need(&c->fenv_pi[ps][s], npi)) return rc;
+            if (int rc = need(&c->fenv_sigma[ps][s], sig_mult * npi)) return rc;
+            DS_CUDA_CHECK(cudaMemsetAsync(c->fenv_pi[ps][s], 0, (size_t)d.A * c->npar[s] * sizeof(double), st));
+            DS_CUDA_CHECK(cudaMemsetAsync(c->fenv_sigma[ps][s], 0, sig_mult * d.A * c->npar[s] * sizeof(double), st));
+        }
+    }
+    if (batch > 0) {
+        DS_REQUIRE(x, "null argument");
+        c->fact_on = true;
+        int Wc = 0;
+        int rc = plan_chunk(c, batch, false, &Wc, true);
+        if (!rc && (size_t)Wc > c->fones_n) {
+            const size_t n = (size_t)Wc;
+            double* buf = nullptr;
+            rc = dev_alloc(c, &buf, 2 * n);
+            if (!rc) {
+                std::vector<double> h(2 * n, 0.0);
+                for (size_t q = 0; q < n; ++q) h[q] = 1.0;
+                cudaError_t e = cudaMemcpyAsync(buf, h.data(), 2 * n * sizeof(double), cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) { ds_set_error("unit cotangent upload failed: %s", cudaGetErrorString(e)); rc = DS_ERR_CUDA; }
+                c->fones = buf; c->fones_n = n;
+            }
+        }
+        const int n3 = 3 * N;
+        static const double dummy = 0.0;
+        for (long long w0 = 0; w0 < batch && !rc; w0 += Wc) {
+            int wc = (int)std::min<long long>(Wc, batch - w0);
+            rc = run_chunk(c, x + w0 * n3, wc, false, nullptr, nullptr, nullptr, nullptr, nullptr, st, &dummy, &dummy);
+        }
+        c->fact_on = false;
+        if (rc) return rc;
+    }
+    // pack into the reference's layouts
+    int li = 0;
+    for (int l = 0; l < L; ++l, ++li) {
+        const int C = (l == 0) ? d.C0 : H, K = (l == 0) ? d.K0 : d.K1;
+        const int nin = 2 * C + K + 1, ldx = nin + 1;
+        DS_REQUIRE(a_sizes[li] == (int64_t)nin * nin && g_sizes[li] == (int64_t)H * H, "factor %d has the wrong size", li);
+        if (int rc = ds_launch_copy2d(c->fA1[l], ldx, a_out[li], nin, nin, nin, st)) return rc;
+        DS_CUDA_CHECK(cudaMemcpyAsync(g_out[li], c->fG1[l], (size_t)H * H * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    for (int l = 0; l < L - 1; ++l, ++li) {
+        const int pin = (l == 0) ? d.F : P;
+        DS_REQUIRE(a_sizes[li] == (int64_t)(pin + 1) * (pin + 1) && g_sizes[li] == (int64_t)P * P, "factor %d has the wrong size", li);
+        if (int rc = ds_launch_pair_fact_pack(c->fAp[l], c->fAps[l], (double)batch * N * N, pin, a_out[li], st)) return rc;
+        if (int rc = ds_launch_copy2d(c->fGp[l], 32, g_out[li], P, P, P, st)) return rc;
+    }
+    for (int s = 0; s < 2; ++s, ++li) {
+        const int64_t np2 = 2 * (int64_t)c->npar[s];
+        DS_REQUIRE(a_sizes[li] == (int64_t)(H + 1) * (H + 1) && g_sizes[li] == np2 * np2, "factor %d has the wrong size", li);
+        if (int rc = ds_launch_copy2d(c->fAo[s], H + 2, a_out[li], H + 1, H + 1, H + 1, st)) return rc;
+        if (int rc = ds_launch_deinterleave2(c->fGo[s], g_out[li], c->npar[s], st)) return rc;
+    }
+    for (int s = 0; s < 2; ++s) {
+        const int64_t npi = (int64_t)d.A * c->npar[s];
+        DS_REQUIRE(env_sizes[2 * s] == npi && env_sizes[2 * s + 1] == (int64_t)sig_mult * npi, "envelope leaf %d has the wrong size", 2 * s);
+        DS_CUDA_CHECK(cudaMemcpyAsync(env_abs[2 * s], c->fenv_pi[0][s], npi * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        DS_CUDA_CHECK(cudaMemcpyAsync(env_abs[2 * s + 1], c->fenv_sigma[0][s], sig_mult * npi * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        DS_CUDA_CHECK(cudaMemcpyAsync(env_phase[2 * s], c->fenv_pi[1][s], npi * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        DS_CUDA_CHECK(cudaMemcpyAsync(env_phase[2 * s + 1], c->fenv_sigma[1][s], sig_mult * npi * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     return 0;
 }

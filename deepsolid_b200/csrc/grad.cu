@@ -173,9 +173,12 @@ __global__ void __launch_bounds__(256) hin_kernel(DsDims dm, GradBufs gb, int C,
 constexpr int PG_THREADS = 256;
 
 // NPL = number of P x P pair layers (= L - 2): sizes the per-lane weight-gradient accumulators
-template <int NPL>
-__global__ void __launch_bounds__(PG_THREADS, NPL <= 1 ? 2 : 1) pair_grad_kernel(const DsSys sys, const FeatParams fp,
-                                                                                 const GradBufs gb, long long n_e) {
+// FACT = 0: parameter gradients.  FACT = 1 / 2: Kronecker-factor statistics of the tagged pair layers
+// (curvature_blocks.py:262-281 through RepeatedDenseBlock, curvature_tags_and_blocks.py:142-156): sums over all pairs of
+// x x^T of the layer inputs (1, forward only) or of gz gz^T of the pre-activation cotangents (2).
+template <int NPL, int FACT>
+__global__ void __launch_bounds__(PG_THREADS, (NPL <= 1 && FACT != 2) ? 2 : 1) pair_grad_kernel(const DsSys sys, const FeatParams fp,
+                                                                                                const GradBufs gb, long long n_e) {
     const DsDims& dm = sys.d;
     const int N = dm.N, P = dm.P, L = dm.L, F = dm.F;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -205,11 +208,12 @@ __global__ void __launch_bounds__(PG_THREADS, NPL <= 1 ? 2 : 1) pair_grad_kernel
     __syncthreads();
 
     // per-lane gradient accumulators: column `lane` of every pair-layer weight and bias
-    double gW0[7], gW[NPL > 0 ? NPL : 1][32], gB[DS_MAX_LAYERS];
+    constexpr int NACC = (FACT == 2) ? NPL + 1 : (NPL > 0 ? NPL : 1);
+    double gW0[7], gW[NACC][32], gB[DS_MAX_LAYERS];
 #pragma unroll
     for (int q = 0; q < 7; ++q) gW0[q] = 0.0;
 #pragma unroll
-    for (int l = 0; l < (NPL > 0 ? NPL : 1); ++l)
+    for (int l = 0; l < NACC; ++l)
 #pragma unroll
         for (int c = 0; c < 32; ++c) gW[l][c] = 0.0;
 #pragma unroll
@@ -259,6 +263,20 @@ __global__ void __launch_bounds__(PG_THREADS, NPL <= 1 ? 2 : 1) pair_grad_kernel
             double nv = (l >= 1) ? (cur[l] + t) * rs2 : t;
             cur[l + 1] = (lane < P) ? nv : 0.0;
         }
+        if (FACT == 1) {                                    // Gram matrices of the inputs of every pair layer
+#pragma unroll
+            for (int c = 0; c < 7; ++c) gW0[c] = fma(__shfl_sync(0xffffffffu, cur[0], c), cur[0], gW0[c]);
+            gB[0] += cur[0];
+#pragma unroll
+            for (int l = 1; l <= NPL; ++l) {
+                if (l >= L - 1) break;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    gW[l - 1 < NACC ? l - 1 : 0][c] = fma(__shfl_sync(0xffffffffu, cur[l], c), cur[l], gW[l - 1 < NACC ? l - 1 : 0][c]);
+                gB[l] += cur[l];
+            }
+            continue;
+        }
         // reverse: cotangents of the levels
         double g[DS_MAX_LAYERS];
 #pragma unroll
@@ -277,15 +295,22 @@ __global__ void __launch_bounds__(PG_THREADS, NPL <= 1 ? 2 : 1) pair_grad_kernel
             const double gt = res ? g[lv] * rs2 : g[lv];
             const double gz = (lane < P) ? gt * (1.0 - tv[lv] * tv[lv]) : 0.0;
             gB[l] += gz;
-            if (l == 0) {
+            if (FACT == 2) {
+                if (l < NACC) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) gW[l < NACC ? l : 0][c] = fma(__shfl_sync(0xffffffffu, gz, c), gz, gW[l < NACC ? l : 0][c]);
+                }
+            } else if (l == 0) {
 #pragma unroll
                 for (int c = 0; c < 7; ++c) gW0[c] = fma(__shfl_sync(0xffffffffu, cur[0], c), gz, gW0[c]);      // cur[0] = 0 beyond F
             } else if (l - 1 < NPL) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     const double cv = __shfl_sync(0xffffffffu, cur[l], c);
-                    if (c < P) gW[l - 1 < NPL ? l - 1 : 0][c] = fma(cv, gz, gW[l - 1 < NPL ? l - 1 : 0][c]);
+                    if (c < P) gW[l - 1 < NACC ? l - 1 : 0][c] = fma(cv, gz, gW[l - 1 < NACC ? l - 1 : 0][c]);
                 }
+            }
+            if (l >= 1 && l - 1 < NPL) {
                 // cotangent of level l (it has parameters upstream): W.gz over the output channels + residual path
                 const double* WT = wsm + woff[l] + pin * P + P;      // [P_out][pin]
                 double acc = res ? g[lv] * rs2 : 0.0;
@@ -312,6 +337,31 @@ __global__ void __launch_bounds__(PG_THREADS, NPL <= 1 ? 2 : 1) pair_grad_kernel
             if (valid) atomicAdd(dst, s);
         }
     };
+    if (FACT == 1) {
+        if (L > 1) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c)
+                if (c < F) reduce_and_add(gW0[c], gb.fact_A[0] + c * 32 + lane, true);
+            reduce_and_add(gB[0], gb.fact_As[0] + lane, true);
+        }
+#pragma unroll
+        for (int l = 1; l <= NPL; ++l) {
+            if (l >= L - 1) break;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) reduce_and_add(gW[l - 1 < NACC ? l - 1 : 0][c], gb.fact_A[l] + c * 32 + lane, true);
+            reduce_and_add(gB[l], gb.fact_As[l] + lane, true);
+        }
+        return;
+    }
+    if (FACT == 2) {
+#pragma unroll
+        for (int l = 0; l < NACC; ++l) {
+            if (l >= L - 1) break;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) reduce_and_add(gW[l][c], gb.fact_G[l] + c * 32 + lane, true);
+        }
+        return;
+    }
     if (L > 1) {
 #pragma unroll
         for (int c = 0; c < 7; ++c)
@@ -353,7 +403,88 @@ __global__ void deinterleave_kernel(const double* __restrict__ src, double* __re
     dst[(long long)r * 2 * np + im * np + p] = src[t];
 }
 
+__global__ void layer_input_rows_kernel(const double* __restrict__ Ain, int K, const double* __restrict__ GINV, int C, int N,
+                                        long long rows, double* __restrict__ out) {
+    const int ldx = 2 * C + K + 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * ldx) return;
+    const long long e = t / ldx;
+    const int c = (int)(t - e * ldx);
+    double v;
+    if (c < C) v = Ain[e * K + c];
+    else if (c < 3 * C) v = GINV[(e / N) * 2 * C + (c - C)];
+    else if (c < 2 * C + K) v = Ain[e * K + (c - 2 * C)];
+    else v = (c == 2 * C + K) ? 1.0 : 0.0;
+    out[t] = v;
+}
+
+__global__ void spin_rows_kernel(const double* __restrict__ src, int lds, int cols, int N, int off_s, int ns, long long rows,
+                                 double* __restrict__ out) {
+    const int ldx = cols + 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * ldx) return;
+    const long long r = t / ldx;
+    const int c = (int)(t - r * ldx);
+    const long long w = r / ns;
+    const long long e = w * N + off_s + (r - w * ns);
+    out[t] = (c < cols) ? src[e * lds + c] : (c == cols ? 1.0 : 0.0);
+}
+
+__global__ void pair_fact_pack_kernel(const double* __restrict__ A32, const double* __restrict__ As, double count, int pin,
+                                      double* __restrict__ out) {
+    const int n = pin + 1;
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+        const int r = t / n, c = t - r * n;
+        double v;
+        if (r < pin && c < pin) v = A32[r * 32 + c];
+        else if (r < pin) v = As[r];
+        else if (c < pin) v = As[c];
+        else v = count;
+        out[t] = v;
+    }
+}
+
+__global__ void deinterleave2_kernel(const double* __restrict__ src, double* __restrict__ dst, int np) {
+    const long long n2 = 2LL * np;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n2 * n2) return;
+    const int r = (int)(t / n2), c = (int)(t - (long long)r * n2);
+    const long long qr = (long long)(r & 1) * np + (r >> 1), qc = (long long)(c & 1) * np + (c >> 1);
+    dst[qr * n2 + qc] = src[t];
+}
+
 }  // namespace
+
+int ds_launch_layer_input_rows(const double* Ain, int K, const double* GINV, int C, int N, long long rows, double* out,
+                               cudaStream_t stream) {
+    const long long n = rows * (2 * C + K + 2);
+    if (n <= 0) return 0;
+    layer_input_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(Ain, K, GINV, C, N, rows, out);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_spin_rows(const double* src, int lds, int cols, int N, int off_s, int ns, int Wc, double* out, cudaStream_t stream) {
+    const long long rows = (long long)Wc * ns, n = rows * (cols + 2);
+    if (n <= 0) return 0;
+    spin_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, lds, cols, N, off_s, ns, rows, out);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_pair_fact_pack(const double* A32, const double* As, double count, int pin, double* out, cudaStream_t stream) {
+    pair_fact_pack_kernel<<<1, 256, 0, stream>>>(A32, As, count, pin, out);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_deinterleave2(const double* src, double* dst, int np, cudaStream_t stream) {
+    const long long n = 4LL * np * np;
+    if (n <= 0) return 0;
+    deinterleave2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, np);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
 
 int ds_launch_orb_grad(const DsSys& sys, const SlaterBufs& sb, const GradBufs& gb, int Wc, int npar_max, cudaStream_t stream) {
     DS_REQUIRE(sys.d.D <= 64, "orbital gradient kernel supports at most 64 determinants");
@@ -375,7 +506,7 @@ int ds_launch_hin(const DsDims& dm, const GradBufs& gb, int Wc, int C, int K, bo
     return 0;
 }
 
-int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& gb, int Wc, cudaStream_t stream) {
+int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& gb, int Wc, cudaStream_t stream, int fact) {
     const DsDims& d = sys.d;
     if (d.L < 2) return 0;
     DS_REQUIRE(d.P <= 32, "pair-stream gradient kernel needs hidden_two <= 32");
@@ -386,16 +517,24 @@ int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& 
     const long long n_e = (long long)Wc * d.N;
     const int npl = d.L - 2;
     const int grid = (int)(n_e < 4 * 148 ? n_e : 4 * 148);
-#define DS_PG_LAUNCH(NPL_)                                                                                              \
+    DS_REQUIRE(fact == 0 || npl <= 2, "pair-layer factor statistics support at most 3 pair layers");
+#define DS_PG_LAUNCH2(NPL_, FACT_)                                                                                      \
     do {                                                                                                                \
         if (smem > 48 * 1024)                                                                                           \
-            DS_CUDA_CHECK(cudaFuncSetAttribute(pair_grad_kernel<NPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        pair_grad_kernel<NPL_><<<grid, PG_THREADS, smem, stream>>>(sys, fp, gb, n_e);                                     \
+            DS_CUDA_CHECK(cudaFuncSetAttribute(pair_grad_kernel<NPL_, FACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        pair_grad_kernel<NPL_, FACT_><<<grid, PG_THREADS, smem, stream>>>(sys, fp, gb, n_e);                              \
+    } while (0)
+#define DS_PG_LAUNCH(NPL_)                                                                                              \
+    do {                                                                                                                \
+        if (fact == 0) DS_PG_LAUNCH2(NPL_, 0);                                                                          \
+        else if (fact == 1) DS_PG_LAUNCH2(NPL_, 1);                                                                     \
+        else DS_PG_LAUNCH2(NPL_, 2);                                                                                    \
     } while (0)
     if (npl <= 0) DS_PG_LAUNCH(0);
     else if (npl == 1) DS_PG_LAUNCH(1);
     else DS_PG_LAUNCH(2);
 #undef DS_PG_LAUNCH
+#undef DS_PG_LAUNCH2
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -82,11 +82,24 @@ struct GradBufs {
     // pair stream
     const double* GPMl[DS_MAX_LAYERS];          // cotangents of the pair means of level l (null for l = 0)
     double* g_Wp[DS_MAX_LAYERS]; double* g_bp[DS_MAX_LAYERS];   // accumulated
+    // Kronecker-factor statistics of the pair layers (ds_kfac_factors), accumulated: raw [32][32] Gram matrices of the
+    // layer inputs (fact_A, with their column sums fact_As [32]) and of the pre-activation cotangents (fact_G)
+    double* fact_A[DS_MAX_LAYERS]; double* fact_As[DS_MAX_LAYERS]; double* fact_G[DS_MAX_LAYERS];
 };
 int ds_launch_orb_grad(const DsSys& sys, const SlaterBufs& sb, const GradBufs& gb, int Wc, int npar_max, cudaStream_t stream);
 int ds_launch_gz(const DsDims& dm, const GradBufs& gb, int Wc, bool residual, cudaStream_t stream);
 int ds_launch_hin(const DsDims& dm, const GradBufs& gb, int Wc, int C, int K, bool residual, bool want_pm, cudaStream_t stream);
-int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& gb, int Wc, cudaStream_t stream);
+// fact = 0: weight / bias gradients; 1: Gram matrices of the layer inputs (forward only); 2: of the cotangents
+int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& gb, int Wc, cudaStream_t stream, int fact = 0);
+// rows [own C | spin means 2C | pair means K-C | 1 | 0] of a one-electron layer's input (network.py:305-332), ldx = 2C+K+2
+int ds_launch_layer_input_rows(const double* Ain, int K, const double* GINV, int C, int N, long long rows, double* out,
+                               cudaStream_t stream);
+// rows of one spin channel of src [Wc*N][lds] (first `cols` columns) followed by (1, 0): out [Wc*ns][cols+2]
+int ds_launch_spin_rows(const double* src, int lds, int cols, int N, int off_s, int ns, int Wc, double* out, cudaStream_t stream);
+// [(pin+1) x (pin+1)] Gram matrix of (x, 1) from the raw [32][32] block, the column sums and the row count
+int ds_launch_pair_fact_pack(const double* A32, const double* As, double count, int pin, double* out, cudaStream_t stream);
+// dst[q(r)][q(c)] = src[r][c], q(2p+im) = im*np + p : (re, im)-interleaved -> (re block | im block) on both indices
+int ds_launch_deinterleave2(const double* src, double* dst, int np, cudaStream_t stream);
 // dst[r, c] (+)= src[r, c] for a [rows x cols] block (leading dimensions lds, ldd); deinterleave: see grad.cu
 int ds_launch_copy2d(const double* src, int lds, double* dst, int ldd, int rows, int cols, cudaStream_t stream);
 int ds_launch_colsum_add(const double* src, int lds, int rows, int cols, double* dst, cudaStream_t stream);

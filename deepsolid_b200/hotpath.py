@@ -220,6 +220,57 @@ class HotPath:
         _lib.check(self.lib.ds_orbitals_vjp(self.h, td.data_ptr(), B, cot.data_ptr(), ptrs, sizes, n, self._stream()))
         return unflatten_params(outs, len(self.hidden_dims), self.bias_orbitals)
 
+    def kfac_factors(self, x):
+        """Raw Kronecker-factor sums of every tagged dense layer over the walkers ``x`` (ds_kfac_factors): what the
+        reference's KFAC estimator extracts from total_energy_jvp (train.py:128-133; kfac_ferminet_alpha/
+        estimator.py:284-320, curvature_blocks.py:262-281; curvature_tags_and_blocks.py:142-156).
+
+        Returns a dict with, per tagged layer of ``single``, ``double``, ``orbital``: ``a`` = sum_rows (x,1)(x,1)^T,
+        ``g`` = sum_rows ga ga^T + gp gp^T and ``rows``; plus ``envelope_abs`` / ``envelope_phase``: gradients of
+        sum_w log|psi_w| / sum_w angle(psi_w) w.r.t. the (untagged) envelope leaves.  deepsolid_b200.kfac turns these
+        into the reference's factors."""
+        t, one, on_dev = self._prep(x)
+        td = t if on_dev else t.to(self.tdev)
+        B = td.shape[0]
+        if self._param_key is None:
+            raise ValueError("parameters have not been set")
+        L = len(self.hidden_dims)
+        leaves = self._keep_params
+        kinds, nin, nout, rows = [], [], [], []
+        li = 0
+        for l in range(L):
+            kinds.append(("single", l)); nin.append(leaves[li].shape[0]); nout.append(leaves[li].shape[1])
+            rows.append(B * self.nelec); li += 2
+        for l in range(L - 1):
+            kinds.append(("double", l)); nin.append(leaves[li].shape[0]); nout.append(leaves[li].shape[1])
+            rows.append(B * self.nelec * self.nelec); li += 2
+        for s, ns in enumerate((self.n_up, self.n_dn)):
+            kinds.append(("orbital", s)); nin.append(leaves[li].shape[0]); nout.append(leaves[li].shape[1])
+            rows.append(B * ns); li += 2 if self.bias_orbitals else 1
+        env_leaves = leaves[li:li + 4]
+        a = [torch.empty(n + 1, n + 1, dtype=torch.float64, device=self.tdev) for n in nin]
+        g = [torch.empty(n, n, dtype=torch.float64, device=self.tdev) for n in nout]
+        ea = [torch.empty(tp.shape, dtype=torch.float64, device=self.tdev) for tp in env_leaves]
+        ep = [torch.empty(tp.shape, dtype=torch.float64, device=self.tdev) for tp in env_leaves]
+        n = len(a)
+
+        def arr(ts):
+            return ((C.c_void_p * len(ts))(*[o.data_ptr() for o in ts]), (C.c_int64 * len(ts))(*[o.numel() for o in ts]))
+
+        ap, asz = arr(a)
+        gp, gsz = arr(g)
+        eap, esz = arr(ea)
+        epp, _ = arr(ep)
+        _lib.check(self.lib.ds_kfac_factors(self.h, td.data_ptr(), B, ap, asz, gp, gsz, n, eap, epp, esz, 4,
+                                            self._stream()))
+        out = {"single": [], "double": [], "orbital": []}
+        for (kind, _), ai, gi, r in zip(kinds, a, g, rows):
+            out[kind].append({"a": ai, "g": gi, "rows": r})
+        out["envelope_abs"] = [{"pi": ea[0], "sigma": ea[1]}, {"pi": ea[2], "sigma": ea[3]}]
+        out["envelope_phase"] = [{"pi": ep[0], "sigma": ep[1]}, {"pi": ep[2], "sigma": ep[3]}]
+        out["batch"] = B
+        return out
+
     def logpsi_grad_x(self, x, want_phase_grad: bool = False):
         """(log|psi|, phase, d log|psi|/dx [, d phase/dx]) on the device: jax.value_and_grad of the slog network
         w.r.t. the walker (qmc.py:325), from the first-derivative half of the forward-Laplacian sweep."""

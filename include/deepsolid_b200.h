@@ -135,6 +135,21 @@ DS_API int ds_logpsi_vjp(ds_ctx *ctx, const double *x_dev, int64_t batch, const 
 DS_API int ds_orbitals_vjp(ds_ctx *ctx, const double *x_dev, int64_t batch, const double *cot_mats_dev,
                     double *const *grad_leaves, const int64_t *leaf_sizes, int n_leaves, void *stream);
 
+/* Kronecker-factor statistics of the tagged dense layers: what the reference's KFAC estimator extracts from
+ * total_energy_jvp (train.py:128-133; estimation mode fisher_exact, process.py:221; kfac_ferminet_alpha/estimator.py:
+ * 284-320, tracer.py:196-332, curvature_blocks.py:262-281, DeepSolid/curvature_tags_and_blocks.py:142-156).  For every
+ * register_repeated_dense layer (network.py:443), in the order single[0..L-1], double[0..L-2], orbital[spin 0, 1]:
+ *   a_out[k] = sum_rows (x, 1)(x, 1)^T            [(in+1) x (in+1)], rows = walker x electron (x electron)
+ *   g_out[k] = sum_rows ga ga^T + gp gp^T          [out x out]
+ * ga / gp = cotangents of the layer output for d(sum_w log|psi_w|) / d(sum_w angle psi_w); the reference's output
+ * factor is 2 g_out / rows (its tangent is sqrt(2)(ga - i gp)), its input factor a_out / rows (without the last row
+ * and column when the layer has no bias).  env_abs / env_phase: n_env = 4 DEVICE leaves (pi_0, sigma_0, pi_1,
+ * sigma_1) receiving the gradients of sum_w log|psi_w| and sum_w angle psi_w (the untagged envelope parameters get
+ * a NaiveDiagonal block, curvature_blocks.py:111-133).  All outputs are raw sums over this call's batch. */
+DS_API int ds_kfac_factors(ds_ctx *ctx, const double *x_dev, int64_t batch, double *const *a_out, const int64_t *a_sizes,
+                    double *const *g_out, const int64_t *g_sizes, int n_layers, double *const *env_abs,
+                    double *const *env_phase, const int64_t *env_sizes, int n_env, void *stream);
+
 /* jax.value_and_grad(slog_network, argnums=1), batched (the `func` importance_update receives, qmc.py:325,101-118):
  * log|psi|, phase and d log|psi| / dx, d phase / dx of shape (batch, 3N).  Any output but one gradient may be NULL.
  * The gradients are the first-derivative half of the forward-Laplacian sweep (same cost as ds_local_energy). */

@@ -163,10 +163,16 @@ def logdet_matmul(xs: Sequence[torch.Tensor]):
     return sign_out, slog_out
 
 
+_LAYER_TAP = None       # set by kfac_factors: callable (x, w, b, y) seeing every register_repeated_dense layer
+
+
 def linear_layer(x, w, b=None):
     """network.py:430-443 (the KFAC tag is the identity on values)."""
     y = x @ w
-    return y + b if b is not None else y
+    y = y + b if b is not None else y
+    if _LAYER_TAP is not None:
+        _LAYER_TAP(x, w, b, y)
+    return y
 
 
 def eval_phase(x, klist, spins, full_det=False):
@@ -717,3 +723,65 @@ def make_mcmc_step_importance(slog_apply, batch_per_device, latvec, steps=10):
             masks.append(cond)
         return x1, n_acc / (steps * batch_per_device), torch.stack(masks)
     return mcmc_step
+
+
+# ---------------------------------------------------------------------------
+# KFAC curvature statistics of the tagged layers, as the reference's estimator forms them for one batch:
+# train.py:128-133 (loss tag on conj(log psi), variance 0.5), utils/kfac_ferminet_alpha/estimator.py:284-320
+# (fisher_exact, one index), loss_functions.py:529-537 (tangent = 1/sqrt(variance)), tracer.py:196-332 + vjp_rc.py
+# (complex cotangent dy = sqrt2 (d Re F/dy + i d Im F/dy), F = conj(log psi)), curvature_blocks.py:262-281 and
+# curvature_tags_and_blocks.py:142-156 (RepeatedDenseBlock: rows = every leading index), curvature_blocks.py:111-133
+# (NaiveDiagonal for the untagged envelope leaves).
+# ---------------------------------------------------------------------------
+def kfac_factors(apply_phase_slog, params, X):
+    """-> dict(single=[...], double=[...], orbital=[...], envelope=[...]): per tagged layer
+    {inputs_factor, outputs_factor, extra_scale}; per envelope spin {pi, sigma} complex diagonal factors."""
+    global _LAYER_TAP
+    P = _clone_params(params)
+    ids = {}
+    for kind in ("single", "double", "orbital"):
+        for i, layer in enumerate(P[kind]):
+            ids[id(layer["w"])] = (kind, i)
+    acc = {}
+    env_leaves = [t for env in P["envelope"] for t in (env["pi"], env["sigma"])]
+    dw = [torch.zeros_like(t, dtype=torch.complex128) for t in env_leaves]
+    sqrt2 = math.sqrt(2.0)                                   # 1 / sqrt(variance = 0.5)
+    for x in X:
+        taps = []
+        _LAYER_TAP = lambda xx, w, b, y: taps.append((ids[id(w)], xx, b is not None, y))
+        try:
+            sign, slog = apply_phase_slog(P, x)
+        finally:
+            _LAYER_TAP = None
+        re_f, im_f = slog, -torch.angle(sign)               # F = conj(log psi)
+        ys = [t[3] for t in taps]
+        g_re = torch.autograd.grad(re_f, ys + env_leaves, retain_graph=True, allow_unused=True)
+        g_im = torch.autograd.grad(im_f, ys + env_leaves, retain_graph=False, allow_unused=True)
+        z = lambda g, ref: torch.zeros_like(ref) if g is None else g
+        for k, (key, xx, has_b, y) in enumerate(taps):
+            dy = sqrt2 * (z(g_re[k], y) + 1j * z(g_im[k], y))
+            x2 = xx.reshape(-1, xx.shape[-1])
+            if has_b:
+                x2 = torch.cat([x2, torch.ones_like(x2[:, :1])], dim=1)
+            d2 = dy.reshape(-1, dy.shape[-1])
+            a = acc.setdefault(key, {"xx": 0.0, "dd": 0.0, "xdy": 0.0, "rows": 0})
+            a["xx"] = a["xx"] + x2.T @ x2
+            a["dd"] = a["dd"] + (d2.conj().T @ d2).real
+            a["xdy"] = a["xdy"] + x2.to(d2.dtype).T @ d2
+            a["rows"] += x2.shape[0]
+        for k, leaf in enumerate(env_leaves):
+            dw[k] = dw[k] + sqrt2 * (z(g_re[len(ys) + k], leaf) + 1j * z(g_im[len(ys) + k], leaf))
+    B = len(X)
+    out = {"single": [], "double": [], "orbital": [], "envelope": []}
+    for kind in ("single", "double", "orbital"):
+        for i in range(len(P[kind])):
+            a = acc[(kind, i)]
+            out[kind].append({"inputs_factor": (a["xx"] / a["rows"]).detach(),
+                              "outputs_factor": (a["dd"] / a["rows"]).detach(),
+                              "extra_scale": a["rows"] // B,
+                              # sum_rows (x,1)^T dy = sqrt2 (d sum Re F + i d sum Im F) / d(w; b): a check of the taps
+                              "xdy": a["xdy"].detach()})
+    for s in range(len(P["envelope"])):
+        out["envelope"].append({"pi": (dw[2 * s] * dw[2 * s] / B).detach(),
+                                "sigma": (dw[2 * s + 1] * dw[2 * s + 1] / B).detach()})
+    return out
