@@ -1230,6 +1230,21 @@ extern "C" int ds_ewald(ds_ctx* c, const double* x, int64_t batch, double* ee, d
     return rc;
 }
 
+// Plane-wave sums of estimator.py (make_structure_factor :42-85, make_complex_polarization :15-40): q_dev [nq][3],
+// out_dev [batch][nq] complex (re, im).  mode 0: sum_i exp(i q.x_i); mode 1: exp(i sum_i q.x_i).
+extern "C" int ds_rho_q(ds_ctx* c, const double* x, int64_t batch, const double* q, int nq, int mode, double* out,
+                        void* stream) {
+    DS_REQUIRE(c, "null context");
+    DS_REQUIRE(batch >= 0 && nq >= 0, "negative size");
+    DS_REQUIRE(mode == 0 || mode == 1, "unknown mode %d", mode);
+    if (batch == 0 || nq == 0) return 0;
+    DS_REQUIRE(x && q && out, "null argument");
+    Guard g(c->device);
+    if (int rc = ds_launch_rho_q(x, batch, c->sys.d.N, q, nq, mode, out, (cudaStream_t)stream)) return rc;
+    c->launches++;
+    return 0;
+}
+
 extern "C" double ds_ewald_ii(const ds_ctx* c) { return c ? c->ew.ii_total : 0.0; }
 
 extern "C" int ds_local_energy(ds_ctx* c, const double* x, int64_t batch, int mode, int partition_number,

@@ -123,3 +123,44 @@ int ds_launch_ewald(const EwaldDev& ew, const double* X, long long batch, double
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
+
+
+// ---------------------------------------------------------------------------
+// Observables of estimator.py: plane-wave sums over the electrons of each walker.
+//   mode 0 (structure factor, estimator.py:68-73):  out[b][k] = sum_i exp(i q_k . x_bi)
+//   mode 1 (complex polarisation, estimator.py:27-31): out[b][k] = exp(i sum_i q_k . x_bi)
+// One thread per (walker, q-vector); positions are read through L1 (every q of a walker re-reads the same 3N doubles).
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void rho_q_kernel(const double* __restrict__ X, long long batch, int n_elec, const double* __restrict__ Q, int nq,
+                             int mode, double* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= batch * nq) return;
+    const long long b = t / nq;
+    const int k = (int)(t - b * nq);
+    const double q0 = Q[3 * k], q1 = Q[3 * k + 1], q2 = Q[3 * k + 2];
+    const double* x = X + b * 3 * n_elec;
+    double re = 0.0, im = 0.0, tot = 0.0;
+    for (int i = 0; i < n_elec; ++i) {
+        const double d = q0 * x[3 * i] + q1 * x[3 * i + 1] + q2 * x[3 * i + 2];
+        if (mode == 0) {
+            double sn, cs;
+            sincos(d, &sn, &cs);
+            re += cs; im += sn;
+        } else {
+            tot += d;
+        }
+    }
+    if (mode != 0) sincos(tot, &im, &re);
+    out[2 * t] = re; out[2 * t + 1] = im;
+}
+}  // namespace
+
+int ds_launch_rho_q(const double* X, long long batch, int n_elec, const double* Q, int nq, int mode, double* out,
+                    cudaStream_t stream) {
+    const long long n = batch * nq;
+    if (n <= 0) return 0;
+    rho_q_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(X, batch, n_elec, Q, nq, mode, out);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

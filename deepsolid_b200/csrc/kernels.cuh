@@ -130,5 +130,8 @@ int ds_launch_accept(double* x, const double* x2, double* lp, const double* lp2,
                      const double* u_or_null, unsigned long long seed, unsigned long long step,
                      unsigned char* mask_or_null, double* n_accept, cudaStream_t stream);
 int ds_launch_scale(double* dst, const double* src, double a, long long n, cudaStream_t stream);
+// estimator.py plane-wave sums: out [batch][nq] complex (re, im); mode 0 = sum_i e^{iq.x_i}, 1 = e^{i sum_i q.x_i}
+int ds_launch_rho_q(const double* X, long long batch, int n_elec, const double* Q, int nq, int mode, double* out,
+                    cudaStream_t stream);
 int ds_launch_stats(const double* ke_re, const double* ke_im, const double* ew, long long n, double* out6,
                     cudaStream_t stream);

@@ -220,6 +220,20 @@ class HotPath:
         _lib.check(self.lib.ds_orbitals_vjp(self.h, td.data_ptr(), B, cot.data_ptr(), ptrs, sizes, n, self._stream()))
         return unflatten_params(outs, len(self.hidden_dims), self.bias_orbitals)
 
+    def rho_q(self, x, qvecs, mode: int = 0):
+        """Complex (B, nq) plane-wave sums over the electrons: mode 0 sum_i exp(i q.x_i), mode 1 exp(i sum_i q.x_i)
+        (estimator.py:27-31, 68-70)."""
+        t, one, on_dev = self._prep(x)
+        td = t if on_dev else t.to(self.tdev)
+        q = torch.as_tensor(np.asarray(qvecs, dtype=np.float64).reshape(-1, 3)).to(self.tdev).contiguous()
+        B, nq = td.shape[0], q.shape[0]
+        out = torch.empty(B, nq, 2, dtype=torch.float64, device=self.tdev)
+        _lib.check(self.lib.ds_rho_q(self.h, td.data_ptr(), B, q.data_ptr(), nq, int(mode), out.data_ptr(), self._stream()))
+        res = torch.view_as_complex(out)
+        if not on_dev:
+            res = res.cpu()
+        return res[0] if one else res
+
     def kfac_factors(self, x):
         """Raw Kronecker-factor sums of every tagged dense layer over the walkers ``x`` (ds_kfac_factors): what the
         reference's KFAC estimator extracts from total_energy_jvp (train.py:128-133; kfac_ferminet_alpha/

@@ -135,6 +135,12 @@ DS_API int ds_logpsi_vjp(ds_ctx *ctx, const double *x_dev, int64_t batch, const 
 DS_API int ds_orbitals_vjp(ds_ctx *ctx, const double *x_dev, int64_t batch, const double *cot_mats_dev,
                     double *const *grad_leaves, const int64_t *leaf_sizes, int n_leaves, void *stream);
 
+/* Plane-wave sums behind the observables of estimator.py (make_structure_factor :42-85: rho_q = sum_i exp(i q.x_i);
+ * make_complex_polarization :15-40: exp(i sum_i G.x_i)).  q_dev [nq][3]; out_dev [batch][nq] complex (re, im);
+ * mode 0 = sum of exponentials, 1 = exponential of the sum.  The batch means / pmean stay with the caller. */
+DS_API int ds_rho_q(ds_ctx *ctx, const double *x_dev, int64_t batch, const double *q_dev, int nq, int mode,
+             double *out_dev, void *stream);
+
 /* Kronecker-factor statistics of the tagged dense layers: what the reference's KFAC estimator extracts from
  * total_energy_jvp (train.py:128-133; estimation mode fisher_exact, process.py:221; kfac_ferminet_alpha/estimator.py:
  * 284-320, tracer.py:196-332, curvature_blocks.py:262-281, DeepSolid/curvature_tags_and_blocks.py:142-156).  For every

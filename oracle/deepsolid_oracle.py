@@ -785,3 +785,38 @@ def kfac_factors(apply_phase_slog, params, X):
         out["envelope"].append({"pi": (dw[2 * s] * dw[2 * s] / B).detach(),
                                 "sigma": (dw[2 * s + 1] * dw[2 * s + 1] / B).detach()})
     return out
+
+
+# ---------------------------------------------------------------------------
+# estimator.py:15-85 -- observables (single process: pmean is the identity)
+# ---------------------------------------------------------------------------
+def make_complex_polarization(simulation_cell, direction=0, ndim=3):
+    """estimator.py:15-40."""
+    rec_vec = _t(np.asarray(simulation_cell.reciprocal_vectors())[direction])
+
+    def complex_polarization(data):
+        data = _t(data)
+        data = data.reshape(list(data.shape[:-1]) + [-1, ndim])
+        dots = torch.einsum("i,...i->...", rec_vec, data).sum(dim=-1)
+        return torch.exp(1j * dots).mean(dim=-1)
+
+    return complex_polarization
+
+
+def make_structure_factor(simulation_cell, nq=4, ndim=3):
+    """estimator.py:42-85."""
+    mesh = np.meshgrid(*[np.arange(nq) for _ in range(3)])
+    point_list = np.stack([m.ravel() for m in mesh], axis=0).T
+    qvecs = _t(point_list @ np.asarray(simulation_cell.reciprocal_vectors()))
+    nelec = simulation_cell.nelectron
+
+    def structure_factor(data):
+        data = _t(data)
+        data = data.reshape(list(data.shape[:-1]) + [-1, ndim])
+        dots = torch.einsum("kj,...j->...k", qvecs, data)          # batch, ne, npoint
+        rho_k = torch.exp(1j * dots).sum(dim=1)
+        rho_k_one = rho_k.mean(dim=0)
+        rho_k_two = (rho_k.abs() ** 2).mean(dim=0)
+        return (rho_k_two - rho_k_one.abs() ** 2) / nelec
+
+    return structure_factor
