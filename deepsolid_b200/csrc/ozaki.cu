@@ -1,5 +1,6 @@
 // tcgen05 / TMEM / TMA implementation of the sliced-integer fp64 GEMM.  See ozaki.cuh.
 #include "ozaki.cuh"
+#include <cstdlib>
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -7,7 +8,7 @@
 namespace {
 
 constexpr int EPI_WARPS = 16;                         // four per TMEM lane quarter
-constexpr int EPI_COLS = OZ_TN / (EPI_WARPS / 4);     // columns (rows of A) per epilogue warp
+constexpr int EPI_COLS = 16;                          // columns (rows of A) per epilogue warp
 constexpr int OZ_THREADS = 64 + EPI_WARPS * 32;       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..: epilogue
 constexpr int STAGES = 3;
 constexpr int W_SLICE = OZ_TM * OZ_BK;                // 8192 B
@@ -17,6 +18,18 @@ constexpr int A_STAGE = OZ_S * A_SLICE;               // 24576 B
 constexpr int STAGE_BYTES = W_STAGE + A_STAGE;        // 73728 B
 constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024; // + alignment slack
 constexpr int TMEM_COLS = 512;                        // 6 x 64 used (power of two required)
+// Row tile TN = 64: one accumulator set (6 x 64 columns).  TN = 32: TWO sets (2 x 6 x 32 columns), so the TMEM read of
+// a tile (64 B/clk, ~1.6 us per 196 KB) overlaps the MMAs of the next one; the epilogue warps split into two sets of
+// eight that alternate tiles.
+template <int TN> struct OzCfg {
+    static constexpr int NBUF = (TN == 32) ? 2 : 1;
+    static constexpr int SET_WARPS = EPI_WARPS / NBUF;
+    static constexpr int A_SLICE_T = TN * OZ_BK;
+    static constexpr int A_STAGE_T = OZ_S * A_SLICE_T;
+    static constexpr int STAGE_T = W_STAGE + A_STAGE_T;
+    static constexpr int SMEM_T = STAGES * STAGE_T + 1024;
+    static_assert(TN / (SET_WARPS / 4) == EPI_COLS, "epilogue warps x EPI_COLS must tile the rows of a tile");
+};
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -304,14 +317,16 @@ __device__ __forceinline__ void orbj_block8(const double* zz8, const double* __r
 // ---------------------------------------------------------------------------
 // the GEMM
 // ---------------------------------------------------------------------------
-template <int MODE, bool RES>
+template <int MODE, bool RES, int TN>
 // 18 warps: five share one SM sub-partition (16384 registers), so at most 96 registers per thread
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const OzParams p,
                const int tiles_per_group, const int n_cb, const long long n_tiles) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
+    using Cfg = OzCfg<TN>;
+    constexpr int NBUF = Cfg::NBUF, SET_WARPS = Cfg::SET_WARPS, A_SLICE_T = Cfg::A_SLICE_T, STAGE_T = Cfg::STAGE_T;
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -319,8 +334,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        mbar_init(&tmem_full_bar, 1);
-        mbar_init(&tmem_empty_bar, EPI_WARPS);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], SET_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -337,14 +351,14 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const int cb = (int)(tile % n_cb);
                 const long long rt = tile / n_cb;
                 const int grp = (int)(rt / tiles_per_group);
-                const int q0 = (int)(rt % tiles_per_group) * OZ_TN;
+                const int q0 = (int)(rt % tiles_per_group) * TN;
                 for (int kb = 0; kb < nkb; ++kb, ++cnt) {
                     const int st = (int)(cnt % STAGES);
                     const uint32_t ph = (uint32_t)((cnt / STAGES) & 1);
                     mbar_wait(&empty_bar[st], ph ^ 1u);
-                    unsigned char* sW = smem + st * STAGE_BYTES;
+                    unsigned char* sW = smem + st * STAGE_T;
                     if (p.dbg & 4) { mbar_arrive(&full_bar[st]); continue; }
-                    mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[st], STAGE_T);
                     tma_load_4d(sW, &tmW, &full_bar[st], kb * OZ_BK, cb * OZ_TM, 0, 0);
                     tma_load_4d(sW + W_STAGE, &tmA, &full_bar[st], kb * OZ_BK, q0, 0, grp);
                 }
@@ -356,14 +370,16 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             long long cnt = 0;
             uint32_t it = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                mbar_wait(&tmem_empty_bar, (it & 1u) ^ 1u);
+                const uint32_t buf = it % NBUF, use = it / NBUF;
+                mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);
                 tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * (OZ_S * TN);
                 for (int kb = 0; kb < nkb; ++kb, ++cnt) {
                     const int st = (int)(cnt % STAGES);
                     const uint32_t ph = (uint32_t)((cnt / STAGES) & 1);
                     mbar_wait(&full_bar[st], ph);
                     tc_fence_after();
-                    const uint32_t sW = smem_u32(smem + st * STAGE_BYTES);
+                    const uint32_t sW = smem_u32(smem + st * STAGE_T);
                     const uint32_t sA = sW + W_STAGE;
                     if (!(p.dbg & 2))
 #pragma unroll
@@ -373,17 +389,18 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             // W_t x [A_0 .. A_{5-t}] -> diagonals t .. 5 (TMEM column blocks of 64)
                             const uint64_t wdesc = make_desc(sW + t * W_SLICE + ks * 32);
                             const int nsl = OZ_S - t;
-                            const int n1 = (nsl > 4 ? 4 : nsl) * OZ_TN;
+                            constexpr int MAXSL = 256 / TN;                  // slices of A one instruction can span (N <= 256)
+                            const int n1 = (nsl > MAXSL ? MAXSL : nsl) * TN;
                             const uint32_t acc = (kb > 0 || ks > 0 || t > 0) ? 1u : 0u;
-                            umma_i8(tmem_base + t * OZ_TN, wdesc, make_desc(sA + ks * 32), make_idesc(n1), acc);
-                            if (nsl > 4)
-                                umma_i8(tmem_base + (t + 4) * OZ_TN, wdesc, make_desc(sA + 4 * A_SLICE + ks * 32),
-                                        make_idesc((nsl - 4) * OZ_TN), acc);
+                            umma_i8(tacc + t * TN, wdesc, make_desc(sA + ks * 32), make_idesc(n1), acc);
+                            if (nsl > MAXSL)
+                                umma_i8(tacc + (t + MAXSL) * TN, wdesc, make_desc(sA + MAXSL * A_SLICE_T + ks * 32),
+                                        make_idesc((nsl - MAXSL) * TN), acc);
                         }
                     }
                     umma_commit(&empty_bar[st]);          // frees the smem stage when the MMAs have read it
                 }
-                umma_commit(&tmem_full_bar);              // accumulators complete
+                umma_commit(&tmem_full_bar[buf]);         // accumulators complete
             }
         }
     } else {
@@ -397,17 +414,18 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         // in blocks of 8 columns: rows of A come in aligned groups of 8 that share one electron
         // (NDp and rows-per-group are multiples of 8), so a block needs no per-column bookkeeping.
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
-        const int cg = (warp - 2) >> 2;                   // which EPI_COLS columns
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * EPI_COLS;
+        const int set = (warp - 2) / SET_WARPS;           // accumulator set (and tile parity) of this warp
+        const int cg = ((warp - 2) % SET_WARPS) >> 2;     // which EPI_COLS columns
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (OZ_S * TN) + cg * EPI_COLS;
         uint32_t it = 0;
         const double MAGIC = 6755399441055744.0;          // 2^52 + 2^51
         int cur_cb = -1;
         double sbn = 0.0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (long long tile = blockIdx.x + (long long)set * gridDim.x; tile < n_tiles; tile += (long long)NBUF * gridDim.x, ++it) {
             const int cb = (int)(tile % n_cb);
             const long long rt = tile / n_cb;
             const long long grp = rt / tiles_per_group;
-            const long long q0 = (rt % tiles_per_group) * OZ_TN + cg * EPI_COLS;   // first row (in group) of this warp
+            const long long q0 = (rt % tiles_per_group) * TN + cg * EPI_COLS;      // first row (in group) of this warp
             const int n = cb * OZ_TM + q * 32 + lane;
             const bool nv = n < p.N;
             const bool full = (cb + 1) * OZ_TM <= p.N;                             // warp-uniform
@@ -427,14 +445,14 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             }
 
             double zz[EPI_COLS];
-            mbar_wait(&tmem_full_bar, it & 1u);
+            mbar_wait(&tmem_full_bar[set], it & 1u);
             tc_fence_after();
             if (!(MODE == OZ_PLAIN && (p.dbg & 1))) {
 #pragma unroll
                 for (int c0 = 0; c0 < EPI_COLS; c0 += 8) {
                     int v[OZ_S][8];
 #pragma unroll
-                    for (int g = 0; g < OZ_S; ++g) tmem_ld8(lane_addr + g * OZ_TN + c0, v[g]);
+                    for (int g = 0; g < OZ_S; ++g) tmem_ld8(lane_addr + g * TN + c0, v[g]);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -448,7 +466,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar);
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[set]);
             if (MODE == OZ_PLAIN && (p.dbg & 1)) continue;
 
             if (MODE == OZ_JAC) {
@@ -589,12 +607,13 @@ int make_map(CUtensorMap* tm, const signed char* base, int K, long long rows, lo
     return 0;
 }
 
-template <int MODE, bool RES>
-int launch(const OzParams& p, cudaStream_t stream) {
+template <int MODE, bool RES, int TN>
+int launch_tn(const OzParams& p, cudaStream_t stream) {
     static bool configured = false;
     static int n_sm = 0;
+    constexpr int SMEM_T = OzCfg<TN>::SMEM_T;
     if (!configured) {
-        DS_CUDA_CHECK(cudaFuncSetAttribute(oz_gemm_kernel<MODE, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+        DS_CUDA_CHECK(cudaFuncSetAttribute(oz_gemm_kernel<MODE, RES, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_T));
         int dev = 0;
         DS_CUDA_CHECK(cudaGetDevice(&dev));
         DS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -602,14 +621,24 @@ int launch(const OzParams& p, cudaStream_t stream) {
     }
     CUtensorMap tmW, tmA;
     if (int rc = make_map(&tmW, p.Wd, p.K, p.N, p.N, 1, OZ_TM)) return rc;
-    if (int rc = make_map(&tmA, p.Ad + p.goff * (long long)OZ_S * p.K, p.K, p.rpg, p.gstride, p.n_groups, OZ_TN)) return rc;
-    const int tpg = (int)((p.rpg + OZ_TN - 1) / OZ_TN);
+    if (int rc = make_map(&tmA, p.Ad + p.goff * (long long)OZ_S * p.K, p.K, p.rpg, p.gstride, p.n_groups, TN)) return rc;
+    const int tpg = (int)((p.rpg + TN - 1) / TN);
     const int n_cb = (p.N + OZ_TM - 1) / OZ_TM;
     const long long n_tiles = (long long)tpg * p.n_groups * n_cb;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
-    oz_gemm_kernel<MODE, RES><<<grid, OZ_THREADS, SMEM_DYN, stream>>>(tmW, tmA, p, tpg, n_cb, n_tiles);
+    oz_gemm_kernel<MODE, RES, TN><<<grid, OZ_THREADS, SMEM_T, stream>>>(tmW, tmA, p, tpg, n_cb, n_tiles);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+// Default: 64-row tiles, one accumulator set.  DS_OZ_TN=32 selects 32-row tiles with double-buffered TMEM: it hides the
+// TMEM read but loses more than it gains on B200 (profiles/r1_probe_tn32.log: MMA-only 1.00 ms vs 0.75 ms because
+// the N <= 192 instructions run the pipe at 61 % instead of 81 %, TMA-only 0.88 ms vs 0.49 ms because W is re-read
+// per 32 rows; whole kernel 1.42 ms vs 1.14 ms at 771120 x 256 x 320).
+template <int MODE, bool RES>
+int launch(const OzParams& p, cudaStream_t stream) {
+    static const int tn = [] { const char* e = getenv("DS_OZ_TN"); return (e && atoi(e) == 32) ? 32 : 64; }();
+    return tn == 64 ? launch_tn<MODE, RES, 64>(p, stream) : launch_tn<MODE, RES, 32>(p, stream);
 }
 
 }  // namespace
