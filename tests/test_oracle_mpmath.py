@@ -1,0 +1,29 @@
+"""Pins the floating-point behaviour of the torch oracle: a scalar 40-digit mpmath restatement of the network
+(oracle/mp_reference.py; Laplacian by high-order central differences, no autodiff) against oracle/deepsolid_oracle.py
+on a tiny system (H4 chain: 2+2 electrons, two 16/8-wide layers, 2 determinants).  SURVEY.md §8(c)."""
+import numpy as np
+import torch
+
+from deepsolid_b200 import cell as C
+from oracle import deepsolid_oracle as O
+from oracle import mp_reference as MP
+
+
+def test_torch_oracle_matches_40_digit_restatement():
+    sc = C.build_system("h4")
+    kl = C.make_klist(sc)
+    hidden = ((16, 8), (16, 8))
+    pn = O.init_params(np.random.default_rng(5), sc.original_cell.natm, sc.nelec, hidden_dims=hidden, determinants=2)
+    P = O.params_to_torch(pn)
+    X = C.init_walkers(sc, 2, seed=9)
+    f = O.make_solid_fermi_net(kl, sc, hidden_dims=hidden, determinants=2, method_name="eval_logdet")
+    ke_fun = O.local_kinetic_energy_real_imag(f)
+    for x in X:
+        want_f, want_ke = MP.kinetic(pn, list(x), sc, kl, sc.nelec)
+        got_f = f(P, torch.as_tensor(x))
+        got_ke = ke_fun(P, torch.as_tensor(x))
+        got_ke = complex(got_ke[0]) + complex(got_ke[1]) if isinstance(got_ke, (tuple, list)) else complex(got_ke)
+        assert abs(float(got_f.real) - float(want_f.real)) < 1e-12
+        dphi = float(got_f.imag) - float(want_f.imag)
+        assert abs((dphi + np.pi) % (2 * np.pi) - np.pi) < 1e-12
+        assert abs(got_ke - complex(want_ke)) < 1e-12, (got_ke, complex(want_ke))     # measured 3e-15 .. 6e-15
