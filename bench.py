@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--mcmc", action="store_true", help="also time the Metropolis step (extras)")
     ap.add_argument("--grad", action="store_true", help="also time energy + parameter gradient (value_and_grad; extras)")
+    ap.add_argument("--kfac", action="store_true", help="also time the KFAC curvature statistics and the forward (extras)")
     ap.add_argument("--equil", type=int, default=2, help="Metropolis calls (20 moves each) used to equilibrate walkers")
     return ap.parse_args()
 
@@ -271,6 +272,18 @@ def run_ours(args):
         ms_g = timed(step_grad, max(1, args.steps // 2), 1)
         extras["value_and_grad_walkers_per_sec"] = world * batch * max(1, args.steps // 2) / (ms_g / 1e3)
         extras["grad_single1_w_norm"] = float(keep["gnorm"].norm())
+    if args.kfac:
+        from deepsolid_b200 import kfac as kfac_mod
+
+        def step_kfac():
+            keep["kf"] = kfac_mod.curvature_estimate(hp, P, Xd, sync=world > 1)
+        ms_k = timed(step_kfac, max(1, args.steps // 2), 1)
+        extras["kfac_factor_walkers_per_sec"] = world * batch * max(1, args.steps // 2) / (ms_k / 1e3)
+
+        def step_fwd():
+            keep["lp"] = hp.logpsi(Xd)
+        ms_f = timed(step_fwd, max(1, args.steps // 2) * 4, 1)
+        extras["forwards_per_sec"] = world * batch * max(1, args.steps // 2) * 4 / (ms_f / 1e3)
     if rank != 0:
         if world > 1:
             td.destroy_process_group()

@@ -1037,7 +1037,7 @@ int launch_det_dmma(const DsSys& sys, const SlaterBufs& sb, int Wc, int nmax, cu
 // NMAX >= n is the compile-time row length (8, 16 or 32).
 // ---------------------------------------------------------------------------
 template <int NMAX>
-__global__ void __launch_bounds__(256) det_warp_kernel(const DsSys sys, const SlaterBufs sb, long long n_mats) {
+__global__ void __launch_bounds__(128) det_warp_kernel(const DsSys sys, const SlaterBufs sb, long long n_mats) {
     const DsDims& dm = sys.d;
     const int D = dm.D;
     const int lane = threadIdx.x & 31;
@@ -1056,43 +1056,50 @@ __global__ void __launch_bounds__(256) det_warp_kernel(const DsSys sys, const Sl
         if (lane < n && c < n) v = mat[lane * n + c];
         ar[c] = v.re; ai[c] = v.im;
     }
-    double logabs = 0.0;
-    cplx phase{1.0, 0.0};
+    // det = prod of the pivots, kept as a complex mantissa P (rescaled by a power of two every step) and an exponent:
+    // log|det| = log|P| + esum ln 2, phase = P / |P|: no per-step log / hypot / division by the modulus
+    cplx P{1.0, 0.0};
+    int esum = 0;
     bool done = lane >= n;                       // rows already used as pivots (and the padding lanes)
     int my_step = -1;                            // step at which this row was the pivot
-    for (int kk = 0; kk < n; ++kk) {
-        // a[kk] of this lane (register array indexed by a runtime kk: select through the unrolled scan)
-        double pr = 0.0, pi = 0.0;
+    // fully unrolled over the elimination steps: every register-array index is a compile-time constant
+#pragma unroll(NMAX)
+    for (int kk = 0; kk < NMAX; ++kk) {
+        if (kk < n) {                            // warp-uniform
+            const double pr = ar[kk], pi = ai[kk];
+            double best = done ? -1.0 : fabs(pr) + fabs(pi);
+            int bi = lane;
 #pragma unroll
-        for (int c = 0; c < NMAX; ++c)
-            if (c == kk) { pr = ar[c]; pi = ai[c]; }
-        double best = done ? -1.0 : fabs(pr) + fabs(pi);
-        int bi = lane;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        const int p = bi;                        // warp-uniform pivot row
-        const double pvr = __shfl_sync(0xffffffffu, pr, p), pvi = __shfl_sync(0xffffffffu, pi, p);
-        {
-            const double a = hypot(pvr, pvi);
-            logabs += log(a);
-            phase = cmul(phase, cplx{pvr / a, pvi / a});
-        }
-        if (lane == p) { done = true; my_step = kk; }
-        const cplx ipv = cinv(cplx{pvr, pvi});
-        const cplx f = done ? cplx{0.0, 0.0} : cmul(cplx{pr, pi}, ipv);      // multiplier of the active rows
-#pragma unroll
-        for (int c = 0; c < NMAX; ++c) {
-            if (c > kk && c < n) {               // warp-uniform
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            const int p = bi;                    // warp-uniform pivot row
+            const double pvr = __shfl_sync(0xffffffffu, pr, p), pvi = __shfl_sync(0xffffffffu, pi, p);
+            {
+                P = cmul(P, cplx{pvr, pvi});
+                int e;
+                (void)frexp(fmax(fabs(P.re), fabs(P.im)), &e);
+                if (e > -900 && e < 900) {       // zero / inf / nan products keep their value (and propagate)
+                    P.re = ldexp(P.re, -e); P.im = ldexp(P.im, -e);
+                    esum += e;
+                }
+            }
+            if (lane == p) { done = true; my_step = kk; }
+            const cplx ipv = cinv(cplx{pvr, pvi});
+            const cplx f = done ? cplx{0.0, 0.0} : cmul(cplx{pr, pi}, ipv);      // multiplier of the active rows
+#pragma unroll(NMAX)
+            for (int c = kk + 1; c < NMAX; ++c) {
                 const double br = __shfl_sync(0xffffffffu, ar[c], p), bim = __shfl_sync(0xffffffffu, ai[c], p);
                 ar[c] -= f.re * br - f.im * bim;
                 ai[c] -= f.re * bim + f.im * br;
             }
         }
     }
+    const double pa = hypot(P.re, P.im);
+    const double logabs = log(pa) + (double)esum * 0.69314718055994530942;
+    cplx phase{P.re / pa, P.im / pa};
     // parity of the permutation step -> row: sign = (-1)^(n - #cycles)
     unsigned visited = 0u;
     int cycles = 0;
@@ -1273,10 +1280,12 @@ int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cuda
     static const bool cta_lu = getenv("DS_DET_CTA_LU") && atoi(getenv("DS_DET_CTA_LU")) != 0;
     if (!lap && nmax <= 32 && !cta_lu) {        // value-only: warp-per-matrix LU
         const long long n_mats = (long long)Wc * ds_nblk(sys.d) * sys.d.D;
-        const unsigned blocks = (unsigned)((n_mats + 7) / 8);
-        if (nmax <= 8) det_warp_kernel<8><<<blocks, 256, 0, stream>>>(sys, sb, n_mats);
-        else if (nmax <= 16) det_warp_kernel<16><<<blocks, 256, 0, stream>>>(sys, sb, n_mats);
-        else det_warp_kernel<32><<<blocks, 256, 0, stream>>>(sys, sb, n_mats);
+        const unsigned blocks = (unsigned)((n_mats + 3) / 4);      // 4 warps per CTA: ~170 registers per thread
+        if (nmax <= 8) det_warp_kernel<8><<<blocks, 128, 0, stream>>>(sys, sb, n_mats);
+        else if (nmax <= 16) det_warp_kernel<16><<<blocks, 128, 0, stream>>>(sys, sb, n_mats);
+        else if (nmax <= 24) det_warp_kernel<24><<<blocks, 128, 0, stream>>>(sys, sb, n_mats);
+        else if (nmax <= 28) det_warp_kernel<28><<<blocks, 128, 0, stream>>>(sys, sb, n_mats);
+        else det_warp_kernel<32><<<blocks, 128, 0, stream>>>(sys, sb, n_mats);
         DS_CUDA_CHECK(cudaGetLastError());
         return 0;
     }
