@@ -92,5 +92,9 @@ if __name__ == "__main__":
     hist, secs = run(a.system, a.batch, a.iterations, a.burn_in, lr=a.lr, ckpt_dir=a.ckpt_dir)
     e0 = np.mean([h["energy"] for h in hist[:5]])
     e1 = np.mean([h["energy"] for h in hist[-5:]])
-    print("energy per primitive cell: first 5 steps %.4f, last 5 steps %.4f E_h; %.2f s per iteration"
-          % (e0, e1, secs / max(len(hist), 1)))
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("energy per primitive cell: first 5 steps %.4f, last 5 steps %.4f E_h; %.2f s per iteration"
+              % (e0, e1, secs / max(len(hist), 1)))
+    import torch.distributed as td
+    if td.is_available() and td.is_initialized():
+        td.destroy_process_group()
