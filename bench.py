@@ -303,7 +303,7 @@ def run_ours(args):
         if i8 and system == DEFAULT_SYSTEM:
             traffic = {"oz_gemm_kernel<JAC>": tr["oz_gemm_kernel<1, 1>"]["dram_bytes_per_launch"],
                        "oz_gemm_kernel<ORBJ>": tr["oz_gemm_kernel<2, 0>"]["dram_bytes_per_launch"],
-                       "source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, 85-walker chunk)"}
+                       "source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of one 254-walker chunk; algorithmic bytes of that launch: JAC 54.6 MB, ORBJ 22.7 MB per walker)"}
     except Exception:
         pass
     # DRAM traffic of the WHOLE local-energy pass (every kernel) from the committed ncu launch list
