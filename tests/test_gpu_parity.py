@@ -219,3 +219,35 @@ def test_full_size_invariants(name, batch):
         lap = ((dp + dm) / h ** 2).sum()
         g2 = (((dp - dm) / (2 * h)) ** 2).sum()
         assert abs(complex((-0.5 * (lap + g2)).cpu()) - complex(ke[0].cpu())) < 5e-4 * max(1.0, abs(complex(ke[0].cpu())))
+
+
+def test_non_finite_walkers_propagate_and_stay_local():
+    """The reference never raises on numerics (NaN/Inf propagate, process.py:307-318 optionally catches them): a walker
+    with a NaN / Inf coordinate gives NaN outputs for THAT walker only, and a Metropolis proposal landing on it is
+    rejected (qmc.py:217-221: `nan > log u` is False)."""
+    ld, sl, ps, _, hp = nets("graphene8")
+    sc, kl, _, P = system("graphene8")
+    X = torch.as_tensor(C.init_walkers(sc, 9, seed=31)).to(dev())
+    el = hamiltonian.local_energy_seperate(ld.apply, sc, mode="for")
+    ke0, ew0 = el(P, X)
+    la0 = sl.apply(P, X)
+    Xb = X.clone()
+    Xb[3, 4] = float("nan")
+    Xb[6, 0] = float("inf")
+    ke, ew = el(P, Xb)
+    la = sl.apply(P, Xb)
+    good = [i for i in range(9) if i not in (3, 6)]
+    assert torch.isnan(la[3]) and not torch.isfinite(la[6])
+    assert not torch.isfinite(ke[3].real) and not torch.isfinite(ke[6].real)
+    assert torch.equal(la[good], la0[good])                      # bitwise: no cross-walker contamination
+    # (the sweep accumulates sum_d zJ^2 with atomics: its summation order, hence the last bits, vary from run to run)
+    assert float((ke[good] - ke0[good]).abs().max()) < 1e-10
+    assert torch.equal(ew[good], ew0[good])
+    # Metropolis: a NaN proposal is rejected, the walker keeps its position
+    steps, B, n3 = 2, 9, X.shape[1]
+    xi = torch.zeros(steps, B, n3, dtype=torch.float64)
+    xi[0, 2, 5] = float("nan")
+    u = torch.full((steps, B), 0.5, dtype=torch.float64)
+    step = qmc.make_mcmc_step(sl.apply, B, sc.lattice_vectors(), steps=steps)
+    xn, pmove, masks = step(P, X, (xi, u), 0.02, return_masks=True)
+    assert not bool(masks[0, 2]) and torch.isfinite(xn).all()
