@@ -97,6 +97,13 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
                          " (use_last_layer=True is the one structural option without a CUDA path)")
     if simulation_cell is None or klist is None:
         raise ValueError("simulation_cell and klist are required")
+    hd = tuple(tuple(int(v) for v in h) for h in hidden_dims)
+    if len({h[0] for h in hd}) != 1 or len({h[1] for h in hd}) != 1:
+        raise ValueError("the CUDA hot path needs equal widths in every layer of hidden_dims")
+    if not 2 <= len(hd) <= 4:
+        raise ValueError("the CUDA hot path supports 2 to 4 layers")
+    if hd[0][0] % 2 or hd[0][1] % 2 or not 2 <= hd[0][1] <= 32 or hd[0][0] < 2:
+        raise ValueError("the CUDA hot path needs even stream widths and a two-electron width of at most 32")
 
     state = {"hp": hotpath}
 
