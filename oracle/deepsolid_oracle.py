@@ -820,3 +820,29 @@ def make_structure_factor(simulation_cell, nq=4, ndim=3):
         return (rho_k_two - rho_k_one.abs() ** 2) / nelec
 
     return structure_factor
+
+
+# ---------------------------------------------------------------------------
+# pretrain.py:70-89 -- the Hartree-Fock pretraining loss and its parameter gradient (autograd through eval_mats)
+# ---------------------------------------------------------------------------
+def pretrain_loss_and_grad(apply_mats, params, X, target, full_det=False):
+    """target: list of (B, n_s, n_s) complex tensors.  -> (loss, grads pytree)."""
+    P = _clone_params(params)
+    predict = None
+    for x in X:
+        mats = apply_mats(P, x)                              # list of (D, n, n)
+        predict = [[m] for m in mats] if predict is None else [p + [m] for p, m in zip(predict, mats)]
+    predict = [torch.stack(p) for p in predict]              # (B, D, n, n)
+    if full_det:
+        B, na, nb = target[0].shape[0], target[0].shape[1], target[1].shape[1]
+        t = torch.zeros(B, na + nb, na + nb, dtype=torch.complex128)
+        t[:, :na, :na] = target[0]
+        t[:, na:, na:] = target[1]
+        target = [t]
+    loss = torch.stack([(torch.abs(tar[:, None, ...] - pre) ** 2).mean() for tar, pre in zip(target, predict)]).mean()
+    grads = torch.autograd.grad(loss, _leaves(P), allow_unused=True)
+    it = iter([g if g is not None else torch.zeros_like(l) for g, l in zip(grads, _leaves(P))])
+    return loss.detach(), {"single": [{"w": next(it), "b": next(it)} for _ in params["single"]],
+                           "double": [{"w": next(it), "b": next(it)} for _ in params["double"]],
+                           "orbital": [{"w": next(it)} for _ in params["orbital"]],
+                           "envelope": [{"pi": next(it), "sigma": next(it)} for _ in params["envelope"]]}
