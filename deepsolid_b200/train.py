@@ -94,3 +94,43 @@ def make_loss(network, batch_network, simulation_cell, clip_local_energy=5.0, cl
 
     total_energy.value_and_grad = value_and_grad
     return total_energy
+
+
+def make_training_step(mcmc_step, val_and_grad, opt_update):
+    """train.py:147-185: one iteration = Metropolis sweep, energy and gradient, cross-rank mean of the gradient,
+    optimiser update.  ``val_and_grad(params, data) -> ((loss, aux), grads)`` is ``make_loss(...).value_and_grad``;
+    ``opt_update(t, grads, params, state) -> (state, params)``.  Returns
+    ``step(t, data, params, state, key, mcmc_width) -> (data, params, state, loss, aux, pmove, search_direction)``."""
+    from .hotpath import flatten_params, unflatten_params
+
+    def step(t, data, params, state, key, mcmc_width):
+        data, pmove = mcmc_step(params, data, key, mcmc_width)
+        (loss, aux_data), search_direction = val_and_grad(params, data)
+        leaves = [_dist.pmean(torch.as_tensor(g)) for g in flatten_params(search_direction)]
+        search_direction = unflatten_params(leaves, len(params["single"]), "b" in params["orbital"][0])
+        state, params = opt_update(t, search_direction, params, state)
+        return data, params, state, loss, aux_data, pmove, search_direction
+
+    return step
+
+
+def learning_rate_schedule(rate: float = 5e-2, decay: float = 1.0, delay: float = 10000.0):
+    """process.py:200-202: ``rate * (1 / (1 + t / delay)) ** decay`` (defaults of base_config.py:46-50)."""
+    return lambda t: rate * (1.0 / (1.0 + (t / delay))) ** decay
+
+
+def make_adam_update(schedule=None, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
+    """The 'adam' branch of process.py:205-208, 235-246: scale_by_adam, then the learning-rate schedule, then -1.
+    Returns ``(init(params) -> state, opt_update(t, grads, params, state) -> (state, params))``."""
+    from .hotpath import flatten_params, unflatten_params
+    from .pretrain import Adam
+    schedule = schedule or learning_rate_schedule()
+    adam = Adam(1.0, b1=b1, b2=b2, eps=eps)             # unit step: the schedule supplies the rate
+
+    def opt_update(t, grads, params, state):
+        updates, state = adam.update(grads, state, params)
+        lr = float(schedule(state["count"] - 1))
+        leaves = [torch.as_tensor(p).to(u.device) + lr * u for p, u in zip(flatten_params(params), updates)]
+        return state, unflatten_params(leaves, len(params["single"]), "b" in params["orbital"][0])
+
+    return adam.init, opt_update

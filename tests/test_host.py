@@ -154,3 +154,36 @@ def test_two_rank_gloo_statistics(tmp_path):
     var = float(((e.abs() ** 2).mean(1) - means.real.abs() ** 2).mean())      # mean of per-device variances
     assert abs(vals[0] - loss) < 1e-14 and abs(vals[1] - im) < 1e-14 and abs(vals[2] - var) < 1e-14
     assert abs(vals[3] - 0.5) < 1e-15
+
+
+def test_training_step_composition_and_adam_update():
+    """train.make_training_step (train.py:147-185) with stub closures: order of the calls and what is returned."""
+    import torch
+    from deepsolid_b200 import train
+    calls = []
+    P = {"single": [{"w": torch.ones(2, 2, dtype=torch.float64), "b": torch.zeros(2, dtype=torch.float64)}] * 2,
+         "double": [{"w": torch.ones(1, 1, dtype=torch.float64), "b": torch.zeros(1, dtype=torch.float64)}],
+         "orbital": [{"w": torch.ones(2, 2, dtype=torch.float64)}] * 2,
+         "envelope": [{"pi": torch.ones(1, 1, dtype=torch.float64), "sigma": torch.ones(1, 1, dtype=torch.float64)}] * 2}
+
+    def mcmc_step(params, data, key, width):
+        calls.append("mcmc")
+        return data + width, torch.tensor(0.5)
+
+    def val_and_grad(params, data):
+        calls.append("grad")
+        g = {k: [{kk: torch.full_like(v, 2.0) for kk, v in d.items()} for d in params[k]] for k in params}
+        return (torch.tensor(-1.0), "aux"), g
+
+    init, opt_update = train.make_adam_update(train.learning_rate_schedule(rate=0.1, decay=1.0, delay=10.0))
+    step = train.make_training_step(mcmc_step, val_and_grad, opt_update)
+    state = init(P)
+    data = torch.zeros(3, 6, dtype=torch.float64)
+    data, P1, state, loss, aux, pmove, sd = step(0, data, P, state, 7, 0.02)
+    assert calls == ["mcmc", "grad"] and float(loss) == -1.0 and aux == "aux" and float(pmove) == 0.5
+    assert torch.allclose(data, torch.full((3, 6), 0.02, dtype=torch.float64))
+    # first Adam step moves every parameter by -lr * sign(g) (bias-corrected m / sqrt(v) = 1)
+    assert torch.allclose(P1["single"][0]["w"], P["single"][0]["w"] - 0.1, atol=1e-7)
+    _, P2, state, *_ = step(1, data, P1, state, 8, 0.02)
+    assert torch.allclose(P2["single"][0]["w"], P1["single"][0]["w"] - 0.1 / (1 + 1 / 10.0), atol=1e-7)
+    assert abs(train.learning_rate_schedule()(10000.0) - 0.025) < 1e-15
