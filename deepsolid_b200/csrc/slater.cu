@@ -690,7 +690,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 template <int MT>
-__global__ void __launch_bounds__(256, 2) det_dmma_kernel(const DsSys sys, const SlaterBufs sb, int G, int LDB, int alias) {
+__global__ void __launch_bounds__(256, (MT <= 8) ? 2 : 1) det_dmma_kernel(const DsSys sys, const SlaterBufs sb, int G, int LDB, int alias) {
     const DsDims& dm = sys.d;
     const int D = dm.D, NDp = dm.NDp, ND = dm.ND;
     const int k = blockIdx.x % D;
@@ -733,7 +733,10 @@ __global__ void __launch_bounds__(256, 2) det_dmma_kernel(const DsSys sys, const
     const double* da = sb.DA[s] + (w * D + k) * (long long)NDp * n * n * 2;     // complex (re, im) interleaved
     // every thread owns up to JMAX fixed matrix elements (i, o) = idx / n, idx % n, idx = tid + j * nthr, of every
     // direction: their operand-buffer offsets (straight and transposed) are computed once, not per group
-    constexpr int JMAX = 4;
+    // (matrices beyond 32 x 32 run one CTA per SM: enough registers to keep every element's offsets resident too)
+    constexpr int NMAXT = MT * 4;                    // largest n this instantiation serves
+    constexpr int JMAX = (MT <= 8) ? 4 : (NMAXT * NMAXT + 255) / 256;
+    constexpr int JTRI = (MT <= 8) ? 4 : (NMAXT * (NMAXT + 1) / 2 + 255) / 256;
     const int nn = n * n;
     int off_ab[JMAX];
 #pragma unroll
@@ -745,10 +748,10 @@ __global__ void __launch_bounds__(256, 2) det_dmma_kernel(const DsSys sys, const
     // trace elements: sum_{a,b} Y[a,b] Y[b,a] = sum_a Y[a,a]^2 + 2 sum_{a<b} Y[a,b] Y[b,a]: every thread owns up to
     // JMAX fixed pairs (a <= b) of the upper triangle (linear index idx = tid + j * nthr, row-major over the triangle)
     const int n_tri = n * (n + 1) / 2;
-    int tr_ab[JMAX], tr_ba[JMAX];
-    double tr_w[JMAX];
+    int tr_ab[JTRI], tr_ba[JTRI];
+    double tr_w[JTRI];
 #pragma unroll
-    for (int j = 0; j < JMAX; ++j) {
+    for (int j = 0; j < JTRI; ++j) {
         const int idx = tid + j * nthr;
         tr_ab[j] = -1; tr_ba[j] = 0; tr_w[j] = 0.0;
         if (idx < n_tri) {
@@ -952,7 +955,7 @@ __global__ void __launch_bounds__(256, 2) det_dmma_kernel(const DsSys sys, const
             const double* col = Be + g * n;
             const double* coli = col + n * LDB;
 #pragma unroll
-            for (int j = 0; j < JMAX; ++j) {
+            for (int j = 0; j < JTRI; ++j) {
                 if (tr_ab[j] >= 0) {
                     const double yr = col[tr_ab[j]] * tr_w[j], yi = coli[tr_ab[j]] * tr_w[j];
                     const double zr = col[tr_ba[j]], zi = coli[tr_ba[j]];
@@ -960,7 +963,7 @@ __global__ void __launch_bounds__(256, 2) det_dmma_kernel(const DsSys sys, const
                     sq_im = fma(yr, zi, sq_im); sq_im = fma(yi, zr, sq_im);
                 }
             }
-            for (int idx = tid + JMAX * nthr; idx < n_tri; idx += nthr) {       // triangles larger than JMAX * nthr pairs
+            for (int idx = tid + JTRI * nthr; idx < n_tri; idx += nthr) {       // triangles larger than JTRI * nthr pairs
                 int a = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * idx)) * 0.5);
                 while (a > 0 && a * n - a * (a - 1) / 2 > idx) --a;
                 while ((a + 1) * n - (a + 1) * a / 2 <= idx) ++a;
