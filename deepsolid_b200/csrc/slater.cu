@@ -920,7 +920,8 @@ __global__ void __launch_bounds__(256, (MT <= 8) ? 2 : 1) det_dmma_kernel(const 
             for (int j = 0; j < 2; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
         const int nt0 = warp, nt1 = warp + nwarp;
         const bool has0 = nt0 < ntiles, has1 = nt1 < ntiles;
-        if (has0) {
+        // (two copies of the k loop: a predicated-off DMMA still occupies its issue slot and the pipe)
+        if (has0 && has1) {
             const double* xb0 = Be + tig * LDB + nt0 * 8 + gid;       // B fragment: row tig, column gid of the 4x8 tile
             const double* xb1 = Be + tig * LDB + nt1 * 8 + gid;
 #pragma unroll 2
@@ -929,12 +930,23 @@ __global__ void __launch_bounds__(256, (MT <= 8) ? 2 : 1) det_dmma_kernel(const 
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) a[mt] = xa[mt * 8 * LDX + k0];
                 const double b0 = xb0[k0 * LDB];
-                const double b1 = has1 ? xb1[k0 * LDB] : 0.0;
+                const double b1 = xb1[k0 * LDB];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     dmma884(acc[mt][0][0], acc[mt][0][1], a[mt], b0);
-                    if (has1) dmma884(acc[mt][1][0], acc[mt][1][1], a[mt], b1);
+                    dmma884(acc[mt][1][0], acc[mt][1][1], a[mt], b1);
                 }
+            }
+        } else if (has0) {
+            const double* xb0 = Be + tig * LDB + nt0 * 8 + gid;
+#pragma unroll 2
+            for (int k0 = 0; k0 < MP; k0 += 4) {
+                double a[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) a[mt] = xa[mt * 8 * LDX + k0];
+                const double b0 = xb0[k0 * LDB];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][0][0], acc[mt][0][1], a[mt], b0);
             }
         }
         __syncthreads();                             // every operand of this group has been read
