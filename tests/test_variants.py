@@ -270,6 +270,14 @@ def test_gpu_spin_polarised_matches_oracle(name, nelec, full_det):
     go = O.logpsi_vjp(f_ps, P, X, ca, cp)
     for a, b in zip(flatten_params(g), flatten_params(go)):
         assert float((a.cpu() - b).abs().max()) < 1e-9 * max(1.0, float(b.abs().max()))
+    if not full_det:        # KFAC statistics with different row counts per spin channel
+        from deepsolid_b200 import kfac
+        gf, wf = kfac.curvature_estimate(hp, P, X.to(dev), sync=False), O.kfac_factors(f_ps, P, X)
+        for kind in ("single", "double", "orbital"):
+            for gb, wb in zip(gf[kind], wf[kind]):
+                assert gb["extra_scale"] == wb["extra_scale"]
+                for key in ("inputs_factor", "outputs_factor"):
+                    assert float((gb[key].cpu() - wb[key]).abs().max()) <= 1e-9 * max(float(wb[key].abs().max()), 1e-30)
     B, steps = 4, 2
     gen = torch.Generator().manual_seed(6)
     xi = torch.randn(steps, B, X.shape[1], dtype=torch.float64, generator=gen)
