@@ -132,9 +132,10 @@ __global__ void __launch_bounds__(128) l0_jac2_kernel(DsDims dm, const double* _
     double* o0 = OJ + e * (long long)NDp * ldc;
     for (int n = threadIdx.x; n < H2; n += blockDim.x) {
         const int n1 = n + H2;
-        double wa[KT], wb[KT];
+        // pair-mean weights (every direction) stay in registers; the own-feature weights (3 of 3N directions) come from L1
+        double wa[8], wb[8];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { wa[k] = B[(long long)k * H + n]; wb[k] = B[(long long)k * H + n1]; }
+        for (int k = 0; k < 8; ++k) { wa[k] = B[(long long)(k + KT - 8) * H + n]; wb[k] = B[(long long)(k + KT - 8) * H + n1]; }
         const double ta = T[e * (long long)ldt + n], tb = T[e * (long long)ldt + n1];
         const double da = 1.0 - ta * ta, db_ = 1.0 - tb * tb;
         double sa = 0.0, sb = 0.0;
@@ -158,17 +159,21 @@ __global__ void __launch_bounds__(128) l0_jac2_kernel(DsDims dm, const double* _
                 const double* a = l0_sm + d * KT;
                 if ((d / 3) == i) {                          // warp-uniform: own-feature columns only for own directions
 #pragma unroll
-                    for (int k = 0; k < KT - 8; ++k) { const double av = a[k]; za[u] = fma(av, wa[k], za[u]); zb[u] = fma(av, wb[k], zb[u]); }
+                    for (int k = 0; k < KT - 8; ++k) {
+                        const double av = a[k];
+                        za[u] = fma(av, __ldg(B + (long long)k * H + n), za[u]);
+                        zb[u] = fma(av, __ldg(B + (long long)k * H + n1), zb[u]);
+                    }
                 }
 #pragma unroll
-                for (int k = KT - 8; k < KT; ++k) { const double av = a[k]; za[u] = fma(av, wa[k], za[u]); zb[u] = fma(av, wb[k], zb[u]); }
+                for (int k = KT - 8; k < KT; ++k) { const double av = a[k]; za[u] = fma(av, wa[k - (KT - 8)], za[u]); zb[u] = fma(av, wb[k - (KT - 8)], zb[u]); }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 sa = fma(za[u], za[u], sa);
                 sb = fma(zb[u], zb[u], sb);
-                o0[(long long)(d0 + u) * ldc + n] = da * za[u];
-                o0[(long long)(d0 + u) * ldc + n1] = db_ * zb[u];
+                __stcs(o0 + (long long)(d0 + u) * ldc + n, da * za[u]);      // streamed: next touched by the digit pass
+                __stcs(o0 + (long long)(d0 + u) * ldc + n1, db_ * zb[u]);
             }
         }
         S[e * (long long)ldt + n] = sa;
