@@ -187,3 +187,26 @@ def test_training_step_composition_and_adam_update():
     _, P2, state, *_ = step(1, data, P1, state, 8, 0.02)
     assert torch.allclose(P2["single"][0]["w"], P1["single"][0]["w"] - 0.1 / (1 + 1 / 10.0), atol=1e-7)
     assert abs(train.learning_rate_schedule()(10000.0) - 0.025) < 1e-15
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) runs without a GPU and prints ONE
+    JSON line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--system", "h4",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "local_energies_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"]
