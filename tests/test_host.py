@@ -210,3 +210,55 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+_WORKER_KFAC = r"""
+import os, sys, torch, torch.distributed as td
+sys.path.insert(0, sys.argv[1])
+from deepsolid_b200 import kfac, estimator
+td.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
+r = td.get_rank()
+
+class StubHotPath:                      # raw sums of ds_kfac_factors for a 1-layer toy, different on each rank
+    def set_params(self, p): pass
+    def kfac_factors(self, x):
+        s = float(r + 1)
+        blk = lambda n_in, n_out, rows: {"a": s * torch.ones(n_in + 1, n_in + 1, dtype=torch.float64),
+                                         "g": s * torch.eye(n_out, dtype=torch.float64), "rows": rows}
+        env = lambda v: [{"pi": torch.full((1, 2), v, dtype=torch.float64), "sigma": torch.full((1, 2), 2 * v, dtype=torch.float64)}] * 2
+        return {"single": [blk(3, 2, 8)], "double": [], "orbital": [blk(2, 4, 4), blk(2, 4, 4)],
+                "envelope_abs": env(s), "envelope_phase": env(0.5 * s), "batch": 4}
+
+P = {"single": [{"w": torch.zeros(3, 2), "b": torch.zeros(2)}], "double": [],
+     "orbital": [{"w": torch.zeros(2, 4)}, {"w": torch.zeros(2, 4)}], "envelope": []}
+est = kfac.curvature_estimate(StubHotPath(), P, None, sync=True)
+z = estimator._pmean_c(torch.tensor([1.0 + 2.0j, -1.0j], dtype=torch.complex128) * (r + 1))
+if r == 0:
+    print("RESULT", float(est["single"][0]["inputs_factor"][0, 0]), tuple(est["single"][0]["inputs_factor"].shape),
+          float(est["single"][0]["outputs_factor"][1, 1]), est["single"][0]["extra_scale"],
+          tuple(est["orbital"][0]["inputs_factor"].shape), float(est["orbital"][1]["outputs_factor"][0, 0]),
+          complex(est["envelope"][0]["pi"][0, 0]), complex(z[0]), complex(z[1]))
+td.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_kfac_and_observable_means(tmp_path):
+    """Cross-rank mean of the per-rank curvature factors (utils.py:293-294) and of a complex observable, on CPU."""
+    script = tmp_path / "worker_kfac.py"
+    script.write_text(_WORKER_KFAC)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29578", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = [l for l in outs[0][0].splitlines() if l.startswith("RESULT")][0]
+    got = eval("(" + line[len("RESULT "):].replace(") (", "), (").replace(" ", ", ").replace(",,", ",") + ")")
+    # rank r holds s = r + 1: inputs factor s / rows, outputs factor 2 s / rows; mean over ranks = 1.5 x the s = 1 value
+    assert abs(got[0] - 1.5 / 8) < 1e-15 and got[1] == (4, 4)          # bias layer keeps the homogeneous coordinate
+    assert abs(got[2] - 2 * 1.5 / 8) < 1e-15 and got[3] == 2           # extra_scale = rows / batch
+    assert got[4] == (2, 2)                                            # orbital layer without bias: last row / column dropped
+    assert abs(got[5] - 2 * 1.5 / 4) < 1e-15
+    # NaiveDiagonal statistic dw dw / B with dw = sqrt2 (g_abs - i g_phase): mean over ranks of (s^2) = 2.5
+    want_pi = 2.0 * complex(1.0, -0.5) ** 2 / 4 * 2.5
+    assert abs(got[6] - want_pi) < 1e-14
+    assert abs(got[7] - 1.5 * (1 + 2j)) < 1e-15 and abs(got[8] - 1.5 * (-1j)) < 1e-15
