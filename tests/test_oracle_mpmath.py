@@ -27,3 +27,35 @@ def test_torch_oracle_matches_40_digit_restatement():
         dphi = float(got_f.imag) - float(want_f.imag)
         assert abs((dphi + np.pi) % (2 * np.pi) - np.pi) < 1e-12
         assert abs(got_ke - complex(want_ke)) < 1e-12, (got_ke, complex(want_ke))     # measured 3e-15 .. 6e-15
+
+
+import pytest
+
+
+@pytest.mark.parametrize("distance_type,envelope_type,full_det", [
+    ("tri", "isotropic", False), ("nu", "diagonal", False), ("nu", "full", False), ("nu", "isotropic", True)])
+def test_torch_oracle_variants_match_40_digit_restatement(distance_type, envelope_type, full_det):
+    """The secondary variants (tri features, anisotropic envelopes, full determinants) of the torch oracle against the
+    same scalar mpmath restatement; envelope parameters randomised so that sigma / pi matter."""
+    sc = C.build_system("h4")
+    kl = C.make_klist(sc)
+    hidden = ((12, 6), (12, 6))
+    rng = np.random.default_rng(17)
+    pn = O.init_params(rng, sc.original_cell.natm, sc.nelec, hidden_dims=hidden, determinants=2,
+                       distance_type=distance_type, envelope_type=envelope_type, full_det=full_det)
+    for env in pn["envelope"]:
+        env["pi"] = env["pi"] * (1.0 + 0.3 * rng.standard_normal(env["pi"].shape))
+        env["sigma"] = env["sigma"] + 0.2 * rng.standard_normal(env["sigma"].shape)
+    P = O.params_to_torch(pn)
+    x = C.init_walkers(sc, 1, seed=5)[0]
+    kw = dict(hidden_dims=hidden, determinants=2, distance_type=distance_type, envelope_type=envelope_type, full_det=full_det)
+    f = O.make_solid_fermi_net(kl, sc, method_name="eval_logdet", **kw)
+    want_f, want_ke = MP.kinetic(pn, list(x), sc, kl, sc.nelec, distance_type=distance_type, envelope_type=envelope_type,
+                                 full_det=full_det)
+    got_f = f(P, torch.as_tensor(x))
+    got_ke = O.local_kinetic_energy_real_imag(f)(P, torch.as_tensor(x))
+    got_ke = complex(got_ke[0]) + complex(got_ke[1]) if isinstance(got_ke, (tuple, list)) else complex(got_ke)
+    assert abs(float(got_f.real) - float(want_f.real)) < 1e-12
+    dphi = float(got_f.imag) - float(want_f.imag)
+    assert abs((dphi + np.pi) % (2 * np.pi) - np.pi) < 1e-12
+    assert abs(got_ke - complex(want_ke)) < 1e-11, (got_ke, complex(want_ke))
