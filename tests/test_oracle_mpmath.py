@@ -59,3 +59,35 @@ def test_torch_oracle_variants_match_40_digit_restatement(distance_type, envelop
     dphi = float(got_f.imag) - float(want_f.imag)
     assert abs((dphi + np.pi) % (2 * np.pi) - np.pi) < 1e-12
     assert abs(got_ke - complex(want_ke)) < 1e-11, (got_ke, complex(want_ke))
+
+
+def test_oracle_parameter_gradient_matches_40_digit_finite_differences():
+    """d log|psi| / d theta and d angle(psi) / d theta of the torch oracle (autograd, the pullback the energy-gradient
+    estimator and the KFAC statistics are built on) against central differences of the mpmath restatement."""
+    import copy
+    import mpmath as mp
+    sc = C.build_system("h4")
+    kl = C.make_klist(sc)
+    hidden = ((12, 6), (12, 6))
+    rng = np.random.default_rng(3)
+    pn = O.init_params(rng, sc.original_cell.natm, sc.nelec, hidden_dims=hidden, determinants=2)
+    P = O.params_to_torch(pn)
+    x = C.init_walkers(sc, 1, seed=8)
+    f_ps = O.make_solid_fermi_net(kl, sc, method_name="eval_phase_and_slogdet", hidden_dims=hidden, determinants=2)
+    one, zero = torch.ones(1, dtype=torch.float64), torch.zeros(1, dtype=torch.float64)
+    g_abs = O.logpsi_vjp(f_ps, P, torch.as_tensor(x), one, zero)
+    g_ph = O.logpsi_vjp(f_ps, P, torch.as_tensor(x), zero, one)
+    picks = [("single", 0, "w"), ("single", 1, "b"), ("double", 0, "w"), ("orbital", 1, "w"), ("envelope", 0, "sigma"),
+             ("envelope", 1, "pi")]
+    h = 1e-7                                              # parameters are fp64 inputs: the step must be representable
+    for kind, i, leaf in picks:
+        arr = pn[kind][i][leaf]
+        idx = tuple(int(rng.integers(0, s)) for s in arr.shape)
+        vals = []
+        for sgn in (+1, -1, +2, -2):
+            q = copy.deepcopy(pn)
+            q[kind][i][leaf][idx] = arr[idx] + sgn * h
+            vals.append(MP.log_psi(q, [mp.mpf(float(v)) for v in x[0]], sc, kl, sc.nelec))
+        d = (-vals[2] + 8 * vals[0] - 8 * vals[1] + vals[3]) / (12 * mp.mpf(h))
+        assert abs(float(d.real) - float(g_abs[kind][i][leaf][idx])) < 1e-9 * max(1.0, abs(float(d.real))), (kind, i, leaf)
+        assert abs(float(d.imag) - float(g_ph[kind][i][leaf][idx])) < 1e-9 * max(1.0, abs(float(d.imag))), (kind, i, leaf)
