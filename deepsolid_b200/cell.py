@@ -103,35 +103,61 @@ def set_symmetry_lat(supercell: Cell, sym_type: str = "minimal") -> Cell:
     return supercell
 
 
+def _integer_matrix(S) -> np.ndarray:
+    Si = np.rint(np.asarray(S, dtype=float)).astype(np.int64).reshape(3, 3)
+    if not np.allclose(Si, np.asarray(S, dtype=float), atol=1e-9) or round(float(np.linalg.det(Si))) == 0:
+        raise ValueError("the supercell matrix S must be a non-singular integer matrix")
+    return Si
+
+
+def _adjugate(Si: np.ndarray) -> np.ndarray:
+    """Integer adjugate: Si @ adj == det(Si) * I, exactly."""
+    adj = np.empty((3, 3), dtype=np.int64)
+    for r in range(3):
+        for c in range(3):
+            m = np.delete(np.delete(Si, c, axis=0), r, axis=1)
+            adj[r, c] = (-1) ** (r + c) * (m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0])
+    return adj
+
+
+def _coset_representatives(M: np.ndarray) -> np.ndarray:
+    """Integer row vectors n with n . inv(M) in [0, 1)^3, i.e. one representative of every coset of the lattice
+    spanned by the rows of M inside Z^3, in lexicographic order of n.
+
+    The reference finds the same points (in the same order) by scanning the bounding box of the M-image of the
+    unit cube and testing the floating-point fractional coordinates against [0, 1 - 1e-12)
+    (supercell.py:36-45 with M = S^T, :52-60 with M = S); here membership is decided in exact integer
+    arithmetic: n . adj(M) is det(M) times the fractional coordinate.
+    """
+    det = int(round(float(np.linalg.det(M))))
+    adj = _adjugate(M) * (1 if det > 0 else -1)
+    corners = np.array([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)], dtype=np.int64) @ M
+    lo, hi = corners.min(axis=0), corners.max(axis=0)
+    reps = []
+    for n0 in range(lo[0], hi[0]):
+        for n1 in range(lo[1], hi[1]):
+            for n2 in range(lo[2], hi[2]):
+                f = np.array([n0, n1, n2], dtype=np.int64) @ adj
+                if np.all(f >= 0) and np.all(f < abs(det)):
+                    reps.append((n0, n1, n2))
+    if len(reps) != abs(det):
+        raise ValueError(f"found {len(reps)} cosets for |det S| = {abs(det)}")
+    return np.array(reps, dtype=np.int64).reshape(-1, 3)
+
+
 def get_supercell_copies(latvec: np.ndarray, S: np.ndarray) -> np.ndarray:
-    """Translations of the primitive cell that tile the supercell (supercell.py:51-61)."""
-    S = np.asarray(S, dtype=float)
-    Sinv = np.linalg.inv(S).T
-    u = [0, 1]
-    unit_box = np.stack([x.ravel() for x in np.meshgrid(*[u] * 3, indexing="ij")]).T
-    unit_box_ = np.dot(unit_box, S)
-    xyz_range = np.stack([f(unit_box_, axis=0) for f in (np.amin, np.amax)]).T
-    mesh = np.meshgrid(*[np.arange(*r) for r in xyz_range], indexing="ij")
-    possible_pts = np.dot(np.stack([x.ravel() for x in mesh]).T, Sinv.T)
-    in_unit_box = (possible_pts >= 0) * (possible_pts < 1 - 1e-12)
-    select = np.where(np.all(in_unit_box, axis=1))[0]
-    return np.linalg.multi_dot((possible_pts[select], S, latvec))
+    """Translations R = n . latvec of the primitive cell that tile the supercell S . latvec (what
+    supercell.py:51-61 returns; |det S| of them)."""
+    return _coset_representatives(_integer_matrix(S)).astype(float) @ np.asarray(latvec, dtype=float)
 
 
 def get_supercell_kpts(supercell: Cell) -> np.ndarray:
-    """Supercell k-points inside the primitive reciprocal unit box (supercell.py:32-48)."""
-    S = np.asarray(supercell.S, dtype=float)
-    Sinv = np.linalg.inv(S).T
-    u = [0, 1]
-    unit_box = np.stack([x.ravel() for x in np.meshgrid(*[u] * 3, indexing="ij")]).T
-    unit_box_ = np.dot(unit_box, S.T)
-    xyz_range = np.stack([f(unit_box_, axis=0) for f in (np.amin, np.amax)]).T
-    kptmesh = np.meshgrid(*[np.arange(*r) for r in xyz_range], indexing="ij")
-    possible_kpts = np.dot(np.stack([x.ravel() for x in kptmesh]).T, Sinv)
-    in_unit_box = (possible_kpts >= 0) * (possible_kpts < 1 - 1e-12)
-    select = np.where(np.all(in_unit_box, axis=1))[0]
-    reclatvec = np.linalg.inv(supercell.original_cell.lattice_vectors()).T * 2 * np.pi
-    return np.dot(possible_kpts[select], reclatvec)
+    """Supercell reciprocal-lattice points inside the primitive reciprocal unit cell (what supercell.py:32-48
+    returns): k = (m . inv(S)^T) . B_prim for the coset representatives m of S^T."""
+    Si = _integer_matrix(supercell.S)
+    m = _coset_representatives(Si.T).astype(float)
+    frac = m @ np.linalg.inv(Si.astype(float)).T
+    return frac @ supercell.original_cell.reciprocal_vectors()
 
 
 def get_supercell(cell: Cell, S, sym_type: str = "minimal", spin: int = 0) -> Cell:
@@ -160,6 +186,7 @@ def get_supercell(cell: Cell, S, sym_type: str = "minimal", spin: int = 0) -> Ce
     sc.original_cell = cell
     sc.S = S
     sc.scale = scale
+    sc.extra["sym_type"] = sym_type
     return set_symmetry_lat(sc, sym_type)
 
 

@@ -4,6 +4,10 @@ THIS IS TEST INFRASTRUCTURE.  Only ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The
 product (``deepsolid_b200``) never does.
 
+It stands alone: cell geometry (supercell atoms, AV / BV, k-points) comes from oracle/geometry.py, the Ewald
+tables and the lattice classification from the classes below -- nothing is imported from the product, and a
+cell object handed in by a test is re-derived from its primary inputs (geometry.rederive).
+
 PARITY UNPINNED: the reference (bytedance/DeepSolid @ 812a2b8) is pure JAX + pyscf
 and neither is installable in this image, and its own tests hold no golden numbers
 (test/test_network.py asserts three invariants only).  The oracle is therefore a
@@ -25,6 +29,8 @@ from typing import Callable, Dict, List, Sequence, Tuple
 import numpy as np
 import torch
 from torch.func import grad, jvp, vmap
+
+from .geometry import rederive
 
 DT = torch.float64
 CT = torch.complex128
@@ -318,6 +324,7 @@ def make_solid_fermi_net(klist, simulation_cell, envelope_type="isotropic", bias
     """network.py:609-667; returns apply(params, x) for ONE walker."""
     if method_name not in ["eval_slogdet", "eval_logdet", "eval_mats", "eval_phase_and_slogdet"]:
         raise ValueError("Method name is not in class dir.")
+    simulation_cell = rederive(simulation_cell)      # the oracle's own supercell atoms, AV, BV (oracle/geometry.py)
     atoms = _t(simulation_cell.original_cell.atom_coords())
     spins = tuple(simulation_cell.nelec)
 
@@ -333,15 +340,24 @@ def make_solid_fermi_net(klist, simulation_cell, envelope_type="isotropic", bias
 # ---------------------------------------------------------------------------
 
 class MinimalImageDistance:
-    """distance.py:32-141 (torch)."""
+    """distance.py:32-141 (torch), including the classification of distance.py:41-59 with its `dot < tol` test
+    that has no absolute value (an obtuse lattice is treated as orthogonal by the reference; kept)."""
 
     def __init__(self, latvec):
-        from deepsolid_b200.ewald_tables import classify_lattice, min_image_point_list
         lat = np.asarray(latvec, dtype=float)
-        self.kind = classify_lattice(lat)
+        ortho_tol = 1e-10
+        diagonal = bool(np.all(np.abs(lat - np.diag(np.diagonal(lat))) < ortho_tol))
+        if diagonal:
+            self.kind = 0                                            # diagonal_dist_i
+        else:
+            orthogonal = (np.dot(lat[0], lat[1]) < ortho_tol and np.dot(lat[1], lat[2]) < ortho_tol
+                          and np.dot(lat[2], lat[0]) < ortho_tol)
+            self.kind = 1 if orthogonal else 2                       # orthogonal_dist_i / general_dist_i
         self._latvec = _t(lat)
         self._invvec = torch.linalg.inv(self._latvec)
-        self.point_list = _t(min_image_point_list())
+        # list of all 26 neighbouring cells, distance.py:64-66 (meshgrid with its default 'xy' indexing)
+        mesh_grid = np.meshgrid(*[np.array([0, 1, 2]) for _ in range(3)])
+        self.point_list = _t(np.stack([m.ravel() for m in mesh_grid], axis=0).T - 1)
         self.shifts = self.point_list @ self._latvec
 
     def dist_i(self, configs, vec):
@@ -366,23 +382,92 @@ class MinimalImageDistance:
         return vs * (1 - torch.eye(n, dtype=vs.dtype))[..., None]
 
 
+_GPOINT_CACHE = {}
+
+
+def _select_big(n0, n1, n2, cellvolume, recvec, alpha):
+    """ewaldsum.py:194-200 on the integer mesh n0 x n1 x n2 ('ij' order)."""
+    g = np.stack(np.meshgrid(n0, n1, n2, indexing="ij"), axis=0).reshape(3, -1).astype(float)
+    gpoints = np.einsum("jn,jk->nk", g, recvec) * 2 * np.pi
+    gsquared = np.einsum("nk,nk->n", gpoints, gpoints)
+    gweight = 4 * np.pi * np.exp(-gsquared / (4 * alpha ** 2))
+    gweight /= cellvolume * gsquared
+    bigweight = gweight > 1e-12
+    return gpoints[bigweight], gweight[bigweight]
+
+
+def _reciprocal_points(latvec, ewald_gmax):
+    """ewaldsum.py:58-89, the literal enumeration: every integer triple of the half space up to `ewald_gmax` is
+    weighed (32 M points at 200; evaluated slab by slab along the first index, which keeps the reference's order)."""
+    key = (latvec.tobytes(), int(ewald_gmax))
+    if key not in _GPOINT_CACHE:
+        cellvolume = np.linalg.det(latvec)
+        recvec = np.linalg.inv(latvec).T
+        smallestheight = np.amin(1 / np.linalg.norm(recvec, axis=1))
+        alpha = 5.0 / smallestheight
+        full = np.arange(-ewald_gmax, ewald_gmax + 1)
+        pos = np.arange(1, ewald_gmax + 1)
+        zero = np.array([0])
+        parts = [_select_big(np.array([i]), full, full, cellvolume, recvec, alpha) for i in pos]     # gptsXpos
+        parts.append(_select_big(zero, pos, full, cellvolume, recvec, alpha))                        # gptsX0Ypos
+        parts.append(_select_big(zero, zero, pos, cellvolume, recvec, alpha))                        # gptsX0Y0Zpos
+        _GPOINT_CACHE[key] = (float(alpha), float(cellvolume), np.concatenate([p[0] for p in parts], axis=0),
+                              np.concatenate([p[1] for p in parts], axis=0))
+    return _GPOINT_CACHE[key]
+
+
 class EwaldSum:
-    """Per-walker half of ewaldsum.py (138-191); setup tables come from
-    deepsolid_b200.ewald_tables (which restates ewaldsum.py:33-136)."""
+    """ewaldsum.py:33-200 (torch / numpy), setup and per-walker halves, restated here on its own (nothing is shared
+    with the product's host-side table builder, which `tests/test_geometry.py` checks against this class)."""
 
     def __init__(self, cell, ewald_gmax=200, nlatvec=1):
-        from deepsolid_b200.ewald_tables import build_ewald_tables
-        tb = build_ewald_tables(cell, ewald_gmax, nlatvec)
-        self.tb = tb
+        cell = rederive(cell)
         self.nelec = tuple(cell.nelec)
-        self.atom_coords = _t(tb.atom_coords)
-        self.atom_charges = _t(tb.atom_charges)
-        self.dist = MinimalImageDistance(tb.latvec)
-        self.lattice_displacements = _t(tb.lattice_displacements)
-        self.alpha = tb.alpha
-        self.gpoints, self.gweight = _t(tb.gpoints), _t(tb.gweight)
-        self.ion_exp = torch.as_tensor(tb.ion_exp, dtype=CT)
-        self.ion_ion, self.ii_const = tb.ion_ion, tb.ii_const
+        coords = np.asarray(cell.atom_coords(), dtype=float)
+        charges = np.asarray(cell.atom_charges(), dtype=float)
+        latvec = np.ascontiguousarray(np.asarray(cell.lattice_vectors(), dtype=float))
+        self.atom_coords = _t(coords)
+        self.atom_charges = _t(charges)
+        self.latvec = _t(latvec)
+        self.dist = MinimalImageDistance(latvec)
+        # set_lattice_displacements, ewaldsum.py:48-56
+        XYZ = np.meshgrid(*[np.arange(-nlatvec, nlatvec + 1)] * 3, indexing="ij")
+        xyz = np.stack(XYZ, axis=-1).reshape((-1, 3))
+        self.lattice_displacements = _t(np.dot(xyz, latvec))
+        # set_up_reciprocal_ewald_sum, ewaldsum.py:58-90
+        self.alpha, cellvolume, gpoints, gweight = _reciprocal_points(latvec, ewald_gmax)
+        self.gpoints, self.gweight = _t(gpoints), _t(gweight)
+        # set_ewald_constants, ewaldsum.py:92-101
+        self.i_sum = float(np.sum(charges))
+        ii_sum2 = float(np.sum(charges ** 2))
+        ii_sum = (self.i_sum ** 2 - ii_sum2) / 2
+        self.ijconst = -np.pi / (cellvolume * self.alpha ** 2)
+        self.squareconst = -self.alpha / np.sqrt(np.pi) + self.ijconst / 2
+        self.ii_const = ii_sum * self.ijconst + ii_sum2 * self.squareconst
+        self.ion_ion = self.ewald_ion()
+
+    def ee_const(self, ne):         # ewaldsum.py:109-110
+        return ne * (ne - 1) / 2 * self.ijconst + ne * self.squareconst
+
+    def ei_const(self, ne):         # ewaldsum.py:112-113
+        return -ne * self.i_sum * self.ijconst
+
+    def ewald_ion(self):            # ewaldsum.py:120-136
+        if len(self.atom_charges) == 1:
+            ion_ion_real = 0.0
+        else:
+            ion_distances = self.dist.dist_matrix(self.atom_coords.reshape(-1))
+            rvec = ion_distances[None, :, :, :] + self.lattice_displacements[:, None, None, :]
+            r = torch.linalg.norm(rvec, dim=-1)
+            charge_ij = self.atom_charges[..., None] * self.atom_charges[None, ...]
+            n = len(self.atom_charges)
+            mask = torch.triu(torch.ones(n, n, dtype=torch.bool), diagonal=1)
+            ion_ion_real = float(torch.sum(torch.where(mask[None], charge_ij * torch.erfc(self.alpha * r) / r,
+                                                       torch.zeros((), dtype=DT))))
+        GdotR = self.gpoints @ self.atom_coords.T
+        self.ion_exp = torch.exp(1j * GdotR.to(CT)) @ self.atom_charges.to(CT)
+        ion_ion_rec = float(torch.dot(self.gweight, self.ion_exp.abs() ** 2))
+        return ion_ion_real + ion_ion_rec
 
     def _real_cij(self, dists):
         r = dists[:, :, None, :] + self.lattice_displacements
@@ -411,10 +496,10 @@ class EwaldSum:
         cs = -self.ion_exp.real * scos - self.ion_exp.imag * ssin
         return ee, 2 * torch.dot(cs, self.gweight)
 
-    def energy(self, configs):
+    def energy(self, configs):      # ewaldsum.py:185-191
         ne = sum(self.nelec)
         ee, ei = self.ewald_electron(configs)
-        return ee + self.tb.ee_const(ne), ei + self.tb.ei_const(ne), torch.tensor(self.tb.ii_total, dtype=DT)
+        return ee + self.ee_const(ne), ei + self.ei_const(ne), torch.tensor(self.ion_ion + self.ii_const, dtype=DT)
 
 
 def enforce_pbc_batch(latvec, epos):
@@ -792,6 +877,7 @@ def kfac_factors(apply_phase_slog, params, X):
 # ---------------------------------------------------------------------------
 def make_complex_polarization(simulation_cell, direction=0, ndim=3):
     """estimator.py:15-40."""
+    simulation_cell = rederive(simulation_cell)
     rec_vec = _t(np.asarray(simulation_cell.reciprocal_vectors())[direction])
 
     def complex_polarization(data):
@@ -805,6 +891,7 @@ def make_complex_polarization(simulation_cell, direction=0, ndim=3):
 
 def make_structure_factor(simulation_cell, nq=4, ndim=3):
     """estimator.py:42-85."""
+    simulation_cell = rederive(simulation_cell)
     mesh = np.meshgrid(*[np.arange(nq) for _ in range(3)])
     point_list = np.stack([m.ravel() for m in mesh], axis=0).T
     qvecs = _t(point_list @ np.asarray(simulation_cell.reciprocal_vectors()))

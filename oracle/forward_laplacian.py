@@ -106,6 +106,8 @@ def _stack_jets(js):
 
 def kinetic_forward_laplacian(params: Dict, X: torch.Tensor, sim_cell, klist, want=False):
     """Returns (log|psi| [B], phase angle [B], kinetic complex [B], intermediates dict)."""
+    from .geometry import rederive
+    sim_cell = rederive(sim_cell)
     prim = sim_cell.original_cell
     nu, nd = sim_cell.nelec
     N = nu + nd

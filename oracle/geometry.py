@@ -1,0 +1,259 @@
+"""TEST INFRASTRUCTURE (CPU oracle) -- cell geometry, restated from the reference on its own.
+
+The product (``deepsolid_b200``) never imports this module, and this module never imports the
+product: every number the oracle needs about a cell (supercell atoms, AV / BV, supercell
+k-points, the synthetic k-lists and walkers of the benchmark contract) is produced here, following
+the reference line by line, so that GPU-vs-oracle tests do not compare the product's geometry with
+itself (``tests/test_geometry.py`` then pins ``deepsolid_b200.cell`` to these numbers).
+
+Reference (``/root/reference/DeepSolid``):
+  supercell.py:32-48   get_supercell_kpts        supercell.py:51-61   get_supercell_copies
+  supercell.py:64-95   get_supercell             supercell.py:98-140  set_symmetry_lat
+  config/two_hydrogen_cell.py:27-43, config/graphene.py:25-37, config/diamond.py:24-33,
+  config/rock_salt.py:24-35, config/poscar/bcc_li.vasp, test/test_cell.py:11-25
+  init_guess.py:69-80  Gaussian walkers around atoms
+pyscf supplies only ``lattice_vectors / atom_coords / atom_charges / nelec / reciprocal_vectors``
+to the hot path; ``RefCell`` is a plain record with those accessors (pyscf is not installable here).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+ANGSTROM_BOHR = 0.52917721067          # utils/units.py:25
+
+
+class RefCell:
+    """The attributes of ``pyscf.pbc.gto.Cell`` that network.py / ewaldsum.py / distance.py read."""
+
+    def __init__(self, a, atom, charges, spin=0, name="", nelec=None):
+        self.a = np.array(a, dtype=np.float64)
+        self._atom = [(s, np.array(x, dtype=np.float64)) for s, x in atom]      # pyscf's cell._atom
+        self._charges = {s: float(z) for s, z in charges.items()}
+        self.spin = int(spin)
+        self.name = name
+        if nelec is None:                       # pyscf: neutral cell, n_up - n_dn = spin
+            ne = int(round(sum(self._charges[s] for s, _ in self._atom)))
+            assert (ne + self.spin) % 2 == 0
+            nelec = ((ne + self.spin) // 2, (ne - self.spin) // 2)
+        self.nelec = (int(nelec[0]), int(nelec[1]))
+        self.nelectron = self.nelec[0] + self.nelec[1]
+
+    def lattice_vectors(self):
+        return self.a
+
+    def atom_coords(self):
+        return np.array([x for _, x in self._atom]).reshape(-1, 3)
+
+    def atom_charges(self):
+        return np.array([self._charges[s] for s, _ in self._atom])
+
+    def reciprocal_vectors(self):
+        # pyscf.pbc.gto.Cell.reciprocal_vectors: b = 2 pi inv(a).T
+        return 2 * np.pi * np.linalg.inv(self.a).T
+
+    @property
+    def natm(self):
+        return len(self._atom)
+
+
+def get_supercell_kpts(supercell):
+    """supercell.py:32-48."""
+    Sinv = np.linalg.inv(supercell.S).T
+    u = [0, 1]
+    unit_box = np.stack([x.ravel() for x in np.meshgrid(*[u] * 3, indexing="ij")]).T
+    unit_box_ = np.dot(unit_box, supercell.S.T)
+    xyz_range = np.stack([f(unit_box_, axis=0) for f in (np.amin, np.amax)]).T
+    kptmesh = np.meshgrid(*[np.arange(*r) for r in xyz_range], indexing="ij")
+    possible_kpts = np.dot(np.stack([x.ravel() for x in kptmesh]).T, Sinv)
+    in_unit_box = (possible_kpts >= 0) * (possible_kpts < 1 - 1e-12)
+    select = np.where(np.all(in_unit_box, axis=1))[0]
+    reclatvec = np.linalg.inv(supercell.original_cell.lattice_vectors()).T * 2 * np.pi
+    return np.dot(possible_kpts[select], reclatvec)
+
+
+def get_supercell_copies(latvec, S):
+    """supercell.py:51-61."""
+    Sinv = np.linalg.inv(S).T
+    u = [0, 1]
+    unit_box = np.stack([x.ravel() for x in np.meshgrid(*[u] * 3, indexing="ij")]).T
+    unit_box_ = np.dot(unit_box, S)
+    xyz_range = np.stack([f(unit_box_, axis=0) for f in (np.amin, np.amax)]).T
+    mesh = np.meshgrid(*[np.arange(*r) for r in xyz_range], indexing="ij")
+    possible_pts = np.dot(np.stack([x.ravel() for x in mesh]).T, Sinv.T)
+    in_unit_box = (possible_pts >= 0) * (possible_pts < 1 - 1e-12)
+    select = np.where(np.all(in_unit_box, axis=1))[0]
+    return np.linalg.multi_dot((possible_pts[select], S, latvec))
+
+
+def set_symmetry_lat(supercell, sym_type="minimal"):
+    """supercell.py:98-140."""
+    prim_bv = supercell.original_cell.reciprocal_vectors()
+    sim_bv = supercell.reciprocal_vectors()
+    if sym_type == "minimal":
+        mat = np.eye(3)
+    elif sym_type == "fcc":
+        mat = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]])
+    elif sym_type == "bcc":
+        mat = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, -1, 0], [1, 0, -1], [0, 1, -1]])
+    elif sym_type == "hexagonal":
+        mat = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, -1, 0]])
+    else:
+        mat = np.eye(3)
+    prim_bv = mat @ prim_bv
+    sim_bv = mat @ sim_bv
+    supercell.BV = sim_bv
+    supercell.AV = np.linalg.pinv(sim_bv).T
+    supercell.original_cell.BV = prim_bv
+    supercell.original_cell.AV = np.linalg.pinv(prim_bv).T
+    return supercell
+
+
+def get_supercell(cell, S, sym_type="minimal"):
+    """supercell.py:64-95 (``supercell.build()`` of pyscf replaced by the RefCell constructor)."""
+    S = np.asarray(S, dtype=float)
+    scale = np.abs(int(np.round(np.linalg.det(S))))
+    superlattice = np.dot(S, cell.lattice_vectors())
+    Rpts = get_supercell_copies(cell.lattice_vectors(), S)
+    atom = []
+    for (name, xyz) in cell._atom:
+        atom.extend([(name, xyz + R) for R in Rpts])
+    supercell = RefCell(superlattice, atom, cell._charges, spin=cell.spin * scale, name=cell.name,
+                        nelec=(cell.nelec[0] * scale, cell.nelec[1] * scale))
+    supercell.original_cell = cell
+    supercell.S = S
+    supercell.scale = scale
+    return set_symmetry_lat(supercell, sym_type)
+
+
+# ---------------------------------------------------------------------------
+# primitive cells of the reference's configs, with the effective charges of the benchmark contract
+# (graphite Z = 3 and diamond Z = 4 stand for the pseudo-potential charges pyscf
+# would report; everything else is the literal config)
+# ---------------------------------------------------------------------------
+
+def _h_chain(n, L=2.0):                       # config/two_hydrogen_cell.py:27-43, 'H,n,1,1,L,0,ccpvdz'
+    prim = RefCell([[2 * L, 0, 0], [0, 100, 0], [0, 0, 100]], [("H", [L, 0, 0]), ("H", [0, 0, 0])], {"H": 1.0},
+                   name="H-chain")
+    return get_supercell(prim, np.diag([n, 1, 1]))
+
+
+def _bcc_li(S):                               # config/poscar/bcc_li.vasp, Angstrom -> Bohr
+    a = 3.4268178940 / ANGSTROM_BOHR
+    h = 1.713408947 / ANGSTROM_BOHR
+    prim = RefCell(np.eye(3) * a, [("Li", [0, 0, 0]), ("Li", [h, h, h])], {"Li": 3.0}, name="bcc-Li")
+    return get_supercell(prim, np.diag(S))
+
+
+def _graphene(S, Z=3.0, L_ang=2.46, z=20.0):  # config/graphene.py:25-37
+    L = L_ang / ANGSTROM_BOHR
+    prim = RefCell([[L * np.cos(np.pi / 6), -L * 0.5, 0], [L * np.cos(np.pi / 6), L * 0.5, 0], [0, 0, z]],
+                   [("C", [3 ** (-0.5) * L, 0.0, 0.0]), ("C", [2 * 3 ** (-0.5) * L, 0.0, 0.0])], {"C": Z},
+                   name="graphite")
+    return get_supercell(prim, np.diag(S))
+
+
+def _diamond(S=2, Z=4.0, L_ang=3.567):        # config/diamond.py:24-33
+    L = L_ang / ANGSTROM_BOHR
+    prim = RefCell((np.ones((3, 3)) - np.eye(3)) * L / 2, [("C", [0.0, 0.0, 0.0]), ("C", [0.25 * L] * 3)], {"C": Z},
+                   name="diamond")
+    return get_supercell(prim, np.eye(3) * S)
+
+
+def _rock_salt(S=3, L_ang=4.0):               # config/rock_salt.py:24-35, LiH
+    L = L_ang / ANGSTROM_BOHR
+    prim = RefCell((np.ones((3, 3)) - np.eye(3)) * L / 2, [("Li", [0.0, 0.0, 0.0]), ("H", [0.5 * L] * 3)],
+                   {"Li": 3.0, "H": 1.0}, name="LiH")
+    return get_supercell(prim, np.eye(3) * S)
+
+
+def _test_cell_lih():                         # test/test_cell.py:11-25 (the cell the reference's own tests use)
+    L = 2 / 0.529177
+    prim = RefCell((1 - np.eye(3)) * L / 2, [("Li", [0, 0, 0]), ("H", [L / 2, L / 2, L / 2])], {"Li": 3.0, "H": 1.0},
+                   name="test_cell-LiH")
+    return get_supercell(prim, np.eye(3))
+
+
+SYSTEMS = {
+    "h10": lambda: _h_chain(5),
+    "h4": lambda: _h_chain(2),
+    "li24": lambda: _bcc_li((2, 2, 1)),
+    "li48": lambda: _bcc_li((2, 2, 2)),
+    "graphite54": lambda: _graphene((3, 3, 1)),
+    "graphene8": lambda: _graphene((2, 1, 1), Z=2.0),
+    "diamond64": lambda: _diamond(2),
+    "lih108": lambda: _rock_salt(3),
+    "lih_prim": lambda: _rock_salt(1),
+    "test_cell_lih": _test_cell_lih,
+}
+
+
+def build_system(name):
+    c = SYSTEMS[name]()
+    c.name = name
+    return c
+
+
+def custom_system(latvec, atoms, charges, nelec_spin=0, S=None, name="custom"):
+    """A cell given explicitly (tests of lattice classes no config covers: orthogonal-not-diagonal, obtuse)."""
+    prim = RefCell(latvec, atoms, charges, spin=nelec_spin, name=name)
+    sc = get_supercell(prim, np.eye(3) if S is None else S)
+    sc.name = name
+    return sc
+
+
+def make_klist(simulation_cell, twist=(0.0, 0.0, 0.0)):
+    """Benchmark contract, standing in for hf.SCF.klist (hf.py:84-104): every supercell k-point gets
+    n_s // nk occupied orbitals, the lowest-index k-points take the remainder; one row per occupied orbital."""
+    kpts = get_supercell_kpts(simulation_cell) + np.dot(np.asarray(twist, dtype=float), simulation_cell.reciprocal_vectors())
+    nk = len(kpts)
+    klist = []
+    for n_s in simulation_cell.nelec:
+        rows = []
+        for ik in range(nk):
+            rows += [kpts[ik]] * (n_s // nk + (1 if ik < n_s % nk else 0))
+        klist.append(np.array(rows).reshape(-1, 3))
+    return klist
+
+
+def init_walkers(cell, batch, seed=666, init_width=0.8):
+    """init_guess.py:69-80 with the contract's assignment (electron e of a spin block sits on atom e mod A_sc,
+    spin-up block first), Gaussian width `init_width`, wrapped into the simulation cell."""
+    rng = np.random.default_rng(seed)
+    coords = cell.atom_coords()
+    centres = np.concatenate([coords[e % len(coords)] for n_s in cell.nelec for e in range(n_s)])
+    x = centres[None, :] + init_width * rng.standard_normal((batch, centres.size))
+    frac = np.einsum("bij,jk->bik", x.reshape(batch, -1, 3), np.linalg.inv(cell.lattice_vectors()))
+    frac -= np.floor(frac)
+    return np.einsum("bij,jk->bik", frac, cell.lattice_vectors()).reshape(batch, -1)
+
+
+_REDERIVED = {}
+
+
+def rederive(cell):
+    """The oracle's own geometry for a cell described by ANY object with the pyscf accessors: only the primary
+    inputs are read from it (primitive lattice, primitive atoms, charges, electron counts, S); supercell atoms,
+    supercell lattice, AV and BV are derived again here by the restatement of supercell.py.  This is what keeps a
+    GPU-vs-oracle comparison from checking the product's host-side geometry against itself."""
+    if isinstance(cell, RefCell):
+        return cell
+    hit = _REDERIVED.get(id(cell))
+    if hit is not None and hit[0] is cell:
+        return hit[1]
+
+    def as_ref(c):
+        coords, charges = np.asarray(c.atom_coords(), dtype=float), np.asarray(c.atom_charges(), dtype=float)
+        names = [f"a{i}" for i in range(len(charges))]
+        return RefCell(np.asarray(c.lattice_vectors(), dtype=float), list(zip(names, coords)), dict(zip(names, charges)),
+                       spin=int(c.nelec[0]) - int(c.nelec[1]), name=getattr(c, "name", ""), nelec=tuple(c.nelec))
+
+    prim = getattr(cell, "original_cell", None)
+    if prim is None:
+        out = as_ref(cell)                       # a bare cell (Ewald known-answer tests)
+    else:
+        sym = getattr(cell, "extra", {}).get("sym_type", "minimal") if hasattr(cell, "extra") else "minimal"
+        out = get_supercell(as_ref(prim), np.asarray(cell.S, dtype=float), sym)
+        out.name = getattr(cell, "name", "")
+        assert tuple(out.nelec) == tuple(cell.nelec), "electron counts of the supercell disagree"
+    _REDERIVED[id(cell)] = (cell, out)
+    return out

@@ -59,6 +59,8 @@ def log_psi(params, x, cell, klist, spins, distance_type="nu", envelope_type="is
     """Complex log psi (method eval_logdet) of one walker x (flat list of 3N mpf)."""
     dist = nu_distance if distance_type == "nu" else tri_distance
     nf = 4 if distance_type == "nu" else 7
+    from .geometry import rederive
+    cell = rederive(cell)
     prim = cell.original_cell
     n_e = sum(spins)
     pa, pAV, pBV = _m(prim.a), _m(prim.AV), _m(prim.BV)
