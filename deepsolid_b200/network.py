@@ -18,6 +18,42 @@ from .hotpath import HotPath
 _METHODS = ("eval_slogdet", "eval_logdet", "eval_mats", "eval_phase_and_slogdet")
 
 
+def parameter_schema(natom: int, spins, envelope_type="isotropic", bias_orbitals=False, use_last_layer=False,
+                     full_det=False, hidden_dims=((256, 32),) * 3, determinants=8, distance_type="nu"):
+    """The leaves of the reference parameter pytree (network.py:135-184) as a flat table, in the order their random
+    numbers are drawn: ``(group, index, leaf, shape, init)`` with init ``'ones'``, ``'eye'`` (3x3 identity per atom
+    and orbital), ``'bias'`` (standard normal) or ``('weight', fan_in)`` (standard normal / sqrt(fan_in))."""
+    feat = {"nu": 4, "tri": 7}.get(distance_type)
+    if feat is None:
+        raise ValueError("Unrecognized distance function.")
+    channels = sum(1 for s in spins if s > 0)
+    widths = [(natom * feat, feat)] + [tuple(h) for h in hidden_dims]            # (one-electron, pair) width per level
+    n_layers = len(hidden_dims)
+    sigma_shape = {"isotropic": lambda q: (natom, q), "diagonal": lambda q: (natom, 3, q),
+                   "full": lambda q: (3, 3, natom, q)}
+    rows = []
+    per_spin = [(sum(spins) if full_det else s) * determinants for s in spins if s > 0]
+    for i, q in enumerate(per_spin):
+        rows.append(("envelope", i, "pi", (natom, q), "ones"))
+        if envelope_type in sigma_shape:
+            rows.append(("envelope", i, "sigma", sigma_shape[envelope_type](q), "eye" if envelope_type == "full" else "ones"))
+    for i in range(n_layers):
+        one, two = widths[i]
+        fan_in = (channels + 1) * one + channels * two                            # own + spin means + pair means
+        rows.append(("single", i, "w", (fan_in, widths[i + 1][0]), ("weight", fan_in)))
+        rows.append(("single", i, "b", (widths[i + 1][0],), "bias"))
+        if i < n_layers - 1 or use_last_layer:
+            rows.append(("double", i, "w", (two, widths[i + 1][1]), ("weight", two)))
+            rows.append(("double", i, "b", (widths[i + 1][1],), "bias"))
+    one, two = widths[-1]
+    orb_in = (channels + 1) * one + channels * two if use_last_layer else one
+    for i, q in enumerate(per_spin):
+        rows.append(("orbital", i, "w", (orb_in, 2 * q), ("weight", orb_in)))
+        if bias_orbitals:
+            rows.append(("orbital", i, "b", (2 * q,), "bias"))
+    return rows
+
+
 def init_solid_fermi_net_params(key, data=None, *, atoms, spins, envelope_type="isotropic", bias_orbitals=False,
                                 use_last_layer=False, eps=0.01, full_det=False,
                                 hidden_dims=((256, 32),) * 3, determinants=8, after_determinants=1,
@@ -30,47 +66,20 @@ def init_solid_fermi_net_params(key, data=None, *, atoms, spins, envelope_type="
     del after_determinants, data, eps
     rng = key if isinstance(key, np.random.Generator) else np.random.default_rng(int(key))
     natom = np.asarray(atoms).shape[0]
-    if distance_type == "nu":
-        in_dims = (natom * 4, 4)
-    elif distance_type == "tri":
-        in_dims = (natom * 7, 7)
-    else:
-        raise ValueError("Unrecognized distance function.")
-    active = [s for s in spins if s > 0]
-    nch = len(active)
-    dims_one_in = ([(nch + 1) * in_dims[0] + nch * in_dims[1]] +
-                   [(nch + 1) * h[0] + nch * h[1] for h in hidden_dims])
-    if not use_last_layer:
-        dims_one_in[-1] = hidden_dims[-1][0]
-    dims_one_out = [h[0] for h in hidden_dims]
-    dims_two = [in_dims[1]] + [h[1] for h in hidden_dims]
-    len_double = len(hidden_dims) if use_last_layer else len(hidden_dims) - 1
-    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
     params = {"single": [], "double": [], "orbital": [], "envelope": []}
-    for s in active:
-        npar = sum(spins) * determinants if full_det else s * determinants
-        env = {"pi": t(np.ones((natom, npar)))}
-        if envelope_type == "isotropic":
-            env["sigma"] = t(np.ones((natom, npar)))
-        elif envelope_type == "diagonal":
-            env["sigma"] = t(np.ones((natom, 3, npar)))
-        elif envelope_type == "full":
-            env["sigma"] = t(np.tile(np.eye(3)[..., None, None], [1, 1, natom, npar]))
-        params["envelope"].append(env)
-    for i in range(len(hidden_dims)):
-        params["single"].append({
-            "w": t(rng.standard_normal((dims_one_in[i], dims_one_out[i])) / np.sqrt(float(dims_one_in[i]))),
-            "b": t(rng.standard_normal((dims_one_out[i],)))})
-        if i < len_double:
-            params["double"].append({
-                "w": t(rng.standard_normal((dims_two[i], dims_two[i + 1])) / np.sqrt(float(dims_two[i]))),
-                "b": t(rng.standard_normal((dims_two[i + 1],)))})
-    for s in active:
-        npar = sum(spins) * determinants if full_det else s * determinants
-        orb = {"w": t(rng.standard_normal((dims_one_in[-1], 2 * npar)) / np.sqrt(float(dims_one_in[-1])))}
-        if bias_orbitals:
-            orb["b"] = t(rng.standard_normal((2 * npar,)))
-        params["orbital"].append(orb)
+    for group, index, leaf, shape, init in parameter_schema(natom, spins, envelope_type, bias_orbitals, use_last_layer,
+                                                            full_det, hidden_dims, determinants, distance_type):
+        if init == "ones":
+            value = np.ones(shape)
+        elif init == "eye":
+            value = np.broadcast_to(np.eye(3)[:, :, None, None], shape).copy()
+        elif init == "bias":
+            value = rng.standard_normal(shape)
+        else:
+            value = rng.standard_normal(shape) / np.sqrt(float(init[1]))
+        while len(params[group]) <= index:
+            params[group].append({})
+        params[group][index][leaf] = torch.as_tensor(np.asarray(value, dtype=np.float64))
     return params
 
 

@@ -1,0 +1,235 @@
+"""Write golden vectors from the REAL bytedance/DeepSolid (JAX + pyscf) for the local-energy hot path.
+
+This image has neither jax nor pyscf (nor a network), so this script cannot run here and no
+``tests/golden/reference_*.npz`` is committed: parity stays "unpinned by reference outputs".  A maintainer
+with the reference's environment closes the gap with
+
+    pip install jax==0.2.26 jaxlib==0.1.75 pyscf chex optax ml_collections      # DeepSolid setup.py:19-27
+    python tests/golden/make_reference_golden.py --reference /path/to/DeepSolid --out tests/golden
+
+after which ``tests/test_reference_golden.py`` compares the oracle (CPU) and the CUDA path (GPU) with the file:
+log|psi|, phase, kinetic energy, the three Ewald terms, the orbital matrices, and the Metropolis accept masks for
+recorded noise.  Everything the consumer needs is INSIDE the file (lattice, atoms, charges, S, k-list, parameters,
+walkers, noise), so it needs neither jax nor pyscf.
+
+What is run (all reference code, unmodified; file:line relative to DeepSolid/):
+  cells      test/test_cell.py:11-25 (LiH, sto-3g), supercell.get_supercell (supercell.py:64-95), S = I and diag(2,1,1)
+  k-list     hf.SCF(simulation_cell, twist).init_scf().klist (hf.py:43-104), as test/test_network.py:32-34 does
+  params     network.make_solid_fermi_net(...).init(key) (network.py:609-667, base_config defaults, 8 determinants)
+  walkers    init_guess.init_electrons (init_guess.py:27-80), then `--burn` reference Metropolis moves
+  outputs    eval_phase_and_slogdet / eval_logdet / eval_mats (network.py:563-606),
+             hamiltonian.local_energy_seperate in modes for / partition / dim_batch (hamiltonian.py:194-228),
+             ewaldsum.EwaldSum.energy (ewaldsum.py:185-191),
+             qmc.mh_update step by step (qmc.py:153-224) with the normal / uniform draws of its own key splits recorded.
+
+``--backend oracle`` writes the same file from the repo's CPU oracle instead: it exists ONLY so that the CPU test
+suite can exercise the writer / reader plumbing (the file is stamped source="oracle-selftest" and the parity test
+refuses to treat such a file as a reference pin).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+CASES = {"reference_lih_s111": np.eye(3), "reference_lih_s211": np.diag([2.0, 1.0, 1.0])}
+
+
+def _flatten(params):
+    """Reference pytree -> {name: array} with names 'single/0/w', ... (network.py:135-184)."""
+    out = {}
+    for group in ("single", "double", "orbital", "envelope"):
+        for i, d in enumerate(params[group]):
+            for leaf, v in d.items():
+                out[f"param/{group}/{i}/{leaf}"] = np.asarray(v, dtype=np.float64)
+    return out
+
+
+def run_reference(S, batch, steps, burn, seed, ref_path):
+    if ref_path:
+        sys.path.insert(0, ref_path)
+        sys.path.insert(0, os.path.join(ref_path, "test"))
+    import jax
+    import jax.numpy as jnp
+    jax.config.update("jax_enable_x64", True)
+    from pyscf.pbc import gto
+    from DeepSolid import base_config, distance, ewaldsum, hamiltonian, hf, init_guess, network, qmc, supercell
+
+    # test/test_cell.py:11-25
+    cell = gto.Cell()
+    L = 2 / 0.529177
+    cell.atom = f"""
+    Li 0 0 0
+    H {L/2} {L/2} {L/2}
+    """
+    cell.basis = "sto-3g"
+    cell.a = (1 - np.eye(3)) * L / 2
+    cell.unit = "B"
+    cell.verbose = 0
+    cell.spin = 0
+    cell.exp_to_discard = 0.1
+    cell.build()
+    simulation_cell = supercell.get_supercell(cell, S=S)
+
+    twist = jnp.zeros(3)
+    scf_approx = hf.SCF(simulation_cell, twist=twist)            # test/test_network.py:32-34
+    scf_approx.init_scf()
+    klist = [np.asarray(k, dtype=np.float64) for k in scf_approx.klist]
+
+    cfg = base_config.default()
+    cfg.network.detnet.determinants = 8
+    system_dict = {"klist": scf_approx.klist, "simulation_cell": simulation_cell}
+    system_dict.update(cfg.network.detnet)
+    system_dict["envelope_type"] = "isotropic"
+    system_dict["full_det"] = False
+    nets = {m: network.make_solid_fermi_net(**system_dict, method_name=m)
+            for m in ("eval_logdet", "eval_slogdet", "eval_phase_and_slogdet", "eval_mats")}
+
+    key = jax.random.PRNGKey(seed)
+    key, k_init, k_par, k_burn, k_mc = jax.random.split(key, 5)
+    internal = init_guess.pyscf_to_cell(simulation_cell)
+    data = init_guess.init_electrons(k_init, internal, simulation_cell.a, simulation_cell.nelec, batch_size=batch)
+    params = nets["eval_logdet"].init(k_par, data=None)
+
+    batch_slog = jax.vmap(nets["eval_slogdet"].apply, in_axes=(None, 0))
+    latvec = simulation_cell.lattice_vectors()
+    width = 0.15
+    if burn:
+        burn_step = qmc.make_mcmc_step(batch_slog, batch, latvec=latvec, steps=burn)
+        data, _ = burn_step(params, data, k_burn, width)
+    x0 = np.asarray(data, dtype=np.float64)
+
+    out = {}
+    sign, slog = jax.vmap(nets["eval_phase_and_slogdet"].apply, in_axes=(None, 0))(params, data)
+    out["logabs"] = np.asarray(slog, dtype=np.float64)
+    out["phase"] = np.asarray(jnp.angle(sign), dtype=np.float64)
+    out["logdet"] = np.asarray(jax.vmap(nets["eval_logdet"].apply, in_axes=(None, 0))(params, data), dtype=np.complex128)
+    mats = jax.vmap(nets["eval_mats"].apply, in_axes=(None, 0))(params, data)
+    for s, m in enumerate(mats):
+        out[f"mats{s}"] = np.asarray(m, dtype=np.complex128)
+    for mode in ("for", "partition", "dim_batch"):
+        el = hamiltonian.local_energy_seperate(nets["eval_logdet"].apply, simulation_cell, mode=mode, partition_number=3)
+        ke, ew = jax.vmap(el, in_axes=(None, 0))(params, data)
+        out[f"ke_{mode}"] = np.asarray(ke, dtype=np.complex128)
+        out[f"ewald_{mode}"] = np.asarray(ew, dtype=np.float64)
+    ewald = ewaldsum.EwaldSum(simulation_cell)
+    ee, ei, ii = jax.vmap(ewald.energy)(data)
+    out["ee"], out["ei"], out["ii"] = (np.asarray(v, dtype=np.float64) for v in (ee, ei, ii))
+    out["ewald_alpha"] = np.float64(ewald.alpha)
+    out["ewald_ng"] = np.int64(ewald.gweight.shape[0])
+
+    # Metropolis: qmc.mh_update, one call per move, with the draws of its two key splits recorded (qmc.py:189-218)
+    x1 = data
+    lp = 2.0 * batch_slog(params, x1)
+    xi, u, masks = [], [], []
+    k = k_mc
+    nacc = 0.0
+    for _ in range(steps):
+        k_a, sub_a = jax.random.split(k)
+        xi.append(np.asarray(jax.random.normal(sub_a, shape=x1.shape), dtype=np.float64))
+        _, sub_b = jax.random.split(k_a)
+        u.append(np.asarray(jax.random.uniform(sub_b, shape=lp.shape), dtype=np.float64))
+        x_new, k, lp_new, nacc = qmc.mh_update(params, batch_slog, x1, k, lp, nacc, latvec, stddev=width)
+        masks.append(np.asarray(lp_new != lp) | np.any(np.asarray(x_new != x1), axis=-1))
+        x1, lp = x_new, lp_new
+    # the jitted driver must land on the same walkers (qmc.py:335-362)
+    x_drv, pmove = qmc.make_mcmc_step(batch_slog, batch, latvec=latvec, steps=steps)(params, data, k_mc, width)
+    assert np.allclose(np.asarray(x_drv), np.asarray(x1), atol=1e-12), "step-by-step replay differs from mcmc_step"
+    out.update(xi=np.stack(xi), u=np.stack(u), masks=np.stack(masks), x_new=np.asarray(x1, dtype=np.float64),
+               pmove=np.float64(pmove), width=np.float64(width))
+
+    prim = simulation_cell.original_cell
+    out.update(_flatten(params))
+    out.update(x=x0, S=np.asarray(S, dtype=np.float64), nelec=np.asarray(simulation_cell.nelec, dtype=np.int64),
+               prim_a=np.asarray(prim.lattice_vectors(), dtype=np.float64),
+               prim_atoms=np.asarray(prim.atom_coords(), dtype=np.float64),
+               prim_charges=np.asarray(prim.atom_charges(), dtype=np.float64),
+               sim_a=np.asarray(simulation_cell.lattice_vectors(), dtype=np.float64),
+               sim_atoms=np.asarray(simulation_cell.atom_coords(), dtype=np.float64),
+               sim_charges=np.asarray(simulation_cell.atom_charges(), dtype=np.float64),
+               sim_AV=np.asarray(simulation_cell.AV), sim_BV=np.asarray(simulation_cell.BV),
+               prim_AV=np.asarray(prim.AV), prim_BV=np.asarray(prim.BV),
+               klist0=klist[0], klist1=klist[1], energy_nuc=np.float64(simulation_cell.energy_nuc()),
+               source=np.array("reference"), versions=np.array(f"jax {jax.__version__}"))
+    return out
+
+
+def run_oracle(S, batch, steps, burn, seed):
+    """Plumbing self-test only: the same file layout written from the CPU oracle."""
+    sys.path.insert(0, ROOT)
+    import torch
+    from oracle import deepsolid_oracle as O, geometry as G
+    L = 2 / 0.529177
+    prim = G.RefCell((1 - np.eye(3)) * L / 2, [("Li", [0, 0, 0]), ("H", [L / 2] * 3)], {"Li": 3.0, "H": 1.0})
+    sc = G.get_supercell(prim, S)
+    klist = G.make_klist(sc)
+    rng = np.random.default_rng(seed)
+    pn = O.init_params(rng, prim.natm, sc.nelec)
+    P = O.params_to_torch(pn)
+    X = torch.as_tensor(G.init_walkers(sc, batch, seed=seed))
+    nets = {m: O.make_solid_fermi_net(klist, sc, method_name=m)
+            for m in ("eval_logdet", "eval_slogdet", "eval_phase_and_slogdet", "eval_mats")}
+    bslog = lambda p, x: O.batch_apply(nets["eval_slogdet"], p, x)
+    width = 0.15
+    if burn:
+        X, _, _ = O.make_mcmc_step(bslog, batch, sc.lattice_vectors(), steps=burn)(
+            P, X, (torch.as_tensor(rng.standard_normal((burn,) + tuple(X.shape))), torch.as_tensor(rng.uniform(size=(burn, batch)))), width)
+    out = {"logabs": [], "phase": [], "logdet": [], "mats0": [], "mats1": [], "ee": [], "ei": [], "ii": []}
+    els = {m: O.local_energy_seperate(nets["eval_logdet"], sc, mode=m, partition_number=3) for m in ("for", "partition", "dim_batch")}
+    for m in els:
+        out[f"ke_{m}"], out[f"ewald_{m}"] = [], []
+    ew = O.EwaldSum(sc)
+    for b in range(batch):
+        sign, slog = nets["eval_phase_and_slogdet"](P, X[b])
+        out["logabs"].append(float(slog)); out["phase"].append(float(torch.angle(sign)))
+        out["logdet"].append(complex(nets["eval_logdet"](P, X[b])))
+        mats = nets["eval_mats"](P, X[b])
+        out["mats0"].append(mats[0].numpy()); out["mats1"].append(mats[1].numpy())
+        for m, el in els.items():
+            ke, e = el(P, X[b])
+            out[f"ke_{m}"].append(complex(ke)); out[f"ewald_{m}"].append(float(e))
+        ee, ei, ii = ew.energy(X[b])
+        out["ee"].append(float(ee)); out["ei"].append(float(ei)); out["ii"].append(float(ii))
+    out = {k: np.asarray(v) for k, v in out.items()}
+    xi = rng.standard_normal((steps,) + tuple(X.shape)); u = rng.uniform(size=(steps, batch))
+    xn, pmove, masks = O.make_mcmc_step(bslog, batch, sc.lattice_vectors(), steps=steps)(P, X, (torch.as_tensor(xi), torch.as_tensor(u)), width)
+    out.update(xi=xi, u=u, masks=np.asarray(masks).astype(bool), x_new=xn.numpy(), pmove=np.float64(pmove), width=np.float64(width))
+    out.update(_flatten(pn))
+    out.update(x=X.numpy(), S=np.asarray(S, dtype=np.float64), nelec=np.asarray(sc.nelec, dtype=np.int64),
+               prim_a=prim.a, prim_atoms=prim.atom_coords(), prim_charges=prim.atom_charges(), sim_a=sc.a,
+               sim_atoms=sc.atom_coords(), sim_charges=sc.atom_charges(), sim_AV=sc.AV, sim_BV=sc.BV,
+               prim_AV=prim.AV, prim_BV=prim.BV, klist0=klist[0], klist1=klist[1],
+               ewald_alpha=np.float64(ew.alpha), ewald_ng=np.int64(ew.gweight.shape[0]),
+               energy_nuc=np.float64(ew.ion_ion + ew.ii_const),
+               source=np.array("oracle-selftest"), versions=np.array("oracle"))
+    return out
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
+    ap.add_argument("--reference", default=os.environ.get("DEEPSOLID_PATH", ""), help="checkout of bytedance/DeepSolid")
+    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+    ap.add_argument("--backend", choices=["reference", "oracle"], default="reference")
+    ap.add_argument("--batch", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--burn", type=int, default=30)
+    ap.add_argument("--seed", type=int, default=20260101)
+    ap.add_argument("--cases", nargs="*", default=list(CASES))
+    a = ap.parse_args(argv)
+    os.makedirs(a.out, exist_ok=True)
+    for name in a.cases:
+        S = CASES[name]
+        if a.backend == "reference":
+            data = run_reference(S, a.batch, a.steps, a.burn, a.seed, a.reference)
+        else:
+            data = run_oracle(S, a.batch, a.steps, a.burn, a.seed)
+        path = os.path.join(a.out, name + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"wrote {path}: {len(data)} arrays, source={data['source']}")
+
+
+if __name__ == "__main__":
+    main()
