@@ -45,13 +45,27 @@ def _np_reconstruct(fun, args, arr_state, *unused):
     return value
 
 
+_SAFE_GLOBALS = {
+    ("builtins", n) for n in ("dict", "list", "tuple", "set", "frozenset", "int", "float", "complex", "bool", "str",
+                              "bytes", "bytearray", "slice", "range")
+} | {("collections", "OrderedDict"), ("collections", "defaultdict"), ("collections", "namedtuple")}
+_SAFE_MODULE_ROOTS = ("numpy",)
+
+
 class _NoJaxUnpickler(pickle.Unpickler):
+    """Unpickler for the object members of a checkpoint: numpy reconstructors, plain containers and jax's
+    device-array reconstructor (mapped to numpy) only.  Anything else raises -- a checkpoint is data, and
+    resolving arbitrary globals would execute code chosen by whoever wrote the file."""
+
     def find_class(self, module, name):
-        if module.split(".")[0] in ("jax", "jaxlib"):
+        root = module.split(".")[0]
+        if root in ("jax", "jaxlib"):
             if "reconstruct" in name:
                 return _np_reconstruct
             raise pickle.UnpicklingError(f"checkpoint references {module}.{name}, which cannot be read without jax")
-        return super().find_class(module, name)
+        if root in _SAFE_MODULE_ROOTS or (module, name) in _SAFE_GLOBALS:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"checkpoint references {module}.{name}: not on the allow-list of this reader")
 
 
 def _load_member(z: zipfile.ZipFile, key: str):
@@ -73,30 +87,23 @@ def _to_native(a):
     return a.tolist() if isinstance(a, np.ndarray) else a
 
 
-def _strip_device_axis(tree, n_devices: int, expect_ndim):
-    """Leaves are replicated over a leading device axis in reference checkpoints; drop it."""
-    def conv(v, nd):
+def _strip_device_axis(tree, n_devices: int):
+    """Every parameter leaf of a reference checkpoint is replicated over a leading device axis
+    (process.py:136 `replicate_all_local_devices`; checkpoint.py:92-122 saves it as is): check and drop it, whatever
+    the leaf's own rank is (envelope sigma is (A, q), (A, 3, q) or (3, 3, A, q) depending on envelope_type)."""
+    def conv(v, path):
         if isinstance(v, dict):
-            return {k: conv(x, nd if not isinstance(nd, dict) else nd.get(k)) for k, x in v.items()}
+            return {k: conv(x, f"{path}/{k}") for k, x in v.items()}
         if isinstance(v, (list, tuple)):
-            return [conv(x, nd) for x in v]
+            return [conv(x, f"{path}/{i}") for i, x in enumerate(v)]
         a = np.asarray(v, dtype=np.float64)
-        want = nd if isinstance(nd, int) else None
-        if (want is not None and a.ndim == want + 1) or (want is None and a.ndim >= 1 and a.shape[0] == n_devices
-                                                          and a.ndim in (2, 3)):
-            if want is not None or _looks_replicated(a):
-                a = a[0]
-        return torch.as_tensor(np.ascontiguousarray(a))
-    ndims = {"single": {"w": 2, "b": 1}, "double": {"w": 2, "b": 1}, "orbital": {"w": 2, "b": 1},
-             "envelope": {"pi": 2, "sigma": 2}}
-    out = {}
-    for k, v in tree.items():
-        out[k] = conv(v, ndims.get(k) if expect_ndim else None)
-    return out
-
-
-def _looks_replicated(a: np.ndarray) -> bool:
-    return a.shape[0] == 1 or bool(np.all(a[0] == a[-1]))
+        if a.ndim < 1 or a.shape[0] != n_devices:
+            raise ValueError(f"parameter leaf {path} has shape {a.shape}: no leading axis over the {n_devices} device(s) "
+                             "the walkers were saved from")
+        if n_devices > 1 and not np.array_equal(a[0], a[-1]):
+            raise ValueError(f"parameter leaf {path} differs between devices: replicas have diverged")
+        return torch.as_tensor(np.ascontiguousarray(a[0]))
+    return {k: conv(v, k) for k, v in tree.items()}
 
 
 def restore(restore_filename: str, batch_size: Optional[int] = None, n_devices: Optional[int] = None,
@@ -109,7 +116,10 @@ def restore(restore_filename: str, batch_size: Optional[int] = None, n_devices: 
         t = int(_to_native(_load_member(z, "t"))) + 1
         data = np.asarray(_load_member(z, "data"), dtype=np.float64)
         params = _to_native(_load_member(z, "params"))
-        opt_state = _to_native(_load_member(z, "opt_state"))
+        try:        # optimiser state may pickle classes this reader refuses or cannot import: params / walkers do not need it
+            opt_state = _to_native(_load_member(z, "opt_state"))
+        except (pickle.UnpicklingError, ImportError, AttributeError, KeyError):
+            opt_state = None
         mcmc_width = _to_native(_load_member(z, "mcmc_width"))
     if data.ndim != 3:
         raise ValueError(f"walkers in a checkpoint must have shape (devices, batch/devices, 3N); found {data.shape}")
@@ -121,7 +131,7 @@ def restore(restore_filename: str, batch_size: Optional[int] = None, n_devices: 
                 batch_size, data.shape[0] * data.shape[1]))
     if not isinstance(params, dict) or "single" not in params:
         raise ValueError("checkpoint does not hold a solid-FermiNet parameter pytree")
-    params = _strip_device_axis(params, data.shape[0], expect_ndim=True)
+    params = _strip_device_axis(params, data.shape[0])
     if isinstance(mcmc_width, (list, np.ndarray)):
         mcmc_width = float(np.asarray(mcmc_width).reshape(-1)[0])
     return t, torch.as_tensor(data), params, opt_state, mcmc_width

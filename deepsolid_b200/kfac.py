@@ -109,8 +109,10 @@ class Optimizer:
     """The reference's ``kfac_optim.Optimizer`` (process.py:209-222) reduced to the configuration DeepSolid runs:
     fisher_exact curvature, fixed damping, momentum 0, norm constraint.
 
-    ``value_and_grad(params, data) -> ((loss, aux), grads)`` is ``train.make_loss(...).value_and_grad``; the
-    gradients are already averaged over ranks there.  ``hp`` is the HotPath the loss evaluates."""
+    ``value_and_grad(params, data) -> ((loss, aux), grads)`` is ``train.make_loss(...).value_and_grad``, which returns
+    the gradient of THIS rank's walkers; ``step`` averages it (and the norm-constraint scalar) over ranks, as the
+    reference does (kfac_ferminet_alpha optimizer.py:423, :593), so walker-sharded replicas stay identical.
+    ``hp`` is the HotPath the loss evaluates."""
 
     def __init__(self, value_and_grad: Callable, hp, l2_reg: float = 0.0, norm_constraint: Optional[float] = 1e-3,
                  curvature_ema: float = 0.95, inverse_update_period: int = 1, cov_update_every: int = 1):
@@ -182,7 +184,7 @@ class Optimizer:
         dev = self.hp.tdev
         to_dev = lambda t: torch.as_tensor(t).to(dev)
         leaves_p = [to_dev(t) for t in flatten_params(params)]
-        leaves_g = [to_dev(t) for t in flatten_params(grads)]
+        leaves_g = [dist.pmean(to_dev(t)) for t in flatten_params(grads)]        # optimizer.py:423
         if self.l2_reg:
             leaves_g = [g + self.l2_reg * p for g, p in zip(leaves_g, leaves_p)]
         n_layers = len(params["single"])
@@ -197,7 +199,8 @@ class Optimizer:
         leaves_pre = flatten_params(pre)
         coefficient = 1.0
         if self.norm_constraint is not None:
-            sq = sum(float((a * b).sum()) for a, b in zip(leaves_pre, leaves_g)) * learning_rate ** 2
+            sq = sum((a * b).sum() for a, b in zip(leaves_pre, leaves_g)) * learning_rate ** 2
+            sq = float(dist.pmean(sq))                                               # optimizer.py:593
             coefficient = min(math.sqrt(self.norm_constraint / sq), 1.0) if sq > 0.0 else 1.0
         new_leaves = [p - learning_rate * coefficient * d for p, d in zip(leaves_p, leaves_pre)]
         self.step_counter += 1

@@ -87,3 +87,54 @@ def test_reads_jax_pickled_leaves_without_jax(tmp_path):
     t, d, params, _, width = checkpoint.restore(fname, batch_size=4, n_devices=1)
     assert t == 12 and width == pytest.approx(0.02)
     assert _tree_equal(params, P) and np.array_equal(d.numpy(), data)
+
+
+@pytest.mark.parametrize("envelope_type", ["diagonal", "full"])
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_anisotropic_envelope_leaves_round_trip(tmp_path, envelope_type, ndev):
+    """sigma is (A, 3, q) / (3, 3, A, q) for the diagonal / full envelopes (network.py:146-152): the device axis is
+    dropped whatever the leaf's own rank is."""
+    from deepsolid_b200 import network
+    sc, kl, pn, _ = system("h4")
+    P = network.init_solid_fermi_net_params(3, atoms=sc.original_cell.atom_coords(), spins=sc.nelec,
+                                            envelope_type=envelope_type)
+    data = torch.as_tensor(C.init_walkers(sc, 4, seed=1)).reshape(ndev, 4 // ndev, -1)
+    f = checkpoint.save(str(tmp_path), 1, data, P)
+    _, d, params, _, _ = checkpoint.restore(f, batch_size=4, n_devices=ndev)
+    assert _tree_equal(params, P)
+    want = (2, 3, 16) if envelope_type == "diagonal" else (3, 3, 2, 16)      # A = 2, q = n_s * D = 2 * 8
+    assert tuple(params["envelope"][0]["sigma"].shape) == want
+
+
+def test_diverged_replicas_and_foreign_globals_are_refused(tmp_path):
+    sc, kl, pn, P = system("h4")
+    data = C.init_walkers(sc, 4, seed=2).reshape(2, 2, -1)
+
+    def rep(v, bump=0.0):
+        if isinstance(v, dict):
+            return {k: rep(x, bump) for k, x in v.items()}
+        if isinstance(v, list):
+            return [rep(x, bump) for x in v]
+        a = np.broadcast_to(v.numpy(), (2,) + tuple(v.shape)).copy()
+        a[1] += bump
+        return a
+    fname = str(tmp_path / "qmcjax_ckpt_000001.npz")
+    np.savez(open(fname, "wb"), t=1, data=data, params=np.asarray(rep(P, 1e-3), dtype=object),
+             opt_state=np.asarray(None, dtype=object), mcmc_width=np.asarray(0.02))
+    with pytest.raises(ValueError, match="diverged"):
+        checkpoint.restore(fname)
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ("true",))
+    # a foreign global in the parameters is refused outright ...
+    np.savez(open(fname, "wb"), t=1, data=data, params=np.asarray({"single": Evil()}, dtype=object),
+             opt_state=np.asarray(None, dtype=object), mcmc_width=np.asarray(0.02))
+    with pytest.raises(pickle.UnpicklingError, match="allow-list"):
+        checkpoint.restore(fname)
+    # ... and one in the optimiser state only costs the optimiser state
+    np.savez(open(fname, "wb"), t=1, data=data, params=np.asarray(rep(P), dtype=object),
+             opt_state=np.asarray({"s": Evil()}, dtype=object), mcmc_width=np.asarray(0.02))
+    t, d, params, opt_state, _ = checkpoint.restore(fname)
+    assert opt_state is None and _tree_equal(params, P)

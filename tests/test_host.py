@@ -262,3 +262,56 @@ def test_two_rank_gloo_kfac_and_observable_means(tmp_path):
     want_pi = 2.0 * complex(1.0, -0.5) ** 2 / 4 * 2.5
     assert abs(got[6] - want_pi) < 1e-14
     assert abs(got[7] - 1.5 * (1 + 2j)) < 1e-15 and abs(got[8] - 1.5 * (-1j)) < 1e-15
+
+
+_WORKER_KFAC_STEP = r"""
+import os, sys, torch, torch.distributed as td
+sys.path.insert(0, sys.argv[1])
+from deepsolid_b200 import kfac
+from deepsolid_b200.hotpath import flatten_params
+td.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
+r = td.get_rank()
+
+class StubHotPath:
+    tdev = torch.device("cpu")
+    def set_params(self, p): pass
+    def kfac_factors(self, x):
+        s = float(r + 1)
+        blk = lambda n_in, n_out, rows: {"a": s * (torch.ones(n_in + 1, n_in + 1, dtype=torch.float64) + torch.eye(n_in + 1, dtype=torch.float64)),
+                                         "g": s * torch.eye(n_out, dtype=torch.float64), "rows": rows}
+        env = lambda v: [{"pi": torch.full((1, 2), v, dtype=torch.float64), "sigma": torch.full((1, 2), 2 * v, dtype=torch.float64)}] * 2
+        return {"single": [blk(3, 2, 8)], "double": [], "orbital": [blk(2, 4, 4), blk(2, 4, 4)],
+                "envelope_abs": env(s), "envelope_phase": env(0.5 * s), "batch": 4}
+
+def params(v):
+    f = lambda *shape: torch.full(shape, v, dtype=torch.float64)
+    return {"single": [{"w": f(3, 2), "b": f(2)}], "double": [], "orbital": [{"w": f(2, 4)}, {"w": f(2, 4)}],
+            "envelope": [{"pi": f(1, 2), "sigma": f(1, 2)}, {"pi": f(1, 2), "sigma": f(1, 2)}]}
+
+def vag(scale):
+    return lambda p, d: ((torch.tensor(0.0), None), params(scale))
+
+opt = kfac.Optimizer(vag(float(r + 1)), StubHotPath(), norm_constraint=1e-3)      # per-rank gradients 1 and 2
+new, stats = opt.step(params(0.5), None, learning_rate=0.1, damping=1e-3)
+mine = torch.cat([t.reshape(-1) for t in flatten_params(new)])
+both = [torch.zeros_like(mine) for _ in range(2)]
+td.all_gather(both, mine)
+if r == 0:
+    print("RESULT", bool(torch.equal(both[0], both[1])), float((mine - 0.5).abs().max()), stats["coefficient"])
+td.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_kfac_step_keeps_replicas_identical(tmp_path):
+    """Optimizer.step averages the per-rank energy gradient and the norm-constraint scalar over ranks
+    (kfac_ferminet_alpha optimizer.py:423, :593): ranks that saw different walkers end with the SAME parameters."""
+    script = tmp_path / "worker_kfac_step.py"
+    script.write_text(_WORKER_KFAC_STEP)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29581", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = [l for l in outs[0][0].splitlines() if l.startswith("RESULT")][0].split()
+    assert line[1] == "True", "parameter replicas diverged"
+    assert float(line[2]) > 0.0 and 0.0 < float(line[3]) <= 1.0
