@@ -317,7 +317,7 @@ __device__ __forceinline__ void orbj_block8(const double* zz8, const double* __r
 // ---------------------------------------------------------------------------
 // the GEMM
 // ---------------------------------------------------------------------------
-template <int MODE, bool RES, int TN>
+template <int MODE, bool RES, int TN, int ND>
 // 18 warps: five share one SM sub-partition (16384 registers), so at most 96 registers per thread
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const OzParams p,
@@ -331,6 +331,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.K / OZ_BK;
+    constexpr int ndiag = ND;                            // 6; 5 is an accuracy / speed experiment (DS_OZ_DIAGS=5)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -388,7 +389,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         for (int t = 0; t < OZ_S; ++t) {
                             // W_t x [A_0 .. A_{5-t}] -> diagonals t .. 5 (TMEM column blocks of 64)
                             const uint64_t wdesc = make_desc(sW + t * W_SLICE + ks * 32);
-                            const int nsl = OZ_S - t;
+                            const int nsl = ndiag - t;
+                            if (nsl <= 0) continue;
                             constexpr int MAXSL = 256 / TN;                  // slices of A one instruction can span (N <= 256)
                             const int n1 = (nsl > MAXSL ? MAXSL : nsl) * TN;
                             const uint32_t acc = (kb > 0 || ks > 0 || t > 0) ? 1u : 0u;
@@ -452,7 +454,13 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 for (int c0 = 0; c0 < EPI_COLS; c0 += 8) {
                     int v[OZ_S][8];
 #pragma unroll
-                    for (int g = 0; g < OZ_S; ++g) tmem_ld8(lane_addr + g * TN + c0, v[g]);
+                    for (int g = 0; g < OZ_S; ++g) {
+                        if (g < ndiag) tmem_ld8(lane_addr + g * TN + c0, v[g]);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[g][j] = 0;
+                        }
+                    }
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -607,13 +615,13 @@ int make_map(CUtensorMap* tm, const signed char* base, int K, long long rows, lo
     return 0;
 }
 
-template <int MODE, bool RES, int TN>
+template <int MODE, bool RES, int TN, int ND>
 int launch_tn(const OzParams& p, cudaStream_t stream) {
     static bool configured = false;
     static int n_sm = 0;
     constexpr int SMEM_T = OzCfg<TN>::SMEM_T;
     if (!configured) {
-        DS_CUDA_CHECK(cudaFuncSetAttribute(oz_gemm_kernel<MODE, RES, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_T));
+        DS_CUDA_CHECK(cudaFuncSetAttribute(oz_gemm_kernel<MODE, RES, TN, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_T));
         int dev = 0;
         DS_CUDA_CHECK(cudaGetDevice(&dev));
         DS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -626,7 +634,7 @@ int launch_tn(const OzParams& p, cudaStream_t stream) {
     const int n_cb = (p.N + OZ_TM - 1) / OZ_TM;
     const long long n_tiles = (long long)tpg * p.n_groups * n_cb;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
-    oz_gemm_kernel<MODE, RES, TN><<<grid, OZ_THREADS, SMEM_T, stream>>>(tmW, tmA, p, tpg, n_cb, n_tiles);
+    oz_gemm_kernel<MODE, RES, TN, ND><<<grid, OZ_THREADS, SMEM_T, stream>>>(tmW, tmA, p, tpg, n_cb, n_tiles);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -638,7 +646,9 @@ int launch_tn(const OzParams& p, cudaStream_t stream) {
 template <int MODE, bool RES>
 int launch(const OzParams& p, cudaStream_t stream) {
     static const int tn = [] { const char* e = getenv("DS_OZ_TN"); return (e && atoi(e) == 32) ? 32 : 64; }();
-    return tn == 64 ? launch_tn<MODE, RES, 64>(p, stream) : launch_tn<MODE, RES, 32>(p, stream);
+    static const int diags = [] { const char* e = getenv("DS_OZ_DIAGS"); return (e && atoi(e) == 5) ? 5 : 6; }();
+    if (diags == 5) return launch_tn<MODE, RES, 64, 5>(p, stream);
+    return tn == 64 ? launch_tn<MODE, RES, 64, 6>(p, stream) : launch_tn<MODE, RES, 32, 6>(p, stream);
 }
 
 }  // namespace
