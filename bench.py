@@ -51,6 +51,11 @@ def parse():
     ap.add_argument("--grad", action="store_true", help="also time energy + parameter gradient (value_and_grad; extras)")
     ap.add_argument("--kfac", action="store_true", help="also time the KFAC curvature statistics and the forward (extras)")
     ap.add_argument("--equil", type=int, default=2, help="Metropolis calls (20 moves each) used to equilibrate walkers")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: BASELINE batch per GPU (headline); strong: the BASELINE batch is global and split over "
+                         "the GPUs (process.py:96,134).  The weak line also carries the strong measurement as `strong`.")
+    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--threads", type=int, default=1, help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -84,18 +89,105 @@ def make_params(cell):
 
 
 # ---------------------------------------------------------------------------
-def cpu_oracle_rate(cell, klist, P, X, n_walkers, threads):
-    """Local energies/s of the oracle (reference algorithm) on `threads` host threads.  The oracle is imported
+ORACLE_MODE = ("partition", 3)      # the reference's own faster Laplacian mode on CPU (hamiltonian.py:127-159)
+
+
+def cpu_worker(args):
+    """One single-purpose process of the CPU arm: builds the oracle (reference algorithm, torch fp64) for `--system`,
+    then evaluates one walker per request line {"x": [...]} -> {"ke_re", "ke_im", "ew", "dt"}.  The oracle is imported
     here only: it is the CPU baseline / checker, never part of the measured GPU path."""
+    torch.set_num_threads(max(1, args.threads))
     from oracle import deepsolid_oracle as O
-    torch.set_num_threads(threads)
+    cell = C.build_system(args.system)
+    klist = C.make_klist(cell)
+    P = make_params(cell)
     f = O.make_solid_fermi_net(klist, cell, method_name="eval_logdet")
-    el = O.local_energy_seperate(f, cell, mode="dim_batch")
-    Xs = torch.as_tensor(X[:n_walkers])
-    t0 = time.perf_counter()
-    out = [el(P, x) for x in Xs]
-    dt = time.perf_counter() - t0
-    return n_walkers / dt, dt, out
+    el = O.local_energy_seperate(f, cell, mode=ORACLE_MODE[0], partition_number=ORACLE_MODE[1])
+    sys.stdout.write("ready\n"); sys.stdout.flush()
+    for line in sys.stdin:
+        req = json.loads(line)
+        if "threads" in req:
+            torch.set_num_threads(int(req["threads"]))
+            continue
+        if "quit" in req:
+            break
+        x = torch.as_tensor(np.asarray(req["x"], dtype=np.float64))
+        t0 = time.perf_counter()
+        ke, ew = el(P, x)
+        dt = time.perf_counter() - t0
+        sys.stdout.write(json.dumps({"ke_re": float(ke.real), "ke_im": float(ke.imag), "ew": float(ew), "dt": dt}) + "\n")
+        sys.stdout.flush()
+
+
+class OraclePool:
+    """The CPU arm: one oracle process per host core (single-threaded BLAS each -- measured 1.9x the throughput of
+    one process with all threads on an 8-core host, because the per-direction GEMMs are small), each evaluating one
+    walker per step.  The number of processes is capped by free memory (~0.3 + 3.4e-4 N^2 GB each)."""
+
+    def __init__(self, system, n_elec, cores=None, max_procs=None):
+        cores = cores or (os.cpu_count() or 1)
+        self.cores = cores
+        est_gb = 0.3 + 3.4e-4 * n_elec ** 2
+        try:
+            import psutil
+            by_mem = max(1, int(0.5 * psutil.virtual_memory().available / 2 ** 30 / est_gb))
+        except Exception:
+            by_mem = cores
+        # large systems: fewer processes with more threads each keep one step within tens of seconds
+        t_single = 14.0 * (n_elec / 54.0) ** 2.75
+        threads = 1
+        while t_single / threads ** 0.8 > 30.0 and threads * 2 <= cores:
+            threads *= 2
+        n = max(1, min(cores // threads, by_mem, max_procs or cores))
+        self.threads = threads
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="")
+        self.procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", "--system", system,
+                                        "--threads", str(threads)], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                       stderr=subprocess.DEVNULL, text=True, bufsize=1, env=env) for _ in range(n)]
+        for p in self.procs:
+            line = p.stdout.readline()
+            if line.strip() != "ready":
+                self.close()
+                raise RuntimeError("a CPU oracle worker failed to start")
+
+    def __len__(self):
+        return len(self.procs)
+
+    def shrink(self, n):
+        """Keep n processes; the freed cores go to the survivors as BLAS threads."""
+        n = max(1, min(n, len(self.procs)))
+        for p in self.procs[n:]:
+            self._stop(p)
+        self.procs = self.procs[:n]
+        self.threads = max(1, self.cores // n)
+        for p in self.procs:
+            p.stdin.write(json.dumps({"threads": self.threads}) + "\n"); p.stdin.flush()
+
+    def step(self, X):
+        """One walker per process, all concurrently -> (wall seconds, [(ke, ew)] in walker order)."""
+        X = np.asarray(X, dtype=np.float64)
+        assert X.shape[0] == len(self.procs)
+        t0 = time.perf_counter()
+        for p, x in zip(self.procs, X):
+            p.stdin.write(json.dumps({"x": x.tolist()}) + "\n"); p.stdin.flush()
+        out = []
+        for p in self.procs:
+            r = json.loads(p.stdout.readline())
+            out.append((complex(r["ke_re"], r["ke_im"]), r["ew"]))
+        return time.perf_counter() - t0, out
+
+    @staticmethod
+    def _stop(p):
+        try:
+            p.stdin.write(json.dumps({"quit": 1}) + "\n"); p.stdin.flush()
+            p.wait(timeout=10)
+        except Exception:
+            p.kill()
+
+    def close(self):
+        for p in self.procs:
+            self._stop(p)
+        self.procs = []
 
 
 class ClockSampler:
@@ -166,6 +258,48 @@ def measure_fp64_peak(dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12      # TFLOP/s
 
 
+def measure_int8_mma_rate(hp, dev):
+    """tcgen05 kind::i8 issue rate of THIS GPU: the int8-slice GEMM kernel of the sweep at the benchmark's layer shape
+    with TMA and the epilogue switched off (DS_OZ_DBG=5: operands stay in shared memory, accumulators are never
+    read), i.e. the tensor pipe fed from shared memory at the kernel's own instruction mix.  Tera-int8-ops/s."""
+    import ctypes as Ct
+    m, n, k = 148 * 64 * 80, 256, 320
+    a = torch.randn(m, k, dtype=torch.float64, device=dev)
+    b = torch.randn(k, n, dtype=torch.float64, device=dev)
+    c = torch.empty(m, n, dtype=torch.float64, device=dev)
+    gm, sm = Ct.c_double(), Ct.c_double()
+    old = os.environ.get("DS_OZ_DBG")
+    os.environ["DS_OZ_DBG"] = "5"
+    try:
+        rc = hp.lib.ds_ozaki_dgemm_probe(dev.index or 0, a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, 5,
+                                         Ct.byref(gm), Ct.byref(sm), None)
+    finally:
+        if old is None:
+            os.environ.pop("DS_OZ_DBG", None)
+        else:
+            os.environ["DS_OZ_DBG"] = old
+    torch.cuda.synchronize(dev)
+    del a, b, c
+    if rc or gm.value <= 0:
+        return None
+    return 21 * 2.0 * m * n * k / (gm.value * 1e-3) / 1e12
+
+
+def committed_profile(kind):
+    """Newest profiles/r*_{kind}.json with its provenance (git sha, chunk size) -- ncu numbers cannot be taken in a
+    timed run, so they come from the capture committed with the code and say which code that was."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kind}.json")))
+    for f in reversed(files):
+        try:
+            d = json.load(open(f))
+            d["file"] = os.path.relpath(f, ROOT)
+            return d
+        except Exception:
+            continue
+    return None
+
+
 def run_ours(args):
     import torch.distributed as td
     from deepsolid_b200 import network, train, qmc
@@ -179,7 +313,11 @@ def run_ours(args):
     if world > 1:
         td.init_process_group("nccl", device_id=dev)
     system = args.system
-    batch = args.batch or C.SYSTEMS[system][1]
+    global_batch = args.batch or C.SYSTEMS[system][1]
+    # weak: every GPU holds the BASELINE batch; strong: the BASELINE batch is global, split as (world, batch/world, 3N)
+    batch_weak = global_batch
+    batch_strong = max(1, global_batch // world)
+    batch = batch_strong if args.scaling == "strong" else batch_weak
     mode, pn = C.SYSTEMS[system][2], C.SYSTEMS[system][3]
     cell, klist, X = make_inputs(system, batch, seed=666 + rank)        # every rank its own walkers
     P = make_params(cell)
@@ -225,6 +363,7 @@ def run_ours(args):
         return float(t.item())
 
     fp64_peak = measure_fp64_peak(dev) if rank == 0 else None
+    i8_measured = measure_int8_mma_rate(hp, dev) if rank == 0 else None
     keep = {}
 
     def step_dev():
@@ -249,6 +388,21 @@ def run_ours(args):
     prof = hp.profile_get()
     hp.profile(False)
     value = world * batch * args.steps / (ms / 1e3)
+
+    strong = None
+    if args.scaling == "weak":
+        # the same step on the strong-scaling share of the named global batch (at N = 1 it is the same measurement)
+        if world == 1:
+            strong = {"value": value, "ms_per_step": ms / args.steps, "global_batch": global_batch, "batch_per_gpu": batch}
+        else:
+            Xs = Xd[:batch_strong].contiguous()
+
+            def step_strong():
+                loss_s, _ = total_energy(P, Xs)
+                keep["loss_s"] = loss_s
+            ms_s = timed(step_strong, args.steps, 2)
+            strong = {"value": world * batch_strong * args.steps / (ms_s / 1e3), "ms_per_step": ms_s / args.steps,
+                      "global_batch": batch_strong * world, "batch_per_gpu": batch_strong}
 
     e2e = None
     if not args.no_e2e:
@@ -296,27 +450,21 @@ def run_ours(args):
     except Exception:
         pass
     i8 = os.environ.get("DS_NO_I8", "0") in ("", "0")
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same chunk shape)
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
-        if i8 and system == DEFAULT_SYSTEM:
-            traffic = {"oz_gemm_kernel<JAC>": tr["oz_gemm_kernel<1, 1>"]["dram_bytes_per_launch"],
-                       "oz_gemm_kernel<ORBJ>": tr["oz_gemm_kernel<2, 0>"]["dram_bytes_per_launch"],
-                       "source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of one 254-walker chunk; algorithmic bytes of that launch: JAC 54.6 MB, ORBJ 22.7 MB per walker)"}
-    except Exception:
-        pass
-    # DRAM traffic of the WHOLE local-energy pass (every kernel) from the committed ncu launch list
-    hbm = None
-    try:
-        hb = json.load(open(os.path.join(ROOT, "profiles", "r1_hbm.json")))
-        if i8 and system == DEFAULT_SYSTEM:
+    # ncu-measured DRAM bytes (per launch of the dominant kernel; per walker over the whole pass) from the capture
+    # committed with this code: each file records the git sha and chunk size it was taken at
+    traffic = hbm = None
+    if i8 and system == DEFAULT_SYSTEM:
+        tr = committed_profile("traffic")
+        if tr and "kernels" in tr:
+            traffic = {"per_launch_dram_bytes": {k: v.get("dram_bytes_per_launch") for k, v in tr["kernels"].items()},
+                       "chunk_walkers": tr.get("chunk_walkers"), "git_sha": tr.get("git_sha"), "source": tr["file"]}
+        hb = committed_profile("hbm")
+        if hb and "dram_bytes_per_walker" in hb:
             gbs = hb["dram_bytes_per_walker"] * batch * args.steps / (ms / 1e3) / 1e9
             hbm = {"achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                   "dram_bytes_per_walker": hb["dram_bytes_per_walker"],
-                   "source": "profiles/r1_hbm.json (ncu dram__bytes_read+write summed over every kernel of the pass) / step time"}
-    except Exception:
-        pass
+                   "dram_bytes_per_walker": hb["dram_bytes_per_walker"], "git_sha": hb.get("git_sha"),
+                   "chunk_walkers": hb.get("chunk_walkers"),
+                   "source": hb["file"] + " (ncu dram__bytes_read+write summed over every kernel of one pass) / step time"}
     bf16_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
     peak_note = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks.get("bf16_tflops_sustained")
                  else ("MEASURED_PEAKS.json bf16_tflops" if peaks.get("bf16_tflops") else "fallback 1.59 PFLOP/s (MEASURED_PEAKS.json absent)"))
@@ -334,6 +482,9 @@ def run_ours(args):
             "peak_source": f"fp64-equivalent ceiling of the int8 tensor pipe = 2 x {bf16_peak:.1f} TF/s ({peak_note}; kind::i8 = 2x bf16 rate) "
                            f"/ {oz_products} slice products (6x6 digits, diagonals s+t<6)",
             "int8_tops_executed": (jac_tf * oz_products) if jac_tf else None, "int8_tops_peak": i8_peak,
+            "int8_tops_measured": i8_measured,
+            "int8_tops_measured_def": "this kernel's MMA issue loop alone at 757760x256x320 (no TMA, no epilogue), same run",
+            "frac_of_measured_int8": (jac_tf * oz_products / i8_measured) if (jac_tf and i8_measured) else None,
             "fp64_dmma_peak_tflops": fp64_peak,
             "frac_of_fp64_dmma_peak": (jac_tf / fp64_peak) if (jac_tf and fp64_peak) else None,
             "hbm_gbs_peak": peaks.get("hbm_gbs"), "hbm": hbm,
@@ -356,7 +507,7 @@ def run_ours(args):
         }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{system}: {cell.nelectron} e-, {cell.natm} atoms, batch {batch}/GPU, "
                                f"laplacian mode {mode}, 8 dets, hidden ((256,32),)*3",
@@ -371,19 +522,27 @@ def run_ours(args):
     }
     if e2e:
         line["e2e"] = e2e
+    if strong:
+        line["strong"] = strong
     if extras:
         line["extras"] = extras
     if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        nsamp = args.cpu_sample or max(1, min(8, int(20.0 / max(0.02, 1.5e-3 * cell.nelectron ** 2))))
-        rate, dt, out = cpu_oracle_rate(cell, klist, P, Xh.numpy(), nsamp, threads)
+        pool = OraclePool(system, cell.nelectron)
+        try:
+            S = len(pool)
+            Xc = Xh.numpy()
+            pool.step(Xc[S:2 * S] if Xc.shape[0] >= 2 * S else Xc[:S])       # untimed: first-call costs of every process
+            dt, out = pool.step(Xc[:S])
+        finally:
+            pool.close()
         # the same walkers through the GPU: report the agreement next to the rate
-        ke_g, ew_g = net.apply.hotpath().local_energy(Xd[:nsamp])
-        d = max(abs(complex(k) + float(e) - complex(kg) - float(eg)) for (k, e), kg, eg in
-                zip(out, ke_g.cpu(), ew_g.cpu()))
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{nsamp} walkers of the same batch, oracle dim_batch mode "
-                                          f"(jvp-of-grad over all 3N directions), {dt:.1f} s",
+        ke_g, ew_g = net.apply.hotpath().local_energy(Xd[:S])
+        d = max(abs(k + e - complex(kg) - float(eg)) for (k, e), kg, eg in zip(out, ke_g.cpu(), ew_g.cpu()))
+        line["cpu_baseline"] = {"value": S / dt, "unit": UNIT, "cores": S * pool.threads, "kind": "port",
+                                "sample": f"{S} walkers of the same batch evaluated concurrently by {S} oracle processes x "
+                                          f"{pool.threads} thread(s) (reference algorithm, Laplacian mode "
+                                          f"'{ORACLE_MODE[0]}' P={ORACLE_MODE[1]}: vmapped jvp-of-grad), {dt:.1f} s; "
+                                          f"host has {os.cpu_count()} cores",
                                 "max_abs_diff_vs_gpu_Ha": d}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -391,38 +550,49 @@ def run_ours(args):
 
 
 def run_reference(args):
-    """CPU oracle (reference algorithm) on the host cores; rank 0 only."""
+    """The reference's algorithm on the host cores (CPU oracle; JAX + pyscf are absent from the image): rank 0 only.
+    A step = one walker on each of S single-thread oracle processes, all concurrent; S starts at the core count and is
+    lowered (the survivors get the freed cores as BLAS threads) only if W + K steps would not finish in ~2.5 minutes."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     system = args.system
     batch = args.batch or C.SYSTEMS[system][1]
     cell, klist, X = make_inputs(system, batch)
-    pnum = make_params(cell)
-    threads = os.cpu_count() or 1
-    nsamp = args.cpu_sample or max(1, min(4, int(10.0 / max(0.02, 1.5e-3 * cell.nelectron ** 2))))
-    rates = []
-    for it in range(args.warmup + args.steps):
-        rate, dt, _ = cpu_oracle_rate(cell, klist, pnum, X[it * nsamp:(it + 1) * nsamp], nsamp, threads)
-        if it >= args.warmup:
-            rates.append((nsamp, dt))
-        if it == 0 and dt * (args.warmup + args.steps) > 240 and args.warmup > 0:
-            args.warmup = 0     # keep the whole run within a few minutes
-            rates.append((nsamp, dt))
-    n = sum(r[0] for r in rates)
-    t = sum(r[1] for r in rates)
-    value = n / t
+    pool = OraclePool(system, cell.nelectron)
+    try:
+        S = len(pool)
+        t_first, _ = pool.step(X[:S])                    # untimed: first-call costs of every process; calibrates the step time
+        budget = 200.0
+        n_steps = args.warmup + args.steps
+        if t_first * n_steps > budget and S > 1:
+            pool.shrink(max(1, int(S * budget / (t_first * n_steps))))
+            S = len(pool)
+        off, times = S, []
+        for it in range(n_steps):
+            if off + S > X.shape[0]:
+                off = 0
+            dt, _ = pool.step(X[off:off + S])
+            off += S
+            if it >= args.warmup:
+                times.append(dt)
+        threads = pool.threads
+    finally:
+        pool.close()
+    t = sum(times)
+    value = S * len(times) / t
     mode = C.SYSTEMS[system][2]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(rates), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times), "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{system}: {cell.nelectron} e-, {cell.natm} atoms, batch {batch}/GPU, "
                                f"laplacian mode {mode}, 8 dets, hidden ((256,32),)*3",
                    "system": system, "batch_per_gpu": batch, "global_batch": batch * args.gpus,
                    "note": "CPU torch-fp64 restatement of the reference algorithm (JAX/pyscf absent from the image); "
                            "each step = a bounded sample of the batch, rate is per walker"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{nsamp} walkers per step, oracle dim_batch mode"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": S * threads, "kind": "port",
+                         "sample": f"{S} walkers per step, one per oracle process ({S} processes x {threads} thread(s), "
+                                   f"Laplacian mode '{ORACLE_MODE[0]}' P={ORACLE_MODE[1]}); host has {os.cpu_count()} cores"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -431,7 +601,9 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.cpu_worker:
+        cpu_worker(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

@@ -64,6 +64,11 @@ SIGNATURES = {
     "ds_mcmc_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_uint64, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_energy_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ds_stats_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p,
+                                     C.c_void_p]),
+    "ds_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "ds_nccl_comm_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.c_int, C.c_int]),
+    "ds_nccl_comm_destroy": (C.c_int, [C.c_void_p]),
     "ds_logpsi_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ds_local_energy_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),

@@ -136,7 +136,19 @@ struct ds_ctx {
     size_t fones_n = 0;
     // layout of the last local-energy chunk (for ds_debug_buffer)
     std::vector<Region> last_regions;
+    double* scratch8 = nullptr;             // packed statistics of ds_stats_allreduce
 };
+
+double* ds_ctx_scratch8(ds_ctx* c) {
+    if (!c->scratch8) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, 8 * sizeof(double)) != cudaSuccess) return nullptr;
+        c->owned.push_back(p);
+        c->scratch8 = (double*)p;
+    }
+    return c->scratch8;
+}
+void ds_ctx_count_launches(ds_ctx* c, int n) { c->launches += n; }
 
 namespace {
 
@@ -319,28 +331,34 @@ int plan_chunk(ds_ctx* c, long long batch, bool lap, int* Wc_out, bool grad = fa
     carve(c, probe, L, 1, lap, grad);
     size_t per_walker = probe.used + 64;  // doubles (granule slack)
     size_t limit = c->ws_limit / sizeof(double);
-    long long Wc = (long long)(limit / per_walker);
-    if (Wc < 1) {
+    long long Wmax = (long long)(limit / per_walker);
+    if (Wmax < 1) {
         ds_set_error("workspace limit %zu bytes is below the %zu bytes one walker needs", c->ws_limit,
                      per_walker * sizeof(double));
         return DS_ERR_NOMEM;
     }
-    Wc = std::min<long long>(Wc, batch);
     // keep the row counts of the Jacobian GEMM within int-friendly grid sizes
-    Wc = std::min<long long>(Wc, 1 << 15);
-    *Wc_out = (int)Wc;
-    carve(c, probe, L, (int)Wc, lap, grad);
-    size_t need = probe.used;
-    if (need > c->ws.cap) {
+    Wmax = std::min<long long>(Wmax, 1 << 15);
+    for (;;) {
+        // equal chunks: 512 walkers at a 254-walker limit run as 3 x 171, not 254 + 254 + 4
+        const long long n_chunks = (batch + Wmax - 1) / Wmax;
+        const long long Wc = (batch + n_chunks - 1) / n_chunks;
+        *Wc_out = (int)Wc;
+        carve(c, probe, L, (int)Wc, lap, grad);
+        const size_t need = probe.used;
+        if (need <= c->ws.cap) return 0;
         if (c->ws.base) { DS_CUDA_CHECK(cudaFree(c->ws.base)); c->ws.base = nullptr; c->ws.cap = 0; }
         cudaError_t e = cudaMalloc((void**)&c->ws.base, need * sizeof(double));
-        if (e != cudaSuccess) {
-            ds_set_error("cannot allocate %zu bytes of workspace: %s", need * sizeof(double), cudaGetErrorString(e));
+        if (e == cudaSuccess) { c->ws.cap = need; return 0; }
+        (void)cudaGetLastError();         // clear the sticky allocation error
+        c->ws.base = nullptr;
+        if (Wc <= 1) {
+            ds_set_error("cannot allocate %zu bytes of workspace (one walker): %s", need * sizeof(double), cudaGetErrorString(e));
             return DS_ERR_NOMEM;
         }
-        c->ws.cap = need;
+        // the device is shared with the caller's allocator (torch, NCCL): retry with half the chunk
+        Wmax = std::max<long long>(1, Wc / 2);
     }
-    return 0;
 }
 
 // One chunk of walkers through the network.  lap=false: log psi only.
@@ -450,7 +468,8 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
                 if (int rc = ds_launch_slice_rows(AJ, K, rows, K, Ad, Lo.SA, st)) return rc;
                 c->launches++;
             }
-            ProfScope ps(c, st, true, 2.0 * (double)rows * H * K);     // the tcgen05 GEMM alone
+            // the tcgen05 GEMM alone; algorithmic flops count the 3N real directions, not the NDp padded rows
+            ProfScope ps(c, st, true, 2.0 * (double)Wc * N * d.ND * H * K);
             OzParams o{};
             o.Ad = Ad; o.sa = Lo.SA; o.rpg = rows; o.gstride = rows; o.goff = 0; o.n_groups = 1;
             o.Wd = c->Wd_am[l]; o.sb = c->sb_am[l]; o.N = H; o.K = K;
@@ -509,7 +528,7 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             if (int rc = gemm(c, o, GEMM_PLAIN, false, st)) return rc;
         }
         if (i8) {
-            ProfScope ps(c, st, true, 2.0 * (double)Wc * ns * d.NDp * H * 2.0 * c->npar[s]);
+            ProfScope ps(c, st, true, 2.0 * (double)Wc * ns * d.ND * H * 2.0 * c->npar[s]);
             OzParams z{};
             z.Ad = reinterpret_cast<signed char*>(Lo.AD); z.sa = Lo.SA;
             z.rpg = (long long)ns * d.NDp; z.gstride = (long long)N * d.NDp; z.goff = (long long)c->off_s[s] * d.NDp;

@@ -133,5 +133,8 @@ int ds_launch_scale(double* dst, const double* src, double a, long long n, cudaS
 // estimator.py plane-wave sums: out [batch][nq] complex (re, im); mode 0 = sum_i e^{iq.x_i}, 1 = e^{i sum_i q.x_i}
 int ds_launch_rho_q(const double* X, long long batch, int n_elec, const double* Q, int nq, int mode, double* out,
                     cudaStream_t stream);
+struct ds_ctx;
+double* ds_ctx_scratch8(ds_ctx* c);          // 8 doubles of device scratch owned by the context
+void ds_ctx_count_launches(ds_ctx* c, int n);
 int ds_launch_stats(const double* ke_re, const double* ke_im, const double* ew, long long n, double* out6,
                     cudaStream_t stream);

@@ -96,14 +96,15 @@ __global__ void scale_kernel(double* __restrict__ dst, const double* __restrict_
     if (t < n) dst[t] = a * src[t];
 }
 
-__global__ void __launch_bounds__(256) stats_kernel(const double* __restrict__ ke_re, const double* __restrict__ ke_im,
-                                                    const double* __restrict__ ew, long long n, double* __restrict__ out6) {
+// one block, fixed summation order: the statistics are bit-reproducible from run to run (the reference is deterministic)
+__global__ void __launch_bounds__(1024) stats_kernel(const double* __restrict__ ke_re, const double* __restrict__ ke_im,
+                                                     const double* __restrict__ ew, long long n, double* __restrict__ out6) {
     double v[5] = {0, 0, 0, 0, 0};
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    for (long long t = threadIdx.x; t < n; t += blockDim.x) {
         double re = ke_re[t] + ew[t], im = ke_im[t];
         v[0] += re; v[1] += im; v[2] += re * re + im * im; v[3] += ke_re[t]; v[4] += ew[t];
     }
-    __shared__ double red[5][8];
+    __shared__ double red[5][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
@@ -114,10 +115,10 @@ __global__ void __launch_bounds__(256) stats_kernel(const double* __restrict__ k
     __syncthreads();
     if (threadIdx.x < 5) {
         double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
-        atomicAdd(out6 + threadIdx.x, s);
+        for (int w = 0; w < 32; ++w) s += red[threadIdx.x][w];
+        out6[threadIdx.x] = s;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 5) out6[5] = (double)n;
+    if (threadIdx.x == 5) out6[5] = (double)n;
 }
 
 }  // namespace
@@ -154,9 +155,7 @@ int ds_launch_stats(const double* ke_re, const double* ke_im, const double* ew, 
                     cudaStream_t stream) {
     DS_CUDA_CHECK(cudaMemsetAsync(out6, 0, 6 * sizeof(double), stream));
     if (n <= 0) return 0;
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > 296) blocks = 296;
-    stats_kernel<<<blocks, 256, 0, stream>>>(ke_re, ke_im, ew, n, out6);
+    stats_kernel<<<1, 1024, 0, stream>>>(ke_re, ke_im, ew, n, out6);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -412,6 +412,16 @@ class HotPath:
                                             out.data_ptr(), self._stream()))
         return out
 
+    def stats_allreduce(self, stats6: torch.Tensor, comm=None, n_accept: Optional[torch.Tensor] = None,
+                        moves_per_rank: float = 0.0, global_variance: bool = False) -> torch.Tensor:
+        """ds_stats_allreduce: [loss, imaginary, variance, mean Re ke, mean ewald, n_ranks, n_walkers, pmove] after
+        one ncclAllReduce of the packed statistics on the current stream (``comm`` None: single rank)."""
+        out = torch.empty(8, dtype=torch.float64, device=self.tdev)
+        _lib.check(self.lib.ds_stats_allreduce(
+            self.h, comm, stats6.data_ptr(), n_accept.data_ptr() if n_accept is not None else None,
+            float(moves_per_rank), 1 if global_variance else 0, out.data_ptr(), self._stream()))
+        return out
+
     # ---- instrumentation ------------------------------------------------
     def launch_count(self) -> int:
         return int(self.lib.ds_launch_count(self.h))

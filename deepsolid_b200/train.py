@@ -76,6 +76,11 @@ def make_loss(network, batch_network, simulation_cell, clip_local_energy=5.0, cl
         hp = el_fun.hotpath()
         if ke.is_cuda:
             stats = hp.energy_stats(ke, ew)
+            comm = _dist.native_comm(hp.device)
+            if comm is not None:          # N > 1 over NCCL: the reduction is the library's (ds_stats_allreduce)
+                out8 = hp.stats_allreduce(stats, comm)
+                return out8[0], AuxiliaryLossData(variance=out8[2], local_energy=e_l, imaginary=out8[1], kinetic=ke,
+                                                  ewald=ew)
         else:
             stats = torch.stack([e_l.real.sum(), e_l.imag.sum(), (e_l.abs() ** 2).sum(), ke.real.sum(), ew.sum(),
                                  torch.tensor(float(e_l.numel()), dtype=torch.float64)])

@@ -195,6 +195,25 @@ DS_API int ds_mcmc_step(ds_ctx *ctx, double *x_dev, int64_t batch, int steps, do
 DS_API int ds_energy_stats(ds_ctx *ctx, const double *ke_re_dev, const double *ke_im_dev,
                     const double *ewald_dev, int64_t batch, double *out6_dev, void *stream);
 
+/* The hot path's collective: the statistics of `ds_energy_stats` and the Metropolis acceptance
+ * reduced over the ranks with ONE ncclAllReduce(sum) of 8 doubles on `stream`.  Replaces
+ * constants.pmean_if_pmap in train.py:78-80 (loss, imaginary, variance) and qmc.py:360-361 (pmove).
+ *   comm            ncclComm_t as void* (NULL: single rank, identity).  NCCL is bound at run time from the
+ *                   libnccl.so.2 the process has mapped; there is no link-time dependency.
+ *   stats6_dev      output of ds_energy_stats on this rank
+ *   n_accept_dev    optional: the accepted-move count of ds_mcmc_step; moves_per_rank = steps * batch_per_device
+ *   global_variance 0 = the reference as written: mean over devices of (local <|e|^2> - |local <Re e>|^2)
+ *                   (train.py:76-80 subtracts the LOCAL mean before the pmean); 1 = variance about the global mean
+ *   out8_dev        [loss, imaginary, variance, mean Re ke, mean ewald, n_ranks, n_walkers, pmove]
+ * ds_nccl_unique_id / ds_nccl_comm_init / ds_nccl_comm_destroy wrap ncclGetUniqueId / ncclCommInitRank /
+ * ncclCommDestroy for hosts that have no NCCL binding of their own (rank 0 creates the 128-byte id and ships it to
+ * the other ranks by whatever channel the host has). */
+DS_API int ds_stats_allreduce(ds_ctx *ctx, void *comm, const double *stats6_dev, const double *n_accept_dev,
+                       double moves_per_rank, int global_variance, double *out8_dev, void *stream);
+DS_API int ds_nccl_unique_id(char *id128);
+DS_API int ds_nccl_comm_init(void **comm, int n_ranks, const char *id128, int rank, int device);
+DS_API int ds_nccl_comm_destroy(void *comm);
+
 /* HOST-buffer forms: copy in, compute, copy out, synchronise the stream. */
 DS_API int ds_logpsi_host(ds_ctx *ctx, const double *x_host, int64_t batch, double *log_abs_host, double *phase_host);
 DS_API int ds_local_energy_host(ds_ctx *ctx, const double *x_host, int64_t batch, int mode, int partition_number,

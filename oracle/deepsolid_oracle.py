@@ -161,7 +161,7 @@ def logdet_matmul(xs: Sequence[torch.Tensor]):
     for s, l in slogdets[1:]:
         sign_in, slogdet = sign_in * s, slogdet + l
     # argmax gather: the max carries its own gradient, like slogdet[max_idx] in JAX
-    slogdet_max = slogdet[torch.argmax(slogdet.detach())]
+    slogdet_max = torch.gather(slogdet, 0, torch.argmax(slogdet.detach()).reshape(1))[0]     # (gather: vmap-able)
     det = sign_in * torch.exp(slogdet - slogdet_max)
     result = torch.sum(det)
     sign_out = torch.exp(1j * torch.angle(result))
