@@ -89,6 +89,7 @@ struct ds_ctx {
     bool i8_ok = false;                 // stream widths are multiples of the tcgen05 K block
     bool use_l0_kernel = true;          // layer-0 Jacobian rows by the streaming kernel (false: DMMA GEMM)
     bool use_slice_means = true;        // digits + spin-channel means of a layer's Jacobian rows in one pass
+    bool use_fused_digits = true;       // layers >= 1: the GEMM epilogue writes the next operand's digits (OZ_JACD), no fp64 Jacobian
     double* env_pi[2] = {};
     double* env_sigma[2] = {};
     double* klist[2] = {};
@@ -241,6 +242,10 @@ struct Layout {
     double *MAT[2], *LAPM[2], *DA[2];
     double *LOGDET, *TAU, *TRSQ, *TRLAP;
     double *AD, *SA;        // int8 digits of the current Jacobian operand (as bytes) and its row scales
+    double *AD2, *SA2;      // second digit buffer: with fused digits the operands of consecutive layers alternate
+    double *PMJ[DS_MAX_LAYERS];   // fused digits: compact pair-mean Jacobian rows [rows][2P] of layers >= 2
+    double *SP;             // fused digits: per-8-row partial sums of zJ^2
+    bool fused;
     double *GD, *GS;        // digits and scales of the spin-mean rows GIN (shared-mean GEMM on the int8 path)
     double *VD, *VS;        // digits and scales of the value / Laplacian rows of the current layer (per electron)
     // parameter-gradient path: per-layer activations kept by the forward, cotangent buffers of the reverse sweep
@@ -249,6 +254,13 @@ struct Layout {
     double *XINV[2], *GYs[2], *GH[2], *GZ, *GZS, *GA, *GG, *GPM[DS_MAX_LAYERS];
     double *XF;             // factor statistics: explicit rows of a layer's input
 };
+
+// The fused-digit sweep (OZ_JACD) needs exactly two 128-channel blocks and at most 64 pair-mean columns.
+inline bool fused_digits_on(const ds_ctx* c, bool lap) {
+    const DsDims& d = c->sys.d;
+    return lap && c->use_i8 && c->i8_ok && c->use_fused_digits && c->use_slice_means && d.H == 2 * OZ_TM && 2 * d.P <= 64 &&
+           d.L >= 2 && c->dbg_stop_layer < 0;
+}
 
 void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = false) {
     const DsDims& d = c->sys.d;
@@ -262,10 +274,12 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
     static const char* vn[] = {"V0", "V1", "V2", "V3"};
     static const char* ln[] = {"L0", "L1", "L2", "L3"};
     const int nbuf = grad ? d.L : c->nbuf;          // the reverse sweep needs every layer's input
+    L.fused = fused_digits_on(c, lap);
     for (int b = 0; b < nbuf; ++b) {
         L.V[b] = ws.take(vn[b], W * N * d.K1);
         L.Lp[b] = lap ? ws.take(ln[b], W * N * d.K1) : nullptr;
-        L.J[b] = lap ? ws.take(jn[b], W * N * d.NDp * d.K1) : nullptr;
+        // fused digits: only the layer-0 output exists as fp64 Jacobian rows
+        L.J[b] = (lap && !(L.fused && b > 0)) ? ws.take(jn[b], W * N * d.NDp * d.K1) : nullptr;
     }
     L.T = ws.take("T", W * N * d.H);
     L.S = lap ? ws.take("S", W * N * d.H) : nullptr;
@@ -296,6 +310,12 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
     const bool i8 = lap && c->use_i8 && c->i8_ok;
     L.AD = i8 ? ws.take("AD", (W * N * d.NDp * OZ_S * d.K1 + 7) / 8) : nullptr;
     L.SA = i8 ? ws.take("SA", W * N * d.NDp) : nullptr;
+    L.AD2 = L.fused ? ws.take("AD2", (W * N * d.NDp * OZ_S * d.K1 + 7) / 8) : nullptr;
+    L.SA2 = L.fused ? ws.take("SA2", W * N * d.NDp) : nullptr;
+    L.SP = i8 ? ws.take("SP", W * N * (d.NDp / 8) * d.H) : nullptr;
+    static const char* pmn[] = {"PMJ0", "PMJ1", "PMJ2", "PMJ3"};
+    for (int l = 0; l < DS_MAX_LAYERS; ++l)
+        L.PMJ[l] = (L.fused && l >= 2 && l < d.L) ? ws.take(pmn[l], W * N * d.NDp * 2 * d.P) : nullptr;
     L.GD = i8 ? ws.take("GD", (W * d.NDg * OZ_S * 2 * d.H + 7) / 8) : nullptr;
     L.GS = i8 ? ws.take("GS", W * d.NDg) : nullptr;
     const bool i8v = c->use_i8 && c->i8_ok && c->use_i8_value;
@@ -383,7 +403,12 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
 
     FeatParams fp{};
     fp.X = X; fp.A0V = Lo.A0V; fp.A0L = Lo.A0L; fp.A0J = Lo.A0J; fp.RAE = Lo.RAE;
-    for (int l = 1; l < L; ++l) { fp.AV[l] = Lo.V[inb(l)]; fp.AL[l] = Lo.Lp[inb(l)]; fp.AJ[l] = Lo.J[inb(l)]; }
+    const bool fused = Lo.fused;
+    for (int l = 1; l < L; ++l) {
+        fp.AV[l] = Lo.V[inb(l)]; fp.AL[l] = Lo.Lp[inb(l)];
+        if (fused && l >= 2) { fp.AJ[l] = Lo.PMJ[l]; fp.ldj[l] = 2 * d.P; fp.joff[l] = 0; }      // compact: consumed by OZ_JACD
+        else { fp.AJ[l] = Lo.J[inb(l)]; fp.ldj[l] = d.K1; fp.joff[l] = H; }
+    }
     for (int l = 0; l < L - 1; ++l) { fp.Wp[l] = c->Wp[l]; fp.bp[l] = c->bp[l]; }
     if (int rc = ds_launch_features(sys, fp, Wc, lap, st)) return rc;
     c->launches++;
@@ -399,16 +424,29 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         double* OL = Lo.Lp[outb(l)];
         double* OJ = Lo.J[outb(l)];
         const bool res = (C == H);
-        if (lap) DS_CUDA_CHECK(cudaMemsetAsync(Lo.S, 0, (size_t)Wc * N * H * sizeof(double), st));
+        // fused digits (layers >= 1): the operand digits of consecutive layers alternate between AD and AD2; layer 1's
+        // come from the fp64 rows the layer-0 kernel wrote, every later layer's from the previous GEMM's epilogue
+        const bool fl = fused && l > 0;
+        signed char* dig_in = reinterpret_cast<signed char*>(((l - 1) & 1) ? Lo.AD2 : Lo.AD);
+        double* sa_in = ((l - 1) & 1) ? Lo.SA2 : Lo.SA;
+        signed char* dig_out = reinterpret_cast<signed char*>((l & 1) ? Lo.AD2 : Lo.AD);
+        double* sa_out = (l & 1) ? Lo.SA2 : Lo.SA;
         const bool i8_layer = lap && c->use_i8 && c->i8_ok && l > 0;
+        // (the tcgen05 kernels write per-8-row partial sums of zJ^2, reduced in a fixed order; only the fp64 DMMA
+        //  fallback accumulates into S with atomics and needs it cleared)
+        if (lap && !i8_layer) DS_CUDA_CHECK(cudaMemsetAsync(Lo.S, 0, (size_t)Wc * N * H * sizeof(double), st));
         const bool fused_means = i8_layer && c->use_slice_means;
-        if (fused_means) {
+        if (fl && l >= 2) {
+            // spin-channel means of the Jacobian rows straight from their digits (no fp64 rows exist)
+            if (int rc = ds_launch_means_digits(dig_in, sa_in, K, C, Wc, d.n_up, N, d.NDp, d.NDg, Lo.GIN, 2 * C, st)) return rc;
+            c->launches++;
+        } else if (fused_means) {
             // digits of the Jacobian rows and their spin-channel means in one pass over the fp64 rows
             if (int rc = ds_launch_slice_means(AJ, K, K, C, Wc, d.n_up, N, d.NDp, d.NDg, reinterpret_cast<signed char*>(Lo.AD),
                                                Lo.SA, Lo.GIN, 2 * C, st)) return rc;
             c->launches++;
         }
-        if (int rc = ds_launch_means(d, Wc, C, AJ, K, AV, AL, K, Lo.GIN, 2 * C, lap, st, fused_means)) return rc;
+        if (int rc = ds_launch_means(d, Wc, C, AJ, K, AV, AL, K, Lo.GIN, 2 * C, lap, st, fused_means || fl)) return rc;
         c->launches++;
         {   // shared spin-mean contribution, once per walker and direction
             GemmParams g{};
@@ -461,7 +499,25 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             v.A = AV; v.lda = K; v.M = (long long)Wc * N; v.C = OV; v.ldc = d.K1; v.R = AV; v.ldr = K;
             if (int rc = gemm(c, v, GEMM_VALUE, res, st)) return rc;
         }
-        if (i8_layer) {
+        if (fl) {
+            const long long rows = (long long)Wc * N * d.NDp;
+            const bool last = (l == L - 1);
+            {
+                ProfScope ps(c, st, true, 2.0 * (double)Wc * N * d.ND * H * K);
+                OzParams o{};
+                o.Ad = dig_in; o.sa = sa_in; o.rpg = rows; o.gstride = rows; o.goff = 0; o.n_groups = 1;
+                o.Wd = c->Wd_am[l]; o.sb = c->sb_am[l]; o.N = H; o.K = K;
+                o.G = Lo.GOUT; o.ldg = H; o.n_elec = N; o.NDp = d.NDp; o.NDg = d.NDg;
+                o.T = Lo.T; o.ldt = H; o.SP = Lo.SP;
+                o.Dout = dig_out; o.sa_out = sa_out;
+                // the last layer feeds the orbital projection: own columns only
+                o.Kout = last ? H : d.K1; o.PM = last ? nullptr : Lo.PMJ[l + 1]; o.npm = last ? 0 : 2 * d.P;
+                if (int rc = ds_launch_oz_gemm(o, OZ_JACD, res, st)) return rc;
+                c->launches++;
+            }
+            if (int rc = ds_launch_sp_reduce(Lo.SP, H, (long long)Wc * N, d.NDp / 8, H, Lo.S, st)) return rc;
+            c->launches++;
+        } else if (i8_layer) {
             const long long rows = (long long)Wc * N * d.NDp;
             signed char* Ad = reinterpret_cast<signed char*>(Lo.AD);
             if (!fused_means) {
@@ -474,9 +530,10 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             o.Ad = Ad; o.sa = Lo.SA; o.rpg = rows; o.gstride = rows; o.goff = 0; o.n_groups = 1;
             o.Wd = c->Wd_am[l]; o.sb = c->sb_am[l]; o.N = H; o.K = K;
             o.C = OJ; o.ldc = d.K1; o.G = Lo.GOUT; o.ldg = H; o.n_elec = N; o.NDp = d.NDp; o.NDg = d.NDg;
-            o.T = Lo.T; o.ldt = H; o.S = Lo.S; o.R = AJ; o.ldr = K;
+            o.T = Lo.T; o.ldt = H; o.S = Lo.S; o.SP = Lo.SP; o.R = AJ; o.ldr = K;
             if (int rc = ds_launch_oz_gemm(o, OZ_JAC, res, st)) return rc;
-            c->launches++;
+            if (int rc = ds_launch_sp_reduce(Lo.SP, H, (long long)Wc * N, d.NDp / 8, H, Lo.S, st)) return rc;
+            c->launches += 2;
         } else if (lap && l == 0 && !res && c->use_l0_kernel) {
             if (int rc = ds_launch_l0_jac(d, Wc, AJ, c->B_am[0], Lo.GOUT, H, Lo.T, H, Lo.S, OJ, d.K1, st)) return rc;
             c->launches++;
@@ -508,8 +565,12 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
     c->launches++;
     const bool i8 = lap && c->use_i8 && c->i8_ok;
     const long long jrows = (long long)Wc * N * d.NDp;
-    if (i8) {     // digits of the last layer's Jacobian rows (own columns), shared by both spins
-        if (int rc = ds_launch_slice_rows(hJ, d.K1, jrows, H, reinterpret_cast<signed char*>(Lo.AD), Lo.SA, st)) return rc;
+    // digits of the last layer's Jacobian rows (own columns), shared by both spins: written by the last layer's GEMM
+    // epilogue on the fused path, else formed here from the fp64 rows
+    signed char* orb_dig = reinterpret_cast<signed char*>((fused && ((L - 1) & 1)) ? Lo.AD2 : Lo.AD);
+    double* orb_sa = (fused && ((L - 1) & 1)) ? Lo.SA2 : Lo.SA;
+    if (i8 && !fused) {
+        if (int rc = ds_launch_slice_rows(hJ, d.K1, jrows, H, orb_dig, orb_sa, st)) return rc;
         c->launches++;
     }
     for (int s = 0; s < 2; ++s) {
@@ -530,7 +591,7 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         if (i8) {
             ProfScope ps(c, st, true, 2.0 * (double)Wc * ns * d.ND * H * 2.0 * c->npar[s]);
             OzParams z{};
-            z.Ad = reinterpret_cast<signed char*>(Lo.AD); z.sa = Lo.SA;
+            z.Ad = orb_dig; z.sa = orb_sa;
             z.rpg = (long long)ns * d.NDp; z.gstride = (long long)N * d.NDp; z.goff = (long long)c->off_s[s] * d.NDp;
             z.n_groups = Wc;
             z.Wd = c->Wd_orb[s]; z.sb = c->sb_orb[s]; z.N = 2 * c->npar[s]; z.K = H;
@@ -781,6 +842,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     if (const char* ev = getenv("DS_NO_SLICE_MEANS")) c->use_slice_means = atoi(ev) == 0;
     if (const char* ev = getenv("DS_NO_I8_MEANS")) c->use_i8_means = atoi(ev) == 0;
     if (const char* ev = getenv("DS_NO_I8_VALUE")) c->use_i8_value = atoi(ev) == 0;
+    if (const char* ev = getenv("DS_NO_FUSED_DIGITS")) c->use_fused_digits = atoi(ev) == 0;
     if (const char* ev = getenv("DS_WS_GIB")) { double g = atof(ev); if (g >= 0.25) c->ws_limit = (size_t)(g * 1073741824.0); }
     DsDims& d = c->sys.d;
     d.n_up = sd->n_up; d.n_dn = sd->n_dn; d.N = sd->n_up + sd->n_dn; d.A = sd->n_atoms_prim;
@@ -1464,6 +1526,7 @@ extern "C" int ds_debug_set_int(ds_ctx* c, const char* key, int value) {
     if (!strcmp(key, "i8")) { c->use_i8 = value != 0; return 0; }
     if (!strcmp(key, "l0_kernel")) { c->use_l0_kernel = value != 0; return 0; }
     if (!strcmp(key, "slice_means")) { c->use_slice_means = value != 0; return 0; }
+    if (!strcmp(key, "fused_digits")) { c->use_fused_digits = value != 0; return 0; }
     ds_set_error("unknown debug key %s", key);
     return -1;
 }

@@ -135,10 +135,11 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
                     }
                 } else if (lane < P) {
                     double* aj = fp.AJ[l];
-                    long long c_on = H + sj * P + lane, c_off = H + (1 - sj) * P + lane;
-                    aj[(rj + 0) * K1 + c_on] = cur.g0 * invn; aj[(rj + 0) * K1 + c_off] = 0.0;
-                    aj[(rj + 1) * K1 + c_on] = cur.g1 * invn; aj[(rj + 1) * K1 + c_off] = 0.0;
-                    aj[(rj + 2) * K1 + c_on] = cur.g2 * invn; aj[(rj + 2) * K1 + c_off] = 0.0;
+                    const long long ldj = fp.ldj[l];
+                    long long c_on = fp.joff[l] + sj * P + lane, c_off = fp.joff[l] + (1 - sj) * P + lane;
+                    aj[(rj + 0) * ldj + c_on] = cur.g0 * invn; aj[(rj + 0) * ldj + c_off] = 0.0;
+                    aj[(rj + 1) * ldj + c_on] = cur.g1 * invn; aj[(rj + 1) * ldj + c_off] = 0.0;
+                    aj[(rj + 2) * ldj + c_on] = cur.g2 * invn; aj[(rj + 2) * ldj + c_off] = 0.0;
                 }
             }
             if (l == L - 1) break;
@@ -170,15 +171,21 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
             woff += Pl * P + P;
         }
     }
-    // cross-warp reduction of the sums of this spin channel
+    // cross-warp reduction of the sums of this spin channel, one warp after the other: a fixed summation order, so
+    // that the features (and everything downstream) are bit-reproducible from run to run
+    for (int wp = 0; wp < nwarps; ++wp) {
+        if (warp == wp) {
 #pragma unroll
-    for (int l = 0; l < DS_MAX_LAYERS; ++l) {
-        if (l >= L) break;
+            for (int l = 0; l < DS_MAX_LAYERS; ++l) {
+                if (l >= L) break;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            if (!JETS && c > 0) break;
-            atomicAdd(&sums[((sj * L + l) * 5 + c) * 32 + lane], acc[l][c]);
+                for (int c = 0; c < 5; ++c) {
+                    if (!JETS && c > 0) break;
+                    sums[((sj * L + l) * 5 + c) * 32 + lane] += acc[l][c];
+                }
+            }
         }
+        __syncthreads();
     }
     }   // spin channel
     __syncthreads();
@@ -208,9 +215,10 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
                 fp.AV[l][e * K1 + col] = sv[0] * invn;
                 if (JETS) {
                     fp.AL[l][e * K1 + col] = 2.0 * sv[4 * 32] * invn;
-                    fp.AJ[l][(r + 0) * K1 + col] = -sv[1 * 32] * invn;
-                    fp.AJ[l][(r + 1) * K1 + col] = -sv[2 * 32] * invn;
-                    fp.AJ[l][(r + 2) * K1 + col] = -sv[3 * 32] * invn;
+                    const long long ldj = fp.ldj[l], cj = fp.joff[l] + s * P + lane_c;
+                    fp.AJ[l][(r + 0) * ldj + cj] = -sv[1 * 32] * invn;
+                    fp.AJ[l][(r + 1) * ldj + cj] = -sv[2 * 32] * invn;
+                    fp.AJ[l][(r + 2) * ldj + cj] = -sv[3 * 32] * invn;
                 }
             }
         }
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
         for (int l = 1; l < DS_MAX_LAYERS; ++l) {
             if (l >= L) break;
             for (int t = tid; t < npad * 2 * P; t += blockDim.x)
-                fp.AJ[l][(e * NDp + ND + t / (2 * P)) * K1 + H + t % (2 * P)] = 0.0;
+                fp.AJ[l][(e * NDp + ND + t / (2 * P)) * fp.ldj[l] + fp.joff[l] + t % (2 * P)] = 0.0;
         }
     }
 }

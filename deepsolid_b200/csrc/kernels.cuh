@@ -11,7 +11,8 @@ struct FeatParams {
     double *A0V, *A0L, *A0J;         // layer-0 operand matrices, ld = K0
     double* AV[DS_MAX_LAYERS];       // value rows of layer l >= 1 (ld K1); pair-mean columns written here
     double* AL[DS_MAX_LAYERS];       // Laplacian rows
-    double* AJ[DS_MAX_LAYERS];       // Jacobian rows
+    double* AJ[DS_MAX_LAYERS];       // Jacobian rows: the 2P pair-mean columns of row r live at AJ[l][r * ldj[l] + joff[l] ..]
+    int ldj[DS_MAX_LAYERS], joff[DS_MAX_LAYERS];   // (ld K1, offset H inside the layer's operand; ld 2P, offset 0 when compact)
     double* RAE;                     // [(w*N+i)*A + a][DS_RAE_STRIDE] jets of the electron-atom distance and relative vector
     const double* Wp[DS_MAX_LAYERS]; // pair-stream weights [in x P]
     const double* bp[DS_MAX_LAYERS]; // pair-stream biases [P]

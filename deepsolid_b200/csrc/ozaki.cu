@@ -111,6 +111,109 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- thread-block cluster / distributed shared memory (OZ_JACD: the two 128-channel CTAs of a row tile) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t caddr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(caddr), "r"(v) : "memory");
+}
+// arrive on an mbarrier of another CTA; release at cluster scope orders this thread's earlier remote stores before it
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cbar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cbar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// int32 -> fp64 without the conversion unit: the integer sits in the low mantissa word of 2^52 + 2^31 + v
+__device__ __forceinline__ double i32_to_f64(int v) {
+    return __hiloint2double(0x43300000, (int)((unsigned)v ^ 0x80000000u)) - 4503601774854144.0;
+}
+// transposed warp reductions (max of unsigned): v[r] over the 32 lanes for 16 (4) rows in 16 (6) shuffles.
+// Result for row r(lane) = 8 b4 + 4 b3 + 2 b2 + b1 (resp. 2 b4 + b3) of the lane index is returned in every lane.
+__device__ __forceinline__ unsigned warp_rowmax16(const unsigned (&v)[16], int lane) {
+    unsigned a[8], b[4], c[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const unsigned keep = h16 ? v[i + 8] : v[i], give = h16 ? v[i] : v[i + 8];
+        a[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 16));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const unsigned keep = h8 ? a[i + 4] : a[i], give = h8 ? a[i] : a[i + 4];
+        b[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 8));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const unsigned keep = h4 ? b[i + 2] : b[i], give = h4 ? b[i] : b[i + 2];
+        c[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 4));
+    }
+    const unsigned keep = h2 ? c[1] : c[0], give = h2 ? c[0] : c[1];
+    unsigned m = max(keep, __shfl_xor_sync(0xffffffffu, give, 2));
+    return max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+}
+__device__ __forceinline__ unsigned warp_rowmax4(const unsigned (&v)[4], int lane) {
+    unsigned a[2];
+    const bool h16 = lane & 16, h8 = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const unsigned keep = h16 ? v[i + 2] : v[i], give = h16 ? v[i] : v[i + 2];
+        a[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 16));
+    }
+    const unsigned keep = h8 ? a[1] : a[0], give = h8 ? a[0] : a[1];
+    unsigned m = max(keep, __shfl_xor_sync(0xffffffffu, give, 8));
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    return max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+}
+// six balanced base-256 digits of x at row exponent e (see slice_row_warp), stored at out[s * pitch], s = 0..5
+__device__ __forceinline__ void store_digits(double x, double f, bool bad, signed char* __restrict__ out, long long pitch) {
+    const double MAGIC = 6755399441055744.0;          // 2^52 + 2^51
+    const double t = bad ? MAGIC : fma(x, f, MAGIC);
+    unsigned l = (unsigned)__double2loint(t), h = (unsigned)__double2hiint(t);
+    const unsigned l2 = l + 0x80808080u;
+    h += 0x80u + (l2 < l ? 1u : 0u);
+    l = l2 ^ 0x80808080u;
+    h ^= 0x80u;
+    out[0] = (signed char)(h >> 8);
+    out[pitch] = (signed char)h;
+    out[2 * pitch] = (signed char)(l >> 24);
+    out[3 * pitch] = (signed char)(l >> 16);
+    out[4 * pitch] = (signed char)(l >> 8);
+    out[5 * pitch] = (signed char)l;
+}
+
 // K-major, SWIZZLE_64B shared-memory matrix descriptor (rows of 64 bytes, 8-row groups 512 B apart)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -328,6 +431,11 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     constexpr int NBUF = Cfg::NBUF, SET_WARPS = Cfg::SET_WARPS, A_SLICE_T = Cfg::A_SLICE_T, STAGE_T = Cfg::STAGE_T;
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
+    // OZ_JACD: row maxima (IEEE high words of |x|) of a tile's 64 rows -- per epilogue warp, of the pair-mean columns,
+    // and the other CTA's (written by it through DSMEM, two slots alternating with the tile parity)
+    constexpr bool JD = (MODE == OZ_JACD);
+    __shared__ unsigned xown[JD ? 2 : 1][4][4][16], xpm[JD ? 2 : 1][4][16], xrem[JD ? 2 : 1][64];
+    __shared__ __align__(8) uint64_t xbar[JD ? 2 : 1][4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.K / OZ_BK;
@@ -336,12 +444,16 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], SET_WARPS); }
+        if (JD)
+            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 4; ++j) mbar_init(&xbar[i][j], 16);     // 16 row maxima arrive from the other CTA
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (JD) cluster_sync_all();          // the peer's barriers exist before anything is sent to them
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0) {
@@ -483,27 +595,125 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 int d = (int)((unsigned)prow0 - e * (unsigned)p.NDp);
                 unsigned w = e / (unsigned)p.n_elec;
                 int ie = (int)(e - w * (unsigned)p.n_elec);
-                long long cur_e = -1;
-                double sacc = 0.0, d1 = 0.0;
 #pragma unroll
                 for (int b = 0; b < EPI_COLS / 8; ++b) {
                     if (8 * b < nvalid) {                                   // warp-uniform; blocks are all-or-nothing
-                        if ((long long)e != cur_e) {
-                            if (cur_e >= 0 && nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc);
-                            cur_e = e; sacc = 0.0;
-                            const double t = nv ? p.T[(long long)e * p.ldt + n] : 0.0;
-                            d1 = 1.0 - t * t;
-                        }
+                        const double t = nv ? p.T[(long long)e * p.ldt + n] : 0.0;
+                        const double d1 = 1.0 - t * t;
                         const double* gp = p.G + ((long long)w * p.NDg + d) * p.ldg + n;
                         const double* rp = RES ? p.R + (prow0 + 8 * b) * (long long)p.ldr + n : nullptr;
                         double* cp = p.C + (prow0 + 8 * b) * (long long)p.ldc + n;
-                        if (full) sacc = jac_block8<RES, true>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbn, d1, true, sacc);
-                        else sacc = jac_block8<RES, false>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbn, d1, nv, sacc);
+                        double sacc;
+                        if (full) sacc = jac_block8<RES, true>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbn, d1, true, 0.0);
+                        else sacc = jac_block8<RES, false>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbn, d1, nv, 0.0);
+                        // partial sum of zJ^2 over this aligned group of 8 directions; summed per electron in a fixed
+                        // order by sp_reduce_kernel (deterministic, unlike an atomicAdd into S)
+                        if (nv) p.SP[((prow0 + 8 * b) >> 3) * (long long)p.ldt + n] = sacc;
                     }
                     d += 8;
                     if (d >= p.NDp) { d -= p.NDp; ++e; if (++ie == p.n_elec) { ie = 0; ++w; } }
                 }
-                if (cur_e >= 0 && nv) atomicAdd(p.S + cur_e * (long long)p.ldt + n, sacc);
+            } else if (MODE == OZ_JACD) {
+                // Both channel blocks are full (N == 2 OZ_TM, checked by the launcher): no channel predicates.
+                // B1: the Jacobian rows of the layer output, kept in registers (zz[j] <- J'[(e,d_j), n]).
+                const double rs2 = 0.70710678118654752440;
+                {
+                    unsigned e = (unsigned)prow0 / (unsigned)p.NDp;
+                    int d = (int)((unsigned)prow0 - e * (unsigned)p.NDp);
+                    unsigned w = e / (unsigned)p.n_elec;
+                    int ie = (int)(e - w * (unsigned)p.n_elec);
+#pragma unroll
+                    for (int b = 0; b < EPI_COLS / 8; ++b) {
+                        if (8 * b < nvalid) {                               // warp-uniform; aligned groups of 8 rows share an electron
+                            const double t = p.T[(long long)e * p.ldt + n];
+                            const double d1 = 1.0 - t * t;
+                            const double* gp = p.G + ((long long)w * p.NDg + d) * p.ldg + n;
+                            double gv[8], sc[8];
+                            int rh[8], rl[8];
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) {
+                                sc[jj] = __ldg(sap + 8 * b + jj);
+                                gv[jj] = gp[(long long)jj * p.ldg];
+                                if (RES) {
+                                    // residual row = own columns of the INPUT operand, from its digits (L2-resident: the
+                                    // TMA producer fetched this tile a few microseconds ago)
+                                    const signed char* rp = p.Ad + (prow0 + 8 * b + jj) * (long long)(OZ_S * p.K) + n;
+                                    rh[jj] = ((int)rp[0] * 256 + (int)rp[p.K]) * 256 + (int)rp[2 * p.K];
+                                    rl[jj] = ((int)rp[3 * p.K] * 256 + (int)rp[4 * p.K]) * 256 + (int)rp[5 * p.K];
+                                }
+                            }
+                            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) {
+                                const double zj = fma(zz[8 * b + jj], sc[jj] * sbn, gv[jj]);
+                                if (jj & 1) s1 = fma(zj, zj, s1); else s0 = fma(zj, zj, s0);
+                                double o = d1 * zj;
+                                if (RES) {
+                                    const double r = fma(i32_to_f64(rh[jj]), 16777216.0, i32_to_f64(rl[jj])) * (sc[jj] * 9.094947017729282e-13);  // 2^-40
+                                    o = (r + o) * rs2;
+                                }
+                                zz[8 * b + jj] = o;
+                            }
+                            p.SP[((prow0 + 8 * b) >> 3) * (long long)p.ldt + n] = s0 + s1;
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) zz[8 * b + jj] = 0.0;
+                        }
+                        d += 8;
+                        if (d >= p.NDp) { d -= p.NDp; ++e; if (++ie == p.n_elec) { ie = 0; ++w; } }
+                    }
+                }
+                // B2: row maximum over the 2 x 128 channels and the pair-mean columns.
+                const uint32_t crank = cluster_ctarank();
+                const int slot = (int)(it & 1u);
+                const int pmc = (int)crank * 32 + lane;                      // pair-mean column of this lane (this CTA's half)
+                const bool pmv_ok = p.PM != nullptr && pmc < p.npm;
+                double pmv[4];
+                {
+                    unsigned hw[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) hw[j] = (unsigned)__double2hiint(zz[j]) & 0x7fffffffu;
+                    const unsigned m = warp_rowmax16(hw, lane);
+                    if ((lane & 1) == 0) xown[slot][cg][q][((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = m;
+                    unsigned hp[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int j = 4 * q + r;                             // this warp digitises pair-mean rows 4q .. 4q+3 of the 16
+                        pmv[r] = (pmv_ok && j < nvalid) ? p.PM[(prow0 + j) * (long long)p.npm + pmc] : 0.0;
+                        hp[r] = (unsigned)__double2hiint(pmv[r]) & 0x7fffffffu;
+                    }
+                    const unsigned mp = warp_rowmax4(hp, lane);
+                    if ((lane & 7) == 0) xpm[slot][cg][4 * q + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)] = mp;
+                }
+                named_bar_sync(1 + cg, 128);                                 // the four warps of this 16-row group
+                unsigned mine = 0u;
+                if (lane < 16) {
+                    mine = max(max(xown[slot][cg][0][lane], xown[slot][cg][1][lane]), max(xown[slot][cg][2][lane], xown[slot][cg][3][lane]));
+                    mine = max(mine, xpm[slot][cg][lane]);
+                    if (q == 0) {                                            // one warp of the group tells the other CTA
+                        st_cluster_u32(map_to_cta(smem_u32(&xrem[slot][cg * 16 + lane]), crank ^ 1u), mine);
+                        mbar_arrive_cluster(map_to_cta(smem_u32(&xbar[slot][cg]), crank ^ 1u));
+                    }
+                }
+                mbar_wait_cluster(&xbar[slot][cg], (it >> 1) & 1u);
+                if (lane < 16) mine = max(mine, xrem[slot][cg * 16 + lane]);
+                // B3: digits of the own channel and of this CTA's share of the pair-mean columns, row scales.
+                const long long opitch = (long long)p.Kout;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const unsigned mxh = __shfl_sync(0xffffffffu, mine, j);
+                    if (j < nvalid) {
+                        const bool bad = mxh >= 0x7ff00000u;
+                        int ex = (int)(mxh >> 20) - 1022;
+                        if (ex < -900) ex = -900;
+                        const double f = __hiloint2double((1023 + 8 * OZ_S - 2 - ex) << 20, 0);
+                        signed char* orow = p.Dout + (prow0 + j) * (OZ_S * opitch);
+                        store_digits(zz[j], f, bad, orow + n, opitch);
+                        if ((j >> 2) == q && pmv_ok) store_digits(pmv[j & 3], f, bad, orow + p.N + pmc, opitch);
+                        if (crank == 0 && q == 0 && lane == j)
+                            p.sa_out[prow0 + j] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __hiloint2double((1023 + ex - 6) << 20, 0);
+                    }
+                }
             } else if (MODE == OZ_VALUE || MODE == OZ_LAP) {
                 // rows are electrons e = prow0 + j (value or Laplacian row of each); walker = e / n_elec
                 unsigned w = (unsigned)prow0 / (unsigned)p.n_elec;
@@ -569,6 +779,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (JD) cluster_sync_all();          // neither CTA leaves while the other may still write into its shared memory
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
@@ -581,6 +792,59 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
     if (i >= (long long)K * N) return;
     const int n = (int)(i / K), k = (int)(i - (long long)n * K);
     Bt[i] = B[(long long)k * N + n];
+}
+
+// S[e][n] = sum over the NDp/8 aligned 8-row groups of electron e of the partial sums written by OZ_JACD (fixed order)
+__global__ void __launch_bounds__(256) sp_reduce_kernel(const double* __restrict__ SP, int ld, int nblk, int H,
+                                                        double* __restrict__ S) {
+    const long long e = blockIdx.x;
+    for (int n = threadIdx.x; n < H; n += blockDim.x) {
+        const double* src = SP + e * (long long)nblk * ld + n;
+        double acc = 0.0;
+        for (int b = 0; b < nblk; ++b) acc += src[(long long)b * ld];
+        S[e * (long long)ld + n] = acc;
+    }
+}
+
+// Spin-channel means of Jacobian rows that exist only as digits: a warp owns (walker w, direction d), a lane 8
+// consecutive columns; row value = sa[r] 2^-40 (d0 2^40 + ... + d5).
+__global__ void __launch_bounds__(256) means_digits_kernel(const signed char* __restrict__ Ad, const double* __restrict__ sa,
+                                                           int K, int C, int n_walkers, int n_up, int n_elec, int NDp,
+                                                           int NDg, double* __restrict__ GIN, int ldgin) {
+    const long long wd = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wd >= (long long)n_walkers * NDp) return;
+    const int lane = threadIdx.x & 31;
+    const int w = (int)(wd / NDp), d = (int)(wd - (long long)w * NDp);
+    double* gout = GIN + ((long long)w * NDg + d) * ldgin;
+    const int c0 = lane * 8;
+    if (c0 >= C) return;                                  // C <= 256: one 8-column group per lane
+    long long r = ((long long)w * n_elec) * NDp + d;
+    for (int s = 0; s < 2; ++s) {
+        const int ibeg = s ? n_up : 0, iend = s ? n_elec : n_up;
+        double sum[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum[j] = 0.0;
+        for (int i = ibeg; i < iend; ++i, r += NDp) {
+            const signed char* rp = Ad + r * (long long)(OZ_S * K) + c0;
+            uint2 dg[OZ_S];
+#pragma unroll
+            for (int t = 0; t < OZ_S; ++t) dg[t] = *reinterpret_cast<const uint2*>(rp + (long long)t * K);
+            const double scale = sa[r] * 9.094947017729282e-13;              // 2^-40
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int sh = (j & 3) * 8;
+                int b[OZ_S];
+#pragma unroll
+                for (int t = 0; t < OZ_S; ++t) b[t] = (int)(signed char)(((j < 4 ? dg[t].x : dg[t].y) >> sh) & 0xffu);
+                const int hi = (b[0] * 256 + b[1]) * 256 + b[2], lo = (b[3] * 256 + b[4]) * 256 + b[5];
+                sum[j] = fma(fma((double)hi, 16777216.0, (double)lo), scale, sum[j]);
+            }
+        }
+        const double inv = 1.0 / (double)(iend - ibeg);
+        double2* o = reinterpret_cast<double2*>(gout + s * C + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = make_double2(sum[2 * j] * inv, sum[2 * j + 1] * inv);
+    }
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -633,7 +897,23 @@ int launch_tn(const OzParams& p, cudaStream_t stream) {
     const int tpg = (int)((p.rpg + TN - 1) / TN);
     const int n_cb = (p.N + OZ_TM - 1) / OZ_TM;
     const long long n_tiles = (long long)tpg * p.n_groups * n_cb;
-    const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
+    int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
+    if (MODE == OZ_JACD) {
+        // CTA pairs (2j, 2j+1) = the two channel blocks of one row tile: launched as clusters of two so that the
+        // row maxima can cross through distributed shared memory (n_cb == 2: tile % 2 = blockIdx.x % 2 when the grid is even)
+        grid &= ~1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(OZ_THREADS);
+        cfg.dynamicSmemBytes = SMEM_T;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        DS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, oz_gemm_kernel<MODE, RES, TN, ND>, tmW, tmA, p, tpg, n_cb, n_tiles));
+        return 0;
+    }
     oz_gemm_kernel<MODE, RES, TN, ND><<<grid, OZ_THREADS, SMEM_T, stream>>>(tmW, tmA, p, tpg, n_cb, n_tiles);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -676,6 +956,26 @@ int ds_launch_slice_means(const double* A, int lda, int K, int C, int n_walkers,
     return 0;
 }
 
+int ds_launch_sp_reduce(const double* SP, int ld, long long n_elec_rows, int blocks_per_electron, int H, double* S,
+                        cudaStream_t stream) {
+    if (n_elec_rows <= 0) return 0;
+    sp_reduce_kernel<<<(unsigned)n_elec_rows, 256, 0, stream>>>(SP, ld, blocks_per_electron, H, S);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_means_digits(const signed char* Ad, const double* sa, int K, int C, int n_walkers, int n_up, int n_elec,
+                           int NDp, int NDg, double* GIN, int ldgin, cudaStream_t stream) {
+    if (n_walkers <= 0) return 0;
+    DS_REQUIRE(K % 8 == 0 && C % 8 == 0 && C <= 256 && C <= K && ldgin % 2 == 0, "means_digits: C must be a multiple of 8, <= 256 (K=%d C=%d)", K, C);
+    const long long warps = (long long)n_walkers * NDp;
+    const int wpb = 8;
+    means_digits_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(Ad, sa, K, C, n_walkers, n_up, n_elec, NDp,
+                                                                                     NDg, GIN, ldgin);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 int ds_launch_transpose(const double* B, int K, int N, double* Bt, cudaStream_t stream) {
     const long long tot = (long long)K * N;
     if (tot <= 0) return 0;
@@ -691,10 +991,16 @@ int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t s
                "oz_gemm: digit buffers must be 16-byte aligned");
     if (mode == OZ_VALUE || mode == OZ_LAP)
         DS_REQUIRE(p.n_groups == 1 && p.rpg < (1LL << 31), "oz_gemm: value / Laplacian rows come as one group");
-    if (mode == OZ_JAC || mode == OZ_ORBJ) {
+    if (mode == OZ_JACD) {
+        DS_REQUIRE(p.N == 2 * OZ_TM && p.n_groups == 1 && p.goff == 0, "oz_gemm: the fused-digit mode needs exactly two channel blocks (N = %d)", p.N);
+        DS_REQUIRE(p.Dout && p.sa_out && p.SP && p.Kout % 16 == 0 && p.Kout >= p.N + p.npm && p.npm <= 64 && p.npm >= 0,
+                   "oz_gemm: bad digit output (Kout=%d npm=%d)", p.Kout, p.npm);
+        DS_REQUIRE(!residual || p.K >= p.N, "oz_gemm: the residual rows are the first N columns of the operand");
+    }
+    if (mode == OZ_JAC || mode == OZ_ORBJ || mode == OZ_JACD) {
         DS_REQUIRE(p.NDp % 8 == 0 && p.rpg % 8 == 0 && p.goff % 8 == 0 && p.gstride % 8 == 0,
                    "oz_gemm: Jacobian rows must come in aligned groups of 8 (NDp=%d rpg=%lld)", p.NDp, p.rpg);
-        DS_REQUIRE(p.rpg * (mode == OZ_JAC ? 1 : p.n_groups) < (1LL << 31), "oz_gemm: too many Jacobian rows in one launch");
+        DS_REQUIRE(p.rpg * (mode == OZ_ORBJ ? p.n_groups : 1) < (1LL << 31), "oz_gemm: too many Jacobian rows in one launch");
     }
     switch (mode) {
         case OZ_PLAIN: return launch<OZ_PLAIN, false>(p, stream);
@@ -702,6 +1008,7 @@ int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t s
         case OZ_ORBJ: return launch<OZ_ORBJ, false>(p, stream);
         case OZ_VALUE: return residual ? launch<OZ_VALUE, true>(p, stream) : launch<OZ_VALUE, false>(p, stream);
         case OZ_LAP: return residual ? launch<OZ_LAP, true>(p, stream) : launch<OZ_LAP, false>(p, stream);
+        case OZ_JACD: return residual ? launch_tn<OZ_JACD, true, 64, 6>(p, stream) : launch_tn<OZ_JACD, false, 64, 6>(p, stream);
     }
     ds_set_error("oz_gemm: unknown mode %d", mode);
     return -1;

@@ -30,7 +30,11 @@ enum OzMode {
     OZ_JAC = 1,     // one-electron stream Jacobian rows (see gemm_f64.cuh GEMM_JAC)
     OZ_ORBJ = 2,    // orbital-layer Jacobian rows (see gemm_f64.cuh GEMM_ORBJ)
     OZ_VALUE = 3,   // one-electron stream value rows:     h' = res(tanh(Z + G_val + b)), tanh values kept in Tout
-    OZ_LAP = 4      // one-electron stream Laplacian rows: l' = res((1-t^2)(Z + G_lap) - 2t(1-t^2) S)
+    OZ_LAP = 4,     // one-electron stream Laplacian rows: l' = res((1-t^2)(Z + G_lap) - 2t(1-t^2) S)
+    OZ_JACD = 5     // OZ_JAC whose output IS the next GEMM's operand: the epilogue forms the int8 digits and row scales
+                    // of [J' | pair-mean columns] itself (row maximum over both 128-channel CTAs of a cluster pair through
+                    // distributed shared memory), reads the residual rows from the INPUT digits, and writes per-8-row
+                    // partial sums of zJ^2 (fixed order: deterministic) -- no fp64 Jacobian ever reaches HBM
 };
 
 struct OzParams {
@@ -56,6 +60,10 @@ struct OzParams {
     int n_orb, n_rows_mat, row0;   // orbitals per determinant (matrix columns), matrix rows, row of this channel's first electron
     double* DA; double* YOWN;
     int dbg;                 // probe only: 1 = epilogue skips TMEM reads/stores, 2 = no MMA issue, 4 = no TMA
+    // OZ_JACD outputs: digits [rows][OZ_S][Kout] + scales of the rows [own N channels | npm pair-mean columns]
+    signed char* Dout; double* sa_out; int Kout;
+    const double* PM; int npm;   // fp64 pair-mean Jacobian rows [rows][npm] of the NEXT layer (null / 0: own columns only)
+    double* SP;                  // [rows / 8][ldt] partial sums of zJ^2 over aligned groups of 8 rows
 };
 
 // digits + scales of `rows` rows of a row-major fp64 matrix (leading dimension lda, K columns)
@@ -68,3 +76,9 @@ int ds_launch_slice_means(const double* A, int lda, int K, int C, int n_walkers,
 // Bt[N][K] = B[K][N]^T
 int ds_launch_transpose(const double* B, int K, int N, double* Bt, cudaStream_t stream);
 int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t stream);
+// S[e][n] = sum_b SP[e * (NDp/8) + b][n], fixed order
+int ds_launch_sp_reduce(const double* SP, int ld, long long n_elec_rows, int blocks_per_electron, int H, double* S,
+                        cudaStream_t stream);
+// spin-channel means of Jacobian rows given as digits: GIN[(w*NDg + d)*ldgin + s*C + c] = mean_{i in s} A[(w,i,d), c], c < C
+int ds_launch_means_digits(const signed char* Ad, const double* sa, int K, int C, int n_walkers, int n_up, int n_elec,
+                           int NDp, int NDg, double* GIN, int ldgin, cudaStream_t stream);
