@@ -308,10 +308,12 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
     L.TRSQ = lap ? ws.take("TRSQ", W * 2 * d.D * 2) : nullptr;
     L.TRLAP = lap ? ws.take("TRLAP", W * 2 * d.D * 2) : nullptr;
     const bool i8 = lap && c->use_i8 && c->i8_ok;
-    L.AD = i8 ? ws.take("AD", (W * N * d.NDp * OZ_S * d.K1 + 7) / 8) : nullptr;
-    L.SA = i8 ? ws.take("SA", W * N * d.NDp) : nullptr;
-    L.AD2 = L.fused ? ws.take("AD2", (W * N * d.NDp * OZ_S * d.K1 + 7) / 8) : nullptr;
-    L.SA2 = L.fused ? ws.take("SA2", W * N * d.NDp) : nullptr;
+    // (row pitch of the row-contiguous digit layout the fused-digit epilogue writes: rows rounded up to the 64-row tile)
+    const size_t Rp = (W * N * d.NDp + 63) / 64 * 64;
+    L.AD = i8 ? ws.take("AD", (Rp * OZ_S * d.K1 + 7) / 8) : nullptr;
+    L.SA = i8 ? ws.take("SA", Rp) : nullptr;
+    L.AD2 = L.fused ? ws.take("AD2", (Rp * OZ_S * d.K1 + 7) / 8) : nullptr;
+    L.SA2 = L.fused ? ws.take("SA2", Rp) : nullptr;
     L.SP = i8 ? ws.take("SP", W * N * (d.NDp / 8) * d.H) : nullptr;
     static const char* pmn[] = {"PMJ0", "PMJ1", "PMJ2", "PMJ3"};
     for (int l = 0; l < DS_MAX_LAYERS; ++l)
@@ -436,9 +438,10 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         //  fallback accumulates into S with atomics and needs it cleared)
         if (lap && !i8_layer) DS_CUDA_CHECK(cudaMemsetAsync(Lo.S, 0, (size_t)Wc * N * H * sizeof(double), st));
         const bool fused_means = i8_layer && c->use_slice_means;
+        const long long Rp = ((long long)Wc * N * d.NDp + 63) / 64 * 64;
         if (fl && l >= 2) {
             // spin-channel means of the Jacobian rows straight from their digits (no fp64 rows exist)
-            if (int rc = ds_launch_means_digits(dig_in, sa_in, K, C, Wc, d.n_up, N, d.NDp, d.NDg, Lo.GIN, 2 * C, st)) return rc;
+            if (int rc = ds_launch_means_digits(dig_in, sa_in, K, Rp, C, Wc, d.n_up, N, d.NDp, d.NDg, Lo.GIN, 2 * C, st)) return rc;
             c->launches++;
         } else if (fused_means) {
             // digits of the Jacobian rows and their spin-channel means in one pass over the fp64 rows
@@ -509,7 +512,10 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
                 o.Wd = c->Wd_am[l]; o.sb = c->sb_am[l]; o.N = H; o.K = K;
                 o.G = Lo.GOUT; o.ldg = H; o.n_elec = N; o.NDp = d.NDp; o.NDg = d.NDg;
                 o.T = Lo.T; o.ldt = H; o.SP = Lo.SP;
-                o.Dout = dig_out; o.sa_out = sa_out;
+                // layer 1 reads the K-major digits slice_means formed from the layer-0 kernel's fp64 rows (which are also
+                // its residual); later layers read the row-contiguous digits the previous epilogue wrote
+                o.bmn = (l >= 2) ? 1 : 0; o.Rp_in = Rp; o.R = AJ; o.ldr = K;
+                o.Dout = dig_out; o.sa_out = sa_out; o.Rp_out = Rp;
                 // the last layer feeds the orbital projection: own columns only
                 o.Kout = last ? H : d.K1; o.PM = last ? nullptr : Lo.PMJ[l + 1]; o.npm = last ? 0 : 2 * d.P;
                 if (int rc = ds_launch_oz_gemm(o, OZ_JACD, res, st)) return rc;
@@ -592,6 +598,7 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             ProfScope ps(c, st, true, 2.0 * (double)Wc * ns * d.ND * H * 2.0 * c->npar[s]);
             OzParams z{};
             z.Ad = orb_dig; z.sa = orb_sa;
+            z.bmn = fused ? 1 : 0; z.Rp_in = ((long long)Wc * N * d.NDp + 63) / 64 * 64;
             z.rpg = (long long)ns * d.NDp; z.gstride = (long long)N * d.NDp; z.goff = (long long)c->off_s[s] * d.NDp;
             z.n_groups = Wc;
             z.Wd = c->Wd_orb[s]; z.sb = c->sb_orb[s]; z.N = 2 * c->npar[s]; z.K = H;
@@ -1566,7 +1573,9 @@ extern "C" int ds_ozaki_dgemm_probe(int device, const double* a, const double* b
     DS_REQUIRE(m > 0 && n > 0 && k > 0 && reps >= 1, "bad probe sizes");
     signed char *Ad = nullptr, *Wd = nullptr;
     double *sa = nullptr, *sb = nullptr, *bt = nullptr;
-    DS_CUDA_CHECK(cudaMalloc((void**)&Ad, (size_t)m * OZ_S * k));
+    const bool mn = getenv("DS_OZ_PROBE_MN") && atoi(getenv("DS_OZ_PROBE_MN")) != 0;   // A as row-contiguous digits (MN-major operand)
+    const long long Rp = (m + 63) / 64 * 64;
+    DS_CUDA_CHECK(cudaMalloc((void**)&Ad, (size_t)Rp * OZ_S * k));
     DS_CUDA_CHECK(cudaMalloc((void**)&Wd, (size_t)n * OZ_S * k));
     DS_CUDA_CHECK(cudaMalloc((void**)&sa, (size_t)m * sizeof(double)));
     DS_CUDA_CHECK(cudaMalloc((void**)&sb, (size_t)n * sizeof(double)));
@@ -1576,15 +1585,18 @@ extern "C" int ds_ozaki_dgemm_probe(int device, const double* a, const double* b
     int rc = ds_launch_transpose(b, k, n, bt, st);
     if (!rc) rc = ds_launch_slice_rows(bt, k, n, k, Wd, sb, st);
     cudaEventRecord(e0, st);
-    if (!rc) rc = ds_launch_slice_rows(a, k, m, k, Ad, sa, st);
+    if (mn) { cudaMemsetAsync(Ad, 0, (size_t)Rp * OZ_S * k, st); if (!rc) rc = ds_launch_slice_rows_mn(a, k, m, k, Rp, Ad, sa, st); }
+    else if (!rc) rc = ds_launch_slice_rows(a, k, m, k, Ad, sa, st);
     cudaEventRecord(e1, st);
     OzParams p{};
     p.Ad = Ad; p.sa = sa; p.rpg = m; p.gstride = m; p.goff = 0; p.n_groups = 1;
     p.Wd = Wd; p.sb = sb; p.N = n; p.K = k; p.C = cc; p.ldc = n;
+    p.bmn = mn ? 1 : 0; p.Rp_in = Rp;
+    const int pmode = mn ? OZ_PLAIN + 100 : OZ_PLAIN;
     if (const char* dv = getenv("DS_OZ_DBG")) p.dbg = atoi(dv);
-    if (!rc) rc = ds_launch_oz_gemm(p, OZ_PLAIN, false, st);        // warm-up (also configures the kernel)
+    if (!rc) rc = ds_launch_oz_gemm(p, pmode, false, st);        // warm-up (also configures the kernel)
     cudaEventRecord(e2, st);
-    for (int i = 0; i < reps && !rc; ++i) rc = ds_launch_oz_gemm(p, OZ_PLAIN, false, st);
+    for (int i = 0; i < reps && !rc; ++i) rc = ds_launch_oz_gemm(p, pmode, false, st);
     cudaEventRecord(e3, st);
     cudaError_t ce = cudaStreamSynchronize(st);
     float t01 = 0.f, t23 = 0.f;

@@ -71,6 +71,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                  : "memory");
@@ -152,6 +158,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+// asynchronous store into another CTA's shared memory that completes 4 transaction bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_u32(uint32_t caddr, uint32_t v, uint32_t cbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(caddr), "r"(v), "r"(cbar)
+                 : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -224,9 +235,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)4 << 61;                     // SWIZZLE_64B
     return d;
 }
-// kind::i8 instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_TM >> 4) << 24);
+// MN-major, SWIZZLE_64B descriptor of the B operand when the digits are stored row-contiguous ([slice][k][row], the
+// layout the fused-digit epilogue writes): per k one 64-byte line of 64 consecutive rows, 8 k = one 512 B swizzle atom
+// (stride byte offset), the next 64 rows = the next digit slice, OZ_BK * 64 B further (leading byte offset).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((OZ_BK * 64) >> 4) << 16;   // leading byte offset: between 64-row blocks (= digit slices)
+    d |= (uint64_t)(512 >> 4) << 32;            // stride byte offset: between groups of 8 k
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                     // SWIZZLE_64B
+    return d;
+}
+// kind::i8 instruction descriptor: D = s32, A = B = signed int8, M = 128, N = n; A K-major, B K-major or MN-major
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool b_mn = false) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(OZ_TM >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------
@@ -420,7 +444,7 @@ __device__ __forceinline__ void orbj_block8(const double* zz8, const double* __r
 // ---------------------------------------------------------------------------
 // the GEMM
 // ---------------------------------------------------------------------------
-template <int MODE, bool RES, int TN, int ND>
+template <int MODE, bool RES, int TN, int ND, bool BMN>
 // 18 warps: five share one SM sub-partition (16384 registers), so at most 96 registers per thread
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const OzParams p,
@@ -446,7 +470,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], SET_WARPS); }
         if (JD)
             for (int i = 0; i < 2; ++i)
-                for (int j = 0; j < 4; ++j) mbar_init(&xbar[i][j], 16);     // 16 row maxima arrive from the other CTA
+                for (int j = 0; j < 4; ++j) mbar_init(&xbar[i][j], 1);      // one local arrive.expect_tx(64) per use; the other CTA's 16 stores complete the bytes
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -473,7 +497,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     if (p.dbg & 4) { mbar_arrive(&full_bar[st]); continue; }
                     mbar_expect_tx(&full_bar[st], STAGE_T);
                     tma_load_4d(sW, &tmW, &full_bar[st], kb * OZ_BK, cb * OZ_TM, 0, 0);
-                    tma_load_4d(sW + W_STAGE, &tmA, &full_bar[st], kb * OZ_BK, q0, 0, grp);
+                    if (BMN) tma_load_3d(sW + W_STAGE, &tmA, &full_bar[st], (int)(grp * p.gstride + p.goff) + q0, kb * OZ_BK, 0);
+                    else tma_load_4d(sW + W_STAGE, &tmA, &full_bar[st], kb * OZ_BK, q0, 0, grp);
                 }
             }
         }
@@ -506,10 +531,13 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             constexpr int MAXSL = 256 / TN;                  // slices of A one instruction can span (N <= 256)
                             const int n1 = (nsl > MAXSL ? MAXSL : nsl) * TN;
                             const uint32_t acc = (kb > 0 || ks > 0 || t > 0) ? 1u : 0u;
-                            umma_i8(tacc + t * TN, wdesc, make_desc(sA + ks * 32), make_idesc(n1), acc);
+                            // K-major rows: 32 k = 32 B along a row; MN-major lines: 32 k = 32 lines of 64 B
+                            const uint32_t koff = BMN ? ks * 32 * 64 : ks * 32;
+                            umma_i8(tacc + t * TN, wdesc, BMN ? make_desc_mn(sA + koff) : make_desc(sA + koff), make_idesc(n1, BMN), acc);
                             if (nsl > MAXSL)
-                                umma_i8(tacc + (t + MAXSL) * TN, wdesc, make_desc(sA + MAXSL * A_SLICE_T + ks * 32),
-                                        make_idesc((nsl - MAXSL) * TN), acc);
+                                umma_i8(tacc + (t + MAXSL) * TN, wdesc,
+                                        BMN ? make_desc_mn(sA + MAXSL * A_SLICE_T + koff) : make_desc(sA + MAXSL * A_SLICE_T + koff),
+                                        make_idesc((nsl - MAXSL) * TN, BMN), acc);
                         }
                     }
                     umma_commit(&empty_bar[st]);          // frees the smem stage when the MMAs have read it
@@ -615,31 +643,65 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 }
             } else if (MODE == OZ_JACD) {
                 // Both channel blocks are full (N == 2 OZ_TM, checked by the launcher): no channel predicates.
+                // Digits are written ROW-CONTIGUOUS, [slice][k][row] with row pitch Rp: this thread's 16 rows of one
+                // slice are 16 consecutive bytes (one 128-bit store / load), and the next GEMM reads them as an
+                // MN-major operand.  prow0 is a multiple of 16.
                 // B1: the Jacobian rows of the layer output, kept in registers (zz[j] <- J'[(e,d_j), n]).
                 const double rs2 = 0.70710678118654752440;
+                const double MAGICJ = 6755399441055744.0;      // 2^52 + 2^51
                 {
                     unsigned e = (unsigned)prow0 / (unsigned)p.NDp;
                     int d = (int)((unsigned)prow0 - e * (unsigned)p.NDp);
                     unsigned w = e / (unsigned)p.n_elec;
                     int ie = (int)(e - w * (unsigned)p.n_elec);
+                    // residual rows = own columns of the INPUT operand: from its digits when those are row-contiguous
+                    // (6 x 128-bit loads, L2-resident: the TMA producer fetched this tile microseconds ago), else from
+                    // the fp64 rows the layer-0 kernel wrote
+                    uint4 rd[OZ_S];
+                    if (RES && BMN && nvalid > 0) {
+#pragma unroll
+                        for (int t = 0; t < OZ_S; ++t)
+                            rd[t] = *reinterpret_cast<const uint4*>(p.Ad + ((long long)t * p.K + n) * p.Rp_in + prow0);
+                    }
 #pragma unroll
                     for (int b = 0; b < EPI_COLS / 8; ++b) {
                         if (8 * b < nvalid) {                               // warp-uniform; aligned groups of 8 rows share an electron
                             const double t = p.T[(long long)e * p.ldt + n];
                             const double d1 = 1.0 - t * t;
                             const double* gp = p.G + ((long long)w * p.NDg + d) * p.ldg + n;
-                            double gv[8], sc[8];
-                            int rh[8], rl[8];
+                            double gv[8], sc[8], rv[8];
 #pragma unroll
                             for (int jj = 0; jj < 8; ++jj) {
                                 sc[jj] = __ldg(sap + 8 * b + jj);
                                 gv[jj] = gp[(long long)jj * p.ldg];
-                                if (RES) {
-                                    // residual row = own columns of the INPUT operand, from its digits (L2-resident: the
-                                    // TMA producer fetched this tile a few microseconds ago)
-                                    const signed char* rp = p.Ad + (prow0 + 8 * b + jj) * (long long)(OZ_S * p.K) + n;
-                                    rh[jj] = ((int)rp[0] * 256 + (int)rp[p.K]) * 256 + (int)rp[2 * p.K];
-                                    rl[jj] = ((int)rp[3 * p.K] * 256 + (int)rp[4 * p.K]) * 256 + (int)rp[5 * p.K];
+                                if (RES && !BMN) rv[jj] = p.R[(prow0 + 8 * b + jj) * (long long)p.ldr + n];
+                            }
+                            if (RES && BMN) {
+                                // rows 8b .. 8b+7 = words 2b, 2b+1 of every slice: 4 x 4 byte transposes give the
+                                // biased 48-bit integer (hi16 : lo32) of each row; undo the bias, rebuild the double
+#pragma unroll
+                                for (int hw = 0; hw < 2; ++hw) {
+                                    const int wi = 2 * b + hw;
+                                    unsigned W[OZ_S];
+#pragma unroll
+                                    for (int t2 = 0; t2 < OZ_S; ++t2)
+                                        W[t2] = wi == 0 ? rd[t2].x : wi == 1 ? rd[t2].y : wi == 2 ? rd[t2].z : rd[t2].w;
+                                    const unsigned a54 = __byte_perm(W[5], W[4], 0x5140), b54 = __byte_perm(W[5], W[4], 0x7362);
+                                    const unsigned a32 = __byte_perm(W[3], W[2], 0x5140), b32 = __byte_perm(W[3], W[2], 0x7362);
+                                    const unsigned a10 = __byte_perm(W[1], W[0], 0x5140), b10 = __byte_perm(W[1], W[0], 0x7362);
+                                    unsigned lo[4], hi[4];
+                                    lo[0] = __byte_perm(a54, a32, 0x5410); lo[1] = __byte_perm(a54, a32, 0x7632);
+                                    lo[2] = __byte_perm(b54, b32, 0x5410); lo[3] = __byte_perm(b54, b32, 0x7632);
+                                    hi[0] = __byte_perm(a10, 0u, 0x4410); hi[1] = __byte_perm(a10, 0u, 0x4432);
+                                    hi[2] = __byte_perm(b10, 0u, 0x4410); hi[3] = __byte_perm(b10, 0u, 0x4432);
+#pragma unroll
+                                    for (int r4 = 0; r4 < 4; ++r4) {
+                                        const unsigned l2 = lo[r4] ^ 0x80808080u;
+                                        const int hh = (int)(short)(hi[r4] ^ 0x80u);           // digit 0 is the signed top byte
+                                        const unsigned l = l2 - 0x80808080u;
+                                        const int hq = hh - 0x80 - (l2 < 0x80808080u ? 1 : 0);
+                                        rv[4 * hw + r4] = (__hiloint2double(0x43380000 + hq, (int)l) - MAGICJ) * (sc[4 * hw + r4] * 9.094947017729282e-13);
+                                    }
                                 }
                             }
                             double s0 = 0.0, s1 = 0.0;
@@ -648,10 +710,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                                 const double zj = fma(zz[8 * b + jj], sc[jj] * sbn, gv[jj]);
                                 if (jj & 1) s1 = fma(zj, zj, s1); else s0 = fma(zj, zj, s0);
                                 double o = d1 * zj;
-                                if (RES) {
-                                    const double r = fma(i32_to_f64(rh[jj]), 16777216.0, i32_to_f64(rl[jj])) * (sc[jj] * 9.094947017729282e-13);  // 2^-40
-                                    o = (r + o) * rs2;
-                                }
+                                if (RES) o = (rv[jj] + o) * rs2;
                                 zz[8 * b + jj] = o;
                             }
                             p.SP[((prow0 + 8 * b) >> 3) * (long long)p.ldt + n] = s0 + s1;
@@ -690,28 +749,74 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 if (lane < 16) {
                     mine = max(max(xown[slot][cg][0][lane], xown[slot][cg][1][lane]), max(xown[slot][cg][2][lane], xown[slot][cg][3][lane]));
                     mine = max(mine, xpm[slot][cg][lane]);
-                    if (q == 0) {                                            // one warp of the group tells the other CTA
-                        st_cluster_u32(map_to_cta(smem_u32(&xrem[slot][cg * 16 + lane]), crank ^ 1u), mine);
-                        mbar_arrive_cluster(map_to_cta(smem_u32(&xbar[slot][cg]), crank ^ 1u));
+                    if (q == 0) {
+                        // one warp of the group sends the 16 maxima to the other CTA: asynchronous DSMEM stores that
+                        // complete transaction bytes on ITS barrier (no fences, no L1 invalidation on either side)
+                        if (lane == 0) mbar_expect_tx(&xbar[slot][cg], 64);  // the 64 bytes the other CTA sends to us
+                        st_async_u32(map_to_cta(smem_u32(&xrem[slot][cg * 16 + lane]), crank ^ 1u), mine,
+                                     map_to_cta(smem_u32(&xbar[slot][cg]), crank ^ 1u));
                     }
                 }
-                mbar_wait_cluster(&xbar[slot][cg], (it >> 1) & 1u);
+                mbar_wait(&xbar[slot][cg], (it >> 1) & 1u);
                 if (lane < 16) mine = max(mine, xrem[slot][cg * 16 + lane]);
-                // B3: digits of the own channel and of this CTA's share of the pair-mean columns, row scales.
-                const long long opitch = (long long)p.Kout;
+                // B3: digits of the own channel (16 rows x 6 slices -> six 128-bit stores) and of this CTA's share of
+                // the pair-mean columns (4 rows x 6 slices -> six 32-bit stores), row scales.
+                {
+                    unsigned dl[16], dh[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const unsigned mxh = __shfl_sync(0xffffffffu, mine, j);
-                    if (j < nvalid) {
+                    for (int j = 0; j < 16; ++j) {
+                        const unsigned mxh = __shfl_sync(0xffffffffu, mine, j);
                         const bool bad = mxh >= 0x7ff00000u;
                         int ex = (int)(mxh >> 20) - 1022;
                         if (ex < -900) ex = -900;
                         const double f = __hiloint2double((1023 + 8 * OZ_S - 2 - ex) << 20, 0);
-                        signed char* orow = p.Dout + (prow0 + j) * (OZ_S * opitch);
-                        store_digits(zz[j], f, bad, orow + n, opitch);
-                        if ((j >> 2) == q && pmv_ok) store_digits(pmv[j & 3], f, bad, orow + p.N + pmc, opitch);
-                        if (crank == 0 && q == 0 && lane == j)
+                        const double tq = bad ? MAGICJ : fma(zz[j], f, MAGICJ);
+                        unsigned l = (unsigned)__double2loint(tq), h = (unsigned)__double2hiint(tq);
+                        const unsigned l2 = l + 0x80808080u;
+                        h += 0x80u + (l2 < l ? 1u : 0u);
+                        dl[j] = l2 ^ 0x80808080u;
+                        dh[j] = h ^ 0x80u;
+                        if ((j >> 2) == q) {                                 // pair-mean rows of this warp: same scale
+                            const double tp = bad ? MAGICJ : fma(pmv[j & 3], f, MAGICJ);
+                            unsigned pl = (unsigned)__double2loint(tp), ph = (unsigned)__double2hiint(tp);
+                            const unsigned pl2 = pl + 0x80808080u;
+                            ph += 0x80u + (pl2 < pl ? 1u : 0u);
+                            pmv[j & 3] = __hiloint2double((int)(ph ^ 0x80u), (int)(pl2 ^ 0x80808080u));   // (digits 0,1 | digits 2..5)
+                        }
+                        if (crank == 0 && q == 0 && lane == j && j < nvalid)
                             p.sa_out[prow0 + j] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __hiloint2double((1023 + ex - 6) << 20, 0);
+                    }
+                    // byte transposes: word g of slice s = digit s of rows 4g .. 4g+3
+                    signed char* ob = p.Dout + (long long)n * p.Rp_out + prow0;
+                    const long long spitch = (long long)p.Kout * p.Rp_out;
+                    unsigned sw[OZ_S][4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const unsigned *L = dl + 4 * g, *Hh = dh + 4 * g;
+                        const unsigned t01 = __byte_perm(L[0], L[1], 0x5140), t23 = __byte_perm(L[2], L[3], 0x5140);
+                        const unsigned u01 = __byte_perm(L[0], L[1], 0x7362), u23 = __byte_perm(L[2], L[3], 0x7362);
+                        const unsigned h01 = __byte_perm(Hh[0], Hh[1], 0x5140), h23 = __byte_perm(Hh[2], Hh[3], 0x5140);
+                        sw[5][g] = __byte_perm(t01, t23, 0x5410); sw[4][g] = __byte_perm(t01, t23, 0x7632);
+                        sw[3][g] = __byte_perm(u01, u23, 0x5410); sw[2][g] = __byte_perm(u01, u23, 0x7632);
+                        sw[1][g] = __byte_perm(h01, h23, 0x5410); sw[0][g] = __byte_perm(h01, h23, 0x7632);
+                    }
+#pragma unroll
+                    for (int t2 = 0; t2 < OZ_S; ++t2)
+                        *reinterpret_cast<uint4*>(ob + t2 * spitch) = make_uint4(sw[t2][0], sw[t2][1], sw[t2][2], sw[t2][3]);
+                    if (pmv_ok) {
+                        unsigned L[4], Hh[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) { L[r] = (unsigned)__double2loint(pmv[r]); Hh[r] = (unsigned)__double2hiint(pmv[r]); }
+                        const unsigned t01 = __byte_perm(L[0], L[1], 0x5140), t23 = __byte_perm(L[2], L[3], 0x5140);
+                        const unsigned u01 = __byte_perm(L[0], L[1], 0x7362), u23 = __byte_perm(L[2], L[3], 0x7362);
+                        const unsigned h01 = __byte_perm(Hh[0], Hh[1], 0x5140), h23 = __byte_perm(Hh[2], Hh[3], 0x5140);
+                        signed char* op = p.Dout + (long long)(p.N + pmc) * p.Rp_out + prow0 + 4 * q;
+                        *reinterpret_cast<unsigned*>(op + 5 * spitch) = __byte_perm(t01, t23, 0x5410);
+                        *reinterpret_cast<unsigned*>(op + 4 * spitch) = __byte_perm(t01, t23, 0x7632);
+                        *reinterpret_cast<unsigned*>(op + 3 * spitch) = __byte_perm(u01, u23, 0x5410);
+                        *reinterpret_cast<unsigned*>(op + 2 * spitch) = __byte_perm(u01, u23, 0x7632);
+                        *reinterpret_cast<unsigned*>(op + 1 * spitch) = __byte_perm(h01, h23, 0x5410);
+                        *reinterpret_cast<unsigned*>(op + 0 * spitch) = __byte_perm(h01, h23, 0x7632);
                     }
                 }
             } else if (MODE == OZ_VALUE || MODE == OZ_LAP) {
@@ -806,44 +911,93 @@ __global__ void __launch_bounds__(256) sp_reduce_kernel(const double* __restrict
     }
 }
 
-// Spin-channel means of Jacobian rows that exist only as digits: a warp owns (walker w, direction d), a lane 8
-// consecutive columns; row value = sa[r] 2^-40 (d0 2^40 + ... + d5).
+// decode 4 rows (one 32-bit word per digit slice, byte r = row r) of row-contiguous digits into the exact integers
+// q_r = x_r 2^(46-e) as doubles (the inverse of the digit formation in slice_row_warp / OZ_JACD)
+__device__ __forceinline__ void decode4(const unsigned (&W)[OZ_S], double (&q)[4]) {
+    const double MAGIC = 6755399441055744.0;
+    const unsigned a54 = __byte_perm(W[5], W[4], 0x5140), b54 = __byte_perm(W[5], W[4], 0x7362);
+    const unsigned a32 = __byte_perm(W[3], W[2], 0x5140), b32 = __byte_perm(W[3], W[2], 0x7362);
+    const unsigned a10 = __byte_perm(W[1], W[0], 0x5140), b10 = __byte_perm(W[1], W[0], 0x7362);
+    unsigned lo[4], hi[4];
+    lo[0] = __byte_perm(a54, a32, 0x5410); lo[1] = __byte_perm(a54, a32, 0x7632);
+    lo[2] = __byte_perm(b54, b32, 0x5410); lo[3] = __byte_perm(b54, b32, 0x7632);
+    hi[0] = __byte_perm(a10, 0u, 0x4410); hi[1] = __byte_perm(a10, 0u, 0x4432);
+    hi[2] = __byte_perm(b10, 0u, 0x4410); hi[3] = __byte_perm(b10, 0u, 0x4432);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const unsigned l2 = lo[r] ^ 0x80808080u;
+        const int hh = (int)(short)(hi[r] ^ 0x80u);
+        const unsigned l = l2 - 0x80808080u;
+        const int hq = hh - 0x80 - (l2 < 0x80808080u ? 1 : 0);
+        q[r] = __hiloint2double(0x43380000 + hq, (int)l) - MAGIC;
+    }
+}
+
+// Spin-channel means of Jacobian rows that exist only as ROW-CONTIGUOUS digits ([slice][k][Rp]): a warp owns
+// (walker w, channel k), a lane 8 consecutive directions d (one 64-bit load per slice and electron, the lanes of a
+// warp read NDp contiguous bytes); GIN[(w*NDg + d)*ldgin + s*C + k] = mean_{i in s} sa[r] 2^-40 q[r, k].
 __global__ void __launch_bounds__(256) means_digits_kernel(const signed char* __restrict__ Ad, const double* __restrict__ sa,
-                                                           int K, int C, int n_walkers, int n_up, int n_elec, int NDp,
+                                                           int K, long long Rp, int C, int n_up, int n_elec, int NDp,
                                                            int NDg, double* __restrict__ GIN, int ldgin) {
-    const long long wd = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wd >= (long long)n_walkers * NDp) return;
+    const int w = blockIdx.y;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= C) return;
     const int lane = threadIdx.x & 31;
-    const int w = (int)(wd / NDp), d = (int)(wd - (long long)w * NDp);
-    double* gout = GIN + ((long long)w * NDg + d) * ldgin;
-    const int c0 = lane * 8;
-    if (c0 >= C) return;                                  // C <= 256: one 8-column group per lane
-    long long r = ((long long)w * n_elec) * NDp + d;
-    for (int s = 0; s < 2; ++s) {
-        const int ibeg = s ? n_up : 0, iend = s ? n_elec : n_up;
-        double sum[8];
+    const long long r0 = (long long)w * n_elec * NDp;
+    for (int g = lane; g < NDp / 8; g += 32) {
+        for (int s = 0; s < 2; ++s) {
+            const int ibeg = s ? n_up : 0, iend = s ? n_elec : n_up;
+            double sum[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum[j] = 0.0;
-        for (int i = ibeg; i < iend; ++i, r += NDp) {
-            const signed char* rp = Ad + r * (long long)(OZ_S * K) + c0;
-            uint2 dg[OZ_S];
+            for (int j = 0; j < 8; ++j) sum[j] = 0.0;
+            for (int i = ibeg; i < iend; ++i) {
+                const long long r = r0 + (long long)i * NDp + 8 * g;
+                uint2 dg[OZ_S];
 #pragma unroll
-            for (int t = 0; t < OZ_S; ++t) dg[t] = *reinterpret_cast<const uint2*>(rp + (long long)t * K);
-            const double scale = sa[r] * 9.094947017729282e-13;              // 2^-40
+                for (int t = 0; t < OZ_S; ++t) dg[t] = *reinterpret_cast<const uint2*>(Ad + ((long long)t * K + k) * Rp + r);
+                unsigned Wx[OZ_S], Wy[OZ_S];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int sh = (j & 3) * 8;
-                int b[OZ_S];
-#pragma unroll
-                for (int t = 0; t < OZ_S; ++t) b[t] = (int)(signed char)(((j < 4 ? dg[t].x : dg[t].y) >> sh) & 0xffu);
-                const int hi = (b[0] * 256 + b[1]) * 256 + b[2], lo = (b[3] * 256 + b[4]) * 256 + b[5];
-                sum[j] = fma(fma((double)hi, 16777216.0, (double)lo), scale, sum[j]);
+                for (int t = 0; t < OZ_S; ++t) { Wx[t] = dg[t].x; Wy[t] = dg[t].y; }
+                double q0[4], q1[4];
+                decode4(Wx, q0);
+                decode4(Wy, q1);
+                const double4 sA = *reinterpret_cast<const double4*>(sa + r), sB = *reinterpret_cast<const double4*>(sa + r + 4);
+                sum[0] = fma(q0[0], sA.x, sum[0]); sum[1] = fma(q0[1], sA.y, sum[1]);
+                sum[2] = fma(q0[2], sA.z, sum[2]); sum[3] = fma(q0[3], sA.w, sum[3]);
+                sum[4] = fma(q1[0], sB.x, sum[4]); sum[5] = fma(q1[1], sB.y, sum[5]);
+                sum[6] = fma(q1[2], sB.z, sum[6]); sum[7] = fma(q1[3], sB.w, sum[7]);
             }
-        }
-        const double inv = 1.0 / (double)(iend - ibeg);
-        double2* o = reinterpret_cast<double2*>(gout + s * C + c0);
+            const double inv = 9.094947017729282e-13 / (double)(iend - ibeg);      // 2^-40 / n_s
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = make_double2(sum[2 * j] * inv, sum[2 * j + 1] * inv);
+            for (int j = 0; j < 8; ++j) GIN[((long long)w * NDg + 8 * g + j) * ldgin + s * C + k] = sum[j] * inv;
+        }
+    }
+}
+
+// fp64 rows -> row-contiguous digits (probe / tests only: byte-scattered stores)
+__global__ void __launch_bounds__(256) slice_rows_mn_kernel(const double* __restrict__ A, int lda, long long rows, int K,
+                                                            long long Rp, signed char* __restrict__ Ad, double* __restrict__ sa) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    unsigned mxh = 0u;
+    for (int k = lane; k < K; k += 32) mxh = max(mxh, (unsigned)__double2hiint(A[r * lda + k]) & 0x7fffffffu);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mxh = max(mxh, __shfl_xor_sync(0xffffffffu, mxh, off));
+    int e = (int)(mxh >> 20) - 1022;
+    if (e < -900) e = -900;
+    const double f = __hiloint2double((1023 + 8 * OZ_S - 2 - e) << 20, 0);
+    if (lane == 0) sa[r] = __hiloint2double((1023 + e - 6) << 20, 0);
+    const double MAGIC = 6755399441055744.0;
+    for (int k = lane; k < K; k += 32) {
+        const double t = fma(A[r * lda + k], f, MAGIC);
+        unsigned l = (unsigned)__double2loint(t), h = (unsigned)__double2hiint(t);
+        const unsigned l2 = l + 0x80808080u;
+        h += 0x80u + (l2 < l ? 1u : 0u);
+        l = l2 ^ 0x80808080u; h ^= 0x80u;
+        const unsigned dgt[OZ_S] = {h >> 8, h, l >> 24, l >> 16, l >> 8, l};
+#pragma unroll
+        for (int t2 = 0; t2 < OZ_S; ++t2) Ad[((long long)t2 * K + k) * Rp + r] = (signed char)dgt[t2];
     }
 }
 
@@ -879,13 +1033,31 @@ int make_map(CUtensorMap* tm, const signed char* base, int K, long long rows, lo
     return 0;
 }
 
-template <int MODE, bool RES, int TN, int ND>
+// 3-D map over row-contiguous digits [slice][k][Rp]: dims (row, k, slice), box (64 rows, OZ_BK k, OZ_S slices)
+int make_map_mn(CUtensorMap* tm, const signed char* base, int K, long long Rp) {
+    auto enc = get_encode();
+    if (!enc) { ds_set_error("cuTensorMapEncodeTiled is not available from the driver"); return -2; }
+    cuuint64_t dims[3] = {(cuuint64_t)Rp, (cuuint64_t)K, (cuuint64_t)OZ_S};
+    cuuint64_t strides[2] = {(cuuint64_t)Rp, (cuuint64_t)K * (cuuint64_t)Rp};
+    cuuint32_t box[3] = {(cuuint32_t)OZ_TN, (cuuint32_t)OZ_BK, (cuuint32_t)OZ_S};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<signed char*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ds_set_error("cuTensorMapEncodeTiled (row-contiguous digits) failed with code %d (K=%d Rp=%lld)", (int)r, K, Rp);
+        return -2;
+    }
+    return 0;
+}
+
+template <int MODE, bool RES, int TN, int ND, bool BMN>
 int launch_tn(const OzParams& p, cudaStream_t stream) {
     static bool configured = false;
     static int n_sm = 0;
     constexpr int SMEM_T = OzCfg<TN>::SMEM_T;
     if (!configured) {
-        DS_CUDA_CHECK(cudaFuncSetAttribute(oz_gemm_kernel<MODE, RES, TN, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_T));
+        DS_CUDA_CHECK(cudaFuncSetAttribute(oz_gemm_kernel<MODE, RES, TN, ND, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_T));
         int dev = 0;
         DS_CUDA_CHECK(cudaGetDevice(&dev));
         DS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -893,7 +1065,9 @@ int launch_tn(const OzParams& p, cudaStream_t stream) {
     }
     CUtensorMap tmW, tmA;
     if (int rc = make_map(&tmW, p.Wd, p.K, p.N, p.N, 1, OZ_TM)) return rc;
-    if (int rc = make_map(&tmA, p.Ad + p.goff * (long long)OZ_S * p.K, p.K, p.rpg, p.gstride, p.n_groups, TN)) return rc;
+    if (BMN) {
+        if (int rc = make_map_mn(&tmA, p.Ad, p.K, p.Rp_in)) return rc;
+    } else if (int rc = make_map(&tmA, p.Ad + p.goff * (long long)OZ_S * p.K, p.K, p.rpg, p.gstride, p.n_groups, TN)) return rc;
     const int tpg = (int)((p.rpg + TN - 1) / TN);
     const int n_cb = (p.N + OZ_TM - 1) / OZ_TM;
     const long long n_tiles = (long long)tpg * p.n_groups * n_cb;
@@ -911,24 +1085,21 @@ int launch_tn(const OzParams& p, cudaStream_t stream) {
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        DS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, oz_gemm_kernel<MODE, RES, TN, ND>, tmW, tmA, p, tpg, n_cb, n_tiles));
+        DS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, oz_gemm_kernel<MODE, RES, TN, ND, BMN>, tmW, tmA, p, tpg, n_cb, n_tiles));
         return 0;
     }
-    oz_gemm_kernel<MODE, RES, TN, ND><<<grid, OZ_THREADS, SMEM_T, stream>>>(tmW, tmA, p, tpg, n_cb, n_tiles);
+    oz_gemm_kernel<MODE, RES, TN, ND, BMN><<<grid, OZ_THREADS, SMEM_T, stream>>>(tmW, tmA, p, tpg, n_cb, n_tiles);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
-// Default: 64-row tiles, one accumulator set.  DS_OZ_TN=32 selects 32-row tiles with double-buffered TMEM: it hides the
-// TMEM read but loses more than it gains on B200 (profiles/r1_probe_tn32.log: MMA-only 1.00 ms vs 0.75 ms because
-// the N <= 192 instructions run the pipe at 61 % instead of 81 %, TMA-only 0.88 ms vs 0.49 ms because W is re-read
-// per 32 rows; whole kernel 1.42 ms vs 1.14 ms at 771120 x 256 x 320).
+// 64-row tiles, one accumulator set of 6 diagonals.  Two measured-and-rejected variants are no longer built:
+// 32-row tiles with double-buffered TMEM (profiles/r1_probe_tn32.log: hides the TMEM read but MMA-only 1.00 ms vs
+// 0.75 ms and W re-read per 32 rows, 1.42 ms vs 1.14 ms in total) and 5 diagonals / 15 slice products
+// (profiles/r2_diag5.log: +6 % local energies/s but max |dE_L| 2e-8 .. 2e-7 Ha against the fp64 path, over the 1e-8 budget).
 template <int MODE, bool RES>
 int launch(const OzParams& p, cudaStream_t stream) {
-    static const int tn = [] { const char* e = getenv("DS_OZ_TN"); return (e && atoi(e) == 32) ? 32 : 64; }();
-    static const int diags = [] { const char* e = getenv("DS_OZ_DIAGS"); return (e && atoi(e) == 5) ? 5 : 6; }();
-    if (diags == 5) return launch_tn<MODE, RES, 64, 5>(p, stream);
-    return tn == 64 ? launch_tn<MODE, RES, 64, 6>(p, stream) : launch_tn<MODE, RES, 32, 6>(p, stream);
+    return launch_tn<MODE, RES, 64, 6, false>(p, stream);
 }
 
 }  // namespace
@@ -964,14 +1135,20 @@ int ds_launch_sp_reduce(const double* SP, int ld, long long n_elec_rows, int blo
     return 0;
 }
 
-int ds_launch_means_digits(const signed char* Ad, const double* sa, int K, int C, int n_walkers, int n_up, int n_elec,
-                           int NDp, int NDg, double* GIN, int ldgin, cudaStream_t stream) {
+int ds_launch_means_digits(const signed char* Ad, const double* sa, int K, long long Rp, int C, int n_walkers, int n_up,
+                           int n_elec, int NDp, int NDg, double* GIN, int ldgin, cudaStream_t stream) {
     if (n_walkers <= 0) return 0;
-    DS_REQUIRE(K % 8 == 0 && C % 8 == 0 && C <= 256 && C <= K && ldgin % 2 == 0, "means_digits: C must be a multiple of 8, <= 256 (K=%d C=%d)", K, C);
-    const long long warps = (long long)n_walkers * NDp;
-    const int wpb = 8;
-    means_digits_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(Ad, sa, K, C, n_walkers, n_up, n_elec, NDp,
-                                                                                     NDg, GIN, ldgin);
+    DS_REQUIRE(NDp % 8 == 0 && C <= K && Rp % 64 == 0, "means_digits: NDp must be a multiple of 8 (NDp=%d C=%d K=%d)", NDp, C, K);
+    dim3 grid((unsigned)((C + 7) / 8), (unsigned)n_walkers);
+    means_digits_kernel<<<grid, 256, 0, stream>>>(Ad, sa, K, Rp, C, n_up, n_elec, NDp, NDg, GIN, ldgin);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_slice_rows_mn(const double* A, int lda, long long rows, int K, long long Rp, signed char* Ad, double* sa,
+                            cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    slice_rows_mn_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(A, lda, rows, K, Rp, Ad, sa);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -989,13 +1166,16 @@ int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t s
     DS_REQUIRE(p.K % OZ_BK == 0 && p.K >= OZ_BK, "oz_gemm: K must be a multiple of %d (K=%d)", OZ_BK, p.K);
     DS_REQUIRE((reinterpret_cast<uintptr_t>(p.Ad) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Wd) & 15) == 0,
                "oz_gemm: digit buffers must be 16-byte aligned");
+    if (p.bmn) DS_REQUIRE(p.Rp_in % 64 == 0 && p.Rp_in >= 64, "oz_gemm: row pitch of row-contiguous digits must be a multiple of 64");
     if (mode == OZ_VALUE || mode == OZ_LAP)
         DS_REQUIRE(p.n_groups == 1 && p.rpg < (1LL << 31), "oz_gemm: value / Laplacian rows come as one group");
     if (mode == OZ_JACD) {
         DS_REQUIRE(p.N == 2 * OZ_TM && p.n_groups == 1 && p.goff == 0, "oz_gemm: the fused-digit mode needs exactly two channel blocks (N = %d)", p.N);
-        DS_REQUIRE(p.Dout && p.sa_out && p.SP && p.Kout % 16 == 0 && p.Kout >= p.N + p.npm && p.npm <= 64 && p.npm >= 0,
-                   "oz_gemm: bad digit output (Kout=%d npm=%d)", p.Kout, p.npm);
+        DS_REQUIRE(p.Dout && p.sa_out && p.SP && p.Kout >= p.N + p.npm && p.npm <= 64 && p.npm >= 0 && p.Rp_out % 64 == 0 &&
+                       p.Rp_out >= p.rpg && (reinterpret_cast<uintptr_t>(p.Dout) & 15) == 0,
+                   "oz_gemm: bad digit output (Kout=%d npm=%d Rp=%lld)", p.Kout, p.npm, p.Rp_out);
         DS_REQUIRE(!residual || p.K >= p.N, "oz_gemm: the residual rows are the first N columns of the operand");
+        DS_REQUIRE(!residual || p.bmn || p.R, "oz_gemm: residual rows need fp64 rows or row-contiguous input digits");
     }
     if (mode == OZ_JAC || mode == OZ_ORBJ || mode == OZ_JACD) {
         DS_REQUIRE(p.NDp % 8 == 0 && p.rpg % 8 == 0 && p.goff % 8 == 0 && p.gstride % 8 == 0,
@@ -1005,10 +1185,13 @@ int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t s
     switch (mode) {
         case OZ_PLAIN: return launch<OZ_PLAIN, false>(p, stream);
         case OZ_JAC: return residual ? launch<OZ_JAC, true>(p, stream) : launch<OZ_JAC, false>(p, stream);
-        case OZ_ORBJ: return launch<OZ_ORBJ, false>(p, stream);
+        case OZ_ORBJ: return p.bmn ? launch_tn<OZ_ORBJ, false, 64, 6, true>(p, stream) : launch<OZ_ORBJ, false>(p, stream);
         case OZ_VALUE: return residual ? launch<OZ_VALUE, true>(p, stream) : launch<OZ_VALUE, false>(p, stream);
         case OZ_LAP: return residual ? launch<OZ_LAP, true>(p, stream) : launch<OZ_LAP, false>(p, stream);
-        case OZ_JACD: return residual ? launch_tn<OZ_JACD, true, 64, 6>(p, stream) : launch_tn<OZ_JACD, false, 64, 6>(p, stream);
+        case OZ_JACD:
+            if (p.bmn) return residual ? launch_tn<OZ_JACD, true, 64, 6, true>(p, stream) : launch_tn<OZ_JACD, false, 64, 6, true>(p, stream);
+            return residual ? launch_tn<OZ_JACD, true, 64, 6, false>(p, stream) : launch_tn<OZ_JACD, false, 64, 6, false>(p, stream);
+        case OZ_PLAIN + 100: return launch_tn<OZ_PLAIN, false, 64, 6, true>(p, stream);      // probe: plain product from row-contiguous digits
     }
     ds_set_error("oz_gemm: unknown mode %d", mode);
     return -1;

@@ -60,8 +60,11 @@ struct OzParams {
     int n_orb, n_rows_mat, row0;   // orbitals per determinant (matrix columns), matrix rows, row of this channel's first electron
     double* DA; double* YOWN;
     int dbg;                 // probe only: 1 = epilogue skips TMEM reads/stores, 2 = no MMA issue, 4 = no TMA
-    // OZ_JACD outputs: digits [rows][OZ_S][Kout] + scales of the rows [own N channels | npm pair-mean columns]
-    signed char* Dout; double* sa_out; int Kout;
+    // Row-contiguous digit layout ([OZ_S][K][Rp] bytes, Rp = row pitch, a multiple of 64): what OZ_JACD writes and what
+    // the next GEMM then reads as an MN-major operand.  bmn != 0: Ad is in this layout with row pitch Rp_in.
+    int bmn; long long Rp_in;
+    // OZ_JACD outputs: digits [OZ_S][Kout][Rp_out] + scales of the rows [own N channels | npm pair-mean columns]
+    signed char* Dout; double* sa_out; int Kout; long long Rp_out;
     const double* PM; int npm;   // fp64 pair-mean Jacobian rows [rows][npm] of the NEXT layer (null / 0: own columns only)
     double* SP;                  // [rows / 8][ldt] partial sums of zJ^2 over aligned groups of 8 rows
 };
@@ -79,6 +82,10 @@ int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t s
 // S[e][n] = sum_b SP[e * (NDp/8) + b][n], fixed order
 int ds_launch_sp_reduce(const double* SP, int ld, long long n_elec_rows, int blocks_per_electron, int H, double* S,
                         cudaStream_t stream);
-// spin-channel means of Jacobian rows given as digits: GIN[(w*NDg + d)*ldgin + s*C + c] = mean_{i in s} A[(w,i,d), c], c < C
-int ds_launch_means_digits(const signed char* Ad, const double* sa, int K, int C, int n_walkers, int n_up, int n_elec,
-                           int NDp, int NDg, double* GIN, int ldgin, cudaStream_t stream);
+// spin-channel means of Jacobian rows given as row-contiguous digits [OZ_S][K][Rp]:
+// GIN[(w*NDg + d)*ldgin + s*C + c] = mean_{i in s} A[(w,i,d), c], c < C
+int ds_launch_means_digits(const signed char* Ad, const double* sa, int K, long long Rp, int C, int n_walkers, int n_up,
+                           int n_elec, int NDp, int NDg, double* GIN, int ldgin, cudaStream_t stream);
+// fp64 rows -> row-contiguous digits (probe / tests)
+int ds_launch_slice_rows_mn(const double* A, int lda, long long rows, int K, long long Rp, signed char* Ad, double* sa,
+                            cudaStream_t stream);
