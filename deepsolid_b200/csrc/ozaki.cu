@@ -858,12 +858,17 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const int kdet = pp / p.n_orb, oo = pp - kdet * p.n_orb;
                 const int ND = 3 * p.n_elec;
                 const long long ns2 = 2LL * p.n_rows_mat * p.n_orb;
-                int is = (int)((unsigned)q0 / (unsigned)p.NDp);
-                int d = (int)q0 - is * p.NDp;
+                // row_skip (0 or 8): the window of a group may start 8 rows early so that its first row is 16-byte
+                // aligned in the row-contiguous digit layout (TMA start coordinate); those rows belong to the group before
+                const long long qg = q0 - p.row_skip;                      // first row of this warp inside the group proper
+                const long long rpg_real = p.rpg - p.row_skip;
                 double* dab = p.DA + 2 * ((((long long)grp * p.n_det + kdet) * p.NDp) * p.n_rows_mat * p.n_orb + oo) + im;
 #pragma unroll
                 for (int b = 0; b < EPI_COLS / 8; ++b) {
-                    if (8 * b < nvalid) {                                   // warp-uniform
+                    const long long qb = qg + 8 * b;
+                    if (qb >= 0 && qb < rpg_real) {                         // warp-uniform
+                        const int is = (int)((unsigned)qb / (unsigned)p.NDp);
+                        const int d = (int)qb - is * p.NDp;
                         const long long e = grp * p.n_elec + p.off_s + is;
                         double Ex = 0.0, Ey = 0.0;
                         if (nv) {
@@ -876,8 +881,6 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         if (full) orbj_block8<true>(zz + 8 * b, sap + 8 * b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, true);
                         else orbj_block8<false>(zz + 8 * b, sap + 8 * b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, nv);
                     }
-                    d += 8;
-                    if (d >= p.NDp) { d -= p.NDp; ++is; }
                 }
             }
         }

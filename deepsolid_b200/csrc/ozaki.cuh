@@ -63,6 +63,7 @@ struct OzParams {
     // Row-contiguous digit layout ([OZ_S][K][Rp] bytes, Rp = row pitch, a multiple of 64): what OZ_JACD writes and what
     // the next GEMM then reads as an MN-major operand.  bmn != 0: Ad is in this layout with row pitch Rp_in.
     int bmn; long long Rp_in;
+    int row_skip;            // OZ_ORBJ with bmn: leading rows of every group's window that belong to the group before (0 or 8)
     // OZ_JACD outputs: digits [OZ_S][Kout][Rp_out] + scales of the rows [own N channels | npm pair-mean columns]
     signed char* Dout; double* sa_out; int Kout; long long Rp_out;
     const double* PM; int npm;   // fp64 pair-mean Jacobian rows [rows][npm] of the NEXT layer (null / 0: own columns only)
