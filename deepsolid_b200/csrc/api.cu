@@ -259,7 +259,7 @@ struct Layout {
 inline bool fused_digits_on(const ds_ctx* c, bool lap) {
     const DsDims& d = c->sys.d;
     return lap && c->use_i8 && c->i8_ok && c->use_fused_digits && c->use_slice_means && d.H == 2 * OZ_TM && 2 * d.P <= 64 &&
-           d.L >= 2 && c->dbg_stop_layer < 0 && ((long long)d.N * d.NDp) % 16 == 0;     // (16-byte aligned walker blocks of rows)
+           d.L >= 2 && c->dbg_stop_layer < 0;
 }
 
 void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = false) {
@@ -601,10 +601,6 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             z.bmn = fused ? 1 : 0; z.Rp_in = ((long long)Wc * N * d.NDp + 63) / 64 * 64;
             z.rpg = (long long)ns * d.NDp; z.gstride = (long long)N * d.NDp; z.goff = (long long)c->off_s[s] * d.NDp;
             z.n_groups = Wc;
-            if (z.bmn) {        // 16-byte aligned window start in the row-contiguous layout
-                z.row_skip = (int)(z.goff % 16);
-                z.goff -= z.row_skip; z.rpg += z.row_skip;
-            }
             z.Wd = c->Wd_orb[s]; z.sb = c->sb_orb[s]; z.N = 2 * c->npar[s]; z.K = H;
             z.n_elec = N; z.NDp = d.NDp; z.etab = Lo.ETAB; z.npar_max = c->npar_max;
             z.n_s = ns; z.off_s = c->off_s[s]; z.n_det = d.D; z.DA = Lo.DA[d.full_det ? 0 : s]; z.YOWN = Lo.YOWN;

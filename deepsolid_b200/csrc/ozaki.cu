@@ -497,7 +497,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     if (p.dbg & 4) { mbar_arrive(&full_bar[st]); continue; }
                     mbar_expect_tx(&full_bar[st], STAGE_T);
                     tma_load_4d(sW, &tmW, &full_bar[st], kb * OZ_BK, cb * OZ_TM, 0, 0);
-                    if (BMN) tma_load_3d(sW + W_STAGE, &tmA, &full_bar[st], (int)(grp * p.gstride + p.goff) + q0, kb * OZ_BK, 0);
+                    // blocked digits: the window of a group starts at the 64-row block that holds its first row
+                    if (BMN) tma_load_4d(sW + W_STAGE, &tmA, &full_bar[st], 0, kb * OZ_BK, 0, (int)(((grp * p.gstride + p.goff) >> 6) + q0 / TN));
                     else tma_load_4d(sW + W_STAGE, &tmA, &full_bar[st], kb * OZ_BK, q0, 0, grp);
                 }
             }
@@ -572,8 +573,12 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             const bool nv = n < p.N;
             const bool full = (cb + 1) * OZ_TM <= p.N;                             // warp-uniform
             if (cb != cur_cb) { cur_cb = cb; sbn = nv ? p.sb[n] * (1.0 / 65536.0) : 0.0; }   // a CTA normally keeps its cb
-            const long long prow0 = grp * p.gstride + p.goff + q0;                 // physical row of column 0
-            const long long left = p.rpg - q0;
+            // physical row of column 0; with blocked digits (BMN) a group's window starts at the 64-row block holding
+            // its first row, gskip rows early
+            const long long gstart = grp * p.gstride + p.goff;
+            const int gskip = BMN ? (int)(gstart & 63) : 0;
+            const long long prow0 = gstart - gskip + q0;
+            const long long left = p.rpg + gskip - q0;                             // (modes with gskip > 0 test validity per 8-row block)
             const int nvalid = left < 0 ? 0 : (left < EPI_COLS ? (int)left : EPI_COLS);   // warp-uniform
             const double* sap = p.sa + prow0;                                      // scales of this warp's rows
             if (MODE == OZ_JAC && RES && nv && nvalid == EPI_COLS) {
@@ -661,7 +666,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     if (RES && BMN && nvalid > 0) {
 #pragma unroll
                         for (int t = 0; t < OZ_S; ++t)
-                            rd[t] = *reinterpret_cast<const uint4*>(p.Ad + ((long long)t * p.K + n) * p.Rp_in + prow0);
+                            rd[t] = *reinterpret_cast<const uint4*>(p.Ad + ((((prow0 >> 6) * OZ_S + t) * p.K + n) << 6) + (prow0 & 63));
                     }
 #pragma unroll
                     for (int b = 0; b < EPI_COLS / 8; ++b) {
@@ -787,8 +792,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             p.sa_out[prow0 + j] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __hiloint2double((1023 + ex - 6) << 20, 0);
                     }
                     // byte transposes: word g of slice s = digit s of rows 4g .. 4g+3
-                    signed char* ob = p.Dout + (long long)n * p.Rp_out + prow0;
-                    const long long spitch = (long long)p.Kout * p.Rp_out;
+                    // blocked layout [64-row block][slice][k][64 rows]: a tile is one contiguous 6 Kout 64-byte region
+                    signed char* ob = p.Dout + ((((prow0 >> 6) * OZ_S) * p.Kout + n) << 6) + (prow0 & 63);
+                    const long long spitch = (long long)p.Kout << 6;
                     unsigned sw[OZ_S][4];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -810,7 +816,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         const unsigned t01 = __byte_perm(L[0], L[1], 0x5140), t23 = __byte_perm(L[2], L[3], 0x5140);
                         const unsigned u01 = __byte_perm(L[0], L[1], 0x7362), u23 = __byte_perm(L[2], L[3], 0x7362);
                         const unsigned h01 = __byte_perm(Hh[0], Hh[1], 0x5140), h23 = __byte_perm(Hh[2], Hh[3], 0x5140);
-                        signed char* op = p.Dout + (long long)(p.N + pmc) * p.Rp_out + prow0 + 4 * q;
+                        signed char* op = p.Dout + ((((prow0 >> 6) * OZ_S) * p.Kout + p.N + pmc) << 6) + (prow0 & 63) + 4 * q;
                         *reinterpret_cast<unsigned*>(op + 5 * spitch) = __byte_perm(t01, t23, 0x5410);
                         *reinterpret_cast<unsigned*>(op + 4 * spitch) = __byte_perm(t01, t23, 0x7632);
                         *reinterpret_cast<unsigned*>(op + 3 * spitch) = __byte_perm(u01, u23, 0x5410);
@@ -858,10 +864,10 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const int kdet = pp / p.n_orb, oo = pp - kdet * p.n_orb;
                 const int ND = 3 * p.n_elec;
                 const long long ns2 = 2LL * p.n_rows_mat * p.n_orb;
-                // row_skip (0 or 8): the window of a group may start 8 rows early so that its first row is 16-byte
-                // aligned in the row-contiguous digit layout (TMA start coordinate); those rows belong to the group before
-                const long long qg = q0 - p.row_skip;                      // first row of this warp inside the group proper
-                const long long rpg_real = p.rpg - p.row_skip;
+                // gskip (a multiple of 8): with blocked digits the window of a group starts at a 64-row block boundary; the
+                // rows before the group's first row belong to the group before and are skipped block by block
+                const long long qg = q0 - gskip;                           // first row of this warp inside the group proper
+                const long long rpg_real = p.rpg;
                 double* dab = p.DA + 2 * ((((long long)grp * p.n_det + kdet) * p.NDp) * p.n_rows_mat * p.n_orb + oo) + im;
 #pragma unroll
                 for (int b = 0; b < EPI_COLS / 8; ++b) {
@@ -936,7 +942,7 @@ __device__ __forceinline__ void decode4(const unsigned (&W)[OZ_S], double (&q)[4
     }
 }
 
-// Spin-channel means of Jacobian rows that exist only as ROW-CONTIGUOUS digits ([slice][k][Rp]): a warp owns
+// Spin-channel means of Jacobian rows that exist only as blocked row-contiguous digits ([block][slice][k][64]): a warp owns
 // (walker w, channel k), a lane 8 consecutive directions d (one 64-bit load per slice and electron, the lanes of a
 // warp read NDp contiguous bytes); GIN[(w*NDg + d)*ldgin + s*C + k] = mean_{i in s} sa[r] 2^-40 q[r, k].
 __global__ void __launch_bounds__(256) means_digits_kernel(const signed char* __restrict__ Ad, const double* __restrict__ sa,
@@ -957,7 +963,8 @@ __global__ void __launch_bounds__(256) means_digits_kernel(const signed char* __
                 const long long r = r0 + (long long)i * NDp + 8 * g;
                 uint2 dg[OZ_S];
 #pragma unroll
-                for (int t = 0; t < OZ_S; ++t) dg[t] = *reinterpret_cast<const uint2*>(Ad + ((long long)t * K + k) * Rp + r);
+                for (int t = 0; t < OZ_S; ++t)
+                    dg[t] = *reinterpret_cast<const uint2*>(Ad + ((((r >> 6) * OZ_S + t) * K + k) << 6) + (r & 63));
                 unsigned Wx[OZ_S], Wy[OZ_S];
 #pragma unroll
                 for (int t = 0; t < OZ_S; ++t) { Wx[t] = dg[t].x; Wy[t] = dg[t].y; }
@@ -1000,7 +1007,7 @@ __global__ void __launch_bounds__(256) slice_rows_mn_kernel(const double* __rest
         l = l2 ^ 0x80808080u; h ^= 0x80u;
         const unsigned dgt[OZ_S] = {h >> 8, h, l >> 24, l >> 16, l >> 8, l};
 #pragma unroll
-        for (int t2 = 0; t2 < OZ_S; ++t2) Ad[((long long)t2 * K + k) * Rp + r] = (signed char)dgt[t2];
+        for (int t2 = 0; t2 < OZ_S; ++t2) Ad[((((r >> 6) * OZ_S + t2) * K + k) << 6) + (r & 63)] = (signed char)dgt[t2];
     }
 }
 
@@ -1036,19 +1043,19 @@ int make_map(CUtensorMap* tm, const signed char* base, int K, long long rows, lo
     return 0;
 }
 
-// 3-D map over row-contiguous digits [slice][k][Rp]: dims (row, k, slice), box (64 rows, OZ_BK k, OZ_S slices)
+// 4-D map over blocked row-contiguous digits [64-row block][slice][k][64 rows]: dims (row in block, k, slice, block)
 int make_map_mn(CUtensorMap* tm, const signed char* base, int K, long long Rp) {
     auto enc = get_encode();
     if (!enc) { ds_set_error("cuTensorMapEncodeTiled is not available from the driver"); return -2; }
-    cuuint64_t dims[3] = {(cuuint64_t)Rp, (cuuint64_t)K, (cuuint64_t)OZ_S};
-    cuuint64_t strides[2] = {(cuuint64_t)Rp, (cuuint64_t)K * (cuuint64_t)Rp};
-    cuuint32_t box[3] = {(cuuint32_t)OZ_TN, (cuuint32_t)OZ_BK, (cuuint32_t)OZ_S};
-    cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<signed char*>(base), dims, strides, box, estr,
+    cuuint64_t dims[4] = {(cuuint64_t)OZ_TN, (cuuint64_t)K, (cuuint64_t)OZ_S, (cuuint64_t)(Rp / OZ_TN)};
+    cuuint64_t strides[3] = {(cuuint64_t)OZ_TN, (cuuint64_t)K * OZ_TN, (cuuint64_t)OZ_S * K * OZ_TN};
+    cuuint32_t box[4] = {(cuuint32_t)OZ_TN, (cuuint32_t)OZ_BK, (cuuint32_t)OZ_S, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<signed char*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        ds_set_error("cuTensorMapEncodeTiled (row-contiguous digits) failed with code %d (K=%d Rp=%lld)", (int)r, K, Rp);
+        ds_set_error("cuTensorMapEncodeTiled (blocked digits) failed with code %d (K=%d Rp=%lld)", (int)r, K, Rp);
         return -2;
     }
     return 0;
@@ -1071,7 +1078,8 @@ int launch_tn(const OzParams& p, cudaStream_t stream) {
     if (BMN) {
         if (int rc = make_map_mn(&tmA, p.Ad, p.K, p.Rp_in)) return rc;
     } else if (int rc = make_map(&tmA, p.Ad + p.goff * (long long)OZ_S * p.K, p.K, p.rpg, p.gstride, p.n_groups, TN)) return rc;
-    const int tpg = (int)((p.rpg + TN - 1) / TN);
+    // blocked digits: a group's window starts up to 56 rows before its first row (64-row block boundary)
+    const int tpg = (int)((p.rpg + (BMN ? 56 : 0) + TN - 1) / TN);
     const int n_cb = (p.N + OZ_TM - 1) / OZ_TM;
     const long long n_tiles = (long long)tpg * p.n_groups * n_cb;
     int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);

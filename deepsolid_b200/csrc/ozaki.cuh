@@ -60,11 +60,11 @@ struct OzParams {
     int n_orb, n_rows_mat, row0;   // orbitals per determinant (matrix columns), matrix rows, row of this channel's first electron
     double* DA; double* YOWN;
     int dbg;                 // probe only: 1 = epilogue skips TMEM reads/stores, 2 = no MMA issue, 4 = no TMA
-    // Row-contiguous digit layout ([OZ_S][K][Rp] bytes, Rp = row pitch, a multiple of 64): what OZ_JACD writes and what
-    // the next GEMM then reads as an MN-major operand.  bmn != 0: Ad is in this layout with row pitch Rp_in.
+    // Blocked row-contiguous digit layout [Rp/64 blocks][OZ_S][K][64 rows] (bytes; Rp = rows rounded up to 64): what
+    // OZ_JACD writes -- a thread's 16 rows of one slice are one 128-bit store, a 64-row tile is one contiguous region --
+    // and what the next GEMM reads as an MN-major operand.  bmn != 0: Ad is in this layout (Rp_in rows).
     int bmn; long long Rp_in;
-    int row_skip;            // OZ_ORBJ with bmn: leading rows of every group's window that belong to the group before (0 or 8)
-    // OZ_JACD outputs: digits [OZ_S][Kout][Rp_out] + scales of the rows [own N channels | npm pair-mean columns]
+    // OZ_JACD outputs: blocked digits [Rp_out/64][OZ_S][Kout][64] + scales of the rows [own N channels | npm pair-mean columns]
     signed char* Dout; double* sa_out; int Kout; long long Rp_out;
     const double* PM; int npm;   // fp64 pair-mean Jacobian rows [rows][npm] of the NEXT layer (null / 0: own columns only)
     double* SP;                  // [rows / 8][ldt] partial sums of zJ^2 over aligned groups of 8 rows
