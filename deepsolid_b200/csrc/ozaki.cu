@@ -1079,7 +1079,10 @@ int launch_tn(const OzParams& p, cudaStream_t stream) {
         if (int rc = make_map_mn(&tmA, p.Ad, p.K, p.Rp_in)) return rc;
     } else if (int rc = make_map(&tmA, p.Ad + p.goff * (long long)OZ_S * p.K, p.K, p.rpg, p.gstride, p.n_groups, TN)) return rc;
     // blocked digits: a group's window starts up to 56 rows before its first row (64-row block boundary)
-    const int tpg = (int)((p.rpg + (BMN ? 56 : 0) + TN - 1) / TN);
+    // (only groups that can start inside a block need it: a single group at row 0 -- OZ_JACD, whose extra tile would
+    //  write digits past the operand -- starts on a block boundary)
+    const bool windows = BMN && (p.n_groups > 1 || (p.goff & 63) != 0);
+    const int tpg = (int)((p.rpg + (windows ? 56 : 0) + TN - 1) / TN);
     const int n_cb = (p.N + OZ_TM - 1) / OZ_TM;
     const long long n_tiles = (long long)tpg * p.n_groups * n_cb;
     int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
