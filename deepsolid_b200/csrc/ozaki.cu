@@ -767,14 +767,23 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 // B3: digits of the own channel (16 rows x 6 slices -> six 128-bit stores) and of this CTA's share of
                 // the pair-mean columns (4 rows x 6 slices -> six 32-bit stores), row scales.
                 {
+                    // lane j < 16 turns the maximum of row j into the high word of 2^(46-e) once (0 = inf / nan in the
+                    // row); every lane then fetches the 16 words with one shuffle each
+                    unsigned fhi = 0u;
+                    if (lane < 16) {
+                        const bool badr = mine >= 0x7ff00000u;
+                        int ex = (int)(mine >> 20) - 1022;
+                        if (ex < -900) ex = -900;
+                        fhi = badr ? 0u : (unsigned)((1023 + 8 * OZ_S - 2 - ex) << 20);
+                        if (crank == 0 && q == 0 && lane < nvalid)
+                            p.sa_out[prow0 + lane] = badr ? __longlong_as_double(0x7ff8000000000000LL) : __hiloint2double((1023 + ex - 6) << 20, 0);
+                    }
                     unsigned dl[16], dh[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const unsigned mxh = __shfl_sync(0xffffffffu, mine, j);
-                        const bool bad = mxh >= 0x7ff00000u;
-                        int ex = (int)(mxh >> 20) - 1022;
-                        if (ex < -900) ex = -900;
-                        const double f = __hiloint2double((1023 + 8 * OZ_S - 2 - ex) << 20, 0);
+                        const unsigned fw = __shfl_sync(0xffffffffu, fhi, j);
+                        const bool bad = fw == 0u;
+                        const double f = __hiloint2double((int)fw, 0);
                         const double tq = bad ? MAGICJ : fma(zz[j], f, MAGICJ);
                         unsigned l = (unsigned)__double2loint(tq), h = (unsigned)__double2hiint(tq);
                         const unsigned l2 = l + 0x80808080u;
@@ -788,8 +797,6 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             ph += 0x80u + (pl2 < pl ? 1u : 0u);
                             pmv[j & 3] = __hiloint2double((int)(ph ^ 0x80u), (int)(pl2 ^ 0x80808080u));   // (digits 0,1 | digits 2..5)
                         }
-                        if (crank == 0 && q == 0 && lane == j && j < nvalid)
-                            p.sa_out[prow0 + j] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __hiloint2double((1023 + ex - 6) << 20, 0);
                     }
                     // byte transposes: word g of slice s = digit s of rows 4g .. 4g+3
                     // blocked layout [64-row block][slice][k][64 rows]: a tile is one contiguous 6 Kout 64-byte region
