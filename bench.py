@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: BASELINE batch per GPU (headline); strong: the BASELINE batch is global and split over "
                          "the GPUs (process.py:96,134).  The weak line also carries the strong measurement as `strong`.")
+    ap.add_argument("--no-probes", action="store_true", help="skip the cuBLAS DGEMM / int8 MMA peak probes (ncu launch lists)")
     ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--threads", type=int, default=1, help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -285,6 +286,14 @@ def measure_int8_mma_rate(hp, dev):
     return 21 * 2.0 * m * n * k / (gm.value * 1e-3) / 1e12
 
 
+def git_sha():
+    try:
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True,
+                              timeout=10).stdout.strip() or None
+    except Exception:
+        return None
+
+
 def committed_profile(kind):
     """Newest profiles/r*_{kind}.json with its provenance (git sha, chunk size) -- ncu numbers cannot be taken in a
     timed run, so they come from the capture committed with the code and say which code that was."""
@@ -362,8 +371,8 @@ def run_ours(args):
             td.all_reduce(t, op=td.ReduceOp.MAX)
         return float(t.item())
 
-    fp64_peak = measure_fp64_peak(dev) if rank == 0 else None
-    i8_measured = measure_int8_mma_rate(hp, dev) if rank == 0 else None
+    fp64_peak = measure_fp64_peak(dev) if (rank == 0 and not args.no_probes) else None
+    i8_measured = measure_int8_mma_rate(hp, dev) if (rank == 0 and not args.no_probes) else None
     keep = {}
 
     def step_dev():
@@ -514,6 +523,7 @@ def run_ours(args):
                    "system": system, "batch_per_gpu": batch, "global_batch": batch * world,
                    "walkers": f"gaussian init (seed 666+rank) + {20 * args.equil} GPU Metropolis moves; params N(0,1)/sqrt(fan_in) seed 888",
                    "l2": "256 MB flush between timed steps; per-step workspace >> L2",
+                   "chunk_walkers": hp.workspace_info()["chunk_walkers"], "git_sha": git_sha(),
                    "gemm_arith": ("fp64 results; Jacobian-sweep GEMMs as error-free int8 digit slices on tcgen05 (int32 accumulation, "
                                   "one fp64 rounding per output)") if i8 else "fp64 DMMA",
                    "parallelism": f"walker-sharded dp{world}, one all-reduce of 4 doubles per step"},

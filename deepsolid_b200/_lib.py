@@ -78,6 +78,7 @@ SIGNATURES = {
     "ds_profile_reset": (C.c_int, [C.c_void_p]),
     "ds_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "ds_profile_get": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64), c_double_p, c_double_p]),
+    "ds_workspace_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ds_debug_buffer": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "ds_debug_set_int": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "ds_ozaki_dgemm_probe": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,

@@ -138,6 +138,7 @@ struct ds_ctx {
     // layout of the last local-energy chunk (for ds_debug_buffer)
     std::vector<Region> last_regions;
     double* scratch8 = nullptr;             // packed statistics of ds_stats_allreduce
+    long long last_chunk = 0;               // walkers per chunk of the last batched call
 };
 
 double* ds_ctx_scratch8(ds_ctx* c) {
@@ -782,6 +783,7 @@ int run_batched(ds_ctx* c, const double* X, long long batch, bool lap, double* l
     DS_REQUIRE(X != nullptr, "null walker pointer");
     int Wc = 0;
     if (int rc = plan_chunk(c, batch, lap, &Wc)) return rc;
+    c->last_chunk = Wc;
     const int n3 = 3 * c->sys.d.N;
     const size_t mat_per = mats_per_walker(c);
     double* const gxa = c->gx_abs;
@@ -1524,6 +1526,13 @@ extern "C" int ds_profile_get(ds_ctx* c, double* jac_ms, int64_t* jac_launches, 
     if (jac_launches) *jac_launches = (int64_t)c->prof.size();
     if (jac_flops) *jac_flops = fl;
     if (total_ms) *total_ms = c->tot_ms;
+    return 0;
+}
+
+extern "C" int ds_workspace_info(ds_ctx* c, int64_t* chunk_walkers, int64_t* workspace_bytes) {
+    DS_REQUIRE(c, "null context");
+    if (chunk_walkers) *chunk_walkers = c->last_chunk;
+    if (workspace_bytes) *workspace_bytes = (int64_t)(c->ws.cap * sizeof(double));
     return 0;
 }
 

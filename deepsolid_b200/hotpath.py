@@ -436,6 +436,11 @@ class HotPath:
         _lib.check(self.lib.ds_profile_get(self.h, C.byref(ms), C.byref(n), C.byref(fl), C.byref(tot)))
         return {"jac_ms": ms.value, "jac_launches": n.value, "jac_flops": fl.value, "total_ms": tot.value}
 
+    def workspace_info(self) -> Dict[str, int]:
+        cw, wb = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.ds_workspace_info(self.h, C.byref(cw), C.byref(wb)))
+        return {"chunk_walkers": int(cw.value), "workspace_bytes": int(wb.value)}
+
     def debug_buffer(self, name: str) -> torch.Tensor:
         n = int(self.lib.ds_debug_buffer(self.h, name.encode(), None, 0))
         if n < 0:

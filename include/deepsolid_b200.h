@@ -239,6 +239,8 @@ DS_API int ds_profile_get(ds_ctx *ctx, double *jac_ms, int64_t *jac_launches, do
                    double *total_ms);
 /* Copy an internal per-chunk buffer of the last ds_local_energy call (first chunk) to
  * dst_dev for stage-by-stage parity tests.  Returns number of doubles (or <0). */
+/* walkers per chunk of the last batched call and the bytes of workspace held by the context */
+DS_API int ds_workspace_info(ds_ctx *ctx, int64_t *chunk_walkers, int64_t *workspace_bytes);
 DS_API int64_t ds_debug_buffer(ds_ctx *ctx, const char *name, double *dst_dev, int64_t max_doubles);
 /* debug knobs: "stop_layer" = l stops ds_local_energy/ds_logpsi after one-electron layer l (-1: off);
  * "i8" = 0 runs the Jacobian-sweep GEMMs on the fp64 DMMA kernels instead of the tcgen05 int8-slice

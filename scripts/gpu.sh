@@ -33,11 +33,20 @@ import json
 for l in open('$O/${TAG}_other_configs.jsonl'):
     d=json.loads(l); print(d['config']['system'], d['config']['batch_per_gpu'], round(d['value'],1), round(d['ms_per_step'],1), (d.get('cpu_baseline') or {}).get('max_abs_diff_vs_gpu_Ha'))" ;;
     launches)  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1500 --csv --log-file $O/${TAG}_launches.csv \
-                 $B --batch 1024 --steps 1 --warmup 3 --equil 0 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu_launch.log 2>&1
-               python scripts/launch_summary.py $O/${TAG}_launches.csv > $O/${TAG}_launch_summary.txt; head -14 $O/${TAG}_launch_summary.txt ;;
+                 $B --batch 1024 --steps 1 --warmup 3 --equil 0 --no-cpu-baseline --no-e2e --no-probes > $O/${TAG}_ncu_launch.log 2>&1
+               python scripts/launch_summary.py $O/${TAG}_launches.csv > $O/${TAG}_launch_summary.txt; head -14 $O/${TAG}_launch_summary.txt
+               read CH SHA <<< $(python -c "
+import json
+d=[json.loads(l) for l in open('$O/${TAG}_ncu_launch.log') if l.startswith('{')][-1]['config']; print(d['chunk_walkers'], d['git_sha'])")
+               python scripts/hbm_from_launches.py $O/${TAG}_launches.csv 4096 $O/${TAG}_hbm.json $CH $SHA ;;
     profile)   timeout 900 ncu --set full --clock-control none --import-source on \
-                 -k regex:'oz_gemm_kernel|det_dmma_kernel|slice_means_kernel|slice_rows_kernel|features_pair_kernel|l0_jac2_kernel|pair_mma_kernel' -s 12 -c 14 \
-                 -o $O/${TAG}_prof $B --batch 256 --steps 1 --warmup 3 --equil 0 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu_full.log 2>&1; ls -la $O/${TAG}_prof* ;;
+                 -k regex:'oz_gemm_kernel|det_dmma_kernel|slice_means_kernel|slice_rows_kernel|features_pair_kernel|l0_jac2_kernel|means_digits_kernel' -s 14 -c 16 \
+                 -o $O/${TAG}_prof $B --batch 256 --steps 1 --warmup 3 --equil 0 --no-cpu-baseline --no-e2e --no-probes > $O/${TAG}_ncu_full.log 2>&1; ls -la $O/${TAG}_prof*
+               read CH SHA <<< $(python -c "
+import json
+d=[json.loads(l) for l in open('$O/${TAG}_ncu_full.log') if l.startswith('{')][-1]['config']; print(d['chunk_walkers'], d['git_sha'])")
+               python scripts/traffic_from_ncu.py $O/${TAG}_prof.ncu-rep $O/${TAG}_traffic.json $CH $SHA
+               python scripts/ncu_summary.py $O/${TAG}_prof.ncu-rep > $O/${TAG}_ncu_full_summary.txt ;;
     probe)     for dbg in 0 1 2 3 4 5; do
                  echo "== DS_OZ_DBG=$dbg"
                  DS_OZ_DBG=$dbg timeout 120 python scripts/oz_check.py 771120x256x320 385560x432x256 2>&1 | grep -v "first bad\|  c  :\|  ref:" | cut -c1-200

@@ -1,6 +1,6 @@
 """DRAM bytes per walker of one local-energy pass from an ncu launch list that carries
 gpu__time_duration.sum, dram__bytes_read.sum and dram__bytes_write.sum per launch:
-python scripts/hbm_from_launches.py launches.csv <walkers covered by the listed launches> out.json"""
+python scripts/hbm_from_launches.py launches.csv <walkers covered by the listed launches> out.json [chunk_walkers] [git_sha]"""
 import collections, csv, json, re, sys
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 walkers = float(sys.argv[2])
@@ -21,7 +21,8 @@ for row in csv.DictReader(lines):
     per[name][m] += v
 tot_b = sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in per.values())
 tot_t = sum(d["gpu__time_duration.sum"] for d in per.values())
-out = {"walkers": walkers, "dram_bytes_per_walker": tot_b / walkers, "kernel_us_per_walker": tot_t / walkers,
+out = {"walkers": walkers, "chunk_walkers": int(sys.argv[4]) if len(sys.argv) > 4 else None,
+       "git_sha": sys.argv[5] if len(sys.argv) > 5 else None, "source_launch_list": sys.argv[1], "dram_bytes_per_walker": tot_b / walkers, "kernel_us_per_walker": tot_t / walkers,
        "kernels": {k: {"launches": cnt[k], "us": d["gpu__time_duration.sum"],
                        "dram_bytes": d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"],
                        "gb_per_s": (d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]) / max(d["gpu__time_duration.sum"], 1e-9) / 1e3}
