@@ -705,18 +705,19 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                                         const int hh = (int)(short)(hi[r4] ^ 0x80u);           // digit 0 is the signed top byte
                                         const unsigned l = l2 - 0x80808080u;
                                         const int hq = hh - 0x80 - (l2 < 0x80808080u ? 1 : 0);
-                                        rv[4 * hw + r4] = (__hiloint2double(0x43380000 + hq, (int)l) - MAGICJ) * (sc[4 * hw + r4] * 9.094947017729282e-13);
+                                        // (2^-40 / sqrt 2: the residual's 1/sqrt2 is folded into the row scale)
+                                        rv[4 * hw + r4] = (__hiloint2double(0x43380000 + hq, (int)l) - MAGICJ) * (sc[4 * hw + r4] * 6.4310986037924438e-13);
                                     }
                                 }
                             }
                             double s0 = 0.0, s1 = 0.0;
+                            const double d1s = RES ? d1 * rs2 : d1;            // (r + d1 z) / sqrt2 = r / sqrt2 + (d1 / sqrt2) z
 #pragma unroll
                             for (int jj = 0; jj < 8; ++jj) {
                                 const double zj = fma(zz[8 * b + jj], sc[jj] * sbn, gv[jj]);
                                 if (jj & 1) s1 = fma(zj, zj, s1); else s0 = fma(zj, zj, s0);
-                                double o = d1 * zj;
-                                if (RES) o = (rv[jj] + o) * rs2;
-                                zz[8 * b + jj] = o;
+                                if (RES) zz[8 * b + jj] = fma(d1s, zj, BMN ? rv[jj] : rv[jj] * rs2);
+                                else zz[8 * b + jj] = d1s * zj;
                             }
                             p.SP[((prow0 + 8 * b) >> 3) * (long long)p.ldt + n] = s0 + s1;
                         } else {
@@ -956,38 +957,41 @@ __global__ void __launch_bounds__(256) means_digits_kernel(const signed char* __
                                                            int K, long long Rp, int C, int n_up, int n_elec, int NDp,
                                                            int NDg, double* __restrict__ GIN, int ldgin) {
     const int w = blockIdx.y;
-    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (k >= C) return;
-    const int lane = threadIdx.x & 31;
-    const long long r0 = (long long)w * n_elec * NDp;
-    for (int g = lane; g < NDp / 8; g += 32) {
-        for (int s = 0; s < 2; ++s) {
-            const int ibeg = s ? n_up : 0, iend = s ? n_elec : n_up;
-            double sum[8];
+    const int G8 = NDp / 8;
+    // work item = (channel k, group g of 8 consecutive directions): consecutive threads walk the directions of one
+    // channel (contiguous bytes), then the next channel
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= C * G8) return;
+    const int k = item / G8, g = item - k * G8;
+    const long long r0 = (long long)w * n_elec * NDp + 8 * g;
+    (void)Rp;
+    for (int s = 0; s < 2; ++s) {
+        const int ibeg = s ? n_up : 0, iend = s ? n_elec : n_up;
+        double sum[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sum[j] = 0.0;
-            for (int i = ibeg; i < iend; ++i) {
-                const long long r = r0 + (long long)i * NDp + 8 * g;
-                uint2 dg[OZ_S];
+        for (int j = 0; j < 8; ++j) sum[j] = 0.0;
+#pragma unroll 2
+        for (int i = ibeg; i < iend; ++i) {
+            const long long r = r0 + (long long)i * NDp;
+            uint2 dg[OZ_S];
 #pragma unroll
-                for (int t = 0; t < OZ_S; ++t)
-                    dg[t] = *reinterpret_cast<const uint2*>(Ad + ((((r >> 6) * OZ_S + t) * K + k) << 6) + (r & 63));
-                unsigned Wx[OZ_S], Wy[OZ_S];
+            for (int t = 0; t < OZ_S; ++t)
+                dg[t] = *reinterpret_cast<const uint2*>(Ad + ((((r >> 6) * OZ_S + t) * K + k) << 6) + (r & 63));
+            const double4 sA = *reinterpret_cast<const double4*>(sa + r), sB = *reinterpret_cast<const double4*>(sa + r + 4);
+            unsigned Wx[OZ_S], Wy[OZ_S];
 #pragma unroll
-                for (int t = 0; t < OZ_S; ++t) { Wx[t] = dg[t].x; Wy[t] = dg[t].y; }
-                double q0[4], q1[4];
-                decode4(Wx, q0);
-                decode4(Wy, q1);
-                const double4 sA = *reinterpret_cast<const double4*>(sa + r), sB = *reinterpret_cast<const double4*>(sa + r + 4);
-                sum[0] = fma(q0[0], sA.x, sum[0]); sum[1] = fma(q0[1], sA.y, sum[1]);
-                sum[2] = fma(q0[2], sA.z, sum[2]); sum[3] = fma(q0[3], sA.w, sum[3]);
-                sum[4] = fma(q1[0], sB.x, sum[4]); sum[5] = fma(q1[1], sB.y, sum[5]);
-                sum[6] = fma(q1[2], sB.z, sum[6]); sum[7] = fma(q1[3], sB.w, sum[7]);
-            }
-            const double inv = 9.094947017729282e-13 / (double)(iend - ibeg);      // 2^-40 / n_s
-#pragma unroll
-            for (int j = 0; j < 8; ++j) GIN[((long long)w * NDg + 8 * g + j) * ldgin + s * C + k] = sum[j] * inv;
+            for (int t = 0; t < OZ_S; ++t) { Wx[t] = dg[t].x; Wy[t] = dg[t].y; }
+            double q0[4], q1[4];
+            decode4(Wx, q0);
+            decode4(Wy, q1);
+            sum[0] = fma(q0[0], sA.x, sum[0]); sum[1] = fma(q0[1], sA.y, sum[1]);
+            sum[2] = fma(q0[2], sA.z, sum[2]); sum[3] = fma(q0[3], sA.w, sum[3]);
+            sum[4] = fma(q1[0], sB.x, sum[4]); sum[5] = fma(q1[1], sB.y, sum[5]);
+            sum[6] = fma(q1[2], sB.z, sum[6]); sum[7] = fma(q1[3], sB.w, sum[7]);
         }
+        const double inv = 9.094947017729282e-13 / (double)(iend - ibeg);      // 2^-40 / n_s
+#pragma unroll
+        for (int j = 0; j < 8; ++j) GIN[((long long)w * NDg + 8 * g + j) * ldgin + s * C + k] = sum[j] * inv;
     }
 }
 
@@ -1160,7 +1164,7 @@ int ds_launch_means_digits(const signed char* Ad, const double* sa, int K, long 
                            int n_elec, int NDp, int NDg, double* GIN, int ldgin, cudaStream_t stream) {
     if (n_walkers <= 0) return 0;
     DS_REQUIRE(NDp % 8 == 0 && C <= K && Rp % 64 == 0, "means_digits: NDp must be a multiple of 8 (NDp=%d C=%d K=%d)", NDp, C, K);
-    dim3 grid((unsigned)((C + 7) / 8), (unsigned)n_walkers);
+    dim3 grid((unsigned)((C * (NDp / 8) + 255) / 256), (unsigned)n_walkers);
     means_digits_kernel<<<grid, 256, 0, stream>>>(Ad, sa, K, Rp, C, n_up, n_elec, NDp, NDg, GIN, ldgin);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
