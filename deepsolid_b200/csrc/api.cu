@@ -89,7 +89,10 @@ struct ds_ctx {
     bool i8_ok = false;                 // stream widths are multiples of the tcgen05 K block
     bool use_l0_kernel = true;          // layer-0 Jacobian rows by the streaming kernel (false: DMMA GEMM)
     bool use_slice_means = true;        // digits + spin-channel means of a layer's Jacobian rows in one pass
-    bool use_fused_digits = true;       // layers >= 1: the GEMM epilogue writes the next operand's digits (OZ_JACD), no fp64 Jacobian
+    // layers >= 1: the GEMM epilogue writes the next operand's digits (OZ_JACD) and no fp64 Jacobian reaches HBM.  Off by
+    // default: in-call A/B on B200 (profiles/r2_fused_ab.log) 7.26-7.30 k vs 7.38-7.43 k local energies/s -- digit formation
+    // costs the same issue slots in the epilogue as in the separate HBM-bound pass; DS_FUSED_DIGITS=1 selects it
+    bool use_fused_digits = false;
     double* env_pi[2] = {};
     double* env_sigma[2] = {};
     double* klist[2] = {};
@@ -851,7 +854,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     if (const char* ev = getenv("DS_NO_SLICE_MEANS")) c->use_slice_means = atoi(ev) == 0;
     if (const char* ev = getenv("DS_NO_I8_MEANS")) c->use_i8_means = atoi(ev) == 0;
     if (const char* ev = getenv("DS_NO_I8_VALUE")) c->use_i8_value = atoi(ev) == 0;
-    if (const char* ev = getenv("DS_NO_FUSED_DIGITS")) c->use_fused_digits = atoi(ev) == 0;
+    if (const char* ev = getenv("DS_FUSED_DIGITS")) c->use_fused_digits = atoi(ev) != 0;
     if (const char* ev = getenv("DS_WS_GIB")) { double g = atof(ev); if (g >= 0.25) c->ws_limit = (size_t)(g * 1073741824.0); }
     DsDims& d = c->sys.d;
     d.n_up = sd->n_up; d.n_dn = sd->n_dn; d.N = sd->n_up + sd->n_dn; d.A = sd->n_atoms_prim;

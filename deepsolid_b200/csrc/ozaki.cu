@@ -706,7 +706,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                                         const unsigned l = l2 - 0x80808080u;
                                         const int hq = hh - 0x80 - (l2 < 0x80808080u ? 1 : 0);
                                         // (2^-40 / sqrt 2: the residual's 1/sqrt2 is folded into the row scale)
-                                        rv[4 * hw + r4] = (__hiloint2double(0x43380000 + hq, (int)l) - MAGICJ) * (sc[4 * hw + r4] * 6.4310986037924438e-13);
+                                        rv[4 * hw + r4] = (__hiloint2double(0x43380000 + hq, (int)l) - MAGICJ) * (sc[4 * hw + r4] * (9.094947017729282e-13 * 0.70710678118654752440));
                                     }
                                 }
                             }

@@ -94,3 +94,22 @@ def test_int8_slice_path_matches_fp64_dmma_path_full_batch(name, n):
           f"99.9 % = {q999:.3e}, median = {np.median(d):.3e}; max |E_kin| = {float(ke64.abs().max()):.3e}")
     assert d.max() < TOL_E
     assert torch.equal(ew8, ew64)
+
+
+@pytest.mark.parametrize("name,n", [("graphite54", 512), ("lih108", 128)])
+def test_fused_digit_path_matches_default_at_baseline_size(name, n):
+    """The fused-digit sweep (cluster pairs, DSMEM row-max exchange, MN-major operands) on equilibrated walkers of the
+    benchmark systems against the default path: same tolerance as the int8-vs-fp64 comparison."""
+    ld, hp, P, X = setup(name, n)
+    sc, kl, _, _ = system(name)
+    el = hamiltonian.local_energy_seperate(ld.apply, sc, mode=C.SYSTEMS[name][2], partition_number=C.SYSTEMS[name][3])
+    ke0, _ = el(P, X)
+    hp.debug_set("fused_digits", 1)
+    try:
+        ke1, _ = el(P, X)
+        ke2, _ = el(P, X)
+    finally:
+        hp.debug_set("fused_digits", 0)
+    d = (ke1 - ke0).abs().double().cpu().numpy()
+    print(f"\n[{name}] fused-digit vs default sweep on {n} walkers: max |dE_L| = {d.max():.3e} Ha, median = {np.median(d):.3e}")
+    assert torch.equal(ke1, ke2) and d.max() < TOL_E

@@ -256,8 +256,9 @@ def test_non_finite_walkers_propagate_and_stay_local():
 def test_sweep_is_bit_reproducible_and_fused_digits_match_the_unfused_path(name, batch):
     """The reference is deterministic on fixed inputs; so is the sweep (per-8-row partial sums of zJ^2 reduced in a fixed
     order, ordered cross-warp sums in the feature kernel -- no floating-point atomics on the default path).  The
-    fused-digit GEMM epilogue (OZ_JACD: digits of the next operand formed in the epilogue, residual rows read back from
-    the input digits) agrees with the path that materialises fp64 Jacobian rows and slices them in a separate pass."""
+    optional fused-digit GEMM epilogue (OZ_JACD: digits of the next operand formed in the epilogue of a cluster pair,
+    residual rows read back from the input digits, no fp64 Jacobian in HBM) agrees with the default path that
+    materialises fp64 Jacobian rows and slices them in a separate pass."""
     ld, sl, _, _, hp = nets(name)
     sc, kl, _, P = system(name)
     X = torch.as_tensor(C.init_walkers(sc, batch, seed=123)).to(dev())
@@ -271,11 +272,11 @@ def test_sweep_is_bit_reproducible_and_fused_digits_match_the_unfused_path(name,
     finally:
         hp.set_workspace_limit(24 << 30)
     assert torch.equal(ke1, ke3)
-    hp.debug_set("fused_digits", 0)
+    hp.debug_set("fused_digits", 1)
     try:
         ke4, _ = el(P, X)
         ke5, _ = el(P, X)
     finally:
-        hp.debug_set("fused_digits", 1)
+        hp.debug_set("fused_digits", 0)
     assert torch.equal(ke4, ke5)
     assert float((ke4 - ke1).abs().max()) < 1e-9
