@@ -623,74 +623,29 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             if (MODE == OZ_PLAIN && (p.dbg & 1)) continue;
 
             if (MODE == OZ_JAC) {
-                // physical row = e * NDp + d  (e = walker * n_elec + electron); rows < 2^31 (checked by the launcher).
-                // Aligned groups of 8 rows share an electron.  The 16 rows of this warp are processed as four groups of
-                // four with the loads of group g+1 (row scale, shared-mean addend, residual) issued before the arithmetic
-                // of group g: the L2 / HBM latency of a group hides behind the previous one instead of stalling every block.
-                const double rs2 = 0.70710678118654752440;
-                bool ok[2];
-                double d1b[2];
-                const double* gpb[2];
-                const double* rpb[2];
-                double* cpb[2];
-                {
-                    unsigned e = (unsigned)prow0 / (unsigned)p.NDp;
-                    int d = (int)((unsigned)prow0 - e * (unsigned)p.NDp);
-                    unsigned w = e / (unsigned)p.n_elec;
-                    int ie = (int)(e - w * (unsigned)p.n_elec);
+                // physical row = e * NDp + d  (e = walker * n_elec + electron); rows < 2^31 (checked by the launcher)
+                unsigned e = (unsigned)prow0 / (unsigned)p.NDp;
+                int d = (int)((unsigned)prow0 - e * (unsigned)p.NDp);
+                unsigned w = e / (unsigned)p.n_elec;
+                int ie = (int)(e - w * (unsigned)p.n_elec);
 #pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        ok[b] = 8 * b < nvalid;                             // warp-uniform; blocks are all-or-nothing
-                        const double t = (ok[b] && nv) ? p.T[(long long)e * p.ldt + n] : 0.0;
-                        d1b[b] = RES ? (1.0 - t * t) * rs2 : 1.0 - t * t;
-                        gpb[b] = p.G + ((long long)w * p.NDg + d) * p.ldg + n;
-                        rpb[b] = RES ? p.R + (prow0 + 8 * b) * (long long)p.ldr + n : nullptr;
-                        cpb[b] = p.C + (prow0 + 8 * b) * (long long)p.ldc + n;
-                        d += 8;
-                        if (d >= p.NDp) { d -= p.NDp; ++e; if (++ie == p.n_elec) { ie = 0; ++w; } }
+                for (int b = 0; b < EPI_COLS / 8; ++b) {
+                    if (8 * b < nvalid) {                                   // warp-uniform; blocks are all-or-nothing
+                        const double t = nv ? p.T[(long long)e * p.ldt + n] : 0.0;
+                        const double d1 = 1.0 - t * t;
+                        const double* gp = p.G + ((long long)w * p.NDg + d) * p.ldg + n;
+                        const double* rp = RES ? p.R + (prow0 + 8 * b) * (long long)p.ldr + n : nullptr;
+                        double* cp = p.C + (prow0 + 8 * b) * (long long)p.ldc + n;
+                        double sacc;
+                        if (full) sacc = jac_block8<RES, true>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbn, d1, true, 0.0);
+                        else sacc = jac_block8<RES, false>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbn, d1, nv, 0.0);
+                        // partial sum of zJ^2 over this aligned group of 8 directions; summed per electron in a fixed
+                        // order by sp_reduce_kernel (deterministic, unlike an atomicAdd into S)
+                        if (nv) p.SP[((prow0 + 8 * b) >> 3) * (long long)p.ldt + n] = sacc;
                     }
+                    d += 8;
+                    if (d >= p.NDp) { d -= p.NDp; ++e; if (++ie == p.n_elec) { ie = 0; ++w; } }
                 }
-                const bool act = full || nv;
-                // row scale x column scale of row j lives in lane j (one load per warp instead of 16 per lane)
-                const double scl = (lane < nvalid) ? __ldg(sap + lane) : 0.0;
-                double gv[2][4], rv[2][4];
-#define OZ_JAC_LOAD(G_, BUF_)                                                                             \
-                {                                                                                         \
-                    constexpr int bb = (G_) >> 1, o4 = 4 * ((G_) & 1);                                    \
-                    _Pragma("unroll") for (int jj = 0; jj < 4; ++jj) {                                    \
-                        gv[BUF_][jj] = (ok[bb] && act) ? gpb[bb][(long long)(o4 + jj) * p.ldg] : 0.0;     \
-                        rv[BUF_][jj] = (RES && ok[bb] && act) ? rpb[bb][(long long)(o4 + jj) * p.ldr] : 0.0; \
-                    }                                                                                     \
-                }
-                OZ_JAC_LOAD(0, 0)
-                double s0 = 0.0, s1 = 0.0;
-#define OZ_JAC_STEP(G_)                                                                                   \
-                {                                                                                         \
-                    constexpr int bb = (G_) >> 1, o4 = 4 * ((G_) & 1), buf = (G_) & 1;                    \
-                    if (ok[bb]) {                                                                         \
-                        _Pragma("unroll") for (int jj = 0; jj < 4; ++jj) {                                \
-                            const double zj = fma(zz[4 * (G_) + jj], __shfl_sync(0xffffffffu, scl, 4 * (G_) + jj) * sbn, gv[buf][jj]); \
-                            if (jj & 1) s1 = fma(zj, zj, s1); else s0 = fma(zj, zj, s0);                  \
-                            const double o = RES ? fma(d1b[bb], zj, rv[buf][jj] * rs2) : d1b[bb] * zj;    \
-                            if (act) cpb[bb][(long long)(o4 + jj) * p.ldc] = o;                           \
-                        }                                                                                 \
-                        if ((G_) & 1) {                                                                   \
-                            /* partial sum of zJ^2 over this aligned group of 8 directions; summed per electron in a */ \
-                            /* fixed order by sp_reduce_kernel (deterministic, unlike an atomicAdd into S) */ \
-                            if (nv) p.SP[((prow0 + 8 * bb) >> 3) * (long long)p.ldt + n] = s0 + s1;       \
-                            s0 = 0.0; s1 = 0.0;                                                           \
-                        }                                                                                 \
-                    }                                                                                     \
-                }
-                OZ_JAC_LOAD(1, 1)
-                OZ_JAC_STEP(0)
-                OZ_JAC_LOAD(2, 0)
-                OZ_JAC_STEP(1)
-                OZ_JAC_LOAD(3, 1)
-                OZ_JAC_STEP(2)
-                OZ_JAC_STEP(3)
-#undef OZ_JAC_LOAD
-#undef OZ_JAC_STEP
             } else if (MODE == OZ_JACD) {
                 // Both channel blocks are full (N == 2 OZ_TM, checked by the launcher): no channel predicates.
                 // Digits are written ROW-CONTIGUOUS, [slice][k][row] with row pitch Rp: this thread's 16 rows of one
