@@ -288,8 +288,14 @@ def measure_int8_mma_rate(hp, dev):
 
 def git_sha():
     try:
-        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True,
-                              timeout=10).stdout.strip() or None
+        sha = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True,
+                             timeout=10).stdout.strip()
+        if sha:
+            return sha
+    except Exception:
+        pass
+    try:        # snapshot on a GPU box (no .git): the revision the build recorded
+        return open(os.path.join(ROOT, "deepsolid_b200", "_build", "git_sha.txt")).read().strip() or None
     except Exception:
         return None
 
@@ -298,7 +304,9 @@ def committed_profile(kind):
     """Newest profiles/r*_{kind}.json with its provenance (git sha, chunk size) -- ncu numbers cannot be taken in a
     timed run, so they come from the capture committed with the code and say which code that was."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kind}.json")))
+    import re
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", f"r*_{kind}.json"))
+                   if re.fullmatch(rf"r\d+_{kind}\.json", os.path.basename(f)))       # default-path captures only
     for f in reversed(files):
         try:
             d = json.load(open(f))

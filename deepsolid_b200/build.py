@@ -47,6 +47,13 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     if force:
         for o in OBJ.glob("*.o"):
             o.unlink()
+    try:        # the GPU box gets a snapshot without .git: leave the revision where bench.py can read it
+        sha = subprocess.run(["git", "-C", str(HERE.parent), "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True).stdout.strip()
+        dirty = subprocess.run(["git", "-C", str(HERE.parent), "status", "--porcelain", "--untracked-files=no"], capture_output=True, text=True).stdout.strip()
+        if sha:
+            (OBJ / "git_sha.txt").write_text(sha + ("+dirty" if dirty else "") + "\n")
+    except Exception:
+        pass
     srcs = sorted(CSRC.glob("*.cu"))
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), srcs))

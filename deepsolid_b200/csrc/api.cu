@@ -1026,6 +1026,9 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
                 if (int rc = digits(c->Worb[s], H, 2 * c->npar[s], &c->Wd_orb[s], &c->sb_orb[s])) return rc;
         }
     }
+    // the re-layout kernels above ran on the legacy default stream: callers launch on their own (possibly non-blocking)
+    // streams afterwards, so the new weights must be complete before this returns
+    DS_CUDA_CHECK(cudaStreamSynchronize(0));
     c->params_set = true;
     c->transposes_ready = false;
     return 0;

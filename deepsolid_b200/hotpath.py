@@ -120,8 +120,13 @@ class HotPath:
             pass
 
     # ------------------------------------------------------------------
-    def set_params(self, params) -> None:
-        """Upload the reference parameter pytree (network.py:135-184) if it changed."""
+    def set_params(self, params, force: bool = False) -> None:
+        """Upload the reference parameter pytree (network.py:135-184) if it changed.
+
+        "Changed" is detected from (data_ptr, torch version counter, shape) of every leaf: an in-place edit made
+        through a numpy view or ``tensor.data`` does not bump the version counter -- pass ``force=True`` after one.
+        ``ds_set_params`` copies on the legacy default stream and synchronises it; device leaves written on the
+        current torch stream are made visible by synchronising that stream first."""
         leaves = flatten_params(params)
         tens = []
         for lf in leaves:
@@ -130,8 +135,10 @@ class HotPath:
                 t = t.to(torch.float64).contiguous()
             tens.append(t)
         key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tens)
-        if key == self._param_key:
+        if key == self._param_key and not force:
             return
+        if any(t.is_cuda for t in tens):
+            torch.cuda.current_stream(self.tdev).synchronize()
         n = len(tens)
         ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tens])
         sizes = (C.c_int64 * n)(*[t.numel() for t in tens])

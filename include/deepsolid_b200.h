@@ -111,7 +111,18 @@ DS_API int ds_set_workspace_limit(ds_ctx *ctx, size_t bytes);
  *   orbital[0].w, [orbital[0].b,] orbital[1].w, [orbital[1].b,]      (b only with bias_orbitals)
  *   envelope[0].pi, envelope[0].sigma, envelope[1].pi, envelope[1].sigma
  * Every leaf is row-major fp64; pointers may be host or device memory; the data is
- * copied (and re-laid-out) so the caller may free or mutate it afterwards. */
+ * copied (and re-laid-out) on the legacy default stream, which is synchronised before the call returns, so the
+ * caller may free or mutate it afterwards; device leaves produced on another stream must be complete before the call.
+ *
+ * Shapes this library implements (anything else is refused with DS_ERR_INVALID / DS_ERR_UNSUPPORTED at
+ * ds_ctx_create; the reference accepts arbitrary hidden_dims, network.py:100-134):
+ *   - 2 <= n_layers <= 4, the same (hidden_one, hidden_two) in every layer, hidden_two even and <= 32,
+ *     use_last_layer = False, envelope isotropic / diagonal / full, at most 6 primitive-cell atoms with 'nu'
+ *     features (layer-0 operand rows <= 32 columns);
+ *   - the tcgen05 int8-slice path of the Laplacian sweep needs hidden_one and hidden_one + 2 hidden_two to be
+ *     multiples of 64 and <= 512 (digit kernels: K % 8 == 0, K <= 512) and fewer than 2^31 Jacobian rows per chunk
+ *     (the workspace limit keeps chunks far below that); other widths run the fp64 DMMA kernels;
+ *   - the optional fused-digit sweep (DS_FUSED_DIGITS=1) additionally needs hidden_one == 256 and hidden_two <= 32. */
 DS_API int ds_set_params(ds_ctx *ctx, const double *const *leaves, const int64_t *leaf_sizes, int n_leaves);
 
 /* network.eval_func, methods eval_slogdet / eval_logdet / eval_phase_and_slogdet
