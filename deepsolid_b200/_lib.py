@@ -31,7 +31,7 @@ class SystemDesc(C.Structure):
 class NetDesc(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("hidden_one", C.c_int32), ("hidden_two", C.c_int32), ("n_det", C.c_int32),
                 ("distance_type", C.c_int32), ("envelope_type", C.c_int32),
-                ("bias_orbitals", C.c_int32), ("full_det", C.c_int32)]
+                ("bias_orbitals", C.c_int32), ("full_det", C.c_int32), ("use_last_layer", C.c_int32)]
 
 
 #: name -> (restype, argtypes); must list every DS_API symbol of the header

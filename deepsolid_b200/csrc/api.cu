@@ -72,7 +72,8 @@ struct ds_ctx {
     double* bias1[DS_MAX_LAYERS] = {};  // [H]
     double* Wp[DS_MAX_LAYERS] = {};     // pair-stream weights
     double* bp[DS_MAX_LAYERS] = {};
-    double* Worb[2] = {};               // [H x 2 npar_s], columns interleaved (re, im)
+    double* Worb[2] = {};               // [H x 2 npar_s] (use_last: [K1 x 2 npar_s], own + pair-mean rows), columns interleaved (re, im)
+    double* WorbG[2] = {};              // use_last: [2H x 2 npar_s] spin-mean rows of the orbital projection
     double* borb[2] = {};               // [2 npar_s] orbital bias (bias_orbitals=True), interleaved like Worb; else null
     double* gborb[2] = {};
     bool bias_orb = false;
@@ -243,6 +244,7 @@ struct Layout {
     double *A0V, *A0L, *A0J;
     double *J[DS_MAX_LAYERS], *V[DS_MAX_LAYERS], *Lp[DS_MAX_LAYERS];
     double *T, *S, *GIN, *GOUT, *RAE, *ETAB, *YV, *YL, *YOWN;
+    double *GOO[2];         // use_last_layer: shared spin-mean contribution to the raw orbital outputs, per spin [Wc*NDg x 2 npar_max]
     double *MAT[2], *LAPM[2], *DA[2];
     double *LOGDET, *TAU, *TRSQ, *TRLAP;
     double *AD, *SA;        // int8 digits of the current Jacobian operand (as bytes) and its row scales
@@ -263,7 +265,7 @@ struct Layout {
 inline bool fused_digits_on(const ds_ctx* c, bool lap) {
     const DsDims& d = c->sys.d;
     return lap && c->use_i8 && c->i8_ok && c->use_fused_digits && c->use_slice_means && d.H == 2 * OZ_TM && 2 * d.P <= 64 &&
-           d.L >= 2 && c->dbg_stop_layer < 0;
+           d.L >= 2 && c->dbg_stop_layer < 0 && !d.use_last;
 }
 
 void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = false) {
@@ -290,6 +292,8 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
     const size_t cmax = (size_t)std::max(d.C0, d.H);
     L.GIN = ws.take("GIN", W * d.NDg * 2 * cmax);
     L.GOUT = ws.take("GOUT", W * d.NDg * d.H);
+    for (int s = 0; s < 2; ++s)
+        L.GOO[s] = d.use_last ? ws.take(s ? "GOO1" : "GOO0", W * (lap ? d.NDg : 1) * 2 * (size_t)c->npar_max) : nullptr;
     L.RAE = ws.take("RAE", W * N * d.A * DS_RAE_STRIDE);
     const size_t npm = c->npar_max;
     L.ETAB = ws.take("ETAB", W * N * 5 * npm * 2);
@@ -405,7 +409,7 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
 
     // buffer of the inputs of layer l >= 1 is (l-1); the last layer writes into buffer `outb(L-1)`
     auto inb = [&](int l) { return l - 1; };
-    auto outb = [&](int l) { return (grad || l + 1 < L) ? l : ((L - 1 >= 2) ? 0 : 1); };
+    auto outb = [&](int l) { return (grad || d.use_last || l + 1 < L) ? l : ((L - 1 >= 2) ? 0 : 1); };
 
     FeatParams fp{};
     fp.X = X; fp.A0V = Lo.A0V; fp.A0L = Lo.A0L; fp.A0J = Lo.A0J; fp.RAE = Lo.RAE;
@@ -415,7 +419,10 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         if (fused && l >= 2) { fp.AJ[l] = Lo.PMJ[l]; fp.ldj[l] = 2 * d.P; fp.joff[l] = 0; }      // compact: consumed by OZ_JACD
         else { fp.AJ[l] = Lo.J[inb(l)]; fp.ldj[l] = d.K1; fp.joff[l] = H; }
     }
-    for (int l = 0; l < L - 1; ++l) { fp.Wp[l] = c->Wp[l]; fp.bp[l] = c->bp[l]; }
+    if (d.use_last) {       // level L of the pair stream feeds the orbital projection: pair-mean columns of the last layer's output
+        fp.AV[L] = Lo.V[L - 1]; fp.AL[L] = Lo.Lp[L - 1]; fp.AJ[L] = Lo.J[L - 1]; fp.ldj[L] = d.K1; fp.joff[L] = H;
+    }
+    for (int l = 0; l < ds_pair_levels(d) - 1; ++l) { fp.Wp[l] = c->Wp[l]; fp.bp[l] = c->bp[l]; }
     if (int rc = ds_launch_features(sys, fp, Wc, lap, st)) return rc;
     c->launches++;
 
@@ -579,14 +586,33 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
     // epilogue on the fused path, else formed here from the fp64 rows
     signed char* orb_dig = reinterpret_cast<signed char*>((fused && ((L - 1) & 1)) ? Lo.AD2 : Lo.AD);
     double* orb_sa = (fused && ((L - 1) & 1)) ? Lo.SA2 : Lo.SA;
-    if (i8 && !fused) {
+    // use_last_layer: the projection takes [own | pair means] per electron (K1 columns) plus the spin means of the last
+    // layer, whose product with the mean rows of the weights is shared by the electrons of a walker (GOO)
+    const int Korb = d.use_last ? d.K1 : H;
+    if (d.use_last) {
+        if (i8) {       // digits of [own | pair-mean] Jacobian rows and their spin-channel means in one pass
+            if (int rc = ds_launch_slice_means(hJ, d.K1, d.K1, H, Wc, d.n_up, N, d.NDp, d.NDg, orb_dig, orb_sa, Lo.GIN, 2 * H, st)) return rc;
+            c->launches++;
+        }
+        if (int rc = ds_launch_means(d, Wc, H, hJ, d.K1, hV, hL, d.K1, Lo.GIN, 2 * H, lap, st, i8)) return rc;
+        c->launches++;
+        for (int s = 0; s < 2; ++s) {
+            if (c->n_s[s] == 0) continue;
+            GemmParams g{};
+            g.B = c->WorbG[s]; g.ldb = 2 * c->npar[s]; g.N = 2 * c->npar[s]; g.K = 2 * H; g.rpg = 0;
+            g.C = Lo.GOO[s]; g.ldc = 2 * c->npar_max;
+            if (lap) { g.A = Lo.GIN; g.lda = 2 * H; g.M = (long long)Wc * d.NDg; }
+            else { g.A = Lo.GIN + (size_t)d.NDp * 2 * H; g.lda = d.NDg * 2 * H; g.M = Wc; }   // the value row of every walker
+            if (int rc = gemm(c, g, GEMM_PLAIN, false, st)) return rc;
+        }
+    } else if (i8 && !fused) {
         if (int rc = ds_launch_slice_rows(hJ, d.K1, jrows, H, orb_dig, orb_sa, st)) return rc;
         c->launches++;
     }
     for (int s = 0; s < 2; ++s) {
         const int ns = c->n_s[s];
         GemmParams o{};
-        o.B = c->Worb[s]; o.ldb = 2 * c->npar[s]; o.N = 2 * c->npar[s]; o.K = H;
+        o.B = c->Worb[s]; o.ldb = 2 * c->npar[s]; o.N = 2 * c->npar[s]; o.K = Korb;
         o.lda = d.K1; o.cmap = 1; o.ldc = 2 * c->npar_max;
         o.rpg = ns; o.gstride = N; o.goff = c->off_s[s];
         o.M = (long long)Wc * ns;
@@ -599,13 +625,13 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             if (int rc = gemm(c, o, GEMM_PLAIN, false, st)) return rc;
         }
         if (i8) {
-            ProfScope ps(c, st, true, 2.0 * (double)Wc * ns * d.ND * H * 2.0 * c->npar[s]);
+            ProfScope ps(c, st, true, 2.0 * (double)Wc * ns * d.ND * Korb * 2.0 * c->npar[s]);
             OzParams z{};
             z.Ad = orb_dig; z.sa = orb_sa;
             z.bmn = fused ? 1 : 0; z.Rp_in = ((long long)Wc * N * d.NDp + 63) / 64 * 64;
             z.rpg = (long long)ns * d.NDp; z.gstride = (long long)N * d.NDp; z.goff = (long long)c->off_s[s] * d.NDp;
             z.n_groups = Wc;
-            z.Wd = c->Wd_orb[s]; z.sb = c->sb_orb[s]; z.N = 2 * c->npar[s]; z.K = H;
+            z.Wd = c->Wd_orb[s]; z.sb = c->sb_orb[s]; z.N = 2 * c->npar[s]; z.K = Korb;
             z.n_elec = N; z.NDp = d.NDp; z.etab = Lo.ETAB; z.npar_max = c->npar_max;
             z.n_s = ns; z.off_s = c->off_s[s]; z.n_det = d.D; z.DA = Lo.DA[d.full_det ? 0 : s]; z.YOWN = Lo.YOWN;
             z.n_orb = ds_norb(d, s); z.n_rows_mat = ds_blk_n(d, d.full_det ? 0 : s); z.row0 = d.full_det ? c->off_s[s] : 0;
@@ -621,6 +647,10 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
             j.n_orb = ds_norb(d, s); j.n_rows_mat = ds_blk_n(d, d.full_det ? 0 : s); j.row0 = d.full_det ? c->off_s[s] : 0;
             if (int rc = gemm(c, j, GEMM_ORBJ, false, st, /*profile*/ true)) return rc;
         }
+    }
+    if (d.use_last) {       // add the shared spin-mean contribution to the raw outputs (value, Laplacian, Jacobian rows)
+        if (int rc = ds_launch_orb_mean_addend(sys, sb, Wc, c->npar_max, Lo.GOO[0], Lo.GOO[1], 2 * c->npar_max, lap, st)) return rc;
+        c->launches++;
     }
     if (int rc = ds_launch_orb_assemble(sys, sb, Wc, c->npar_max, lap, st)) return rc;
     c->launches++;
@@ -833,6 +863,7 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     DS_REQUIRE(sd->n_atoms_prim > 0 && sd->n_atoms_prim <= DS_MAX_ATOMS_PRIM,
                "primitive cell must have 1..%d atoms", DS_MAX_ATOMS_PRIM);
     DS_REQUIRE(nd->n_layers >= 2 && nd->n_layers <= DS_MAX_LAYERS, "n_layers must be in 2..%d", DS_MAX_LAYERS);
+    DS_REQUIRE(!nd->use_last_layer || nd->n_layers < DS_MAX_LAYERS, "use_last_layer needs n_layers <= %d", DS_MAX_LAYERS - 1);
     DS_REQUIRE(nd->hidden_two >= 2 && nd->hidden_two <= 32 && nd->hidden_two % 2 == 0,
                "two-electron stream width must be even and <= 32 (got %d)", nd->hidden_two);
     DS_REQUIRE(nd->hidden_one >= 2 && nd->hidden_one % 2 == 0, "one-electron stream width must be even");
@@ -864,13 +895,14 @@ extern "C" int ds_ctx_create(const ds_system_desc* sd, const ds_net_desc* nd, in
     d.env_type = nd->envelope_type;
     c->bias_orb = nd->bias_orbitals != 0;
     d.full_det = nd->full_det != 0;
+    d.use_last = nd->use_last_layer != 0;
     d.C0 = d.F * d.A; d.K0 = d.C0 + 2 * d.F; d.K1 = d.H + 2 * d.P;
     fill_lattice(c->sys.prim, sd->prim_latvec, sd->prim_AV, sd->prim_BV);
     fill_lattice(c->sys.sim, sd->sim_latvec, sd->sim_AV, sd->sim_BV);
     memcpy(c->sys.atoms, sd->prim_atoms, sizeof(double) * 3 * d.A);
     c->n_s[0] = d.n_up; c->n_s[1] = d.n_dn; c->off_s[0] = 0; c->off_s[1] = d.n_up;
     c->npar[0] = ds_norb(d, 0) * d.D; c->npar[1] = ds_norb(d, 1) * d.D; c->npar_max = std::max(c->npar[0], c->npar[1]);
-    c->nbuf = std::max(2, d.L - 1);
+    c->nbuf = d.use_last ? d.L : std::max(2, d.L - 1);      // use_last: every layer keeps its own output buffer
 
     EwaldDev& ew = c->ew;
     ew.n_elec = d.N; ew.n_atoms = sd->n_atoms_sim; ew.dist_kind = sd->dist_kind; ew.n_g = sd->n_g;
@@ -928,7 +960,9 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
     Guard g(c->device);
     const DsDims& d = c->sys.d;
     const int L = d.L, H = d.H, P = d.P;
-    const int expect = 2 * L + 2 * (L - 1) + (c->bias_orb ? 4 : 2) + 4;
+    const int Lpair = d.use_last ? L : L - 1;        // pair layers
+    const int Korb = d.use_last ? 3 * H + 2 * P : H; // rows of the orbital weights
+    const int expect = 2 * L + 2 * Lpair + (c->bias_orb ? 4 : 2) + 4;
     DS_REQUIRE(n_leaves == expect, "expected %d parameter leaves for %d layers, got %d", expect, L, n_leaves);
     // expected sizes
     std::vector<int64_t> want;
@@ -937,19 +971,19 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
         want.push_back((int64_t)(3 * C + 2 * Pl) * H);
         want.push_back(H);
     }
-    for (int l = 0; l < L - 1; ++l) {
+    for (int l = 0; l < Lpair; ++l) {
         want.push_back((int64_t)((l == 0) ? d.F : P) * P);
         want.push_back(P);
     }
     for (int s = 0; s < 2; ++s) {
-        want.push_back((int64_t)H * 2 * c->npar[s]);
+        want.push_back((int64_t)Korb * 2 * c->npar[s]);
         if (c->bias_orb) want.push_back((int64_t)2 * c->npar[s]);
     }
     const int64_t sig_mult = (d.env_type == 0) ? 1 : (d.env_type == 1 ? 3 : 9);
     for (int s = 0; s < 2; ++s) { want.push_back((int64_t)d.A * c->npar[s]); want.push_back(sig_mult * d.A * c->npar[s]); }
     for (int i = 0; i < n_leaves; ++i)
         DS_REQUIRE(sizes[i] == want[i], "parameter leaf %d has %lld elements, expected %lld "
-                   "(full_det=False, use_last_layer=False are implemented; envelope / orbital-bias leaves follow the net descriptor)",
+                   "(the leaves follow the net descriptor: layers, widths, use_last_layer, full_det, envelope, orbital bias)",
                    i, (long long)sizes[i], (long long)want[i]);
     // stage every leaf on the host (pointers may be host or device memory)
     std::vector<std::vector<double>> h(n_leaves);
@@ -975,20 +1009,33 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
         if (int rc = put(&c->B_g[l], gg)) return rc;
         if (int rc = put(&c->bias1[l], b)) return rc;
     }
-    for (int l = 0; l < L - 1; ++l) {
+    for (int l = 0; l < Lpair; ++l) {
         if (int rc = put(&c->Wp[l], h[li++])) return rc;
         if (int rc = put(&c->bp[l], h[li++])) return rc;
     }
     for (int s = 0; s < 2; ++s) {
         const std::vector<double>& W = h[li++];
         const int np = c->npar[s];
-        std::vector<double> wi((size_t)H * 2 * np);
-        for (int r = 0; r < H; ++r)
+        // rows of the reference leaf: own [0,H) (| spin means [H,3H) | pair means [3H,3H+2P) with use_last_layer);
+        // device copies: own + pair-mean rows (the per-electron operand), spin-mean rows (shared per walker)
+        const int Kam = d.use_last ? d.K1 : H;
+        std::vector<double> wi((size_t)Kam * 2 * np);
+        auto src_row = [&](int r) { return (!d.use_last || r < H) ? r : 3 * H + (r - H); };
+        for (int r = 0; r < Kam; ++r)
             for (int p = 0; p < np; ++p) {
-                wi[(size_t)r * 2 * np + 2 * p] = W[(size_t)r * 2 * np + p];
-                wi[(size_t)r * 2 * np + 2 * p + 1] = W[(size_t)r * 2 * np + np + p];
+                wi[(size_t)r * 2 * np + 2 * p] = W[(size_t)src_row(r) * 2 * np + p];
+                wi[(size_t)r * 2 * np + 2 * p + 1] = W[(size_t)src_row(r) * 2 * np + np + p];
             }
         if (int rc = put(&c->Worb[s], wi)) return rc;
+        if (d.use_last) {
+            std::vector<double> wg((size_t)2 * H * 2 * np);
+            for (int r = 0; r < 2 * H; ++r)
+                for (int p = 0; p < np; ++p) {
+                    wg[(size_t)r * 2 * np + 2 * p] = W[(size_t)(H + r) * 2 * np + p];
+                    wg[(size_t)r * 2 * np + 2 * p + 1] = W[(size_t)(H + r) * 2 * np + np + p];
+                }
+            if (int rc = put(&c->WorbG[s], wg)) return rc;
+        }
         if (c->bias_orb) {
             const std::vector<double>& bv = h[li++];
             std::vector<double> bi((size_t)2 * np);
@@ -1023,7 +1070,7 @@ extern "C" int ds_set_params(ds_ctx* c, const double* const* leaves, const int64
                 for (int l = 1; l < L; ++l)
                     if (int rc = digits(c->B_g[l], 2 * H, H, &c->Wd_g[l], &c->sb_g[l])) return rc;
             for (int s = 0; s < 2; ++s)
-                if (int rc = digits(c->Worb[s], H, 2 * c->npar[s], &c->Wd_orb[s], &c->sb_orb[s])) return rc;
+                if (int rc = digits(c->Worb[s], d.use_last ? d.K1 : H, 2 * c->npar[s], &c->Wd_orb[s], &c->sb_orb[s])) return rc;
         }
     }
     // the re-layout kernels above ran on the legacy default stream: callers launch on their own (possibly non-blocking)
@@ -1113,13 +1160,20 @@ extern "C" int ds_orbitals_vjp(ds_ctx* c, const double* x, int64_t batch, const 
 static int vjp_impl(ds_ctx* c, const double* x, int64_t batch, const double* cot_abs, const double* cot_phase,
                     const double* cot_mats, double* const* grads, const int64_t* sizes, int n_leaves, void* stream) {
     DS_REQUIRE(c && c->params_set, "parameters have not been set (ds_set_params)");
+    if (c->sys.d.use_last) {
+        ds_set_error("use_last_layer=True is implemented for the forward paths only (log psi, orbitals, local energy, Metropolis); "
+                     "the parameter gradient is not");
+        return DS_ERR_UNSUPPORTED;
+    }
     DS_REQUIRE(grads && sizes, "null argument");
     DS_REQUIRE(batch >= 0, "negative batch");
     Guard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     const DsDims& d = c->sys.d;
     const int L = d.L, H = d.H, P = d.P;
-    const int expect = 2 * L + 2 * (L - 1) + (c->bias_orb ? 4 : 2) + 4;
+    const int Lpair = d.use_last ? L : L - 1;        // pair layers
+    const int Korb = d.use_last ? 3 * H + 2 * P : H; // rows of the orbital weights
+    const int expect = 2 * L + 2 * Lpair + (c->bias_orb ? 4 : 2) + 4;
     DS_REQUIRE(n_leaves == expect, "expected %d gradient leaves for %d layers, got %d", expect, L, n_leaves);
     if (int rc = prepare_grad(c, st)) return rc;
     if (batch > 0) {
@@ -1193,6 +1247,10 @@ extern "C" int ds_kfac_factors(ds_ctx* c, const double* x, int64_t batch, double
     DS_REQUIRE(c && c->params_set, "parameters have not been set (ds_set_params)");
     DS_REQUIRE(a_out && a_sizes && g_out && g_sizes && env_abs && env_phase && env_sizes, "null argument");
     DS_REQUIRE(batch >= 0, "negative batch");
+    if (c->sys.d.use_last) {
+        ds_set_error("use_last_layer=True is implemented for the forward paths only; the Kronecker-factor statistics are not");
+        return DS_ERR_UNSUPPORTED;
+    }
     Guard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     const DsDims& d = c->sys.d;

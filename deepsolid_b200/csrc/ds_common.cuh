@@ -33,7 +33,11 @@ struct DsDims {
                             //    (network.py:552-559); 0: one n_s x n_s determinant per spin channel
     int C0, K0;             // F*A, F*A + 2F (layer-0 one-electron inputs, own + pair-mean)
     int K1;                 // H + 2P  (own + pair-mean columns of layers >= 1)
+    int use_last;           // use_last_layer (network.py:129-134, 528-533): L pair layers instead of L-1, and the orbital
+                            // projection takes the symmetric features of the last layer (own | spin means | pair means)
 };
+// number of two-electron feature levels (level 0 = input features; level l = output of pair layer l-1)
+__host__ __device__ __forceinline__ int ds_pair_levels(const DsDims& d) { return d.L + (d.use_last ? 1 : 0); }
 
 // orbitals per spin channel, and the Slater matrix an electron row goes to: block index, its size, the row index
 __host__ __device__ __forceinline__ int ds_norb(const DsDims& d, int s) { return d.full_det ? d.N : (s ? d.n_dn : d.n_up); }

@@ -28,7 +28,9 @@ __device__ __forceinline__ Jet pick4(const Jet (&f)[FT], int q) {    // f[q] wit
 template <bool JETS, int FT>
 __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const DsSys sys, const FeatParams fp) {
     const DsDims& dm = sys.d;
-    const int N = dm.N, A = dm.A, P = dm.P, L = dm.L, C0 = dm.C0, K0 = dm.K0, K1 = dm.K1, H = dm.H;
+    // L counts the two-electron feature LEVELS here (dm.L, or dm.L + 1 with use_last_layer): level l feeds layer l,
+    // the last level the orbital projection; pair layers 0 .. L-2
+    const int N = dm.N, A = dm.A, P = dm.P, L = ds_pair_levels(dm), C0 = dm.C0, K0 = dm.K0, K1 = dm.K1, H = dm.H;
     const int NDp = dm.NDp, ND = dm.ND;
     constexpr int F = FT;
     const long long e = blockIdx.x;             // w*N + i
@@ -253,7 +255,9 @@ __host__ __device__ inline int fv_pin_pad(int pin) { return (pin + 1) & ~1; }
 template <int FT>
 __global__ void __launch_bounds__(FV_WARPS * 32, 4) features_value_kernel(const DsSys sys, const FeatParams fp, long long n_items) {
     const DsDims& dm = sys.d;
-    const int N = dm.N, A = dm.A, P = dm.P, L = dm.L, C0 = dm.C0, K0 = dm.K0, K1 = dm.K1, H = dm.H;
+    // L counts the two-electron feature LEVELS here (dm.L, or dm.L + 1 with use_last_layer): level l feeds layer l,
+    // the last level the orbital projection; pair layers 0 .. L-2
+    const int N = dm.N, A = dm.A, P = dm.P, L = ds_pair_levels(dm), C0 = dm.C0, K0 = dm.K0, K1 = dm.K1, H = dm.H;
     constexpr int F = FT;
     constexpr int FP = (FT + 1) & ~1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -430,8 +434,9 @@ __global__ void __launch_bounds__(FV_WARPS * 32, 4) features_value_kernel(const 
 }  // namespace
 
 size_t ds_features_smem(const DsDims& d) {
-    size_t n = 3 * d.N + 2 * d.L * 5 * 32;
-    for (int l = 0; l < d.L - 1; ++l) n += ((l == 0) ? d.F : d.P) * d.P + d.P;
+    const int Lv = ds_pair_levels(d);
+    size_t n = 3 * d.N + 2 * Lv * 5 * 32;
+    for (int l = 0; l < Lv - 1; ++l) n += ((l == 0) ? d.F : d.P) * d.P + d.P;
     return n * sizeof(double);
 }
 
@@ -459,7 +464,8 @@ int ds_launch_features(const DsSys& sys, const FeatParams& fp, int Wc, bool jets
     if (!jets && sys.d.P <= 32 && !old_value) {
         // lane-per-pair value kernel
         const int fpad = fv_pin_pad(sys.d.F);
-        size_t n = (size_t)FV_WARPS * 32 * 33 + 32 * fpad + 32 + (size_t)(sys.d.L > 2 ? sys.d.L - 2 : 0) * (32 * 32 + 32);
+        const int Lv = ds_pair_levels(sys.d);
+        size_t n = (size_t)FV_WARPS * 32 * 33 + 32 * fpad + 32 + (size_t)(Lv > 2 ? Lv - 2 : 0) * (32 * 32 + 32);
         const size_t sm2 = n * sizeof(double);
         const long long n_items = 2LL * Wc * sys.d.N;
         long long blocks = (n_items + FV_WARPS - 1) / FV_WARPS;

@@ -51,6 +51,9 @@ struct SlaterBufs {
     double* XINV[2];        // complex inverse matrices [(w*D+k)][o][i] (parameter-gradient path only, else null)
 };
 int ds_launch_etab(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max, bool jets, cudaStream_t stream);
+// use_last_layer: add the shared spin-mean contribution GO (per spin, [Wc*rows x ldgo], rows = NDg with jets else 1) to YV / YL / YOWN / DA
+int ds_launch_orb_mean_addend(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max, const double* GO0, const double* GO1,
+                              int ldgo, bool jets, cudaStream_t stream);
 int ds_launch_orb_assemble(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max, bool jets, cudaStream_t stream);
 int ds_launch_det(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, cudaStream_t stream);
 int ds_launch_combine(const DsSys& sys, const SlaterBufs& sb, int Wc, bool lap, double* log_abs, double* phase,

@@ -150,6 +150,60 @@ __global__ void __launch_bounds__(256) assemble_kernel(const DsSys sys, const Sl
 }
 
 // ---------------------------------------------------------------------------
+// use_last_layer (network.py:528-533): the orbital projection also takes the spin-channel means of the last layer.
+// Their product with the mean rows of the weights, GO[w, row, (p, re|im)], is the same for every electron of a walker
+// and is added here to the raw outputs the per-electron GEMMs produced: value rows YV (row NDp of GO, or row 0 when
+// only values exist), Laplacian rows YL (row NDp+1), the own-gradient rows YOWN (rows 3i+c), and -- times the
+// envelope-phase factor E -- every Jacobian row d of the derivative matrices DA.  grid = Wc*N, before assemble.
+// ---------------------------------------------------------------------------
+template <bool JETS>
+__global__ void __launch_bounds__(256) orb_mean_addend_kernel(const DsSys sys, const SlaterBufs sb, int npar_max,
+                                                              const double* __restrict__ GO0, const double* __restrict__ GO1,
+                                                              int ldgo) {
+    const DsDims& dm = sys.d;
+    const long long e = blockIdx.x;
+    const int N = dm.N, D = dm.D, NDp = dm.NDp, ND = dm.ND;
+    const long long w = e / N;
+    const int i = (int)(e % N);
+    const int s = (i < dm.n_up) ? 0 : 1;
+    const int ns = ds_norb(dm, s);
+    const int blk = dm.full_det ? 0 : s;
+    const int nrow = ds_blk_n(dm, blk);
+    const int is = dm.full_det ? i : (s ? i - dm.n_up : i);
+    const int npar = ns * D;
+    const int rows = JETS ? dm.NDg : 1, vrow = JETS ? NDp : 0;
+    const cplx* go = reinterpret_cast<const cplx*>((s ? GO1 : GO0) + w * (long long)rows * ldgo);
+    const long long ldc = ldgo / 2;
+    const cplx* E = reinterpret_cast<const cplx*>(sb.ETAB) + e * 5LL * npar_max;
+    cplx* yv = reinterpret_cast<cplx*>(const_cast<double*>(sb.YV)) + e * (long long)npar_max;
+    for (int p = threadIdx.x; p < npar; p += blockDim.x) {
+        const cplx g = go[vrow * ldc + p];
+        yv[p].re += g.re; yv[p].im += g.im;
+    }
+    if (!JETS) return;
+    cplx* yl = reinterpret_cast<cplx*>(const_cast<double*>(sb.YL)) + e * (long long)npar_max;
+    cplx* yo = reinterpret_cast<cplx*>(const_cast<double*>(sb.YOWN)) + e * 3LL * npar_max;
+    for (int p = threadIdx.x; p < npar; p += blockDim.x) {
+        const cplx gl = go[(NDp + 1) * ldc + p];
+        yl[p].re += gl.re; yl[p].im += gl.im;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const cplx gc = go[(3 * i + c) * ldc + p];
+            yo[(long long)c * npar_max + p].re += gc.re; yo[(long long)c * npar_max + p].im += gc.im;
+        }
+    }
+    cplx* da = reinterpret_cast<cplx*>(sb.DA[blk]);
+    for (int idx = threadIdx.x; idx < ND * npar; idx += blockDim.x) {
+        const int d = idx / npar, p = idx - d * npar;
+        const int k = p / ns, o = p - k * ns;
+        const long long di = (((w * D + k) * NDp + d) * nrow + is) * (long long)ns + o;
+        cplx cur = da[di];
+        cfma(cur, go[d * ldc + p], E[p]);
+        da[di] = cur;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Determinant kernel: one CTA per (walker, spin, determinant).
 //   LAP=false: LU with partial pivoting -> log|det|, phase.
 //   LAP=true : in-place Gauss-Jordan inverse, then tr(X lapM), tr(X dM_d), tr((X dM_d)^2).
@@ -1236,6 +1290,15 @@ int ds_launch_orb_assemble(const DsSys& sys, const SlaterBufs& sb, int Wc, int n
     dim3 grid((unsigned)((long long)Wc * sys.d.N));
     if (jets) assemble_kernel<true><<<grid, 256, 0, stream>>>(sys, sb, npar_max);
     else assemble_kernel<false><<<grid, 256, 0, stream>>>(sys, sb, npar_max);
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ds_launch_orb_mean_addend(const DsSys& sys, const SlaterBufs& sb, int Wc, int npar_max, const double* GO0, const double* GO1,
+                              int ldgo, bool jets, cudaStream_t stream) {
+    dim3 grid((unsigned)((long long)Wc * sys.d.N));
+    if (jets) orb_mean_addend_kernel<true><<<grid, 256, 0, stream>>>(sys, sb, npar_max, GO0, GO1, ldgo);
+    else orb_mean_addend_kernel<false><<<grid, 256, 0, stream>>>(sys, sb, npar_max, GO0, GO1, ldgo);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

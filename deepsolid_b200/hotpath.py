@@ -41,11 +41,11 @@ def flatten_params(params) -> list:
     return leaves
 
 
-def unflatten_params(leaves, n_layers: int, bias_orbitals: bool = False) -> dict:
+def unflatten_params(leaves, n_layers: int, bias_orbitals: bool = False, use_last_layer: bool = False) -> dict:
     """Inverse of flatten_params."""
     it = iter(leaves)
     single = [{"w": next(it), "b": next(it)} for _ in range(n_layers)]
-    double = [{"w": next(it), "b": next(it)} for _ in range(n_layers - 1)]
+    double = [{"w": next(it), "b": next(it)} for _ in range(n_layers if use_last_layer else n_layers - 1)]
     orbital = [({"w": next(it), "b": next(it)} if bias_orbitals else {"w": next(it)}) for _ in range(2)]
     envelope = [{"pi": next(it), "sigma": next(it)} for _ in range(2)]
     return {"single": single, "double": double, "orbital": orbital, "envelope": envelope}
@@ -54,7 +54,7 @@ def unflatten_params(leaves, n_layers: int, bias_orbitals: bool = False) -> dict
 class HotPath:
     def __init__(self, simulation_cell, klist, hidden_dims=((256, 32),) * 3, determinants: int = 8,
                  device: Optional[int] = None, distance_type: str = "nu", envelope_type: str = "isotropic",
-                 bias_orbitals: bool = False, full_det: bool = False):
+                 bias_orbitals: bool = False, full_det: bool = False, use_last_layer: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("deepsolid_b200 needs a CUDA device: the local-energy hot path has no CPU fallback")
         self.lib = _lib.load()
@@ -78,6 +78,9 @@ class HotPath:
         self.envelope_type = envelope_type
         self.bias_orbitals = bool(bias_orbitals)
         self.full_det = bool(full_det)
+        self.use_last_layer = bool(use_last_layer)
+        if self.use_last_layer and len(hidden_dims) > 3:
+            raise ValueError("use_last_layer=True is implemented for at most 3 layers")
         self.n_up, self.n_dn = simulation_cell.nelec
         self.nelec = self.n_up + self.n_dn
         tb = build_ewald_tables(simulation_cell)
@@ -105,7 +108,7 @@ class HotPath:
         nd = _lib.NetDesc(n_layers=len(hidden_dims), hidden_one=hidden_dims[0][0], hidden_two=hidden_dims[0][1],
                           n_det=self.determinants, distance_type=1 if distance_type == "tri" else 0,
                           envelope_type=envs[envelope_type], bias_orbitals=1 if bias_orbitals else 0,
-                          full_det=1 if full_det else 0)
+                          full_det=1 if full_det else 0, use_last_layer=1 if use_last_layer else 0)
         h = C.c_void_p()
         _lib.check(self.lib.ds_ctx_create(C.byref(sd), C.byref(nd), self.device, C.byref(h)))
         self.h = h

@@ -99,11 +99,10 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
     unsupported = []
     if envelope_type not in ("isotropic", "diagonal", "full"):
         unsupported.append(f"envelope_type={envelope_type!r}")
-    if use_last_layer:
-        unsupported.append("use_last_layer=True")
     if unsupported:
-        raise ValueError("not implemented in the CUDA hot path: " + ", ".join(unsupported) +
-                         " (use_last_layer=True is the one structural option without a CUDA path)")
+        raise ValueError("not implemented in the CUDA hot path: " + ", ".join(unsupported))
+    if use_last_layer and len(hidden_dims) > 3:
+        raise ValueError("use_last_layer=True is implemented for at most 3 layers (forward paths only)")
     if simulation_cell is None or klist is None:
         raise ValueError("simulation_cell and klist are required")
     hd = tuple(tuple(int(v) for v in h) for h in hidden_dims)
@@ -120,7 +119,7 @@ def make_solid_fermi_net(envelope_type: str = "full", bias_orbitals: bool = Fals
         if state["hp"] is None:
             state["hp"] = HotPath(simulation_cell, klist, hidden_dims=hidden_dims, determinants=determinants,
                                   device=device, distance_type=distance_type, envelope_type=envelope_type,
-                                  bias_orbitals=bias_orbitals, full_det=full_det)
+                                  bias_orbitals=bias_orbitals, full_det=full_det, use_last_layer=use_last_layer)
         return state["hp"]
 
     def init(key, data=None):

@@ -92,6 +92,9 @@ typedef struct ds_net_desc {
     int32_t bias_orbitals; /* 1: every orbital[s] has a bias leaf b (2*n_s*D,) right after its w (network.py:177-179) */
     int32_t full_det;      /* 1: every spin channel makes N orbitals per determinant and ONE (N x N) determinant per k is
                             * taken (network.py:552-559): orbital w (H, 2*N*D), envelope (A, N*D), ds_orbitals -> (D, N, N) */
+    int32_t use_last_layer;/* 1: `double` has n_layers entries and orbital w has 3*H + 2*P rows (network.py:129-134, 528-533).
+                            * Forward paths only (log psi, orbitals, local energy, Metropolis); the parameter-gradient entry
+                            * points return DS_ERR_UNSUPPORTED for it. */
 } ds_net_desc;
 
 DS_API const char *ds_last_error(void);
@@ -107,7 +110,7 @@ DS_API int ds_set_workspace_limit(ds_ctx *ctx, size_t bytes);
 /* Parameter pytree of init_solid_fermi_net_params (network.py:135-184), flattened in
  * this order (L = n_layers):
  *   single[0].w, single[0].b, ..., single[L-1].w, single[L-1].b,
- *   double[0].w, double[0].b, ..., double[L-2].w, double[L-2].b,
+ *   double[0].w, double[0].b, ..., double[L-2].w, double[L-2].b,        (... double[L-1] with use_last_layer)
  *   orbital[0].w, [orbital[0].b,] orbital[1].w, [orbital[1].b,]      (b only with bias_orbitals)
  *   envelope[0].pi, envelope[0].sigma, envelope[1].pi, envelope[1].sigma
  * Every leaf is row-major fp64; pointers may be host or device memory; the data is
@@ -117,7 +120,7 @@ DS_API int ds_set_workspace_limit(ds_ctx *ctx, size_t bytes);
  * Shapes this library implements (anything else is refused with DS_ERR_INVALID / DS_ERR_UNSUPPORTED at
  * ds_ctx_create; the reference accepts arbitrary hidden_dims, network.py:100-134):
  *   - 2 <= n_layers <= 4, the same (hidden_one, hidden_two) in every layer, hidden_two even and <= 32,
- *     use_last_layer = False, envelope isotropic / diagonal / full, at most 6 primitive-cell atoms with 'nu'
+ *     use_last_layer only with n_layers <= 3 and only for the forward paths, envelope isotropic / diagonal / full, at most 6 primitive-cell atoms with 'nu'
  *     features (layer-0 operand rows <= 32 columns);
  *   - the tcgen05 int8-slice path of the Laplacian sweep needs hidden_one and hidden_one + 2 hidden_two to be
  *     multiples of 64 and <= 512 (digit kernels: K % 8 == 0, K <= 512) and fewer than 2^31 Jacobian rows per chunk

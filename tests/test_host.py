@@ -61,8 +61,9 @@ def test_constructor_errors_match_reference():
         network.make_solid_fermi_net(klist=kl, simulation_cell=sc, method_name="nope")
     with pytest.raises(ValueError, match="distance"):
         network.make_solid_fermi_net(klist=kl, simulation_cell=sc, distance_type="l2", envelope_type="isotropic", full_det=False)
-    with pytest.raises(ValueError, match="not implemented"):
-        network.make_solid_fermi_net(klist=kl, simulation_cell=sc, use_last_layer=True)
+    with pytest.raises(ValueError, match="at most 3 layers"):
+        network.make_solid_fermi_net(klist=kl, simulation_cell=sc, use_last_layer=True, hidden_dims=((256, 32),) * 4)
+    network.make_solid_fermi_net(klist=kl, simulation_cell=sc, use_last_layer=True)    # constructs (forward paths)
     with pytest.raises(ValueError, match="not implemented"):
         network.make_solid_fermi_net(klist=kl, simulation_cell=sc, envelope_type="output")
     network.make_solid_fermi_net(klist=kl, simulation_cell=sc)                  # reference defaults (full / full_det) construct

@@ -286,3 +286,59 @@ def test_gpu_spin_polarised_matches_oracle(name, nelec, full_det):
     xn, pm, masks = qmc.make_mcmc_step(sl.apply, B, lat, steps=steps)(P, X[:B].to(dev), (xi, u), 0.3, return_masks=True)
     xo, po, mo = O.make_mcmc_step(lambda p, x: O.batch_apply(f_sl, p, x), B, lat, steps=steps)(P, X[:B], (xi, u), 0.3)
     assert torch.equal(masks.cpu().bool(), mo)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,opts", [("h4", {}), ("graphene8", {}), ("lih_prim", {"bias_orbitals": True}),
+                                       ("h4", {"full_det": True}), ("graphene8", {"i8": False}),
+                                       ("li24", {"hidden_dims": ((256, 32), (256, 32))})])
+def test_gpu_use_last_layer_matches_oracle(name, opts):
+    """use_last_layer=True (network.py:129-134, 528-533): one more pair layer, and the orbital projection takes the
+    832-wide symmetric features of the last layer (own | spin means | pair means).  Forward paths against the oracle:
+    log psi, phase, orbital matrices, kinetic energy, accept masks; the parameter gradient is refused."""
+    from deepsolid_b200 import network, hamiltonian, qmc
+    opts = dict(opts)
+    i8 = opts.pop("i8", True)
+    hd = opts.pop("hidden_dims", ((256, 32),) * 3)
+    sc, kl, _, _ = system(name)
+    P = O.params_to_torch(O.init_params(np.random.default_rng(77), sc.original_cell.natm, sc.nelec, use_last_layer=True,
+                                        hidden_dims=hd, **opts))
+    assert len(P["double"]) == len(P["single"]) and P["orbital"][0]["w"].shape[0] == 3 * hd[0][0] + 2 * hd[0][1]
+    dev = torch.device("cuda", 0)
+    kw = dict(envelope_type="isotropic", klist=kl, simulation_cell=sc, determinants=8, use_last_layer=True, hidden_dims=hd,
+              full_det=opts.get("full_det", False), bias_orbitals=opts.get("bias_orbitals", False))
+    ld = network.make_solid_fermi_net(method_name="eval_logdet", **kw)
+    hp = ld.apply.hotpath()
+    sl = network.make_solid_fermi_net(method_name="eval_slogdet", hotpath=hp, **kw)
+    mt = network.make_solid_fermi_net(method_name="eval_mats", hotpath=hp, **kw)
+    okw = dict(full_det=opts.get("full_det", False), bias_orbitals=opts.get("bias_orbitals", False), hidden_dims=hd)
+    f_ld = O.make_solid_fermi_net(kl, sc, method_name="eval_logdet", **okw)
+    f_mt = O.make_solid_fermi_net(kl, sc, method_name="eval_mats", **okw)
+    f_sl = O.make_solid_fermi_net(kl, sc, method_name="eval_slogdet", **okw)
+    nw = 4
+    X = torch.as_tensor(C.init_walkers(sc, nw, seed=19))
+    if not i8:
+        hp.debug_set("i8", 0)
+    v = ld.apply(P, X.to(dev)).cpu()
+    mats = mt.apply(P, X.to(dev))
+    ke, ew = hamiltonian.local_energy_seperate(ld.apply, sc, mode="for")(P, X.to(dev))
+    elo = O.local_energy_seperate(f_ld, sc, mode="dim_batch")
+    for b in range(nw):
+        vo = f_ld(P, X[b])
+        assert abs(float(vo.real) - float(v[b].real)) < 1e-10
+        assert float(angle_diff(v[b].imag, vo.imag)) < 1e-10
+        mo = f_mt(P, X[b])
+        for s in range(len(mo)):
+            assert float((mats[s][b].cpu() - mo[s]).abs().max()) < 1e-11
+        ko, eo = elo(P, X[b])
+        assert abs(complex(ko) - complex(ke[b].cpu())) < 1e-8
+    steps = 3
+    rng = np.random.default_rng(5)
+    xi = torch.as_tensor(rng.standard_normal((steps, nw, X.shape[1])))
+    u = torch.as_tensor(rng.uniform(size=(steps, nw)))
+    xn, pm, masks = qmc.make_mcmc_step(sl.apply, nw, sc.lattice_vectors(), steps=steps)(P, X.to(dev), (xi, u), 0.3, return_masks=True)
+    xo, po, mo = O.make_mcmc_step(lambda p, x: O.batch_apply(f_sl, p, x), nw, sc.lattice_vectors(), steps=steps)(P, X, (xi, u), 0.3)
+    assert (masks.cpu().numpy().astype(bool) == mo.numpy().astype(bool)).all()
+    assert float((xn.cpu() - xo).abs().max()) < 1e-12
+    with pytest.raises(ValueError, match="forward paths only"):
+        hp.logpsi_vjp(X.to(dev), torch.ones(nw, dtype=torch.float64), torch.zeros(nw, dtype=torch.float64))
