@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import angle_diff
+from conftest import angle_diff, system
 from deepsolid_b200 import cell as C
 from oracle import deepsolid_oracle as O
 
