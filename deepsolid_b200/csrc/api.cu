@@ -100,7 +100,9 @@ struct ds_ctx {
     // transposed weights and gradient accumulators of the parameter-gradient path (ds_logpsi_vjp)
     double* B_amT[DS_MAX_LAYERS] = {};  // [H x (C + 2Pl)]
     double* B_gT[DS_MAX_LAYERS] = {};   // [H x 2C]
-    double* WorbT[2] = {};              // [2 npar_s x H]
+    double* WorbT[2] = {};              // [2 npar_s x H]  (use_last: [2 npar_s x K1])
+    double* WorbGT[2] = {};             // use_last: [2 npar_s x 2H]
+    double* gWorbG[2] = {};             // use_last: gradient of the spin-mean rows [2H x 2 npar_s]
     bool transposes_ready = false;
     double* gB_am[DS_MAX_LAYERS] = {};
     double* gB_g[DS_MAX_LAYERS] = {};
@@ -258,6 +260,7 @@ struct Layout {
     bool grad;
     double *Tl[DS_MAX_LAYERS], *GINV[DS_MAX_LAYERS];
     double *XINV[2], *GYs[2], *GH[2], *GZ, *GZS, *GA, *GG, *GPM[DS_MAX_LAYERS];
+    double *GYS[2];         // use_last: per-walker sums over the electrons of a spin channel of the orbital-output cotangents
     double *XF;             // factor statistics: explicit rows of a layer's input
 };
 
@@ -340,10 +343,15 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
             L.GINV[l] = ws.take(gn[l], W * 2 * (size_t)((l == 0) ? d.C0 : d.H));
             L.GPM[l] = (l > 0) ? ws.take(pn[l], W * N * 2 * d.P) : nullptr;
         }
+        if (d.use_last) {       // the orbital projection acts like one more (linear) layer on the symmetric features
+            L.GINV[d.L] = ws.take(gn[d.L], W * 2 * (size_t)d.H);
+            L.GPM[d.L] = ws.take(pn[d.L], W * N * 2 * d.P);
+        }
         for (int s = 0; s < 2; ++s) {
             size_t ns = c->n_s[s];
             L.XINV[s] = (s < nblk_of(c)) ? ws.take(s ? "XINV1" : "XINV0", W * d.D * blk_n(c, s) * blk_n(c, s) * 2) : nullptr;
             L.GYs[s] = ws.take(s ? "GY1" : "GY0", W * ns * 2 * c->npar[s]);
+            L.GYS[s] = d.use_last ? ws.take(s ? "GYS1" : "GYS0", W * 2 * (size_t)c->npar[s]) : nullptr;
         }
         L.GH[0] = ws.take("GH0", W * N * d.H);
         L.GH[1] = ws.take("GH1", W * N * d.H);
@@ -596,6 +604,10 @@ int run_chunk(ds_ctx* c, const double* X, int Wc, bool lap, double* log_abs, dou
         }
         if (int rc = ds_launch_means(d, Wc, H, hJ, d.K1, hV, hL, d.K1, Lo.GIN, 2 * H, lap, st, i8)) return rc;
         c->launches++;
+        if (grad)   // value rows of the spin means: operand of the gradient of the mean rows of the orbital weights
+            DS_CUDA_CHECK(cudaMemcpy2DAsync(Lo.GINV[L], (size_t)2 * H * sizeof(double), Lo.GIN + (size_t)d.NDp * 2 * H,
+                                            (size_t)d.NDg * 2 * H * sizeof(double), (size_t)2 * H * sizeof(double), Wc,
+                                            cudaMemcpyDeviceToDevice, st));
         for (int s = 0; s < 2; ++s) {
             if (c->n_s[s] == 0) continue;
             GemmParams g{};
@@ -707,10 +719,12 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
     const double* hL = Lo.V[L - 1];                   // output of the last layer (own columns)
     double* GHcur = Lo.GH[0];
     double* GHnext = Lo.GH[1];
+    const int Kam = d.use_last ? d.K1 : H;           // per-electron operand columns of the orbital projection
+    if (d.use_last) DS_CUDA_CHECK(cudaMemsetAsync(Lo.GG, 0, (size_t)Wc * 2 * H * sizeof(double), st));
     for (int s = 0; s < 2; ++s) {
         const int ns = c->n_s[s], np2 = 2 * c->npar[s];
-        GemmParams t{};                               // gWorb[s] += hL_s^T . GY_s
-        t.A = hL; t.lda = d.K1; t.M = H; t.K = Wc * ns; t.rpg = ns; t.gstride = N; t.goff = c->off_s[s];
+        GemmParams t{};                               // gWorb[s] += [hL | pair means]_s^T . GY_s
+        t.A = hL; t.lda = d.K1; t.M = Kam; t.K = Wc * ns; t.rpg = ns; t.gstride = N; t.goff = c->off_s[s];
         t.B = Lo.GYs[s]; t.ldb = np2; t.N = np2; t.C = c->gWorb[s]; t.ldc = np2; t.accumulate = 1;
         if (fact) {                                   // fGo[s] += GY_s^T . GY_s
             t.A = Lo.GYs[s]; t.lda = np2; t.M = np2; t.rpg = 0; t.C = c->fGo[s];
@@ -723,9 +737,30 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
         }
         GemmParams g{};                               // cotangent of h_L (rows of spin s) = GY_s . Worb_s^T
         g.A = Lo.GYs[s]; g.lda = np2; g.M = (long long)Wc * ns; g.K = np2; g.no_amap = 1;
-        g.B = c->WorbT[s]; g.ldb = H; g.N = H;
-        g.C = GHcur; g.ldc = H; g.cmap = 1; g.rpg = ns; g.gstride = N; g.goff = c->off_s[s];
-        if (int rc = gemm(c, g, GEMM_PLAIN, false, st)) return rc;
+        g.B = c->WorbT[s]; g.ldb = Kam; g.N = Kam;
+        // use_last: cotangent of [h_L | pair means of level L]; the spin-mean share is added by hin below
+        g.C = d.use_last ? Lo.GA : GHcur; g.ldc = Kam; g.cmap = 1; g.rpg = ns; g.gstride = N; g.goff = c->off_s[s];
+        if (ns > 0)
+            if (int rc = gemm(c, g, GEMM_PLAIN, false, st)) return rc;
+        if (d.use_last && ns > 0 && !fact) {
+            // per-walker sums of GY_s: cotangent of the shared spin-mean contribution GOO_s
+            if (int rc = ds_launch_group_rowsum(Lo.GYs[s], np2, ns, Wc, np2, Lo.GYS[s], st)) return rc;
+            c->launches++;
+            GemmParams m{};                           // gWorbG[s] += GINV_L^T . GYS_s
+            m.A = Lo.GINV[L]; m.lda = 2 * H; m.M = 2 * H; m.K = Wc; m.rpg = 0;
+            m.B = Lo.GYS[s]; m.ldb = np2; m.N = np2; m.C = c->gWorbG[s]; m.ldc = np2; m.accumulate = 1;
+            if (int rc = gemm(c, m, GEMM_TN, false, st)) return rc;
+            GemmParams q{};                           // GG += GYS_s . WorbG_s^T : cotangent of the spin means of h_L
+            q.A = Lo.GYS[s]; q.lda = np2; q.M = Wc; q.K = np2; q.rpg = 0;
+            q.B = c->WorbGT[s]; q.ldb = 2 * H; q.N = 2 * H; q.C = Lo.GG; q.ldc = 2 * H; q.accumulate = 1;
+            if (int rc = gemm(c, q, GEMM_PLAIN, false, st)) return rc;
+        }
+    }
+    if (d.use_last) {
+        // cotangent of h_L = own columns + the electron's share of the spin-mean cotangents; pair-mean columns -> level L
+        gb.GA = Lo.GA; gb.lda = d.K1; gb.GG = Lo.GG; gb.ldgg = 2 * H; gb.GHin = GHcur; gb.GPM = Lo.GPM[L]; gb.GH = GHcur;
+        if (int rc = ds_launch_hin(d, gb, Wc, H, d.K1, false, true, st)) return rc;
+        c->launches++;
     }
     for (int l = L - 1; l >= 0; --l) {
         const int C = (l == 0) ? d.C0 : H;
@@ -762,8 +797,8 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
         c->launches++;
         std::swap(GHcur, GHnext);
     }
-    for (int l = 1; l < L; ++l) gb.GPMl[l] = Lo.GPM[l];
-    for (int l = 0; l < L - 1; ++l) { gb.g_Wp[l] = c->gWp[l]; gb.g_bp[l] = c->gbp[l]; gb.fact_G[l] = c->fGp[l]; }
+    for (int l = 1; l < ds_pair_levels(d); ++l) gb.GPMl[l] = Lo.GPM[l];
+    for (int l = 0; l < ds_pair_levels(d) - 1; ++l) { gb.g_Wp[l] = c->gWp[l]; gb.g_bp[l] = c->gbp[l]; gb.fact_G[l] = c->fGp[l]; }
     (void)P;
     if (int rc = ds_launch_pair_grad(sys, fp, gb, Wc, st, fact ? 2 : 0)) return rc;
     c->launches++;
@@ -1108,7 +1143,7 @@ int prepare_grad(ds_ctx* c, cudaStream_t st) {
             if (int rc = ds_launch_transpose(c->B_g[l], 2 * C, H, c->B_gT[l], st)) return rc;
         }
     }
-    for (int l = 0; l < L - 1; ++l) {
+    for (int l = 0; l < ds_pair_levels(d) - 1; ++l) {
         const int pin = (l == 0) ? d.F : P;
         if (int rc = need(&c->gWp[l], (size_t)pin * P)) return rc;
         if (int rc = need(&c->gbp[l], (size_t)P)) return rc;
@@ -1117,8 +1152,16 @@ int prepare_grad(ds_ctx* c, cudaStream_t st) {
     }
     for (int s = 0; s < 2; ++s) {
         const size_t np2 = 2 * (size_t)c->npar[s];
-        if (int rc = need(&c->WorbT[s], np2 * H)) return rc;
-        if (int rc = need(&c->gWorb[s], np2 * H)) return rc;
+        const int Kam = d.use_last ? d.K1 : H;             // own (+ pair-mean) rows of the orbital weights
+        if (int rc = need(&c->WorbT[s], np2 * Kam)) return rc;
+        if (int rc = need(&c->gWorb[s], np2 * Kam)) return rc;
+        if (d.use_last) {
+            if (int rc = need(&c->WorbGT[s], np2 * 2 * H)) return rc;
+            if (int rc = need(&c->gWorbG[s], np2 * 2 * H)) return rc;
+            DS_CUDA_CHECK(cudaMemsetAsync(c->gWorbG[s], 0, np2 * 2 * H * sizeof(double), st));
+            if (!c->transposes_ready)
+                if (int rc = ds_launch_transpose(c->WorbG[s], 2 * H, (int)np2, c->WorbGT[s], st)) return rc;
+        }
         if (c->bias_orb) {
             if (int rc = need(&c->gborb[s], np2)) return rc;
             DS_CUDA_CHECK(cudaMemsetAsync(c->gborb[s], 0, np2 * sizeof(double), st));
@@ -1126,11 +1169,11 @@ int prepare_grad(ds_ctx* c, cudaStream_t st) {
         if (int rc = need(&c->genv_pi[s], (size_t)d.A * c->npar[s])) return rc;
         const size_t sig_mult = (d.env_type == 0) ? 1 : (d.env_type == 1 ? 3 : 9);
         if (int rc = need(&c->genv_sigma[s], sig_mult * d.A * c->npar[s])) return rc;
-        DS_CUDA_CHECK(cudaMemsetAsync(c->gWorb[s], 0, np2 * H * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->gWorb[s], 0, np2 * Kam * sizeof(double), st));
         DS_CUDA_CHECK(cudaMemsetAsync(c->genv_pi[s], 0, (size_t)d.A * c->npar[s] * sizeof(double), st));
         DS_CUDA_CHECK(cudaMemsetAsync(c->genv_sigma[s], 0, sig_mult * d.A * c->npar[s] * sizeof(double), st));
         if (!c->transposes_ready)
-            if (int rc = ds_launch_transpose(c->Worb[s], H, (int)np2, c->WorbT[s], st)) return rc;
+            if (int rc = ds_launch_transpose(c->Worb[s], Kam, (int)np2, c->WorbT[s], st)) return rc;
     }
     c->transposes_ready = true;
     return 0;
@@ -1160,11 +1203,6 @@ extern "C" int ds_orbitals_vjp(ds_ctx* c, const double* x, int64_t batch, const 
 static int vjp_impl(ds_ctx* c, const double* x, int64_t batch, const double* cot_abs, const double* cot_phase,
                     const double* cot_mats, double* const* grads, const int64_t* sizes, int n_leaves, void* stream) {
     DS_REQUIRE(c && c->params_set, "parameters have not been set (ds_set_params)");
-    if (c->sys.d.use_last) {
-        ds_set_error("use_last_layer=True is implemented for the forward paths only (log psi, orbitals, local energy, Metropolis); "
-                     "the parameter gradient is not");
-        return DS_ERR_UNSUPPORTED;
-    }
     DS_REQUIRE(grads && sizes, "null argument");
     DS_REQUIRE(batch >= 0, "negative batch");
     Guard g(c->device);
@@ -1206,15 +1244,24 @@ static int vjp_impl(ds_ctx* c, const double* x, int64_t batch, const double* cot
                                       cudaMemcpyDeviceToDevice, st));
         DS_CUDA_CHECK(cudaMemcpyAsync(b, c->gbias1[l], (size_t)H * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
-    for (int l = 0; l < L - 1; ++l) {
+    for (int l = 0; l < Lpair; ++l) {
         const int pin = (l == 0) ? d.F : P;
         DS_REQUIRE(sizes[li] == (int64_t)pin * P && sizes[li + 1] == P, "gradient leaf %d has the wrong size", li);
         DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->gWp[l], (size_t)pin * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
         DS_CUDA_CHECK(cudaMemcpyAsync(grads[li++], c->gbp[l], (size_t)P * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     for (int s = 0; s < 2; ++s) {
-        DS_REQUIRE(sizes[li] == (int64_t)H * 2 * c->npar[s], "gradient leaf %d has the wrong size", li);
-        if (int rc = ds_launch_deinterleave(c->gWorb[s], grads[li++], H, c->npar[s], st)) return rc;
+        DS_REQUIRE(sizes[li] == (int64_t)Korb * 2 * c->npar[s], "gradient leaf %d has the wrong size", li);
+        {
+            double* leaf = grads[li++];
+            const size_t np2 = 2 * (size_t)c->npar[s];
+            // reference rows: own [0,H) | spin means [H,3H) | pair means [3H,3H+2P)
+            if (int rc = ds_launch_deinterleave(c->gWorb[s], leaf, H, c->npar[s], st)) return rc;
+            if (d.use_last) {
+                if (int rc = ds_launch_deinterleave(c->gWorbG[s], leaf + (size_t)H * np2, 2 * H, c->npar[s], st)) return rc;
+                if (int rc = ds_launch_deinterleave(c->gWorb[s] + (size_t)H * np2, leaf + (size_t)3 * H * np2, 2 * P, c->npar[s], st)) return rc;
+            }
+        }
         if (c->bias_orb) {
             DS_REQUIRE(sizes[li] == (int64_t)2 * c->npar[s], "gradient leaf %d has the wrong size", li);
             if (int rc = ds_launch_deinterleave(c->gborb[s], grads[li++], 1, c->npar[s], st)) return rc;

@@ -180,7 +180,8 @@ template <int NPL, int FACT>
 __global__ void __launch_bounds__(PG_THREADS, (NPL <= 1 && FACT != 2) ? 2 : 1) pair_grad_kernel(const DsSys sys, const FeatParams fp,
                                                                                                 const GradBufs gb, long long n_e) {
     const DsDims& dm = sys.d;
-    const int N = dm.N, P = dm.P, L = dm.L, F = dm.F;
+    // L counts the pair-stream LEVELS (dm.L, or dm.L + 1 with use_last_layer: the last level feeds the orbital projection)
+    const int N = dm.N, P = dm.P, L = ds_pair_levels(dm), F = dm.F;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const double rs2 = 0.70710678118654752440;
 
@@ -508,14 +509,15 @@ int ds_launch_hin(const DsDims& dm, const GradBufs& gb, int Wc, int C, int K, bo
 
 int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& gb, int Wc, cudaStream_t stream, int fact) {
     const DsDims& d = sys.d;
-    if (d.L < 2) return 0;
+    const int Lv = ds_pair_levels(d);
+    if (Lv < 2) return 0;
     DS_REQUIRE(d.P <= 32, "pair-stream gradient kernel needs hidden_two <= 32");
     size_t n = 3 * d.N;
-    for (int l = 0; l < d.L - 1; ++l) n += 2 * ((l == 0) ? d.F : d.P) * d.P + d.P;
+    for (int l = 0; l < Lv - 1; ++l) n += 2 * ((l == 0) ? d.F : d.P) * d.P + d.P;
     n += (PG_THREADS / 32) * 33;
     const size_t smem = n * sizeof(double);
     const long long n_e = (long long)Wc * d.N;
-    const int npl = d.L - 2;
+    const int npl = Lv - 2;
     const int grid = (int)(n_e < 4 * 148 ? n_e : 4 * 148);
     DS_REQUIRE(fact == 0 || npl <= 2, "pair-layer factor statistics support at most 3 pair layers");
 #define DS_PG_LAUNCH2(NPL_, FACT_)                                                                                      \
@@ -535,6 +537,24 @@ int ds_launch_pair_grad(const DsSys& sys, const FeatParams& fp, const GradBufs& 
     else DS_PG_LAUNCH(2);
 #undef DS_PG_LAUNCH
 #undef DS_PG_LAUNCH2
+    DS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// dst[g][c] = sum_{r < rows_per_group} src[(g * rows_per_group + r) * lds + c]
+__global__ void __launch_bounds__(256) group_rowsum_kernel(const double* __restrict__ src, int lds, int rows_per_group, int cols,
+                                                           double* __restrict__ dst, int ldd) {
+    const long long g = blockIdx.x;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < rows_per_group; ++r) acc += src[(g * rows_per_group + r) * (long long)lds + c];
+        dst[g * (long long)ldd + c] = acc;
+    }
+}
+
+int ds_launch_group_rowsum(const double* src, int lds, int rows_per_group, int n_groups, int cols, double* dst, cudaStream_t stream) {
+    if (n_groups <= 0 || cols <= 0) return 0;
+    group_rowsum_kernel<<<(unsigned)n_groups, 256, 0, stream>>>(src, lds, rows_per_group, cols, dst, cols);
     DS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

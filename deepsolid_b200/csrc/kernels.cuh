@@ -106,6 +106,8 @@ int ds_launch_pair_fact_pack(const double* A32, const double* As, double count, 
 int ds_launch_deinterleave2(const double* src, double* dst, int np, cudaStream_t stream);
 // dst[r, c] (+)= src[r, c] for a [rows x cols] block (leading dimensions lds, ldd); deinterleave: see grad.cu
 int ds_launch_copy2d(const double* src, int lds, double* dst, int ldd, int rows, int cols, cudaStream_t stream);
+// dst[g][c] = sum over the rows_per_group rows of group g of src[.][c]
+int ds_launch_group_rowsum(const double* src, int lds, int rows_per_group, int n_groups, int cols, double* dst, cudaStream_t stream);
 int ds_launch_colsum_add(const double* src, int lds, int rows, int cols, double* dst, cudaStream_t stream);
 int ds_launch_deinterleave(const double* src, double* dst, int rows, int np, cudaStream_t stream);
 

@@ -204,7 +204,7 @@ class HotPath:
         sizes = (C.c_int64 * n)(*[o.numel() for o in outs])
         _lib.check(self.lib.ds_logpsi_vjp(self.h, td.data_ptr(), B, ca.data_ptr(), cp.data_ptr(), ptrs, sizes, n,
                                           self._stream()))
-        return unflatten_params(outs, len(self.hidden_dims), self.bias_orbitals)
+        return unflatten_params(outs, len(self.hidden_dims), self.bias_orbitals, self.use_last_layer)
 
     def orbitals_vjp(self, x, cot_mats):
         """Parameter gradient pytree of sum Re(conj(cot) * M) over the orbital matrices of ``orbitals(x)``
@@ -228,7 +228,7 @@ class HotPath:
         ptrs = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
         sizes = (C.c_int64 * n)(*[o.numel() for o in outs])
         _lib.check(self.lib.ds_orbitals_vjp(self.h, td.data_ptr(), B, cot.data_ptr(), ptrs, sizes, n, self._stream()))
-        return unflatten_params(outs, len(self.hidden_dims), self.bias_orbitals)
+        return unflatten_params(outs, len(self.hidden_dims), self.bias_orbitals, self.use_last_layer)
 
     def rho_q(self, x, qvecs, mode: int = 0):
         """Complex (B, nq) plane-wave sums over the electrons: mode 0 sum_i exp(i q.x_i), mode 1 exp(i sum_i q.x_i)

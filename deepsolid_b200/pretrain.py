@@ -78,10 +78,11 @@ def make_pretrain_step(batch_orbitals, batch_network, latvec, optimizer, full_de
         loss_val = dist.pmean(loss_val.reshape(1))[0]
         grads = hp.orbitals_vjp(x, cots)
         n_layers, bias_orb = len(params["single"]), "b" in params["orbital"][0]
+        last = len(params["double"]) == n_layers         # use_last_layer pytree
         g = [dist.pmean(t) for t in flatten_params(grads)]
-        updates, state = optimizer.update(unflatten_params(g, n_layers, bias_orb), state, params)
+        updates, state = optimizer.update(unflatten_params(g, n_layers, bias_orb, last), state, params)
         leaves = [torch.as_tensor(p).to(hp.tdev) + u for p, u in zip(flatten_params(params), updates)]
-        params = unflatten_params(leaves, n_layers, bias_orb)
+        params = unflatten_params(leaves, n_layers, bias_orb, last)
         if mh is None:                                   # one move of the default width (qmc.mh_update stddev=0.02)
             mh = qmc.make_mcmc_step(batch_network, x.shape[0], latvec, steps=1)
         logprob = 2.0 * batch_network(params, x)

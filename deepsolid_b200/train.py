@@ -112,7 +112,7 @@ def make_training_step(mcmc_step, val_and_grad, opt_update):
         data, pmove = mcmc_step(params, data, key, mcmc_width)
         (loss, aux_data), search_direction = val_and_grad(params, data)
         leaves = [_dist.pmean(torch.as_tensor(g)) for g in flatten_params(search_direction)]
-        search_direction = unflatten_params(leaves, len(params["single"]), "b" in params["orbital"][0])
+        search_direction = unflatten_params(leaves, len(params["single"]), "b" in params["orbital"][0], len(params["double"]) == len(params["single"]))
         state, params = opt_update(t, search_direction, params, state)
         return data, params, state, loss, aux_data, pmove, search_direction
 
@@ -136,6 +136,6 @@ def make_adam_update(schedule=None, b1: float = 0.9, b2: float = 0.999, eps: flo
         updates, state = adam.update(grads, state, params)
         lr = float(schedule(state["count"] - 1))
         leaves = [torch.as_tensor(p).to(u.device) + lr * u for p, u in zip(flatten_params(params), updates)]
-        return state, unflatten_params(leaves, len(params["single"]), "b" in params["orbital"][0])
+        return state, unflatten_params(leaves, len(params["single"]), "b" in params["orbital"][0], len(params["double"]) == len(params["single"]))
 
     return adam.init, opt_update

@@ -294,8 +294,8 @@ def test_gpu_spin_polarised_matches_oracle(name, nelec, full_det):
                                        ("li24", {"hidden_dims": ((256, 32), (256, 32))})])
 def test_gpu_use_last_layer_matches_oracle(name, opts):
     """use_last_layer=True (network.py:129-134, 528-533): one more pair layer, and the orbital projection takes the
-    832-wide symmetric features of the last layer (own | spin means | pair means).  Forward paths against the oracle:
-    log psi, phase, orbital matrices, kinetic energy, accept masks; the parameter gradient is refused."""
+    832-wide symmetric features of the last layer (own | spin means | pair means).  Against the oracle: log psi, phase,
+    orbital matrices, kinetic energy, accept masks, parameter gradient; only the Kronecker-factor statistics are refused."""
     from deepsolid_b200 import network, hamiltonian, qmc
     opts = dict(opts)
     i8 = opts.pop("i8", True)
@@ -340,5 +340,14 @@ def test_gpu_use_last_layer_matches_oracle(name, opts):
     xo, po, mo = O.make_mcmc_step(lambda p, x: O.batch_apply(f_sl, p, x), nw, sc.lattice_vectors(), steps=steps)(P, X, (xi, u), 0.3)
     assert (masks.cpu().numpy().astype(bool) == mo.numpy().astype(bool)).all()
     assert float((xn.cpu() - xo).abs().max()) < 1e-12
+    # parameter gradient (reverse sweep through the extra pair layer and the 832-row orbital projection) vs oracle autograd
+    from deepsolid_b200.hotpath import flatten_params
+    f_ps = O.make_solid_fermi_net(kl, sc, method_name="eval_phase_and_slogdet", **okw)
+    ca, cp = torch.as_tensor(rng.standard_normal(nw)), torch.as_tensor(rng.standard_normal(nw))
+    g = hp.logpsi_vjp(X.to(dev), ca, cp)
+    go = O.logpsi_vjp(f_ps, P, X, ca, cp)
+    for a, b in zip(flatten_params(g), flatten_params(go)):
+        scale = max(1.0, float(b.abs().max()))
+        assert tuple(a.shape) == tuple(b.shape) and float((a.cpu() - b).abs().max()) < 1e-9 * scale
     with pytest.raises(ValueError, match="forward paths only"):
-        hp.logpsi_vjp(X.to(dev), torch.ones(nw, dtype=torch.float64), torch.zeros(nw, dtype=torch.float64))
+        hp.kfac_factors(X.to(dev))
