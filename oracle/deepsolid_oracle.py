@@ -664,7 +664,7 @@ def _leaves(params):
     for layer in params["double"]:
         out += [layer["w"], layer["b"]]
     for orb in params["orbital"]:
-        out += [orb["w"]]
+        out += [orb["w"]] + ([orb["b"]] if "b" in orb else [])
     for env in params["envelope"]:
         out += [env["pi"], env["sigma"]]
     return out
@@ -692,7 +692,7 @@ def logpsi_vjp(apply_phase_slog, params, X, cot_abs, cot_phase):
     it = iter([g if g is not None else torch.zeros_like(l) for g, l in zip(grads, _leaves(P))])
     return {"single": [{"w": next(it), "b": next(it)} for _ in params["single"]],
             "double": [{"w": next(it), "b": next(it)} for _ in params["double"]],
-            "orbital": [{"w": next(it)} for _ in params["orbital"]],
+            "orbital": [({"w": next(it), "b": next(it)} if "b" in o else {"w": next(it)}) for o in params["orbital"]],
             "envelope": [{"pi": next(it), "sigma": next(it)} for _ in params["envelope"]]}
 
 
@@ -931,5 +931,5 @@ def pretrain_loss_and_grad(apply_mats, params, X, target, full_det=False):
     it = iter([g if g is not None else torch.zeros_like(l) for g, l in zip(grads, _leaves(P))])
     return loss.detach(), {"single": [{"w": next(it), "b": next(it)} for _ in params["single"]],
                            "double": [{"w": next(it), "b": next(it)} for _ in params["double"]],
-                           "orbital": [{"w": next(it)} for _ in params["orbital"]],
+                           "orbital": [({"w": next(it), "b": next(it)} if "b" in o else {"w": next(it)}) for o in params["orbital"]],
                            "envelope": [{"pi": next(it), "sigma": next(it)} for _ in params["envelope"]]}
