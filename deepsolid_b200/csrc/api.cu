@@ -262,6 +262,7 @@ struct Layout {
     double *XINV[2], *GYs[2], *GH[2], *GZ, *GZS, *GA, *GG, *GPM[DS_MAX_LAYERS];
     double *GYS[2];         // use_last: per-walker sums over the electrons of a spin channel of the orbital-output cotangents
     double *XF;             // factor statistics: explicit rows of a layer's input
+    double *XF2;            // use_last: the spin-channel rows of the orbital projection's input, gathered from XF
 };
 
 // The fused-digit sweep (OZ_JACD) needs exactly two 128-channel blocks and at most 64 pair-mean columns.
@@ -360,6 +361,7 @@ void carve(ds_ctx* c, Workspace& ws, Layout& L, int Wc, bool lap, bool grad = fa
         L.GA = ws.take("GA", W * N * d.K1);
         L.GG = ws.take("GG", W * 2 * d.H);
         L.XF = c->fact_on ? ws.take("XF", W * N * (3 * cmax + 2 * (size_t)std::max(d.P, d.F) + 2)) : nullptr;
+        L.XF2 = (c->fact_on && d.use_last) ? ws.take("XF2", W * N * (3 * cmax + 2 * (size_t)std::max(d.P, d.F) + 2)) : nullptr;
     }
 }
 
@@ -822,19 +824,28 @@ int fact_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
         t.B = Lo.XF; t.ldb = ldx; t.N = ldx; t.C = c->fA1[l]; t.ldc = ldx; t.accumulate = 1;
         if (int rc = gemm(c, t, GEMM_TN, false, st)) return rc;
     }
+    if (d.use_last) {       // the projection's input = symmetric features of the last layer: [own | spin means | pair means | 1 | 0]
+        if (int rc = ds_launch_layer_input_rows(Lo.V[L - 1], d.K1, Lo.GINV[L], H, N, (long long)Wc * N, Lo.XF, st)) return rc;
+        c->launches++;
+    }
     for (int s = 0; s < 2; ++s) {
         const int ns = c->n_s[s];
         if (ns == 0) continue;
-        if (int rc = ds_launch_spin_rows(Lo.V[L - 1], d.K1, H, N, c->off_s[s], ns, Wc, Lo.XF, st)) return rc;
+        const int kin = d.use_last ? 3 * H + 2 * d.P : H;
+        const double* rows_s = Lo.XF;
+        if (d.use_last) {
+            if (int rc = ds_launch_spin_rows(Lo.XF, kin + 2, kin, N, c->off_s[s], ns, Wc, Lo.XF2, st)) return rc;
+            rows_s = Lo.XF2;
+        } else if (int rc = ds_launch_spin_rows(Lo.V[L - 1], d.K1, H, N, c->off_s[s], ns, Wc, Lo.XF, st)) return rc;
         c->launches++;
         GemmParams t{};
-        t.A = Lo.XF; t.lda = H + 2; t.M = H + 2; t.K = (long long)Wc * ns; t.rpg = 0;
-        t.B = Lo.XF; t.ldb = H + 2; t.N = H + 2; t.C = c->fAo[s]; t.ldc = H + 2; t.accumulate = 1;
+        t.A = rows_s; t.lda = kin + 2; t.M = kin + 2; t.K = (long long)Wc * ns; t.rpg = 0;
+        t.B = rows_s; t.ldb = kin + 2; t.N = kin + 2; t.C = c->fAo[s]; t.ldc = kin + 2; t.accumulate = 1;
         if (int rc = gemm(c, t, GEMM_TN, false, st)) return rc;
     }
     {
         GradBufs gb{};
-        for (int l = 0; l < L - 1; ++l) { gb.fact_A[l] = c->fAp[l]; gb.fact_As[l] = c->fAps[l]; }
+        for (int l = 0; l < ds_pair_levels(d) - 1; ++l) { gb.fact_A[l] = c->fAp[l]; gb.fact_As[l] = c->fAps[l]; }
         if (int rc = ds_launch_pair_grad(c->sys, fp, gb, Wc, st, 1)) return rc;
         c->launches++;
     }
@@ -1294,15 +1305,13 @@ extern "C" int ds_kfac_factors(ds_ctx* c, const double* x, int64_t batch, double
     DS_REQUIRE(c && c->params_set, "parameters have not been set (ds_set_params)");
     DS_REQUIRE(a_out && a_sizes && g_out && g_sizes && env_abs && env_phase && env_sizes, "null argument");
     DS_REQUIRE(batch >= 0, "negative batch");
-    if (c->sys.d.use_last) {
-        ds_set_error("use_last_layer=True is implemented for the forward paths only; the Kronecker-factor statistics are not");
-        return DS_ERR_UNSUPPORTED;
-    }
     Guard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     const DsDims& d = c->sys.d;
     const int L = d.L, H = d.H, P = d.P, N = d.N;
-    DS_REQUIRE(n_layers == 2 * L - 1 + 2, "expected %d tagged layers, got %d", 2 * L + 1, n_layers);
+    const int Lpair = ds_pair_levels(d) - 1;          // tagged pair layers
+    const int Kin = d.use_last ? 3 * H + 2 * P : H;   // inputs of the orbital projections
+    DS_REQUIRE(n_layers == L + Lpair + 2, "expected %d tagged layers, got %d", L + Lpair + 2, n_layers);
     DS_REQUIRE(n_env == 4, "expected 4 envelope leaves, got %d", n_env);
     if (int rc = prepare_grad(c, st)) return rc;
     auto need = [&](double** p, size_t n) -> int { if (!*p) { if (int rc = dev_alloc(c, p, n)) return rc; } return 0; };
@@ -1315,7 +1324,7 @@ extern "C" int ds_kfac_factors(ds_ctx* c, const double* x, int64_t batch, double
         DS_CUDA_CHECK(cudaMemsetAsync(c->fA1[l], 0, ldx * ldx * sizeof(double), st));
         DS_CUDA_CHECK(cudaMemsetAsync(c->fG1[l], 0, (size_t)H * H * sizeof(double), st));
     }
-    for (int l = 0; l < L - 1; ++l) {
+    for (int l = 0; l < Lpair; ++l) {
         if (int rc = need(&c->fAp[l], 32 * 32)) return rc;
         if (int rc = need(&c->fAps[l], 32)) return rc;
         if (int rc = need(&c->fGp[l], 32 * 32)) return rc;
@@ -1325,9 +1334,9 @@ extern "C" int ds_kfac_factors(ds_ctx* c, const double* x, int64_t batch, double
     }
     for (int s = 0; s < 2; ++s) {
         const size_t np2 = 2 * (size_t)c->npar[s];
-        if (int rc = need(&c->fAo[s], (size_t)(H + 2) * (H + 2))) return rc;
+        if (int rc = need(&c->fAo[s], (size_t)(Kin + 2) * (Kin + 2))) return rc;
         if (int rc = need(&c->fGo[s], std::max<size_t>(np2 * np2, 1))) return rc;
-        DS_CUDA_CHECK(cudaMemsetAsync(c->fAo[s], 0, (size_t)(H + 2) * (H + 2) * sizeof(double), st));
+        DS_CUDA_CHECK(cudaMemsetAsync(c->fAo[s], 0, (size_t)(Kin + 2) * (Kin + 2) * sizeof(double), st));
         DS_CUDA_CHECK(cudaMemsetAsync(c->fGo[s], 0, np2 * np2 * sizeof(double), st));
         for (int ps = 0; ps < 2; ++ps) {
             const size_t npi = std::max<size_t>((size_t)d.A * c->npar[s], 1);
@@ -1373,7 +1382,7 @@ extern "C" int ds_kfac_factors(ds_ctx* c, const double* x, int64_t batch, double
         if (int rc = ds_launch_copy2d(c->fA1[l], ldx, a_out[li], nin, nin, nin, st)) return rc;
         DS_CUDA_CHECK(cudaMemcpyAsync(g_out[li], c->fG1[l], (size_t)H * H * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
-    for (int l = 0; l < L - 1; ++l, ++li) {
+    for (int l = 0; l < Lpair; ++l, ++li) {
         const int pin = (l == 0) ? d.F : P;
         DS_REQUIRE(a_sizes[li] == (int64_t)(pin + 1) * (pin + 1) && g_sizes[li] == (int64_t)P * P, "factor %d has the wrong size", li);
         if (int rc = ds_launch_pair_fact_pack(c->fAp[l], c->fAps[l], (double)batch * N * N, pin, a_out[li], st)) return rc;
@@ -1381,8 +1390,8 @@ extern "C" int ds_kfac_factors(ds_ctx* c, const double* x, int64_t batch, double
     }
     for (int s = 0; s < 2; ++s, ++li) {
         const int64_t np2 = 2 * (int64_t)c->npar[s];
-        DS_REQUIRE(a_sizes[li] == (int64_t)(H + 1) * (H + 1) && g_sizes[li] == np2 * np2, "factor %d has the wrong size", li);
-        if (int rc = ds_launch_copy2d(c->fAo[s], H + 2, a_out[li], H + 1, H + 1, H + 1, st)) return rc;
+        DS_REQUIRE(a_sizes[li] == (int64_t)(Kin + 1) * (Kin + 1) && g_sizes[li] == np2 * np2, "factor %d has the wrong size", li);
+        if (int rc = ds_launch_copy2d(c->fAo[s], Kin + 2, a_out[li], Kin + 1, Kin + 1, Kin + 1, st)) return rc;
         if (int rc = ds_launch_deinterleave2(c->fGo[s], g_out[li], c->npar[s], st)) return rc;
     }
     for (int s = 0; s < 2; ++s) {

@@ -253,9 +253,6 @@ class HotPath:
         ``g`` = sum_rows ga ga^T + gp gp^T and ``rows``; plus ``envelope_abs`` / ``envelope_phase``: gradients of
         sum_w log|psi_w| / sum_w angle(psi_w) w.r.t. the (untagged) envelope leaves.  deepsolid_b200.kfac turns these
         into the reference's factors."""
-        if self.use_last_layer:
-            raise ValueError("use_last_layer=True is implemented for the forward paths only and the parameter gradient; "
-                             "the Kronecker-factor statistics are not")
         t, one, on_dev = self._prep(x)
         td = t if on_dev else t.to(self.tdev)
         B = td.shape[0]
@@ -268,7 +265,7 @@ class HotPath:
         for l in range(L):
             kinds.append(("single", l)); nin.append(leaves[li].shape[0]); nout.append(leaves[li].shape[1])
             rows.append(B * self.nelec); li += 2
-        for l in range(L - 1):
+        for l in range(L if self.use_last_layer else L - 1):
             kinds.append(("double", l)); nin.append(leaves[li].shape[0]); nout.append(leaves[li].shape[1])
             rows.append(B * self.nelec * self.nelec); li += 2
         for s, ns in enumerate((self.n_up, self.n_dn)):

@@ -93,7 +93,7 @@ typedef struct ds_net_desc {
     int32_t full_det;      /* 1: every spin channel makes N orbitals per determinant and ONE (N x N) determinant per k is
                             * taken (network.py:552-559): orbital w (H, 2*N*D), envelope (A, N*D), ds_orbitals -> (D, N, N) */
     int32_t use_last_layer;/* 1: `double` has n_layers entries and orbital w has 3*H + 2*P rows (network.py:129-134, 528-533).
-                            * Every entry point except ds_kfac_factors (DS_ERR_UNSUPPORTED) implements it; n_layers <= 3. */
+                            * Implemented by every entry point; needs n_layers <= 3. */
 } ds_net_desc;
 
 DS_API const char *ds_last_error(void);
@@ -119,7 +119,7 @@ DS_API int ds_set_workspace_limit(ds_ctx *ctx, size_t bytes);
  * Shapes this library implements (anything else is refused with DS_ERR_INVALID / DS_ERR_UNSUPPORTED at
  * ds_ctx_create; the reference accepts arbitrary hidden_dims, network.py:100-134):
  *   - 2 <= n_layers <= 4, the same (hidden_one, hidden_two) in every layer, hidden_two even and <= 32,
- *     use_last_layer only with n_layers <= 3 (no Kronecker-factor statistics), envelope isotropic / diagonal / full, at most 6 primitive-cell atoms with 'nu'
+ *     use_last_layer only with n_layers <= 3, envelope isotropic / diagonal / full, at most 6 primitive-cell atoms with 'nu'
  *     features (layer-0 operand rows <= 32 columns);
  *   - the tcgen05 int8-slice path of the Laplacian sweep needs hidden_one and hidden_one + 2 hidden_two to be
  *     multiples of 64 and <= 512 (digit kernels: K % 8 == 0, K <= 512) and fewer than 2^31 Jacobian rows per chunk

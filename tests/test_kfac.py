@@ -82,6 +82,8 @@ def _rel(a, b):
     ("h4", 3, {"distance_type": "tri"}),
     ("h4", 3, {"full_det": True}),
     ("graphite54", 2, {}),
+    ("h4", 3, {"use_last_layer": True}),
+    ("graphene8", 3, {"use_last_layer": True, "bias_orbitals": True}),
 ])
 def test_gpu_kfac_factors_match_oracle(name, nw, opts):
     from deepsolid_b200 import network
@@ -92,7 +94,8 @@ def test_gpu_kfac_factors_match_oracle(name, nw, opts):
     net = network.make_solid_fermi_net(envelope_type="isotropic", klist=kl, simulation_cell=sc, determinants=8,
                                        method_name="eval_logdet", full_det=opts.get("full_det", False),
                                        bias_orbitals=opts.get("bias_orbitals", False),
-                                       distance_type=opts.get("distance_type", "nu"))
+                                       distance_type=opts.get("distance_type", "nu"),
+                                       use_last_layer=opts.get("use_last_layer", False))
     hp = net.apply.hotpath()
     X = torch.as_tensor(C.init_walkers(sc, nw, seed=21))
     f = O.make_solid_fermi_net(kl, sc, method_name="eval_phase_and_slogdet", full_det=opts.get("full_det", False),

@@ -295,7 +295,7 @@ def test_gpu_spin_polarised_matches_oracle(name, nelec, full_det):
 def test_gpu_use_last_layer_matches_oracle(name, opts):
     """use_last_layer=True (network.py:129-134, 528-533): one more pair layer, and the orbital projection takes the
     832-wide symmetric features of the last layer (own | spin means | pair means).  Against the oracle: log psi, phase,
-    orbital matrices, kinetic energy, accept masks, parameter gradient; only the Kronecker-factor statistics are refused."""
+    orbital matrices, kinetic energy, accept masks, parameter gradient (the Kronecker-factor statistics: test_kfac.py)."""
     from deepsolid_b200 import network, hamiltonian, qmc
     opts = dict(opts)
     i8 = opts.pop("i8", True)
@@ -349,5 +349,3 @@ def test_gpu_use_last_layer_matches_oracle(name, opts):
     for a, b in zip(flatten_params(g), flatten_params(go)):
         scale = max(1.0, float(b.abs().max()))
         assert tuple(a.shape) == tuple(b.shape) and float((a.cpu() - b).abs().max()) < 1e-9 * scale
-    with pytest.raises(ValueError, match="forward paths only"):
-        hp.kfac_factors(X.to(dev))
