@@ -744,14 +744,16 @@ int grad_sweep(ds_ctx* c, Layout& Lo, const FeatParams& fp, SlaterBufs& sb, int 
         g.C = d.use_last ? Lo.GA : GHcur; g.ldc = Kam; g.cmap = 1; g.rpg = ns; g.gstride = N; g.goff = c->off_s[s];
         if (ns > 0)
             if (int rc = gemm(c, g, GEMM_PLAIN, false, st)) return rc;
-        if (d.use_last && ns > 0 && !fact) {
+        if (d.use_last && ns > 0) {
             // per-walker sums of GY_s: cotangent of the shared spin-mean contribution GOO_s
             if (int rc = ds_launch_group_rowsum(Lo.GYs[s], np2, ns, Wc, np2, Lo.GYS[s], st)) return rc;
             c->launches++;
-            GemmParams m{};                           // gWorbG[s] += GINV_L^T . GYS_s
-            m.A = Lo.GINV[L]; m.lda = 2 * H; m.M = 2 * H; m.K = Wc; m.rpg = 0;
-            m.B = Lo.GYS[s]; m.ldb = np2; m.N = np2; m.C = c->gWorbG[s]; m.ldc = np2; m.accumulate = 1;
-            if (int rc = gemm(c, m, GEMM_TN, false, st)) return rc;
+            if (!fact) {
+                GemmParams m{};                       // gWorbG[s] += GINV_L^T . GYS_s
+                m.A = Lo.GINV[L]; m.lda = 2 * H; m.M = 2 * H; m.K = Wc; m.rpg = 0;
+                m.B = Lo.GYS[s]; m.ldb = np2; m.N = np2; m.C = c->gWorbG[s]; m.ldc = np2; m.accumulate = 1;
+                if (int rc = gemm(c, m, GEMM_TN, false, st)) return rc;
+            }
             GemmParams q{};                           // GG += GYS_s . WorbG_s^T : cotangent of the spin means of h_L
             q.A = Lo.GYS[s]; q.lda = np2; q.M = Wc; q.K = np2; q.rpg = 0;
             q.B = c->WorbGT[s]; q.ldb = 2 * H; q.N = 2 * H; q.C = Lo.GG; q.ldc = 2 * H; q.accumulate = 1;
