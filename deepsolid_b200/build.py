@@ -20,6 +20,7 @@ LIB = HERE / "libdeepsolid_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("DS_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DDS_OZ_PROF for the role clocks of oz_gemm_kernel
 
 
 def _deps():

@@ -1672,6 +1672,16 @@ extern "C" int ds_debug_set_int(ds_ctx* c, const char* key, int value) {
 extern "C" int64_t ds_debug_buffer(ds_ctx* c, const char* name, double* dst, int64_t max_doubles) {
     if (!c || !name) return -1;
     Guard g(c->device);
+    if (!strcmp(name, "oz_prof")) {          // role clocks of oz_gemm_kernel (DS_OZ_OPT bit 32), 8 modes x 8 counters; read clears
+        if (dst && max_doubles >= 64) {
+            unsigned long long raw[64];
+            if (ds_oz_prof_read(raw, 1)) return -2;
+            double v[64];
+            for (int i = 0; i < 64; ++i) v[i] = (double)raw[i];
+            if (cudaMemcpy(dst, v, sizeof(v), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+        }
+        return 64;
+    }
     for (const Region& r : c->last_regions) {
         if (!strcmp(r.name, name)) {
             if (!r.p) return 0;

@@ -37,8 +37,11 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
     const int w = (int)(e / N), i = (int)(e % N);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 
-    extern __shared__ double sm[];
-    double* sx = sm;                            // [N*3] wrapped (simulation cell) positions
+    extern __shared__ __align__(16) double sm[];
+    // per-warp broadcast scratch [32 channels][v g0 g1 g2 l pad]: the pair layers read the jets of input channel c
+    // from here (three 128-bit broadcast loads) instead of ten 32-bit shuffles per channel
+    double* cs = sm + warp * (32 * 6);
+    double* sx = sm + 8 * (32 * 6);             // [N*3] wrapped (simulation cell) positions
     double* sums = sx + 3 * N;                  // [2 spins][L levels][5 comps][32 lanes]
     double* wsm = sums + 2 * L * 5 * 32;        // pair weights: level l>=1: [P_in x P] + [P] bias
     const double* x = fp.X + (long long)w * 3 * N;
@@ -149,17 +152,26 @@ __global__ void __launch_bounds__(FEAT_THREADS, 2) features_pair_kernel(const Ds
             const double* W = wsm + woff;
             const double* bb = W + Pl * P;
             Jet z = jet_const(lane < P ? bb[lane] : 0.0);
-            for (int c = 0; c < Pl; ++c) {
-                double wv = (lane < P) ? W[c * P + lane] : 0.0;
-                double cv = __shfl_sync(0xffffffffu, cur.v, c);
-                z.v = fma(cv, wv, z.v);
-                if (JETS) {
-                    double c0 = __shfl_sync(0xffffffffu, cur.g0, c);
-                    double c1 = __shfl_sync(0xffffffffu, cur.g1, c);
-                    double c2 = __shfl_sync(0xffffffffu, cur.g2, c);
-                    double cl = __shfl_sync(0xffffffffu, cur.l, c);
-                    z.g0 = fma(c0, wv, z.g0); z.g1 = fma(c1, wv, z.g1); z.g2 = fma(c2, wv, z.g2);
+            if (JETS) {
+                __syncwarp();
+                *reinterpret_cast<double2*>(cs + lane * 6) = make_double2(cur.v, cur.g0);
+                *reinterpret_cast<double2*>(cs + lane * 6 + 2) = make_double2(cur.g1, cur.g2);
+                cs[lane * 6 + 4] = cur.l;
+                __syncwarp();
+#pragma unroll 4
+                for (int c = 0; c < Pl; ++c) {
+                    const double wv = (lane < P) ? W[c * P + lane] : 0.0;
+                    const double2 a = *reinterpret_cast<const double2*>(cs + c * 6);
+                    const double2 b = *reinterpret_cast<const double2*>(cs + c * 6 + 2);
+                    const double cl = cs[c * 6 + 4];
+                    z.v = fma(a.x, wv, z.v);
+                    z.g0 = fma(a.y, wv, z.g0); z.g1 = fma(b.x, wv, z.g1); z.g2 = fma(b.y, wv, z.g2);
                     z.l = fma(cl, wv, z.l);
+                }
+            } else {
+                for (int c = 0; c < Pl; ++c) {
+                    const double wv = (lane < P) ? W[c * P + lane] : 0.0;
+                    z.v = fma(__shfl_sync(0xffffffffu, cur.v, c), wv, z.v);
                 }
             }
             Jet t;
@@ -435,7 +447,7 @@ __global__ void __launch_bounds__(FV_WARPS * 32, 4) features_value_kernel(const 
 
 size_t ds_features_smem(const DsDims& d) {
     const int Lv = ds_pair_levels(d);
-    size_t n = 3 * d.N + 2 * Lv * 5 * 32;
+    size_t n = 8 * (32 * 6) + 3 * d.N + 2 * Lv * 5 * 32;
     for (int l = 0; l < Lv - 1; ++l) n += ((l == 0) ? d.F : d.P) * d.P + d.P;
     return n * sizeof(double);
 }

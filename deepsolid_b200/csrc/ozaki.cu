@@ -7,6 +7,13 @@
 
 namespace {
 
+// Compiled in only with -DDS_OZ_PROF (the clocks cost the epilogue registers): DS_EXTRA_NVCC_FLAGS=-DDS_OZ_PROF python -m deepsolid_b200.build -f
+#ifdef DS_OZ_PROF
+constexpr bool OZ_PROF = true;
+#else
+constexpr bool OZ_PROF = false;
+#endif
+
 constexpr int EPI_WARPS = 16;                         // four per TMEM lane quarter
 constexpr int EPI_COLS = 16;                          // columns (rows of A) per epilogue warp
 constexpr int OZ_THREADS = 64 + EPI_WARPS * 32;       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..: epilogue
@@ -116,6 +123,25 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 8 doubles <-> 16 consecutive 32-bit columns of this thread's TMEM lane (the 128 columns the accumulators leave free
+// serve as a per-thread parking space of 16 doubles)
+__device__ __forceinline__ void tmem_st8d(uint32_t taddr, const double* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
+          "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])),
+          "r"(__double2loint(v[4])), "r"(__double2hiint(v[4])), "r"(__double2loint(v[5])), "r"(__double2hiint(v[5])),
+          "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(__double2loint(v[7])), "r"(__double2hiint(v[7]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8d(uint32_t taddr, double* v) {
+    int w[16];
+    tmem_ld16(taddr, w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __hiloint2double(w[2 * j + 1], w[2 * j]);
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- thread-block cluster / distributed shared memory (OZ_JACD: the two 128-channel CTAs of a row tile) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -396,23 +422,34 @@ __global__ void __launch_bounds__(256, 2) slice_means_kernel(const double* __res
 // 128-channel block is inside N (no per-lane predicates, straight-line code the scheduler can
 // interleave across the 8 columns); all loads are issued before the first use.
 // ---------------------------------------------------------------------------
+// sa[r] * sb[n] for power-of-two scales, formed on the integer pipe (the epilogue waits on the fp64 pipe): both are
+// 2^k (slice_row_warp) or NaN for a row / column holding inf or nan, so the product is an exponent-field addition.
+// sch = high word of sa[r]; sbo = high word of sb[n] 2^-16 minus the exponent bias; badc = column flagged.
+// A product below the normal range (an all-zero padding row times a small column scale) becomes 0, as fp64 would.
+__device__ __forceinline__ double pow2_scale(int sch, int sbo, bool badc) {
+    int h = max(sch + sbo, 0);
+    if (badc || sch >= 0x7ff00000) h = 0x7ff80000;
+    return __hiloint2double(h, 0);
+}
+
 template <bool RES, bool FULL>
 __device__ __forceinline__ double jac_block8(const double* zz8, const double* __restrict__ gp, long long ldg,
                                              const double* __restrict__ rp, long long ldr, double* __restrict__ cp,
-                                             long long ldc, const double* __restrict__ sap, double sbn, double d1,
+                                             long long ldc, const double* __restrict__ sap, int sbo, bool badc, double d1,
                                              bool nv, double sacc) {
     const double rs2 = 0.70710678118654752440;
-    double gv[8], rv[8], sc[8];
+    double gv[8], rv[8];
+    int sch[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-        sc[jj] = __ldg(sap + jj);                              // same address in every lane: one broadcast transaction
+        sch[jj] = __ldg(reinterpret_cast<const int*>(sap + jj) + 1);   // same address in every lane: one broadcast transaction
         gv[jj] = (FULL || nv) ? gp[jj * ldg] : 0.0;
         rv[jj] = (RES && (FULL || nv)) ? rp[jj * ldr] : 0.0;
     }
     double s1 = 0.0;
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-        const double zj = fma(zz8[jj], sc[jj] * sbn, gv[jj]);
+        const double zj = fma(zz8[jj], pow2_scale(sch[jj], sbo, badc), gv[jj]);
         if (jj & 1) s1 = fma(zj, zj, s1); else sacc = fma(zj, zj, sacc);
         double o = d1 * zj;
         if (RES) o = (rv[jj] + o) * rs2;
@@ -421,22 +458,37 @@ __device__ __forceinline__ double jac_block8(const double* zz8, const double* __
     return sacc + s1;
 }
 
+// One aligned group of 8 rows (directions d .. d+7 of one electron) of the orbital Jacobian for one channel
+// n = 2 pp + (re|im):  dM = (y_re + i y_im)(Ex + i Ey), the partner component comes from the neighbouring lane.
+// Lean on purpose (the epilogue is issue-bound): the column scale and the sign of the cross term are folded into
+// two per-block factors, rows beyond ND are predicated off (no per-row branches), and the three own-coordinate
+// rows (raw orbital derivatives for the Laplacian assembly) are handled by a separate, rarely taken loop.
 template <bool FULL>
-__device__ __forceinline__ void orbj_block8(const double* zz8, const double* __restrict__ sap, double sbn, double Ex,
+__device__ __forceinline__ void orbj_block8(const double* zz8, int sch_l, int b, double sbn, double Ex,
                                             double Ey, int im, double* __restrict__ dp, long long ns2,
                                             double* __restrict__ yp, long long ystride, int d, int ND, int c0, bool nv) {
+    // row scales: powers of two (or NaN for a bad row), so the high word is all of them; lane j of the warp fetched
+    // the one of row j before the accumulators were ready
     double sc[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) sc[jj] = __ldg(sap + jj);
+    for (int jj = 0; jj < 8; ++jj) sc[jj] = __hiloint2double(__shfl_sync(0xffffffffu, sch_l, 8 * b + jj), 0);
+    const double sbp = __shfl_xor_sync(0xffffffffu, sbn, 1);     // column scale of the partner component
+    const double ax = sbn * Ex, ay = im ? sbp * Ey : -(sbp * Ey);
+    const int nrows = ND - d;                                   // rows jj < nrows are real directions
+    const bool ok = FULL || nv;
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-        const double z = zz8[jj] * (sc[jj] * sbn);
-        const double zp = __shfl_xor_sync(0xffffffffu, z, 1);
-        if ((FULL || nv) && d + jj < ND) {
-            // (vr + i vi)(Ex + i Ey): re = vr Ex - vi Ey, im = vr Ey + vi Ex
-            dp[jj * ns2] = im ? fma(zp, Ey, z * Ex) : fma(-zp, Ey, z * Ex);
+        const double zs = zz8[jj] * sc[jj];                     // exact (power-of-two scale)
+        const double zp = __shfl_xor_sync(0xffffffffu, zs, 1);
+        // (vr + i vi)(Ex + i Ey): re = vr Ex - vi Ey, im = vi Ex + vr Ey
+        const double o = fma(zp, ay, zs * ax);
+        if (ok && jj < nrows) dp[jj * ns2] = o;
+    }
+    if (c0 > -8 && c0 < 3) {                                    // this block holds own coordinates of the electron
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
             const unsigned c = (unsigned)(c0 + jj);
-            if (c < 3u) yp[c * ystride] = z;
+            if (ok && c < 3u && jj < nrows) yp[c * ystride] = zz8[jj] * sc[jj] * sbn;
         }
     }
 }
@@ -444,6 +496,11 @@ __device__ __forceinline__ void orbj_block8(const double* zz8, const double* __r
 // ---------------------------------------------------------------------------
 // the GEMM
 // ---------------------------------------------------------------------------
+// dbg & 32: per-role wait / phase clocks, summed over the CTAs, per MODE (ds_oz_prof_read):
+//   [0] kernel clocks of the MMA thread  [1] MMA waits for drained accumulators  [2] MMA waits for a full smem stage
+//   [3] producer waits for a free stage  [4] epilogue warp 2 waits for finished accumulators  [5] its phase A (TMEM read)
+//   [6] its phase B (epilogue math, loads, stores)  [7] tiles of the CTA
+__device__ unsigned long long g_oz_prof[8][8];
 template <int MODE, bool RES, int TN, int ND, bool BMN>
 // 18 warps: five share one SM sub-partition (16384 registers), so at most 96 registers per thread
 __global__ void __launch_bounds__(OZ_THREADS, 1)
@@ -483,40 +540,49 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            long long cnt = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int cb = (int)(tile % n_cb);
-                const long long rt = tile / n_cb;
-                const int grp = (int)(rt / tiles_per_group);
-                const int q0 = (int)(rt % tiles_per_group) * TN;
+            long long cnt = 0, prof_a = 0;
+            // (tile counts fit 32 bits, checked by the launcher: unsigned divisions, not the 64-bit software routine)
+            for (unsigned tile = blockIdx.x; tile < (unsigned)n_tiles; tile += gridDim.x) {
+                const int cb = (int)(tile % (unsigned)n_cb);
+                const unsigned rt = tile / (unsigned)n_cb;
+                const int grp = (int)(rt / (unsigned)tiles_per_group);
+                const int q0 = (int)(rt % (unsigned)tiles_per_group) * TN;
                 for (int kb = 0; kb < nkb; ++kb, ++cnt) {
                     const int st = (int)(cnt % STAGES);
                     const uint32_t ph = (uint32_t)((cnt / STAGES) & 1);
+                    const long long tp0 = (OZ_PROF && (p.dbg & 32)) ? clock64() : 0;
                     mbar_wait(&empty_bar[st], ph ^ 1u);
+                    if (OZ_PROF && (p.dbg & 32)) prof_a += clock64() - tp0;
                     unsigned char* sW = smem + st * STAGE_T;
                     if (p.dbg & 4) { mbar_arrive(&full_bar[st]); continue; }
                     mbar_expect_tx(&full_bar[st], STAGE_T);
                     tma_load_4d(sW, &tmW, &full_bar[st], kb * OZ_BK, cb * OZ_TM, 0, 0);
                     // blocked digits: the window of a group starts at the 64-row block that holds its first row
-                    if (BMN) tma_load_4d(sW + W_STAGE, &tmA, &full_bar[st], 0, kb * OZ_BK, 0, (int)(((grp * p.gstride + p.goff) >> 6) + q0 / TN));
+                    if (BMN) tma_load_4d(sW + W_STAGE, &tmA, &full_bar[st], 0, kb * OZ_BK, 0, (int)((((long long)grp * p.gstride + p.goff) >> 6) + q0 / TN));
                     else tma_load_4d(sW + W_STAGE, &tmA, &full_bar[st], kb * OZ_BK, q0, 0, grp);
                 }
             }
+            if (OZ_PROF && (p.dbg & 32)) atomicAdd(&g_oz_prof[MODE][3], (unsigned long long)prof_a);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            long long cnt = 0;
+            long long cnt = 0, prof_t = 0, prof_f = 0;
+            const long long prof_0 = (OZ_PROF && (p.dbg & 32)) ? clock64() : 0;
             uint32_t it = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (unsigned tile = blockIdx.x; tile < (unsigned)n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t buf = it % NBUF, use = it / NBUF;
+                const long long tm0 = (OZ_PROF && (p.dbg & 32)) ? clock64() : 0;
                 mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);
+                if (OZ_PROF && (p.dbg & 32)) prof_t += clock64() - tm0;
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + buf * (OZ_S * TN);
                 for (int kb = 0; kb < nkb; ++kb, ++cnt) {
                     const int st = (int)(cnt % STAGES);
                     const uint32_t ph = (uint32_t)((cnt / STAGES) & 1);
+                    const long long tf0 = (OZ_PROF && (p.dbg & 32)) ? clock64() : 0;
                     mbar_wait(&full_bar[st], ph);
+                    if (OZ_PROF && (p.dbg & 32)) prof_f += clock64() - tf0;
                     tc_fence_after();
                     const uint32_t sW = smem_u32(smem + st * STAGE_T);
                     const uint32_t sA = sW + W_STAGE;
@@ -545,6 +611,12 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 }
                 umma_commit(&tmem_full_bar[buf]);         // accumulators complete
             }
+            if (OZ_PROF && (p.dbg & 32)) {
+                atomicAdd(&g_oz_prof[MODE][0], (unsigned long long)(clock64() - prof_0));
+                atomicAdd(&g_oz_prof[MODE][1], (unsigned long long)prof_t);
+                atomicAdd(&g_oz_prof[MODE][2], (unsigned long long)prof_f);
+                atomicAdd(&g_oz_prof[MODE][7], (unsigned long long)it);
+            }
         }
     } else {
         // ===================== epilogue: thread = output channel =====================
@@ -561,18 +633,26 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         const int cg = ((warp - 2) % SET_WARPS) >> 2;     // which EPI_COLS columns
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (OZ_S * TN) + cg * EPI_COLS;
         uint32_t it = 0;
-        const double MAGIC = 6755399441055744.0;          // 2^52 + 2^51
+        long long prof_w = 0, prof_pa = 0, prof_pb = 0, te2_prev = 0;
+        const double MAGIC_HL = 6755399441055744.0 + 402653184.0;     // (2^52 + 2^51)(1 + 2^-24), exact
         int cur_cb = -1;
         double sbn = 0.0;
-        for (long long tile = blockIdx.x + (long long)set * gridDim.x; tile < n_tiles; tile += (long long)NBUF * gridDim.x, ++it) {
-            const int cb = (int)(tile % n_cb);
-            const long long rt = tile / n_cb;
-            const long long grp = rt / tiles_per_group;
-            const long long q0 = (rt % tiles_per_group) * TN + cg * EPI_COLS;      // first row (in group) of this warp
+        int sbo = 0;
+        bool badc = false;
+        for (unsigned tile = blockIdx.x + (unsigned)set * gridDim.x; tile < (unsigned)n_tiles; tile += (unsigned)NBUF * gridDim.x, ++it) {
+            const int cb = (int)(tile % (unsigned)n_cb);
+            const unsigned rt = tile / (unsigned)n_cb;
+            const long long grp = rt / (unsigned)tiles_per_group;
+            const long long q0 = (long long)(rt % (unsigned)tiles_per_group) * TN + cg * EPI_COLS;      // first row (in group) of this warp
             const int n = cb * OZ_TM + q * 32 + lane;
             const bool nv = n < p.N;
             const bool full = (cb + 1) * OZ_TM <= p.N;                             // warp-uniform
-            if (cb != cur_cb) { cur_cb = cb; sbn = nv ? p.sb[n] * (1.0 / 65536.0) : 0.0; }   // a CTA normally keeps its cb
+            if (cb != cur_cb) {                                                    // a CTA normally keeps its cb
+                cur_cb = cb;
+                sbn = nv ? p.sb[n] * (1.0 / 65536.0) : 0.0;
+                sbo = __double2hiint(sbn) - 0x3ff00000;                            // (sb[n] is a power of two or NaN)
+                badc = __double2hiint(sbn) >= 0x7ff00000;
+            }
             // physical row of column 0; with blocked digits (BMN) a group's window starts at the 64-row block holding
             // its first row, gskip rows early
             const long long gstart = grp * p.gstride + p.goff;
@@ -581,7 +661,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             const long long left = p.rpg + gskip - q0;                             // (modes with gskip > 0 test validity per 8-row block)
             const int nvalid = left < 0 ? 0 : (left < EPI_COLS ? (int)left : EPI_COLS);   // warp-uniform
             const double* sap = p.sa + prow0;                                      // scales of this warp's rows
-            if (MODE == OZ_JAC && RES && nv && nvalid == EPI_COLS) {
+            if (MODE == OZ_JAC && RES && nv && nvalid == EPI_COLS && !(OZ_PROF && (p.dbg & 8192))) {
                 // pull the residual rows towards L2 while the MMAs of this tile run
                 const double* pr = p.R + prow0 * (long long)p.ldr + n;
 #pragma unroll
@@ -591,8 +671,32 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 }
             }
 
+            // OZ_ORBJ: everything the epilogue math needs from memory is fetched BEFORE the accumulators are awaited (a load
+            // round trip costs ~3000 clocks next to the running MMAs and TMA traffic; it hides under the wait and the TMEM read)
+            double oEx[2] = {0.0, 0.0}, oEy[2] = {0.0, 0.0};
+            int osch = 0;
+            if (MODE == OZ_ORBJ) {
+                const int jr = min(lane & 15, max(nvalid - 1, 0));
+                osch = __ldg(reinterpret_cast<const int*>(sap + jr) + 1);
+                const long long qg = q0 - gskip;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const long long qb = qg + 8 * b;
+                    if (nv && qb >= 0 && qb < p.rpg) {
+                        const int is = (int)((unsigned)qb / (unsigned)p.NDp);
+                        const long long e = grp * p.n_elec + p.off_s + is;
+                        const double2 E = *reinterpret_cast<const double2*>(p.etab + e * 10LL * p.npar_max + 2 * (n >> 1));
+                        oEx[b] = E.x; oEy[b] = E.y;
+                    }
+                }
+            }
+
             double zz[EPI_COLS];
+            const bool prof = (OZ_PROF && (p.dbg & 32)) && warp == 2 && lane == 0;
+            const long long te0 = prof ? clock64() : 0;
+            if (prof && te2_prev) prof_pb += te0 - te2_prev;       // phase B of the previous tile (incl. the prologue of this one)
             mbar_wait(&tmem_full_bar[set], it & 1u);
+            const long long te1 = prof ? clock64() : 0;
             tc_fence_after();
             if (!(MODE == OZ_PLAIN && (p.dbg & 1))) {
 #pragma unroll
@@ -611,9 +715,11 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     for (int j = 0; j < 8; ++j) {
                         const long long hi = (long long)v[0][j] * 65536 + ((long long)v[1][j] * 256 + (long long)v[2][j]);
                         const long long lo = (long long)v[3][j] * 65536 + ((long long)v[4][j] * 256 + (long long)v[5][j]);
-                        const double dh = __longlong_as_double(hi + 0x4338000000000000LL) - MAGIC;
-                        const double dl = __longlong_as_double(lo + 0x4338000000000000LL) - MAGIC;
-                        zz[c0 + j] = fma(dl, 1.0 / 16777216.0, dh);     // one fp64 rounding of the exact integer sum
+                        // (MAGIC + lo) 2^-24 + (MAGIC + hi) - MAGIC (1 + 2^-24): the subtraction of the constant
+                        // 2^52 + 2^51 + 2^28 + 2^27 from MAGIC + hi is exact, so the fma rounds hi + lo 2^-24 ONCE
+                        // (two fp64 instructions per output instead of three: the fp64 pipe is what this epilogue waits on)
+                        const double dh = __longlong_as_double(hi + 0x4338000000000000LL) - MAGIC_HL;
+                        zz[c0 + j] = fma(__longlong_as_double(lo + 0x4338000000000000LL), 1.0 / 16777216.0, dh);
                     }
                 }
             }
@@ -621,8 +727,120 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[set]);
             if (MODE == OZ_PLAIN && (p.dbg & 1)) continue;
+            const long long te2 = prof ? clock64() : 0;
+            if (prof) { prof_w += te1 - te0; prof_pa += te2 - te1; te2_prev = te2; }
+            if (OZ_PROF && (p.dbg & 16384)) {
+                // probe: round trip of the 16 outputs through the spare TMEM columns while the next tile's MMAs run
+                const uint32_t park = tmem_base + ((uint32_t)(q * 32) << 16) + OZ_S * TN + cg * 32;
+                tmem_st8d(park, zz); tmem_st8d(park + 16, zz + 8);
+                tmem_st_wait();
+                tmem_ld8d(park, zz); tmem_ld8d(park + 16, zz + 8);
+            }
+            if (OZ_PROF && (p.dbg & (65536 | 131072 | 262144)) && (MODE == OZ_JAC || MODE == OZ_ORBJ)) {
+                // micro-probes of one pipe each, sized like the real epilogue's use of it (per thread and tile)
+                if (p.dbg & 65536) {                       // 16 double shuffles (= 32 SHFL)
+#pragma unroll
+                    for (int j = 0; j < EPI_COLS; ++j) zz[j] = __shfl_xor_sync(0xffffffffu, zz[j], 1);
+                }
+                if (p.dbg & 131072) {                      // ~512 dependent-free integer multiply-adds
+                    int a = lane, b = warp;
+#pragma unroll 1
+                    for (int r = 0; r < 16; ++r) {
+#pragma unroll
+                        for (int j = 0; j < EPI_COLS; ++j) { a = a * 3 + __double2loint(zz[j]); b = b * 5 + a; }
+                    }
+                    if (a + b == 12345) zz[0] = 1.0;
+                }
+                if (p.dbg & 262144) {                      // 16 broadcast loads of the row scales
+#pragma unroll
+                    for (int j = 0; j < EPI_COLS; ++j) zz[j] += __ldg(sap + j);
+                }
+                if (zz[3] + zz[5] + zz[9] + zz[0] + zz[15] + zz[1] + zz[2] + zz[4] + zz[6] + zz[7] + zz[8] + zz[10] + zz[11] + zz[12] + zz[13] + zz[14] == 1.2345) p.C[n] = zz[3];
+                continue;
+            }
+            if (OZ_PROF && (p.dbg & (256 | 512)) && (MODE == OZ_JAC || MODE == OZ_ORBJ)) {
+                // synthetic phase B (contention probes; results are garbage): 256 = register-only fp64 chain of the real
+                // epilogue's length (8 ops per output), 512 = the real epilogue's global loads and stores without the math
+                if (p.dbg & 256) {
+#pragma unroll 1
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int j = 0; j < EPI_COLS; ++j) zz[j] = fma(zz[j], 1.0000001, 0.5);
+                    if (zz[3] == 1.2345) p.C[n] = zz[3] + zz[7] + zz[11] + zz[0] + zz[15];
+                } else if (MODE == OZ_JAC && nv && nvalid == EPI_COLS) {
+                    const double* gp = p.G + (prow0 & 1023) * p.ldg + n;
+                    const double* rp = p.R + prow0 * (long long)p.ldr + n;
+                    double* cp = p.C + prow0 * (long long)p.ldc + n;
+                    const bool useg = !(p.dbg & 2048), user = !(p.dbg & 1024), st = !(p.dbg & 4096);
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        double gv[8], rv[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            gv[jj] = useg ? gp[(8 * b + jj) * (long long)p.ldg] : 1.0;
+                            rv[jj] = user ? rp[(8 * b + jj) * (long long)p.ldr] : 2.0;
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const double o = gv[jj] + rv[jj] + zz[8 * b + jj];
+                            if (st || o == 1.2345) cp[(8 * b + jj) * (long long)p.ldc] = o;
+                        }
+                    }
+                }
+                continue;
+            }
 
-            if (MODE == OZ_JAC) {
+            if (MODE == OZ_JAC && full && nvalid == EPI_COLS && (p.dbg & 32768)) {
+                // Full tiles: the 16 outputs are PARKED in the 128 TMEM columns the accumulators leave free (16 doubles per
+                // thread), which frees their registers for the 32 shared-mean / residual loads of BOTH row blocks: one
+                // memory round trip per tile instead of two, with every load in flight at once.
+                const uint32_t park = tmem_base + ((uint32_t)(q * 32) << 16) + OZ_S * TN + cg * 32;
+                tmem_st8d(park, zz); tmem_st8d(park + 16, zz + 8);
+                const unsigned e0 = (unsigned)prow0 / (unsigned)p.NDp;
+                const int d0 = (int)((unsigned)prow0 - e0 * (unsigned)p.NDp);
+                const unsigned w0 = e0 / (unsigned)p.n_elec;
+                // second block of 8 rows: next directions of the same electron, or the first ones of the next electron
+                const bool wrap = d0 + 8 >= p.NDp;
+                const unsigned e1 = wrap ? e0 + 1 : e0;
+                const int d1r = wrap ? d0 + 8 - p.NDp : d0 + 8;
+                const unsigned w1 = (wrap && e1 - w0 * (unsigned)p.n_elec == (unsigned)p.n_elec) ? w0 + 1 : w0;
+                const int sch_l = __ldg(reinterpret_cast<const int*>(sap + (lane & 15)) + 1);     // lane j: high word of sa[row j]
+                const double t0 = p.T[(long long)e0 * p.ldt + n], t1 = p.T[(long long)e1 * p.ldt + n];
+                const double* g0 = p.G + ((long long)w0 * p.NDg + d0) * p.ldg + n;
+                const double* g1 = p.G + ((long long)w1 * p.NDg + d1r) * p.ldg + n;
+                const double* rp = RES ? p.R + prow0 * (long long)p.ldr + n : nullptr;
+                double gv[16], rv[16];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    gv[jj] = g0[jj * (long long)p.ldg];
+                    gv[8 + jj] = g1[jj * (long long)p.ldg];
+                }
+                if (RES) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) rv[jj] = rp[jj * (long long)p.ldr];
+                }
+                tmem_st_wait();
+                double* cp = p.C + prow0 * (long long)p.ldc + n;
+                const double rs2 = 0.70710678118654752440;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    double z8[8];
+                    tmem_ld8d(park + 16 * b, z8);
+                    const double t = b ? t1 : t0;
+                    const double dd = 1.0 - t * t;
+                    double sa0 = 0.0, sa1 = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int sch = __shfl_sync(0xffffffffu, sch_l, 8 * b + jj);
+                        const double zj = fma(z8[jj], pow2_scale(sch, sbo, badc), gv[8 * b + jj]);
+                        if (jj & 1) sa1 = fma(zj, zj, sa1); else sa0 = fma(zj, zj, sa0);
+                        double o = dd * zj;
+                        if (RES) o = (rv[8 * b + jj] + o) * rs2;
+                        cp[(8 * b + jj) * (long long)p.ldc] = o;
+                    }
+                    p.SP[((prow0 + 8 * b) >> 3) * (long long)p.ldt + n] = sa0 + sa1;
+                }
+            } else if (MODE == OZ_JAC) {
                 // physical row = e * NDp + d  (e = walker * n_elec + electron); rows < 2^31 (checked by the launcher)
                 unsigned e = (unsigned)prow0 / (unsigned)p.NDp;
                 int d = (int)((unsigned)prow0 - e * (unsigned)p.NDp);
@@ -637,8 +855,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         const double* rp = RES ? p.R + (prow0 + 8 * b) * (long long)p.ldr + n : nullptr;
                         double* cp = p.C + (prow0 + 8 * b) * (long long)p.ldc + n;
                         double sacc;
-                        if (full) sacc = jac_block8<RES, true>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbn, d1, true, 0.0);
-                        else sacc = jac_block8<RES, false>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbn, d1, nv, 0.0);
+                        if (full) sacc = jac_block8<RES, true>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbo, badc, d1, true, 0.0);
+                        else sacc = jac_block8<RES, false>(zz + 8 * b, gp, p.ldg, rp, p.ldr, cp, p.ldc, sap + 8 * b, sbo, badc, d1, nv, 0.0);
                         // partial sum of zJ^2 over this aligned group of 8 directions; summed per electron in a fixed
                         // order by sp_reduce_kernel (deterministic, unlike an atomicAdd into S)
                         if (nv) p.SP[((prow0 + 8 * b) >> 3) * (long long)p.ldt + n] = sacc;
@@ -884,19 +1102,21 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         const int is = (int)((unsigned)qb / (unsigned)p.NDp);
                         const int d = (int)qb - is * p.NDp;
                         const long long e = grp * p.n_elec + p.off_s + is;
-                        double Ex = 0.0, Ey = 0.0;
-                        if (nv) {
-                            const double2 E = *reinterpret_cast<const double2*>(p.etab + e * 10LL * p.npar_max + 2 * pp);
-                            Ex = E.x; Ey = E.y;
-                        }
+                        const double Ex = oEx[b], Ey = oEy[b];
                         double* dp = dab + d * ns2 + 2LL * (p.row0 + is) * p.n_orb;
                         double* yp = p.YOWN + 2 * (e * 3LL * p.npar_max + pp) + im;
                         const int c0 = d - 3 * (p.off_s + is);              // own-coordinate index of column 0
-                        if (full) orbj_block8<true>(zz + 8 * b, sap + 8 * b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, true);
-                        else orbj_block8<false>(zz + 8 * b, sap + 8 * b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, nv);
+                        if (full) orbj_block8<true>(zz + 8 * b, osch, b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, true);
+                        else orbj_block8<false>(zz + 8 * b, osch, b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, nv);
                     }
                 }
             }
+        }
+        if ((OZ_PROF && (p.dbg & 32)) && warp == 2 && lane == 0) {
+            if (te2_prev) prof_pb += clock64() - te2_prev;
+            atomicAdd(&g_oz_prof[MODE][4], (unsigned long long)prof_w);
+            atomicAdd(&g_oz_prof[MODE][5], (unsigned long long)prof_pa);
+            atomicAdd(&g_oz_prof[MODE][6], (unsigned long long)prof_pb);
         }
     }
     tc_fence_before();
@@ -1096,6 +1316,7 @@ int launch_tn(const OzParams& p, cudaStream_t stream) {
     const int tpg = (int)((p.rpg + (windows ? 56 : 0) + TN - 1) / TN);
     const int n_cb = (p.N + OZ_TM - 1) / OZ_TM;
     const long long n_tiles = (long long)tpg * p.n_groups * n_cb;
+    DS_REQUIRE(n_tiles + 2LL * n_sm < (1LL << 31), "oz_gemm: %lld tiles in one launch (the kernel indexes tiles with 32 bits)", n_tiles);
     int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
     if (MODE == OZ_JACD) {
         // CTA pairs (2j, 2j+1) = the two channel blocks of one row tile: launched as clusters of two so that the
@@ -1128,6 +1349,17 @@ int launch(const OzParams& p, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// debug: read (and optionally clear) the dbg & 32 role clocks, 8 modes x 8 counters
+int ds_oz_prof_read(unsigned long long* out, int reset) {
+    DS_CUDA_CHECK(cudaDeviceSynchronize());
+    DS_CUDA_CHECK(cudaMemcpyFromSymbol(out, g_oz_prof, sizeof(unsigned long long) * 64));
+    if (reset) {
+        static const unsigned long long zeros[64] = {};
+        DS_CUDA_CHECK(cudaMemcpyToSymbol(g_oz_prof, zeros, sizeof(zeros)));
+    }
+    return 0;
+}
 
 int ds_launch_slice_rows(const double* A, int lda, long long rows, int K, signed char* Ad, double* sa,
                          cudaStream_t stream) {
@@ -1186,8 +1418,12 @@ int ds_launch_transpose(const double* B, int K, int N, double* Bt, cudaStream_t 
     return 0;
 }
 
-int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t stream) {
-    if (p.rpg <= 0 || p.n_groups <= 0 || p.N <= 0) return 0;
+int ds_launch_oz_gemm(const OzParams& p_in, int mode, bool residual, cudaStream_t stream) {
+    if (p_in.rpg <= 0 || p_in.n_groups <= 0 || p_in.N <= 0) return 0;
+    // DS_OZ_OPT: probe bits ORed into dbg (see OzParams::dbg; 32 = role clocks, needs a -DDS_OZ_PROF build)
+    static const int opt_bits = getenv("DS_OZ_OPT") ? atoi(getenv("DS_OZ_OPT")) : 0;
+    OzParams p = p_in;
+    p.dbg |= opt_bits;
     DS_REQUIRE(p.K % OZ_BK == 0 && p.K >= OZ_BK, "oz_gemm: K must be a multiple of %d (K=%d)", OZ_BK, p.K);
     DS_REQUIRE((reinterpret_cast<uintptr_t>(p.Ad) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Wd) & 15) == 0,
                "oz_gemm: digit buffers must be 16-byte aligned");

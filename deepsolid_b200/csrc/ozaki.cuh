@@ -80,6 +80,7 @@ int ds_launch_slice_means(const double* A, int lda, int K, int C, int n_walkers,
 // Bt[N][K] = B[K][N]^T
 int ds_launch_transpose(const double* B, int K, int N, double* Bt, cudaStream_t stream);
 int ds_launch_oz_gemm(const OzParams& p, int mode, bool residual, cudaStream_t stream);
+int ds_oz_prof_read(unsigned long long* out, int reset);
 // S[e][n] = sum_b SP[e * (NDp/8) + b][n], fixed order
 int ds_launch_sp_reduce(const double* SP, int ld, long long n_elec_rows, int blocks_per_electron, int H, double* S,
                         cudaStream_t stream);

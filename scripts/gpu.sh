@@ -9,6 +9,7 @@
 #   probe        component limits of oz_gemm_kernel (DS_OZ_DBG)  ab         committed HEAD (ab_old/, see make_ab_old.sh) vs working tree
 #   diag5        accuracy + speed of the 5-diagonal experiment   sanitize   compute-sanitizer memcheck of small systems
 #   strong       global batch 4096 split over the visible GPUs (run under gpurun --gpus N)
+#   opts         in-call A/B of environment knobs ($OPTS, ';'-separated)     partests   test_gpu_parity + test_variants only
 TAG=${TAG:-r2}
 O=gpurun_out
 mkdir -p $O
@@ -64,6 +65,14 @@ d=[json.loads(l) for l in open('$O/${TAG}_ncu_full.log') if l.startswith('{')][-
     strong)    N=$(nvidia-smi -L | wc -l)
                timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
                  bench.py --gpus $N --steps 5 --warmup 3 --scaling strong --no-cpu-baseline 2> $O/${TAG}_strong_$N.err | tail -1 | tee $O/${TAG}_strong_$N.json | cut -c1-300 ;;
+    opts)      # in-call A/B of environment knobs: OPTS="DS_OZ_OPT=0;DS_OZ_OPT=8;..." (each entry may hold several VAR=VALUE words)
+               IFS=';' read -ra LIST <<< "$OPTS"
+               for rep in 1 2; do for o in "${LIST[@]}"; do
+                 echo -n "[$o] "; env $o timeout 300 $B --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-probes ${BARGS:-} 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(round(d['value'],1), 'le/s', round(d['ms_per_step'],1), 'ms  gemm', round(d['roofline']['kernel_ms_per_step'],1), 'ms frac', round(d['roofline']['frac'],3))"
+               done; done | tee -a $O/${TAG}_opts.log ;;
+    partests)  timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_variants.py -m gpu -q -x 2>&1 | tail -3 ;;
     *)         echo "unknown task $task" ;;
   esac
 done
