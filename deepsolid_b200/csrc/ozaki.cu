@@ -123,26 +123,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// 8 doubles <-> 16 consecutive 32-bit columns of this thread's TMEM lane (the 128 columns the accumulators leave free
-// serve as a per-thread parking space of 16 doubles)
-__device__ __forceinline__ void tmem_st8d(uint32_t taddr, const double* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-        ::"r"(taddr), "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
-          "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])),
-          "r"(__double2loint(v[4])), "r"(__double2hiint(v[4])), "r"(__double2loint(v[5])), "r"(__double2hiint(v[5])),
-          "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(__double2loint(v[7])), "r"(__double2hiint(v[7]))
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld8d(uint32_t taddr, double* v) {
-    int w[16];
-    tmem_ld16(taddr, w);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __hiloint2double(w[2 * j + 1], w[2 * j]);
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 // ---- thread-block cluster / distributed shared memory (OZ_JACD: the two 128-channel CTAs of a row tile) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -464,14 +444,12 @@ __device__ __forceinline__ double jac_block8(const double* zz8, const double* __
 // two per-block factors, rows beyond ND are predicated off (no per-row branches), and the three own-coordinate
 // rows (raw orbital derivatives for the Laplacian assembly) are handled by a separate, rarely taken loop.
 template <bool FULL>
-__device__ __forceinline__ void orbj_block8(const double* zz8, int sch_l, int b, double sbn, double Ex,
+__device__ __forceinline__ void orbj_block8(const double* zz8, const double* __restrict__ sap, double sbn, double Ex,
                                             double Ey, int im, double* __restrict__ dp, long long ns2,
                                             double* __restrict__ yp, long long ystride, int d, int ND, int c0, bool nv) {
-    // row scales: powers of two (or NaN for a bad row), so the high word is all of them; lane j of the warp fetched
-    // the one of row j before the accumulators were ready
     double sc[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) sc[jj] = __hiloint2double(__shfl_sync(0xffffffffu, sch_l, 8 * b + jj), 0);
+    for (int jj = 0; jj < 8; ++jj) sc[jj] = __ldg(sap + jj);      // powers of two (or NaN for a bad row)
     const double sbp = __shfl_xor_sync(0xffffffffu, sbn, 1);     // column scale of the partner component
     const double ax = sbn * Ex, ay = im ? sbp * Ey : -(sbp * Ey);
     const int nrows = ND - d;                                   // rows jj < nrows are real directions
@@ -671,26 +649,6 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 }
             }
 
-            // OZ_ORBJ: everything the epilogue math needs from memory is fetched BEFORE the accumulators are awaited (a load
-            // round trip costs ~3000 clocks next to the running MMAs and TMA traffic; it hides under the wait and the TMEM read)
-            double oEx[2] = {0.0, 0.0}, oEy[2] = {0.0, 0.0};
-            int osch = 0;
-            if (MODE == OZ_ORBJ) {
-                const int jr = min(lane & 15, max(nvalid - 1, 0));
-                osch = __ldg(reinterpret_cast<const int*>(sap + jr) + 1);
-                const long long qg = q0 - gskip;
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const long long qb = qg + 8 * b;
-                    if (nv && qb >= 0 && qb < p.rpg) {
-                        const int is = (int)((unsigned)qb / (unsigned)p.NDp);
-                        const long long e = grp * p.n_elec + p.off_s + is;
-                        const double2 E = *reinterpret_cast<const double2*>(p.etab + e * 10LL * p.npar_max + 2 * (n >> 1));
-                        oEx[b] = E.x; oEy[b] = E.y;
-                    }
-                }
-            }
-
             double zz[EPI_COLS];
             const bool prof = (OZ_PROF && (p.dbg & 32)) && warp == 2 && lane == 0;
             const long long te0 = prof ? clock64() : 0;
@@ -729,35 +687,6 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             if (MODE == OZ_PLAIN && (p.dbg & 1)) continue;
             const long long te2 = prof ? clock64() : 0;
             if (prof) { prof_w += te1 - te0; prof_pa += te2 - te1; te2_prev = te2; }
-            if (OZ_PROF && (p.dbg & 16384)) {
-                // probe: round trip of the 16 outputs through the spare TMEM columns while the next tile's MMAs run
-                const uint32_t park = tmem_base + ((uint32_t)(q * 32) << 16) + OZ_S * TN + cg * 32;
-                tmem_st8d(park, zz); tmem_st8d(park + 16, zz + 8);
-                tmem_st_wait();
-                tmem_ld8d(park, zz); tmem_ld8d(park + 16, zz + 8);
-            }
-            if (OZ_PROF && (p.dbg & (65536 | 131072 | 262144)) && (MODE == OZ_JAC || MODE == OZ_ORBJ)) {
-                // micro-probes of one pipe each, sized like the real epilogue's use of it (per thread and tile)
-                if (p.dbg & 65536) {                       // 16 double shuffles (= 32 SHFL)
-#pragma unroll
-                    for (int j = 0; j < EPI_COLS; ++j) zz[j] = __shfl_xor_sync(0xffffffffu, zz[j], 1);
-                }
-                if (p.dbg & 131072) {                      // ~512 dependent-free integer multiply-adds
-                    int a = lane, b = warp;
-#pragma unroll 1
-                    for (int r = 0; r < 16; ++r) {
-#pragma unroll
-                        for (int j = 0; j < EPI_COLS; ++j) { a = a * 3 + __double2loint(zz[j]); b = b * 5 + a; }
-                    }
-                    if (a + b == 12345) zz[0] = 1.0;
-                }
-                if (p.dbg & 262144) {                      // 16 broadcast loads of the row scales
-#pragma unroll
-                    for (int j = 0; j < EPI_COLS; ++j) zz[j] += __ldg(sap + j);
-                }
-                if (zz[3] + zz[5] + zz[9] + zz[0] + zz[15] + zz[1] + zz[2] + zz[4] + zz[6] + zz[7] + zz[8] + zz[10] + zz[11] + zz[12] + zz[13] + zz[14] == 1.2345) p.C[n] = zz[3];
-                continue;
-            }
             if (OZ_PROF && (p.dbg & (256 | 512)) && (MODE == OZ_JAC || MODE == OZ_ORBJ)) {
                 // synthetic phase B (contention probes; results are garbage): 256 = register-only fp64 chain of the real
                 // epilogue's length (8 ops per output), 512 = the real epilogue's global loads and stores without the math
@@ -790,57 +719,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 continue;
             }
 
-            if (MODE == OZ_JAC && full && nvalid == EPI_COLS && (p.dbg & 32768)) {
-                // Full tiles: the 16 outputs are PARKED in the 128 TMEM columns the accumulators leave free (16 doubles per
-                // thread), which frees their registers for the 32 shared-mean / residual loads of BOTH row blocks: one
-                // memory round trip per tile instead of two, with every load in flight at once.
-                const uint32_t park = tmem_base + ((uint32_t)(q * 32) << 16) + OZ_S * TN + cg * 32;
-                tmem_st8d(park, zz); tmem_st8d(park + 16, zz + 8);
-                const unsigned e0 = (unsigned)prow0 / (unsigned)p.NDp;
-                const int d0 = (int)((unsigned)prow0 - e0 * (unsigned)p.NDp);
-                const unsigned w0 = e0 / (unsigned)p.n_elec;
-                // second block of 8 rows: next directions of the same electron, or the first ones of the next electron
-                const bool wrap = d0 + 8 >= p.NDp;
-                const unsigned e1 = wrap ? e0 + 1 : e0;
-                const int d1r = wrap ? d0 + 8 - p.NDp : d0 + 8;
-                const unsigned w1 = (wrap && e1 - w0 * (unsigned)p.n_elec == (unsigned)p.n_elec) ? w0 + 1 : w0;
-                const int sch_l = __ldg(reinterpret_cast<const int*>(sap + (lane & 15)) + 1);     // lane j: high word of sa[row j]
-                const double t0 = p.T[(long long)e0 * p.ldt + n], t1 = p.T[(long long)e1 * p.ldt + n];
-                const double* g0 = p.G + ((long long)w0 * p.NDg + d0) * p.ldg + n;
-                const double* g1 = p.G + ((long long)w1 * p.NDg + d1r) * p.ldg + n;
-                const double* rp = RES ? p.R + prow0 * (long long)p.ldr + n : nullptr;
-                double gv[16], rv[16];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    gv[jj] = g0[jj * (long long)p.ldg];
-                    gv[8 + jj] = g1[jj * (long long)p.ldg];
-                }
-                if (RES) {
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) rv[jj] = rp[jj * (long long)p.ldr];
-                }
-                tmem_st_wait();
-                double* cp = p.C + prow0 * (long long)p.ldc + n;
-                const double rs2 = 0.70710678118654752440;
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    double z8[8];
-                    tmem_ld8d(park + 16 * b, z8);
-                    const double t = b ? t1 : t0;
-                    const double dd = 1.0 - t * t;
-                    double sa0 = 0.0, sa1 = 0.0;
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const int sch = __shfl_sync(0xffffffffu, sch_l, 8 * b + jj);
-                        const double zj = fma(z8[jj], pow2_scale(sch, sbo, badc), gv[8 * b + jj]);
-                        if (jj & 1) sa1 = fma(zj, zj, sa1); else sa0 = fma(zj, zj, sa0);
-                        double o = dd * zj;
-                        if (RES) o = (rv[8 * b + jj] + o) * rs2;
-                        cp[(8 * b + jj) * (long long)p.ldc] = o;
-                    }
-                    p.SP[((prow0 + 8 * b) >> 3) * (long long)p.ldt + n] = sa0 + sa1;
-                }
-            } else if (MODE == OZ_JAC) {
+            if (MODE == OZ_JAC) {
                 // physical row = e * NDp + d  (e = walker * n_elec + electron); rows < 2^31 (checked by the launcher)
                 unsigned e = (unsigned)prow0 / (unsigned)p.NDp;
                 int d = (int)((unsigned)prow0 - e * (unsigned)p.NDp);
@@ -1102,12 +981,16 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         const int is = (int)((unsigned)qb / (unsigned)p.NDp);
                         const int d = (int)qb - is * p.NDp;
                         const long long e = grp * p.n_elec + p.off_s + is;
-                        const double Ex = oEx[b], Ey = oEy[b];
+                        double Ex = 0.0, Ey = 0.0;
+                        if (nv) {
+                            const double2 E = *reinterpret_cast<const double2*>(p.etab + e * 10LL * p.npar_max + 2 * pp);
+                            Ex = E.x; Ey = E.y;
+                        }
                         double* dp = dab + d * ns2 + 2LL * (p.row0 + is) * p.n_orb;
                         double* yp = p.YOWN + 2 * (e * 3LL * p.npar_max + pp) + im;
                         const int c0 = d - 3 * (p.off_s + is);              // own-coordinate index of column 0
-                        if (full) orbj_block8<true>(zz + 8 * b, osch, b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, true);
-                        else orbj_block8<false>(zz + 8 * b, osch, b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, nv);
+                        if (full) orbj_block8<true>(zz + 8 * b, sap + 8 * b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, true);
+                        else orbj_block8<false>(zz + 8 * b, sap + 8 * b, sbn, Ex, Ey, im, dp, ns2, yp, 2LL * p.npar_max, d, ND, c0, nv);
                     }
                 }
             }

@@ -59,7 +59,11 @@ struct OzParams {
     int n_s, off_s, n_det;
     int n_orb, n_rows_mat, row0;   // orbitals per determinant (matrix columns), matrix rows, row of this channel's first electron
     double* DA; double* YOWN;
-    int dbg;                 // probe only: 1 = epilogue skips TMEM reads/stores, 2 = no MMA issue, 4 = no TMA
+    int dbg;                 // probe only (DS_OZ_DBG in the stand-alone probe, DS_OZ_OPT on the production path): 1 = epilogue
+                             // skips TMEM reads/stores, 2 = no MMA issue, 4 = no TMA; with a -DDS_OZ_PROF build: 32 = role
+                             // clocks (scripts/oz_roles.py), 256 / 512 (+1024, 2048, 4096) = synthetic phase B (fp64 chain
+                             // only / the loads and stores only, without the shared-mean / residual loads / stores), 8192 =
+                             // no residual prefetch
     // Blocked row-contiguous digit layout [Rp/64 blocks][OZ_S][K][64 rows] (bytes; Rp = rows rounded up to 64): what
     // OZ_JACD writes -- a thread's 16 rows of one slice are one 128-bit store, a 64-row tile is one contiguous region --
     // and what the next GEMM reads as an MN-major operand.  bmn != 0: Ad is in this layout (Rp_in rows).
