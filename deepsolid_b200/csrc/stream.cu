@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) l0_jac2_kernel(DsDims dm, const double* _
                                                       double* __restrict__ OJ, int ldc) {
     constexpr int KT = 16;
     extern __shared__ __align__(16) double l0_sm[];          // [NDp][16]
-    const int H = dm.H, NDp = dm.NDp, H2 = dm.H >> 1;
+    const int H = dm.H, NDp = dm.NDp, H2 = dm.H >> 1, n_up = dm.n_up;
     const long long e = blockIdx.x;
     const int w = (int)(e / dm.N), i = (int)(e - (long long)w * dm.N);
     {
@@ -165,8 +165,18 @@ __global__ void __launch_bounds__(128) l0_jac2_kernel(DsDims dm, const double* _
                         zb[u] = fma(av, __ldg(B + (long long)k * H + n1), zb[u]);
                     }
                 }
+                // pair-mean columns: a direction of another electron j moves only the mean over j's own spin channel
+                // (4 of the 8 columns are zero); own directions move both (minus the sums over all partners)
+                if ((d / 3) == i) {
 #pragma unroll
-                for (int k = KT - 8; k < KT; ++k) { const double av = a[k]; za[u] = fma(av, wa[k - (KT - 8)], za[u]); zb[u] = fma(av, wb[k - (KT - 8)], zb[u]); }
+                    for (int k = 0; k < 8; ++k) { const double av = a[KT - 8 + k]; za[u] = fma(av, wa[k], za[u]); zb[u] = fma(av, wb[k], zb[u]); }
+                } else if (d / 3 < n_up) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const double av = a[KT - 8 + k]; za[u] = fma(av, wa[k], za[u]); zb[u] = fma(av, wb[k], zb[u]); }
+                } else {
+#pragma unroll
+                    for (int k = 4; k < 8; ++k) { const double av = a[KT - 8 + k]; za[u] = fma(av, wa[k], za[u]); zb[u] = fma(av, wb[k], zb[u]); }
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
