@@ -744,7 +744,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 template <int MT>
-__global__ void __launch_bounds__(256, (MT <= 8) ? 2 : 1) det_dmma_kernel(const DsSys sys, const SlaterBufs sb, int G, int LDB, int alias, int stagger_ns) {
+__global__ void __launch_bounds__(256, (MT <= 8) ? 2 : 1) det_dmma_kernel(const DsSys sys, const SlaterBufs sb, int G, int LDB, int alias) {
     const DsDims& dm = sys.d;
     const int D = dm.D, NDp = dm.NDp, ND = dm.ND;
     const int k = blockIdx.x % D;
@@ -763,7 +763,6 @@ __global__ void __launch_bounds__(256, (MT <= 8) ? 2 : 1) det_dmma_kernel(const 
         if (sb.TAU)
             for (int t = threadIdx.x; t < 2 * dm.NDp; t += blockDim.x) sb.TAU[slot1 * 2 * dm.NDp + t] = 0.0;
     }
-    if (stagger_ns > 0 && blockIdx.x >= 148 && blockIdx.x < 296) __nanosleep((unsigned)stagger_ns);   // experiment: de-phase the two CTAs of an SM
     const int np = n;                               // no padding of the complex inverse
     constexpr int MP = MT * 8;                      // rows of Xe / Be (>= 2n)
     constexpr int LDX = MP + 4;                     // = 4 or 12 mod 16
@@ -1093,8 +1092,9 @@ int launch_det_dmma(const DsSys& sys, const SlaterBufs& sb, int Wc, int nmax, cu
         cfg = smem;
     }
     dim3 grid((unsigned)((long long)Wc * ds_nblk(sys.d) * sys.d.D));
-    static const int stagger_ns = getenv("DS_DET_STAGGER") ? atoi(getenv("DS_DET_STAGGER")) : 0;
-    det_dmma_kernel<MT><<<grid, 256, smem, stream>>>(sys, sb, G, ldb_of(G), alias ? 1 : 0, stagger_ns);
+    // (measured and rejected, profiles/r2_det_variants.log: a start-up stagger of the second CTA of every SM, and a
+    //  192-thread configuration with three CTAs per SM)
+    det_dmma_kernel<MT><<<grid, 256, smem, stream>>>(sys, sb, G, ldb_of(G), alias ? 1 : 0);
     DS_CUDA_CHECK(cudaGetLastError());
     *done = true;
     return 0;
