@@ -114,7 +114,10 @@ struct ds_ctx {
     double* genv_sigma[2] = {};
     // workspace
     Workspace ws;
-    size_t ws_limit = size_t(24) << 30; // bytes: ~270 walkers per chunk at 54 electrons (fewer, longer launches)
+    // bytes: 169 walkers per chunk at 54 electrons -> 4096 walkers run as 25 chunks of 164.  The step is power-capped on
+    // B200 (sw_power_cap at ~1 kW) and the chunk length changes the clocks the governor settles at: 25-26 chunks run at
+    // 1.77-1.84 GHz, 17 chunks (24 GiB) at 1.71-1.74 GHz, 27 at 1.69 GHz (profiles/r2_chunk_sweep.log: +2.5-4.5 % on two boxes)
+    size_t ws_limit = size_t(16) << 30;
     // mcmc scratch
     DevBuf mc_x2, mc_lp, mc_lp2, host_stage;
     // instrumentation
@@ -379,6 +382,7 @@ int plan_chunk(ds_ctx* c, long long batch, bool lap, int* Wc_out, bool grad = fa
     }
     // keep the row counts of the Jacobian GEMM within int-friendly grid sizes
     Wmax = std::min<long long>(Wmax, 1 << 15);
+    if (const char* ev = getenv("DS_CHUNK_WALKERS")) { const long long v = atoll(ev); if (v >= 1) Wmax = std::min(Wmax, v); }   // tuning sweeps
     for (;;) {
         // equal chunks: 512 walkers at a 254-walker limit run as 3 x 171, not 254 + 254 + 4
         const long long n_chunks = (batch + Wmax - 1) / Wmax;

@@ -103,7 +103,7 @@ DS_API int ds_ctx_create(const ds_system_desc *sys, const ds_net_desc *net, int 
 DS_API int ds_ctx_destroy(ds_ctx *ctx);
 
 /* Upper bound (bytes) for the internal per-chunk workspace; walkers are processed
- * in chunks that fit.  Default 24 GiB (env DS_WS_GIB overrides at context creation). */
+ * in chunks that fit.  Default 16 GiB (env DS_WS_GIB overrides at context creation; DS_CHUNK_WALKERS caps the chunk directly). */
 DS_API int ds_set_workspace_limit(ds_ctx *ctx, size_t bytes);
 
 /* Parameter pytree of init_solid_fermi_net_params (network.py:135-184), flattened in

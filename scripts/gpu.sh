@@ -70,7 +70,7 @@ d=[json.loads(l) for l in open('$O/${TAG}_ncu_full.log') if l.startswith('{')][-
                for rep in 1 2; do for o in "${LIST[@]}"; do
                  echo -n "[$o] "; env $o timeout 300 $B --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-probes ${BARGS:-} 2>/dev/null | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print(round(d['value'],1), 'le/s', round(d['ms_per_step'],1), 'ms  gemm', round(d['roofline']['kernel_ms_per_step'],1), 'ms frac', round(d['roofline']['frac'],3))"
+d=json.loads(sys.stdin.read()); print(round(d['value'],1), 'le/s', round(d['ms_per_step'],1), 'ms  gemm', round(d['roofline']['kernel_ms_per_step'],1), 'ms frac', round(d['roofline']['frac'],3), 'sm', d['clocks']['sm_mhz'], 'MHz', d['clocks'].get('power_w_max'), 'W chunk', d['config'].get('chunk_walkers'))"
                done; done | tee -a $O/${TAG}_opts.log ;;
     partests)  timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_variants.py -m gpu -q -x 2>&1 | tail -3 ;;
     *)         echo "unknown task $task" ;;
