@@ -107,7 +107,8 @@ def pi_adjusted_inverse(factor_0: torch.Tensor, factor_1: torch.Tensor, damping:
 
 class Optimizer:
     """The reference's ``kfac_optim.Optimizer`` (process.py:209-222) reduced to the configuration DeepSolid runs:
-    fisher_exact curvature, fixed damping, momentum 0, norm constraint.
+    fisher_exact curvature, fixed damping, regular momentum (0 in base_config.py:67), norm constraint; adaptive damping /
+    momentum are "not currently available" in the reference either (base_config.py:69).
 
     ``value_and_grad(params, data) -> ((loss, aux), grads)`` is ``train.make_loss(...).value_and_grad``, which returns
     the gradient of THIS rank's walkers; ``step`` averages it (and the norm-constraint scalar) over ranks, as the
@@ -124,6 +125,7 @@ class Optimizer:
         self.inverse_update_period = int(inverse_update_period)
         self.cov_update_every = int(cov_update_every)
         self.step_counter = 0
+        self.velocities = None          # last update (list of leaves), optimizer.py:617-627
         self.blocks: Optional[Dict[str, list]] = None
 
     # -- curvature state ---------------------------------------------------
@@ -178,8 +180,6 @@ class Optimizer:
     def step(self, params, data, learning_rate: float, damping: float, momentum: float = 0.0):
         """optimizer.py:400-470: gradients, curvature EMA, (periodic) inverses, preconditioned direction with the norm
         constraint, params + delta.  -> (new params, stats dict with loss / aux / coefficient)."""
-        if momentum != 0.0:
-            raise ValueError("momentum is not implemented (base_config.py:67 runs momentum 0.0)")
         (loss, aux), grads = self.value_and_grad(params, data)
         dev = self.hp.tdev
         to_dev = lambda t: torch.as_tensor(t).to(dev)
@@ -202,6 +202,14 @@ class Optimizer:
             sq = sum((a * b).sum() for a, b in zip(leaves_pre, leaves_g)) * learning_rate ** 2
             sq = float(dist.pmean(sq))                                               # optimizer.py:593
             coefficient = min(math.sqrt(self.norm_constraint / sq), 1.0) if sq > 0.0 else 1.0
-        new_leaves = [p - learning_rate * coefficient * d for p, d in zip(leaves_p, leaves_pre)]
+        # optimizer.py:444-463, 617-627: vectors = (preconditioned gradient, velocities), coefficients = (-lr, momentum);
+        # delta = sum of the two, velocities <- delta; the first step treats the momentum as 0 (optimizer.py:562-564)
+        mom = float(momentum) if (self.velocities is not None and self.step_counter > 0) else 0.0
+        delta = [-learning_rate * coefficient * d for d in leaves_pre]
+        if mom != 0.0:
+            delta = [d + mom * v for d, v in zip(delta, self.velocities)]
+        self.velocities = delta
+        new_leaves = [p + d for p, d in zip(leaves_p, delta)]
         self.step_counter += 1
-        return unflatten_params(new_leaves, n_layers, bias_orb), {"loss": loss, "aux": aux, "coefficient": coefficient}
+        return unflatten_params(new_leaves, n_layers, bias_orb), {"loss": loss, "aux": aux, "coefficient": coefficient,
+                                                                  "momentum": mom}

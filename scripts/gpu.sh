@@ -9,6 +9,7 @@
 #   probe        component limits of oz_gemm_kernel (DS_OZ_DBG)  ab         committed HEAD (ab_old/, see make_ab_old.sh) vs working tree
 #   diag5        accuracy + speed of the 5-diagonal experiment   sanitize   compute-sanitizer memcheck of small systems
 #   strong       global batch 4096 split over the visible GPUs (run under gpurun --gpus N)
+#   adopt        copy this call's traffic / HBM JSONs into profiles/ before `bench` (run after launches + profile)
 #   opts         in-call A/B of environment knobs ($OPTS, ';'-separated)     partests   test_gpu_parity + test_variants only
 TAG=${TAG:-r2}
 O=gpurun_out
@@ -72,6 +73,9 @@ d=[json.loads(l) for l in open('$O/${TAG}_ncu_full.log') if l.startswith('{')][-
 import json,sys
 d=json.loads(sys.stdin.read()); print(round(d['value'],1), 'le/s', round(d['ms_per_step'],1), 'ms  gemm', round(d['roofline']['kernel_ms_per_step'],1), 'ms frac', round(d['roofline']['frac'],3), 'sm', d['clocks']['sm_mhz'], 'MHz', d['clocks'].get('power_w_max'), 'W chunk', d['config'].get('chunk_walkers'))"
                done; done | tee -a $O/${TAG}_opts.log ;;
+    adopt)     # make the bench line of THIS call quote the ncu numbers of THIS call: copy the fresh traffic / HBM JSONs
+               # over the committed ones (the same files are committed from gpurun_out/ afterwards)
+               for f in hbm traffic; do [ -f $O/${TAG}_$f.json ] && cp $O/${TAG}_$f.json profiles/${TAG}_$f.json; done; ls -la profiles/${TAG}_hbm.json profiles/${TAG}_traffic.json ;;
     partests)  timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_variants.py -m gpu -q -x 2>&1 | tail -3 ;;
     *)         echo "unknown task $task" ;;
   esac

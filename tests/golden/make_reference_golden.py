@@ -157,6 +157,125 @@ def run_reference(S, batch, steps, burn, seed, ref_path):
     return out
 
 
+def run_shim(S, batch, steps, burn, seed):
+    """The reference's SOURCE FILES (imported unmodified from /root/reference) executed on a torch-backed stand-in for
+    jax / jax.numpy / pyscf.pbc.gto (tests/golden/torch_jax_shim.py): every formula of network.py, hamiltonian.py,
+    ewaldsum.py, distance.py, supercell.py and qmc.mh_update is the reference's; the array library, the autodiff
+    transforms and the cell container are substitutes.  Inputs that the reference takes from pyscf / its RNG (k-point
+    occupation of the HF solution, parameter draws, initial walkers, Metropolis noise) are generated here with numpy and
+    stored in the file, so the consumer sees exactly what the reference code saw."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch_jax_shim as shim
+    shim.install()
+    import jax
+    from DeepSolid import ewaldsum, hamiltonian, network, qmc, supercell
+    from oracle import deepsolid_oracle as O          # parameter shapes / draws and walkers only (inputs, not outputs)
+
+    # test/test_cell.py:11-25
+    cell = shim.Cell()
+    L = 2 / 0.529177
+    cell.atom = [("Li", (0.0, 0.0, 0.0)), ("H", (L / 2, L / 2, L / 2))]
+    cell.basis = "sto-3g"
+    cell.a = (1 - np.eye(3)) * L / 2
+    cell.unit = "B"
+    cell.spin = 0
+    cell.exp_to_discard = 0.1
+    cell.build()
+    simulation_cell = supercell.get_supercell(cell, S=np.asarray(S, dtype=np.float64))      # supercell.py:64-95
+
+    # k-points of the supercell (supercell.py:32-48, reference code); occupation: the lowest-index k-points take the
+    # remainder (the HF solution that orders them in the reference run is an input, not part of the hot path)
+    kpts = np.asarray(supercell.get_supercell_kpts(simulation_cell), dtype=np.float64)
+    klist = []
+    for ns in simulation_cell.nelec:
+        per, rem = divmod(ns, len(kpts))
+        rows = [kpts[i] for i in range(len(kpts)) for _ in range(per + (1 if i < rem else 0))]
+        klist.append(np.stack(rows) if rows else np.zeros((0, 3)))
+
+    kw = dict(envelope_type="isotropic", bias_orbitals=False, use_last_layer=False, klist=klist,
+              simulation_cell=simulation_cell, full_det=False, hidden_dims=((256, 32),) * 3, determinants=8,
+              after_determinants=1, distance_type="nu")
+    nets = {m: network.make_solid_fermi_net(**kw, method_name=m)
+            for m in ("eval_logdet", "eval_slogdet", "eval_phase_and_slogdet", "eval_mats")}
+    # parameters: shapes / distributions of network.py:60-186 drawn with numpy from `seed` (the file stores the seed, the
+    # consumer redraws them: 0.5 M doubles would make a 3.5 MB fixture); everything else from a second stream
+    params = O.params_to_torch(O.init_params(np.random.default_rng(seed), cell.natm, simulation_cell.nelec))
+    rng = np.random.default_rng(seed + 1)
+    latvec = simulation_cell.lattice_vectors()
+    # walkers: electrons on atoms + noise (init_guess.py:69-80 does the same with its own key), wrapped into the cell
+    sim_atoms = simulation_cell.atom_coords()
+    n_up, n_dn = simulation_cell.nelec
+    idx = [i % len(sim_atoms) for i in range(n_up)] + [i % len(sim_atoms) for i in range(n_dn)]
+    x = sim_atoms[idx][None] + 0.8 * rng.standard_normal((batch, n_up + n_dn, 3))
+    frac = x @ np.linalg.inv(latvec)
+    data = torch.as_tensor(((frac - np.floor(frac)) @ latvec).reshape(batch, -1))
+
+    def batched(f):
+        return lambda p, xs: torch.stack([f(p, xs[b]) for b in range(xs.shape[0])])
+
+    batch_slog = batched(nets["eval_slogdet"].apply)
+    width = 0.15
+    nacc = 0.0
+    lp = 2.0 * batch_slog(params, data)
+    key = jax.random.PRNGKey(seed)
+    for _ in range(burn):                                     # burn-in with the reference's own update (qmc.py:153-224)
+        shim.set_random_queue([rng.standard_normal(tuple(data.shape)), rng.random(tuple(lp.shape))])
+        data, key, lp, nacc = qmc.mh_update(params, batch_slog, data, key, lp, nacc, latvec, stddev=width)
+    x0 = data.numpy().copy()
+
+    out = {}
+    res = [nets["eval_phase_and_slogdet"].apply(params, data[b]) for b in range(batch)]
+    out["logabs"] = np.asarray([float(r[1]) for r in res])
+    out["phase"] = np.asarray([float(torch.angle(r[0])) for r in res])
+    out["logdet"] = np.asarray([complex(nets["eval_logdet"].apply(params, data[b])) for b in range(batch)])
+    mats = [nets["eval_mats"].apply(params, data[b]) for b in range(batch)]
+    for s in range(2):
+        out[f"mats{s}"] = np.stack([m[s].numpy() for m in mats]).astype(np.complex128)
+    for mode in ("for", "partition", "dim_batch"):
+        el = hamiltonian.local_energy_seperate(nets["eval_logdet"].apply, simulation_cell, mode=mode, partition_number=3)
+        kes, ews = zip(*[el(params, data[b]) for b in range(batch)])
+        out[f"ke_{mode}"] = np.asarray([complex(k) for k in kes])
+        out[f"ewald_{mode}"] = np.asarray([float(e) for e in ews])
+    ewald = ewaldsum.EwaldSum(simulation_cell)
+    parts = [ewald.energy(data[b]) for b in range(batch)]
+    out["ee"], out["ei"], out["ii"] = (np.asarray([float(p[i]) for p in parts]) for i in range(3))
+    out["ewald_alpha"] = np.float64(ewald.alpha)
+    out["ewald_ng"] = np.int64(ewald.gweight.shape[0])
+
+    x1 = data
+    lp = 2.0 * batch_slog(params, x1)
+    xi, u, masks = [], [], []
+    nacc = 0.0
+    for _ in range(steps):
+        xi.append(rng.standard_normal(tuple(x1.shape)))
+        u.append(rng.random(tuple(lp.shape)))
+        shim.set_random_queue([xi[-1], u[-1]])
+        x_new, key, lp_new, nacc = qmc.mh_update(params, batch_slog, x1, key, lp, nacc, latvec, stddev=width)
+        masks.append((lp_new != lp).numpy() | np.any((x_new != x1).numpy(), axis=-1))
+        x1, lp = x_new, lp_new
+    out.update(xi=np.stack(xi), u=np.stack(u), masks=np.stack(masks), x_new=x1.numpy().astype(np.float64),
+               pmove=np.float64(float(nacc) / (steps * batch)), width=np.float64(width))     # qmc.py:360
+
+    prim = simulation_cell.original_cell
+    flat = _flatten({g: [{k: v.numpy() for k, v in d.items()} for d in params[g]] for g in params})
+    out.update(param_seed=np.int64(seed), param_checksum=np.float64(sum(float(np.abs(v).sum()) for v in flat.values())))
+    out.update(x=x0, S=np.asarray(S, dtype=np.float64), nelec=np.asarray(simulation_cell.nelec, dtype=np.int64),
+               prim_a=np.asarray(prim.lattice_vectors(), dtype=np.float64),
+               prim_atoms=np.asarray(prim.atom_coords(), dtype=np.float64),
+               prim_charges=np.asarray(prim.atom_charges(), dtype=np.float64),
+               sim_a=np.asarray(simulation_cell.lattice_vectors(), dtype=np.float64),
+               sim_atoms=np.asarray(simulation_cell.atom_coords(), dtype=np.float64),
+               sim_charges=np.asarray(simulation_cell.atom_charges(), dtype=np.float64),
+               sim_AV=np.asarray(simulation_cell.AV), sim_BV=np.asarray(simulation_cell.BV),
+               prim_AV=np.asarray(prim.AV), prim_BV=np.asarray(prim.BV),
+               klist0=klist[0], klist1=klist[1], energy_nuc=np.float64(float(ewald.ion_ion + ewald.ii_const)),
+               source=np.array("reference-source/torch-shim"),
+               versions=np.array(f"torch {torch.__version__} stand-in for jax; DeepSolid sources from /root/reference"))
+    return out
+
+
 def run_oracle(S, batch, steps, burn, seed):
     """Plumbing self-test only: the same file layout written from the CPU oracle."""
     sys.path.insert(0, ROOT)
@@ -212,7 +331,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("--reference", default=os.environ.get("DEEPSOLID_PATH", ""), help="checkout of bytedance/DeepSolid")
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
-    ap.add_argument("--backend", choices=["reference", "oracle"], default="reference")
+    ap.add_argument("--backend", choices=["reference", "shim", "oracle"], default="reference")
     ap.add_argument("--batch", type=int, default=6)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--burn", type=int, default=30)
@@ -224,6 +343,9 @@ def main(argv=None):
         S = CASES[name]
         if a.backend == "reference":
             data = run_reference(S, a.batch, a.steps, a.burn, a.seed, a.reference)
+        elif a.backend == "shim":
+            data = run_shim(S, a.batch, a.steps, a.burn, a.seed)
+            name = name.replace("reference_", "reference_shim_")
         else:
             data = run_oracle(S, a.batch, a.steps, a.burn, a.seed)
         path = os.path.join(a.out, name + ".npz")

@@ -1,0 +1,418 @@
+"""A torch-backed stand-in for the parts of ``jax`` / ``jax.numpy`` / ``pyscf.pbc.gto`` that the hot-path modules of
+bytedance/DeepSolid touch, so that the reference's OWN SOURCE FILES (network.py, hamiltonian.py, ewaldsum.py,
+distance.py, supercell.py, qmc.py, imported unmodified from /root/reference) can be executed in an image that has
+neither JAX nor pyscf.  Test infrastructure only: used by ``make_reference_shim_golden.py`` in the build container;
+nothing on the GPU box imports it.
+
+What is substituted, and what is not:
+  * array backend: ``jnp.*`` -> the torch function of the same meaning on float64 / complex128 tensors;
+  * transforms: ``jax.grad / jvp / vmap / hessian / value_and_grad`` -> ``torch.func``; ``lax.fori_loop / scan`` ->
+    Python loops; ``jax.jit`` -> identity;
+  * ``jax.random.normal / uniform`` -> draws handed in by the caller (``set_random_queue``), since the bit stream of
+    JAX's threefry generator is not the parity object -- the accept mask for given (x, xi, U) is;
+  * ``pyscf.pbc.gto.Cell`` -> a plain container with the geometry methods supercell.py / ewaldsum.py call
+    (lattice / reciprocal vectors, atom coordinates and charges, electron counts);
+  * the KFAC tags of curvature_tags_and_blocks.py are the identity on values and are stubbed as such.
+Every formula -- features, network, determinants, Laplacian modes, Ewald sum, minimal image, Metropolis update -- is
+the reference's code, line for line, because it IS the reference's code.
+"""
+from __future__ import annotations
+
+import dataclasses
+import functools
+import math
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF_ROOT = "/root/reference"
+F64 = torch.float64
+
+
+def _t(x, dtype=None):
+    if isinstance(x, torch.Tensor):
+        return x if dtype is None else x.to(dtype)
+    a = np.asarray(x)
+    if a.dtype.kind == "f":
+        a = a.astype(np.float64)
+    if a.dtype.kind == "c":
+        a = a.astype(np.complex128)
+    t = torch.as_tensor(a)
+    return t if dtype is None else t.to(dtype)
+
+
+def _kw(kwargs):
+    out = {}
+    for k, v in kwargs.items():
+        if k == "axis":
+            out["dim"] = v
+        elif k == "keepdims":
+            out["keepdim"] = v
+        else:
+            out[k] = v
+    return out
+
+
+def _wrap(fn, n_tensor_args=1):
+    @functools.wraps(fn)
+    def g(*args, **kwargs):
+        args = list(args)
+        for i in range(min(n_tensor_args, len(args))):
+            args[i] = _t(args[i])
+        return fn(*args, **_kw(kwargs))
+    return g
+
+
+# ---------------------------------------------------------------------------------------------------------
+# jax.numpy
+# ---------------------------------------------------------------------------------------------------------
+jnp = types.ModuleType("jax.numpy")
+jnp.ndarray = torch.Tensor
+jnp.DeviceArray = torch.Tensor
+jnp.pi = math.pi
+jnp.float64 = F64
+jnp.complex128 = torch.complex128
+
+for _name, _fn in dict(exp=torch.exp, abs=torch.abs, sqrt=torch.sqrt, log=torch.log, tanh=torch.tanh, sin=torch.sin,
+                       cos=torch.cos, angle=torch.angle, conjugate=torch.conj, squeeze=torch.squeeze,
+                       argmax=torch.argmax, argmin=torch.argmin, diag=torch.diag,
+                       tile=torch.tile, trace=torch.trace).items():
+    setattr(jnp, _name, _wrap(_fn))
+
+
+def _sum(x, axis=None, keepdims=False):
+    x = _t(x)
+    return x.sum() if axis is None else x.sum(dim=axis, keepdim=keepdims)
+
+
+def _mean(x, axis=None, keepdims=False):
+    x = _t(x)
+    return x.mean() if axis is None else x.mean(dim=axis, keepdim=keepdims)
+
+
+def _amin(x, axis=None):
+    x = _t(x)
+    return x.min() if axis is None else x.min(dim=axis).values
+
+
+def _amax(x, axis=None):
+    x = _t(x)
+    return x.max() if axis is None else x.max(dim=axis).values
+
+
+def _all(x, axis=None):
+    x = _t(x)
+    return x.all() if axis is None else x.all(dim=axis)
+
+
+def _split(x, indices_or_sections, axis=0):
+    if isinstance(indices_or_sections, (list, tuple)):
+        indices_or_sections = [int(i) for i in indices_or_sections]
+    return list(torch.tensor_split(_t(x), indices_or_sections, dim=axis))
+
+
+def _array_split(x, sections, axis=0):
+    return list(torch.tensor_split(_t(x), int(sections), dim=axis))
+
+
+def _asarray(x, dtype=None):
+    if isinstance(x, (list, tuple)) and len(x) and isinstance(x[0], torch.Tensor):
+        return torch.stack([_t(v) for v in x])
+    return _t(x)
+
+
+def _meshgrid(*xs, indexing="xy"):
+    return list(torch.meshgrid(*[_t(x) for x in xs], indexing=indexing))
+
+
+def _divmod(a, b):
+    a = _t(a)
+    q = torch.floor(a / b)
+    return q, a - q * b
+
+
+def _dot(a, b):
+    a, b = _t(a), _t(b)
+    if a.dtype != b.dtype:
+        dt = torch.promote_types(a.dtype, b.dtype)
+        a, b = a.to(dt), b.to(dt)
+    if a.dim() == 0 or b.dim() == 0:
+        return a * b
+    if b.dim() == 1:
+        return torch.tensordot(a, b, dims=([-1], [0]))
+    return torch.tensordot(a, b, dims=([-1], [-2]))        # numpy.dot: last axis of a with second-to-last of b
+
+
+def _matmul(a, b):
+    a, b = _t(a), _t(b)
+    if a.dtype != b.dtype:
+        dt = torch.promote_types(a.dtype, b.dtype)
+        a, b = a.to(dt), b.to(dt)
+    return torch.matmul(a, b)
+
+
+def _einsum(spec, *ops):
+    ops = [_t(o) for o in ops]
+    dt = functools.reduce(torch.promote_types, [o.dtype for o in ops])
+    return torch.einsum(spec, *[o.to(dt) for o in ops])
+
+
+def _arange(*a, **k):
+    return torch.arange(*a, dtype=F64 if any(isinstance(v, float) for v in a) else torch.int64)
+
+
+jnp.sum, jnp.mean, jnp.amin, jnp.amax, jnp.min, jnp.max, jnp.all = _sum, _mean, _amin, _amax, _amin, _amax, _all
+jnp.split, jnp.array_split, jnp.asarray, jnp.array = _split, _array_split, _asarray, _asarray
+jnp.meshgrid, jnp.divmod, jnp.dot, jnp.matmul, jnp.einsum, jnp.arange = _meshgrid, _divmod, _dot, _matmul, _einsum, _arange
+jnp.triu = lambda x, k=0: torch.triu(_t(x), diagonal=k)
+jnp.concatenate = lambda xs, axis=0: torch.cat([_t(x) for x in xs], dim=axis)
+jnp.stack = lambda xs, axis=0: torch.stack([_t(x) for x in xs], dim=axis)
+jnp.reshape = lambda x, shape: _t(x).reshape(tuple(shape) if isinstance(shape, (list, tuple)) else shape)
+jnp.transpose = lambda x, axes=None: _t(x).permute(*axes) if axes is not None else _t(x).T
+jnp.expand_dims = lambda x, axis: _t(x).unsqueeze(axis)
+jnp.shape = lambda x: tuple(_t(x).shape)
+jnp.eye = lambda n, dtype=None: torch.eye(int(n), dtype=F64)
+jnp.ones = lambda shape, dtype=None: torch.ones(shape, dtype=F64)
+jnp.zeros = lambda shape, dtype=None: torch.zeros(shape, dtype=F64)
+jnp.where = lambda c, a, b: torch.where(c, _t(a), _t(b))
+jnp.clip = lambda x, a=None, b=None: torch.clamp(_t(x), a, b)
+jnp.diagonal = lambda x, offset=0, axis1=0, axis2=1: torch.diagonal(_t(x), offset=offset, dim1=axis1, dim2=axis2)
+jnp.allclose = lambda a, b, rtol=1e-5, atol=1e-8: bool(torch.allclose(_t(a, F64), _t(b, F64), rtol=rtol, atol=atol))
+jnp.median = lambda x: torch.quantile(_t(x), 0.5)            # numpy's median (mean of the middle pair)
+
+jnp.linalg = types.ModuleType("jax.numpy.linalg")
+jnp.linalg.norm = lambda x, axis=None, keepdims=False: (torch.linalg.norm(_t(x)) if axis is None
+                                                         else torch.linalg.norm(_t(x), dim=axis, keepdim=keepdims))
+jnp.linalg.inv = lambda x: torch.linalg.inv(_t(x))
+jnp.linalg.det = lambda x: torch.linalg.det(_t(x))
+jnp.linalg.slogdet = lambda x: tuple(torch.linalg.slogdet(_t(x)))
+
+# ---------------------------------------------------------------------------------------------------------
+# jax (transforms, lax, random)
+# ---------------------------------------------------------------------------------------------------------
+jax = types.ModuleType("jax")
+jax.numpy = jnp
+jax.jit = lambda f, *a, **k: f
+jax.vmap = lambda f, in_axes=0, out_axes=0: torch.func.vmap(f, in_dims=in_axes, out_dims=out_axes)
+jax.grad = lambda f, argnums=0, holomorphic=False, has_aux=False: torch.func.grad(f, argnums=argnums, has_aux=has_aux)
+jax.value_and_grad = lambda f, argnums=0, has_aux=False: torch.func.grad_and_value_swapped(f, argnums, has_aux)
+jax.hessian = lambda f, argnums=0: torch.func.hessian(f, argnums=argnums)
+
+
+def _grad_and_value_swapped(f, argnums, has_aux):
+    gv = torch.func.grad_and_value(f, argnums=argnums, has_aux=has_aux)
+
+    def g(*a, **k):
+        grad, val = gv(*a, **k)
+        return val, grad
+    return g
+
+
+torch.func.grad_and_value_swapped = _grad_and_value_swapped
+
+
+def _jvp(f, primals, tangents):
+    return torch.func.jvp(f, tuple(_t(p) for p in primals), tuple(_t(t) for t in tangents))
+
+
+jax.jvp = _jvp
+jax.tree_map = lambda f, tree, *rest: torch.utils._pytree.tree_map(f, tree, *rest)
+jax.tree_multimap = jax.tree_map
+
+lax = types.ModuleType("jax.lax")
+
+
+def _fori_loop(lo, hi, body, init):
+    val = init
+    for i in range(int(lo), int(hi)):
+        val = body(i, val)
+    return val
+
+
+def _scan(f, init, xs, length=None):
+    carry, ys = init, []
+    n = len(xs) if xs is not None else length
+    for i in range(n):
+        carry, y = f(carry, xs[i] if xs is not None else None)
+        ys.append(y)
+    if ys and ys[0] is not None:
+        stacked = torch.utils._pytree.tree_map(lambda *leaves: torch.stack(leaves), *ys)      # ys may be a nested pytree
+    else:
+        stacked = None
+    return carry, stacked
+
+
+lax.fori_loop, lax.scan = _fori_loop, _scan
+lax.erfc = lambda x: torch.special.erfc(_t(x))
+lax.pmean = lambda x, axis_name=None: x
+lax.psum = lambda x, axis_name=None: x
+jax.lax = lax
+
+random = types.ModuleType("jax.random")
+_QUEUE: list = []
+
+
+def set_random_queue(arrays):
+    """Draws that the next jax.random.normal / uniform calls return, in call order."""
+    _QUEUE[:] = [_t(a) for a in arrays]
+
+
+def _pop(shape):
+    if not _QUEUE:
+        raise RuntimeError("torch_jax_shim: jax.random draw requested but the queue is empty")
+    v = _QUEUE.pop(0)
+    assert tuple(v.shape) == tuple(shape), (tuple(v.shape), tuple(shape))
+    return v
+
+
+random.PRNGKey = lambda seed: torch.tensor([0, int(seed)], dtype=torch.int64)
+random.split = lambda key, num=2: tuple(key.clone() for _ in range(num))
+random.normal = lambda key, shape=(), dtype=None: _pop(shape)
+random.uniform = lambda key, shape=(), dtype=None, minval=0.0, maxval=1.0: _pop(shape)
+jax.random = random
+
+core = types.ModuleType("jax.core")
+
+
+def _axis_frame(name):
+    raise NameError(name)              # "not inside a pmap": constants.pmean_if_pmap then returns its argument
+
+
+core.axis_frame = _axis_frame
+jax.core = core
+jax.pmap = lambda f, axis_name=None, **k: f
+jax.custom_jvp = lambda f=None, **k: f if f is not None else (lambda g: g)
+jax.local_device_count = lambda: 1
+jax.host_id = lambda: 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pyscf.pbc.gto.Cell
+# ---------------------------------------------------------------------------------------------------------
+_Z = {"H": 1, "He": 2, "Li": 3, "Be": 4, "B": 5, "C": 6, "N": 7, "O": 8}
+ANGSTROM_BOHR = 0.52917721067          # DeepSolid/utils/units.py:25 (and pyscf's conversion to within 1e-9)
+
+
+class Cell:
+    """Geometry container with the pyscf.pbc.gto.Cell methods the hot path uses.  ``atom`` is a list of (symbol, xyz);
+    ``charges`` optionally overrides the nuclear charges (pyscf returns screened charges under an ECP)."""
+
+    def __init__(self):
+        self.a = None
+        self.atom = None
+        self.unit = "Bohr"
+        self.spin = 0
+        self.ecp = None
+        self.basis = None
+        self.exp_to_discard = None
+        self.charges = None
+        self.verbose = 0
+
+    def build(self, *a, **k):
+        scale = 1.0 if str(self.unit).lower().startswith("b") else 1.0 / ANGSTROM_BOHR
+        self.a = np.asarray(self.a, dtype=np.float64).reshape(3, 3) * (scale if not getattr(self, "_built", False) else 1.0)
+        self._atom = [(n, np.asarray(x, dtype=np.float64) * (scale if not getattr(self, "_built", False) else 1.0))
+                      for n, x in self.atom]
+        self._built = True
+        self.unit = "Bohr"
+        z = self.atom_charges()
+        ntot = int(round(z.sum()))
+        self.nelectron = ntot
+        assert (ntot + self.spin) % 2 == 0
+        self.nelec = ((ntot + self.spin) // 2, (ntot - self.spin) // 2)
+        self.natm = len(self._atom)
+        return self
+
+    def lattice_vectors(self):
+        return np.asarray(self.a, dtype=np.float64)
+
+    def reciprocal_vectors(self):
+        return 2.0 * np.pi * np.linalg.inv(self.lattice_vectors()).T
+
+    def atom_coords(self):
+        return np.stack([x for _, x in self._atom])
+
+    def atom_charges(self):
+        if self.charges is not None:
+            per = dict(self.charges)
+            return np.asarray([float(per[n]) for n, _ in self._atom])
+        return np.asarray([float(_Z[n]) for n, _ in self._atom])
+
+    def energy_nuc(self):
+        # pyscf evaluates the Madelung / ion-ion Ewald energy; the stand-in returns the reference's own value so that
+        # the consistency assertion hamiltonian.py:170-172 (a check AGAINST pyscf) is neutral here
+        from DeepSolid import ewaldsum
+        ew = ewaldsum.EwaldSum(self)
+        return ew.ion_ion + ew.ii_const
+
+
+_orig_size = torch.Tensor.size
+
+
+class _SizeProxy(int):
+    """numpy's ``ndarray.size`` (an int, network.py:327-328) and torch's ``Tensor.size(...)`` (a method) at once."""
+
+    def __new__(cls, t):
+        obj = int.__new__(cls, t.numel())
+        obj._t = t
+        return obj
+
+    def __call__(self, *a, **k):
+        return _orig_size(self._t, *a, **k)
+
+
+class _SizeDescriptor:
+    def __get__(self, obj, typ=None):
+        return _orig_size if obj is None else _SizeProxy(obj)
+
+
+def install():
+    """Put the stand-ins into sys.modules and make ``DeepSolid`` importable from /root/reference without running any
+    module that needs the real JAX / pyscf / chex."""
+    torch.Tensor.size = _SizeDescriptor()           # this process only (the generator script)
+    _orig_mm = torch.Tensor.__matmul__
+
+    def _promoting_matmul(a, b):                    # `@` with jax's int / float / complex promotion (distance.py:68)
+        b = _t(b)
+        if a.dtype != b.dtype:
+            dt = torch.promote_types(a.dtype, b.dtype)
+            a, b = a.to(dt), b.to(dt)
+        return _orig_mm(a, b)
+
+    # `x // 1` (network.py:54, 216): piecewise constant, zero derivative in JAX; torch has no forward-mode rule for it
+    torch.Tensor.__floordiv__ = lambda a, b: torch.floor((a / b).detach())
+    # tensor (op) numpy-array, as jax arrays accept numpy operands (network.py:284: positions minus pyscf's atom_coords)
+    for name in ("__add__", "__sub__", "__mul__", "__truediv__", "__radd__", "__rsub__", "__rmul__", "__rtruediv__"):
+        def make(orig):
+            def op(a, b):
+                return orig(a, _t(b) if isinstance(b, np.ndarray) else b)
+            return op
+        setattr(torch.Tensor, name, make(getattr(torch.Tensor, name)))
+    torch.Tensor.__matmul__ = _promoting_matmul
+    torch.Tensor.__rmatmul__ = lambda b, a: _promoting_matmul(_t(a), b)
+    sys.modules["jax"] = jax
+    sys.modules["jax.numpy"] = jnp
+    sys.modules["jax.lax"] = lax
+    sys.modules["jax.random"] = random
+    sys.modules["jax.core"] = core
+    pyscf = types.ModuleType("pyscf")
+    pbc = types.ModuleType("pyscf.pbc")
+    gto = types.ModuleType("pyscf.pbc.gto")
+    gto.Cell = Cell
+    pbc.gto = gto
+    pyscf.pbc = pbc
+    sys.modules.update({"pyscf": pyscf, "pyscf.pbc": pbc, "pyscf.pbc.gto": gto})
+    chex = types.ModuleType("chex")
+    chex.dataclass = dataclasses.dataclass
+    sys.modules["chex"] = chex
+    pkg = types.ModuleType("DeepSolid")
+    pkg.__path__ = [REF_ROOT + "/DeepSolid"]
+    sys.modules["DeepSolid"] = pkg
+    tags = types.ModuleType("DeepSolid.curvature_tags_and_blocks")
+    tags.register_repeated_dense = lambda y, x, w, b, **k: y          # curvature_tags_and_blocks.py: identity on values
+    tags.register_qmc1 = lambda y, x, w, **k: y
+    tags.register_qmc = tags.register_qmc1
+    sys.modules["DeepSolid.curvature_tags_and_blocks"] = tags
+    pkg.curvature_tags_and_blocks = tags

@@ -176,3 +176,31 @@ def test_gpu_kfac_step_follows_the_block_algebra_on_oracle_factors():
     got = O._leaves({k: [{kk: vv.cpu() for kk, vv in d.items()} for d in new_params[k]] for k in new_params})
     for a, b in zip(got, want):
         assert _rel(a, b) < 1e-7
+
+
+@pytest.mark.gpu
+def test_gpu_kfac_momentum_follows_the_reference_recursion():
+    """optimizer.py:444-463, 617-627: delta = -lr c F^-1 g + momentum * previous delta; velocities <- delta; the first
+    step treats the momentum as 0.  Two optimisers (momentum 0.5 / 0) share step 1, so their curvature states agree and
+    step 2 differs by exactly 0.5 * delta_1."""
+    from deepsolid_b200 import network, train
+    sc, kl, pn, P = system("h4")
+    net = network.make_solid_fermi_net(envelope_type="isotropic", full_det=False, klist=kl, simulation_cell=sc,
+                                       determinants=8, method_name="eval_logdet")
+    hp = net.apply.hotpath()
+    X = torch.as_tensor(C.init_walkers(sc, 8, seed=3)).cuda()
+    loss_fn = train.make_loss(net.apply, None, sc, clip_local_energy=5.0, clip_type="real", mode="for")
+    flat = lambda p: [t.detach().cpu().double() for t in kfac.flatten_params(p)]
+    outs = {}
+    for m in (0.5, 0.0):
+        opt = kfac.Optimizer(loss_fn.value_and_grad, hp, norm_constraint=1e-3)
+        p1, s1 = opt.step(P, X, learning_rate=5e-2, damping=1e-3, momentum=m)
+        assert s1["momentum"] == 0.0
+        p2, s2 = opt.step(p1, X, learning_rate=5e-2, damping=1e-3, momentum=m)
+        assert s2["momentum"] == m
+        outs[m] = (flat(p1), flat(p2))
+    p0 = [torch.as_tensor(t).double() for t in kfac.flatten_params(P)]
+    for a0, a1, b1, a2, b2 in zip(p0, outs[0.5][0], outs[0.0][0], outs[0.5][1], outs[0.0][1]):
+        assert torch.equal(a1, b1)
+        delta1 = a1 - a0.cpu()
+        assert _rel(a2 - b2, 0.5 * delta1) < 1e-9 or float((a2 - b2 - 0.5 * delta1).abs().max()) < 1e-14
