@@ -8,12 +8,15 @@ It stands alone: cell geometry (supercell atoms, AV / BV, k-points) comes from o
 tables and the lattice classification from the classes below -- nothing is imported from the product, and a
 cell object handed in by a test is re-derived from its primary inputs (geometry.rederive).
 
-PARITY UNPINNED: the reference (bytedance/DeepSolid @ 812a2b8) is pure JAX + pyscf
-and neither is installable in this image, and its own tests hold no golden numbers
-(test/test_network.py asserts three invariants only).  The oracle is therefore a
-line-by-line restatement, pinned by (i) those three invariants, (ii) finite
-differences of its own log psi, (iii) Madelung constants for the Ewald setup and
-(iv) an independent forward-Laplacian derivation (oracle/forward_laplacian.py).
+PINNING: the reference (bytedance/DeepSolid @ 812a2b8) is pure JAX + pyscf, neither is installable in this image,
+and its own tests hold no golden numbers (test/test_network.py asserts three invariants only).  The oracle is a
+line-by-line restatement pinned by (i) the reference's OWN SOURCE FILES executed on a torch stand-in for jax / pyscf
+(tests/golden/torch_jax_shim.py; fixtures tests/golden/reference_shim_*.npz written by make_reference_golden.py
+--backend shim; compared in tests/test_reference_golden.py: LiH test cell with every network option, and the
+BASELINE configurations at full size), (ii) those three invariants, (iii) finite differences and a 40-digit mpmath
+restatement of its own log psi, (iv) Madelung constants for the Ewald setup and (v) an independent forward-Laplacian
+derivation (oracle/forward_laplacian.py).  NOT pinned: a run of the real JAX stack (XLA's evaluation order, JAX's
+RNG stream); make_reference_golden.py --backend reference produces that file on a machine that has it.
 
 Every function cites the reference lines (relative to /root/reference/DeepSolid/)
 it follows.  The Laplacian is obtained with the *reference's algorithm*

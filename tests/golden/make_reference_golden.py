@@ -157,13 +157,43 @@ def run_reference(S, batch, steps, burn, seed, ref_path):
     return out
 
 
-def run_shim(S, batch, steps, burn, seed):
+#: fixtures written with --backend shim: system (oracle/geometry.py name: primitive cell, charges and S of the reference's
+#: config files), network options (network.py:609-667), Laplacian modes, walkers, Metropolis moves, burn-in moves
+SHIM_CASES = {
+    # the cell of the reference's own tests (test/test_cell.py), all three Laplacian modes
+    "reference_shim_lih_s111": dict(system="test_cell_lih", S=np.eye(3), batch=4, steps=3, burn=10),
+    "reference_shim_lih_s211": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=4, steps=3, burn=10),
+    # the structural options of make_solid_fermi_net
+    "reference_shim_lih_tri": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
+                                   opts=dict(distance_type="tri"), modes=("for",)),
+    "reference_shim_lih_diagenv": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
+                                       opts=dict(envelope_type="diagonal"), modes=("for",)),
+    "reference_shim_lih_fullenv": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
+                                       opts=dict(envelope_type="full"), modes=("for",)),
+    "reference_shim_lih_fulldet": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
+                                       opts=dict(full_det=True), modes=("for",)),
+    "reference_shim_lih_bias": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
+                                    opts=dict(bias_orbitals=True), modes=("for",)),
+    "reference_shim_lih_lastlayer": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
+                                         opts=dict(use_last_layer=True), modes=("for",)),
+    # BASELINE.json configurations (SURVEY 8 d), one or two walkers each at full size
+    "reference_shim_h10": dict(system="h10", batch=2, steps=2, burn=4, modes=("for", "partition")),
+    "reference_shim_li24": dict(system="li24", batch=2, steps=1, burn=2, modes=("for",)),
+    "reference_shim_graphite54": dict(system="graphite54", batch=2, steps=1, burn=2, modes=("for",)),
+    "reference_shim_diamond64": dict(system="diamond64", batch=1, steps=1, burn=2, modes=("partition",)),
+    "reference_shim_lih108": dict(system="lih108", batch=1, steps=1, burn=1, modes=("partition",)),
+}
+_SYMBOL_OF_Z = {1.0: "H", 2.0: "He", 3.0: "Li", 4.0: "Be", 6.0: "C"}
+
+
+def run_shim(case, seed):
     """The reference's SOURCE FILES (imported unmodified from /root/reference) executed on a torch-backed stand-in for
     jax / jax.numpy / pyscf.pbc.gto (tests/golden/torch_jax_shim.py): every formula of network.py, hamiltonian.py,
     ewaldsum.py, distance.py, supercell.py and qmc.mh_update is the reference's; the array library, the autodiff
-    transforms and the cell container are substitutes.  Inputs that the reference takes from pyscf / its RNG (k-point
-    occupation of the HF solution, parameter draws, initial walkers, Metropolis noise) are generated here with numpy and
-    stored in the file, so the consumer sees exactly what the reference code saw."""
+    transforms and the cell container are substitutes.  Inputs that the reference takes from pyscf / its RNG (primitive
+    cell of the config file, k-point occupation of the HF solution, parameter draws, initial walkers, Metropolis noise)
+    are generated here with numpy and stored in the file, so the consumer sees exactly what the reference code saw."""
+    import json
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, ROOT)
     import torch
@@ -171,19 +201,29 @@ def run_shim(S, batch, steps, burn, seed):
     shim.install()
     import jax
     from DeepSolid import ewaldsum, hamiltonian, network, qmc, supercell
-    from oracle import deepsolid_oracle as O          # parameter shapes / draws and walkers only (inputs, not outputs)
+    from oracle import deepsolid_oracle as O          # parameter shapes / draws only (inputs, not outputs)
+    from oracle import geometry as G                  # the primitive cells of the reference's config files (inputs)
 
-    # test/test_cell.py:11-25
+    batch, steps, burn = case["batch"], case["steps"], case["burn"]
+    opts = dict(case.get("opts", {}))
+    modes = tuple(case.get("modes", ("for", "partition", "dim_batch")))
+    named = G.build_system(case["system"])
+    prim0 = named.original_cell
+    S = np.asarray(case.get("S", named.S), dtype=np.float64)
+    # primitive cell -> the stand-in for pyscf.pbc.gto.Cell; the SUPERCELL is built by the reference (supercell.py:64-95)
     cell = shim.Cell()
-    L = 2 / 0.529177
-    cell.atom = [("Li", (0.0, 0.0, 0.0)), ("H", (L / 2, L / 2, L / 2))]
-    cell.basis = "sto-3g"
-    cell.a = (1 - np.eye(3)) * L / 2
+    syms, charges = [], {}
+    for i, ((sym, xyz), z) in enumerate(zip(prim0._atom, prim0.atom_charges())):
+        syms.append(sym)
+        charges[sym] = float(z)
+    cell.atom = [(sym, tuple(xyz)) for sym, (_, xyz) in zip(syms, prim0._atom)]
+    cell.ecp = charges if any(abs(z - shim._Z.get(sym, -1)) > 1e-12 for sym, z in charges.items()) else None
+    cell.a = np.asarray(prim0.lattice_vectors(), dtype=np.float64)
     cell.unit = "B"
-    cell.spin = 0
-    cell.exp_to_discard = 0.1
+    cell.spin = int(prim0.nelec[0] - prim0.nelec[1])
+    cell.basis, cell.exp_to_discard = "sto-3g", 0.1
     cell.build()
-    simulation_cell = supercell.get_supercell(cell, S=np.asarray(S, dtype=np.float64))      # supercell.py:64-95
+    simulation_cell = supercell.get_supercell(cell, S=S)
 
     # k-points of the supercell (supercell.py:32-48, reference code); occupation: the lowest-index k-points take the
     # remainder (the HF solution that orders them in the reference run is an input, not part of the hot path)
@@ -197,11 +237,13 @@ def run_shim(S, batch, steps, burn, seed):
     kw = dict(envelope_type="isotropic", bias_orbitals=False, use_last_layer=False, klist=klist,
               simulation_cell=simulation_cell, full_det=False, hidden_dims=((256, 32),) * 3, determinants=8,
               after_determinants=1, distance_type="nu")
+    kw.update(opts)
     nets = {m: network.make_solid_fermi_net(**kw, method_name=m)
             for m in ("eval_logdet", "eval_slogdet", "eval_phase_and_slogdet", "eval_mats")}
     # parameters: shapes / distributions of network.py:60-186 drawn with numpy from `seed` (the file stores the seed, the
-    # consumer redraws them: 0.5 M doubles would make a 3.5 MB fixture); everything else from a second stream
-    params = O.params_to_torch(O.init_params(np.random.default_rng(seed), cell.natm, simulation_cell.nelec))
+    # consumer redraws them: 0.5 M doubles would make a multi-MB fixture); everything else from a second stream
+    init_kw = {k: kw[k] for k in ("envelope_type", "bias_orbitals", "use_last_layer", "full_det", "distance_type")}
+    params = O.params_to_torch(O.init_params(np.random.default_rng(seed), cell.natm, simulation_cell.nelec, **init_kw))
     rng = np.random.default_rng(seed + 1)
     latvec = simulation_cell.lattice_vectors()
     # walkers: electrons on atoms + noise (init_guess.py:69-80 does the same with its own key), wrapped into the cell
@@ -231,10 +273,11 @@ def run_shim(S, batch, steps, burn, seed):
     out["phase"] = np.asarray([float(torch.angle(r[0])) for r in res])
     out["logdet"] = np.asarray([complex(nets["eval_logdet"].apply(params, data[b])) for b in range(batch)])
     mats = [nets["eval_mats"].apply(params, data[b]) for b in range(batch)]
-    for s in range(2):
+    for s in range(len(mats[0])):
         out[f"mats{s}"] = np.stack([m[s].numpy() for m in mats]).astype(np.complex128)
-    for mode in ("for", "partition", "dim_batch"):
-        el = hamiltonian.local_energy_seperate(nets["eval_logdet"].apply, simulation_cell, mode=mode, partition_number=3)
+    pn = int(case.get("partition_number", 3))
+    for mode in modes:
+        el = hamiltonian.local_energy_seperate(nets["eval_logdet"].apply, simulation_cell, mode=mode, partition_number=pn)
         kes, ews = zip(*[el(params, data[b]) for b in range(batch)])
         out[f"ke_{mode}"] = np.asarray([complex(k) for k in kes])
         out[f"ewald_{mode}"] = np.asarray([float(e) for e in ews])
@@ -271,6 +314,7 @@ def run_shim(S, batch, steps, burn, seed):
                sim_AV=np.asarray(simulation_cell.AV), sim_BV=np.asarray(simulation_cell.BV),
                prim_AV=np.asarray(prim.AV), prim_BV=np.asarray(prim.BV),
                klist0=klist[0], klist1=klist[1], energy_nuc=np.float64(float(ewald.ion_ion + ewald.ii_const)),
+               opts=np.array(json.dumps(opts)), modes=np.array(",".join(modes)), partition_number=np.int64(pn),
                source=np.array("reference-source/torch-shim"),
                versions=np.array(f"torch {torch.__version__} stand-in for jax; DeepSolid sources from /root/reference"))
     return out
@@ -339,15 +383,15 @@ def main(argv=None):
     ap.add_argument("--cases", nargs="*", default=list(CASES))
     a = ap.parse_args(argv)
     os.makedirs(a.out, exist_ok=True)
+    if a.backend == "shim" and a.cases == list(CASES):
+        a.cases = list(SHIM_CASES)
     for name in a.cases:
-        S = CASES[name]
-        if a.backend == "reference":
-            data = run_reference(S, a.batch, a.steps, a.burn, a.seed, a.reference)
-        elif a.backend == "shim":
-            data = run_shim(S, a.batch, a.steps, a.burn, a.seed)
-            name = name.replace("reference_", "reference_shim_")
+        if a.backend == "shim":
+            data = run_shim(SHIM_CASES[name], a.seed)
+        elif a.backend == "reference":
+            data = run_reference(CASES[name], a.batch, a.steps, a.burn, a.seed, a.reference)
         else:
-            data = run_oracle(S, a.batch, a.steps, a.burn, a.seed)
+            data = run_oracle(CASES[name], a.batch, a.steps, a.burn, a.seed)
         path = os.path.join(a.out, name + ".npz")
         np.savez_compressed(path, **data)
         print(f"wrote {path}: {len(data)} arrays, source={data['source']}")

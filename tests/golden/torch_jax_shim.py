@@ -297,7 +297,7 @@ ANGSTROM_BOHR = 0.52917721067          # DeepSolid/utils/units.py:25 (and pyscf'
 
 class Cell:
     """Geometry container with the pyscf.pbc.gto.Cell methods the hot path uses.  ``atom`` is a list of (symbol, xyz);
-    ``charges`` optionally overrides the nuclear charges (pyscf returns screened charges under an ECP)."""
+    ``ecp`` may be a dict {symbol: effective charge} (pyscf returns screened charges under an ECP)."""
 
     def __init__(self):
         self.a = None
@@ -307,7 +307,6 @@ class Cell:
         self.ecp = None
         self.basis = None
         self.exp_to_discard = None
-        self.charges = None
         self.verbose = 0
 
     def build(self, *a, **k):
@@ -335,9 +334,10 @@ class Cell:
         return np.stack([x for _, x in self._atom])
 
     def atom_charges(self):
-        if self.charges is not None:
-            per = dict(self.charges)
-            return np.asarray([float(per[n]) for n, _ in self._atom])
+        # pyscf returns the SCREENED charges under an effective core potential (init_guess.py:95 relies on it); here
+        # `ecp` is simply {symbol: effective charge}, which supercell.get_supercell copies to the supercell like pyscf's
+        if isinstance(self.ecp, dict):
+            return np.asarray([float(self.ecp.get(n, _Z.get(n, 0))) for n, _ in self._atom])
         return np.asarray([float(_Z[n]) for n, _ in self._atom])
 
     def energy_nuc(self):
@@ -390,6 +390,16 @@ def install():
                 return orig(a, _t(b) if isinstance(b, np.ndarray) else b)
             return op
         setattr(torch.Tensor, name, make(getattr(torch.Tensor, name)))
+    _orig_transpose = torch.Tensor.transpose
+
+    def _np_transpose(self, *axes):                 # ndarray.transpose(axes) (network.py:353-354)
+        if len(axes) == 1 and isinstance(axes[0], (tuple, list)):
+            return self.permute(*axes[0])
+        if len(axes) > 2:
+            return self.permute(*axes)
+        return _orig_transpose(self, *axes)
+
+    torch.Tensor.transpose = _np_transpose
     torch.Tensor.__matmul__ = _promoting_matmul
     torch.Tensor.__rmatmul__ = lambda b, a: _promoting_matmul(_t(a), b)
     sys.modules["jax"] = jax

@@ -201,6 +201,8 @@ def test_gpu_kfac_momentum_follows_the_reference_recursion():
         outs[m] = (flat(p1), flat(p2))
     p0 = [torch.as_tensor(t).double() for t in kfac.flatten_params(P)]
     for a0, a1, b1, a2, b2 in zip(p0, outs[0.5][0], outs[0.0][0], outs[0.5][1], outs[0.0][1]):
-        assert torch.equal(a1, b1)
+        # (the envelope gradients are accumulated with atomics: equal to rounding, not bit for bit)
+        assert float((a1 - b1).abs().max()) <= 1e-12 * max(float(a1.abs().max()), 1.0)
         delta1 = a1 - a0.cpu()
-        assert _rel(a2 - b2, 0.5 * delta1) < 1e-9 or float((a2 - b2 - 0.5 * delta1).abs().max()) < 1e-14
+        err = float((a2 - b2 - 0.5 * delta1).abs().max())
+        assert err <= 1e-6 * float(delta1.abs().max()) + 1e-13, (err, float(delta1.abs().max()))
