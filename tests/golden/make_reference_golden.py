@@ -162,7 +162,8 @@ def run_reference(S, batch, steps, burn, seed, ref_path):
 SHIM_CASES = {
     # the cell of the reference's own tests (test/test_cell.py), all three Laplacian modes
     "reference_shim_lih_s111": dict(system="test_cell_lih", S=np.eye(3), batch=4, steps=3, burn=10),
-    "reference_shim_lih_s211": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=4, steps=3, burn=10),
+    "reference_shim_lih_s211": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=4, steps=3, burn=10,
+                                    total_energy=True),
     # the structural options of make_solid_fermi_net
     "reference_shim_lih_tri": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
                                    opts=dict(distance_type="tri"), modes=("for",)),
@@ -176,6 +177,12 @@ SHIM_CASES = {
                                     opts=dict(bias_orbitals=True), modes=("for",)),
     "reference_shim_lih_lastlayer": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
                                          opts=dict(use_last_layer=True), modes=("for",)),
+    # minimal-image branches no config file reaches (distance.py:41-59, 91-108): an orthogonal lattice
+    # that is not diagonal, and an obtuse one that the reference ALSO classifies as orthogonal (dot < tol without abs)
+    "reference_shim_ortho": dict(custom=dict(a=[[3.0, 3.0, 0.0], [-2.0, 2.0, 0.0], [0.0, 0.0, 5.0]]), S=np.diag([2.0, 1.0, 1.0]),
+                                 batch=3, steps=2, burn=4, modes=("for",), init_width=1.5),
+    "reference_shim_obtuse": dict(custom=dict(a=[[4.0, 0.0, 0.0], [-1.9, 4.2, 0.0], [-1.5, -1.8, 5.0]]), S=np.diag([2.0, 1.0, 1.0]),
+                                  batch=3, steps=2, burn=4, modes=("for",), init_width=1.5),
     # BASELINE.json configurations (SURVEY 8 d), one or two walkers each at full size
     "reference_shim_h10": dict(system="h10", batch=2, steps=2, burn=4, modes=("for", "partition")),
     "reference_shim_li24": dict(system="li24", batch=2, steps=1, burn=2, modes=("for",)),
@@ -207,9 +214,15 @@ def run_shim(case, seed):
     batch, steps, burn = case["batch"], case["steps"], case["burn"]
     opts = dict(case.get("opts", {}))
     modes = tuple(case.get("modes", ("for", "partition", "dim_batch")))
-    named = G.build_system(case["system"])
-    prim0 = named.original_cell
-    S = np.asarray(case.get("S", named.S), dtype=np.float64)
+    if "custom" in case:              # two He atoms at fixed fractional positions in the given lattice
+        lat = np.asarray(case["custom"]["a"], dtype=np.float64)
+        frac = np.array([[0.1, 0.15, 0.2], [0.6, 0.55, 0.7]])
+        prim0 = G.RefCell(lat, [("He", xyz) for xyz in frac @ lat], {"He": 2.0}, name="custom")
+        S = np.asarray(case["S"], dtype=np.float64)
+    else:
+        named = G.build_system(case["system"])
+        prim0 = named.original_cell
+        S = np.asarray(case.get("S", named.S), dtype=np.float64)
     # primitive cell -> the stand-in for pyscf.pbc.gto.Cell; the SUPERCELL is built by the reference (supercell.py:64-95)
     cell = shim.Cell()
     syms, charges = [], {}
@@ -250,7 +263,7 @@ def run_shim(case, seed):
     sim_atoms = simulation_cell.atom_coords()
     n_up, n_dn = simulation_cell.nelec
     idx = [i % len(sim_atoms) for i in range(n_up)] + [i % len(sim_atoms) for i in range(n_dn)]
-    x = sim_atoms[idx][None] + 0.8 * rng.standard_normal((batch, n_up + n_dn, 3))
+    x = sim_atoms[idx][None] + float(case.get("init_width", 0.8)) * rng.standard_normal((batch, n_up + n_dn, 3))
     frac = x @ np.linalg.inv(latvec)
     data = torch.as_tensor(((frac - np.floor(frac)) @ latvec).reshape(batch, -1))
 
@@ -281,6 +294,20 @@ def run_shim(case, seed):
         kes, ews = zip(*[el(params, data[b]) for b in range(batch)])
         out[f"ke_{mode}"] = np.asarray([complex(k) for k in kes])
         out[f"ewald_{mode}"] = np.asarray([float(e) for e in ews])
+    if case.get("total_energy", False):
+        # train.make_loss(...).total_energy forward (train.py:37-89): loss, variance (mean of local variances quirk is a
+        # multi-device matter: one device here), imaginary part and the per-walker aux
+        from DeepSolid import train
+        shim.LOOP_VMAP = True
+        try:
+            te = train.make_loss(nets["eval_logdet"].apply, None, simulation_cell, clip_local_energy=5.0,
+                                 clip_type="real", mode=modes[0], partition_number=pn)
+            loss, aux = te(params, data)
+        finally:
+            shim.LOOP_VMAP = False
+        out.update(te_loss=np.float64(float(loss)), te_variance=np.float64(float(aux.variance)),
+                   te_imaginary=np.float64(float(aux.imaginary)),
+                   te_local_energy=aux.local_energy.numpy().astype(np.complex128))
     ewald = ewaldsum.EwaldSum(simulation_cell)
     parts = [ewald.energy(data[b]) for b in range(batch)]
     out["ee"], out["ei"], out["ii"] = (np.asarray([float(p[i]) for p in parts]) for i in range(3))

@@ -195,7 +195,30 @@ jnp.linalg.slogdet = lambda x: tuple(torch.linalg.slogdet(_t(x)))
 jax = types.ModuleType("jax")
 jax.numpy = jnp
 jax.jit = lambda f, *a, **k: f
-jax.vmap = lambda f, in_axes=0, out_axes=0: torch.func.vmap(f, in_dims=in_axes, out_dims=out_axes)
+LOOP_VMAP = False          # True: jax.vmap as a Python loop + stack (always valid for pure functions; used for the
+                           # batch-level vmap of train.make_loss, whose body indexes with data-dependent integers)
+
+
+def _loop_vmap(f, in_axes=0, out_axes=0):
+    tm = torch.utils._pytree.tree_map
+    leaves = torch.utils._pytree.tree_leaves
+
+    def g(*args):
+        axes = tuple(in_axes) if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+        assert all(ax in (None, 0) for ax in axes) and out_axes == 0
+        n = next(leaves(a)[0].shape[0] for a, ax in zip(args, axes) if ax == 0)
+        outs = [f(*[tm(lambda t: t[i], a) if ax == 0 else a for a, ax in zip(args, axes)]) for i in range(n)]
+        return tm(lambda *ls: torch.stack([_t(v) for v in ls]), *outs)
+    return g
+
+
+def _vmap(f, in_axes=0, out_axes=0):
+    if LOOP_VMAP:
+        return _loop_vmap(f, in_axes, out_axes)
+    return torch.func.vmap(f, in_dims=in_axes, out_dims=out_axes)
+
+
+jax.vmap = _vmap
 jax.grad = lambda f, argnums=0, holomorphic=False, has_aux=False: torch.func.grad(f, argnums=argnums, has_aux=has_aux)
 jax.value_and_grad = lambda f, argnums=0, has_aux=False: torch.func.grad_and_value_swapped(f, argnums, has_aux)
 jax.hessian = lambda f, argnums=0: torch.func.hessian(f, argnums=argnums)
@@ -283,7 +306,24 @@ def _axis_frame(name):
 core.axis_frame = _axis_frame
 jax.core = core
 jax.pmap = lambda f, axis_name=None, **k: f
-jax.custom_jvp = lambda f=None, **k: f if f is not None else (lambda g: g)
+
+
+class _CustomJvp:
+    """jax.custom_jvp for forward evaluation: calls the function; `.defjvp` records the rule and returns it."""
+
+    def __init__(self, f):
+        self.f = f
+        functools.update_wrapper(self, f)
+
+    def __call__(self, *a, **k):
+        return self.f(*a, **k)
+
+    def defjvp(self, rule):
+        self.jvp_rule = rule
+        return rule
+
+
+jax.custom_jvp = _CustomJvp
 jax.local_device_count = lambda: 1
 jax.host_id = lambda: 0
 
@@ -426,3 +466,13 @@ def install():
     tags.register_qmc = tags.register_qmc1
     sys.modules["DeepSolid.curvature_tags_and_blocks"] = tags
     pkg.curvature_tags_and_blocks = tags
+    # train.py:25,133: the KFAC loss tag (identity on values)
+    utils_pkg = types.ModuleType("DeepSolid.utils")
+    utils_pkg.__path__ = [REF_ROOT + "/DeepSolid/utils"]
+    kfa = types.ModuleType("DeepSolid.utils.kfac_ferminet_alpha")
+    kfa.__path__ = []
+    lf = types.ModuleType("DeepSolid.utils.kfac_ferminet_alpha.loss_functions")
+    lf.register_normal_predictive_distribution = lambda mean, **k: mean
+    kfa.loss_functions = lf
+    sys.modules.update({"DeepSolid.utils": utils_pkg, "DeepSolid.utils.kfac_ferminet_alpha": kfa,
+                        "DeepSolid.utils.kfac_ferminet_alpha.loss_functions": lf})
