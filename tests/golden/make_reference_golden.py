@@ -163,7 +163,7 @@ SHIM_CASES = {
     # the cell of the reference's own tests (test/test_cell.py), all three Laplacian modes
     "reference_shim_lih_s111": dict(system="test_cell_lih", S=np.eye(3), batch=4, steps=3, burn=10),
     "reference_shim_lih_s211": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=4, steps=3, burn=10,
-                                    total_energy=True),
+                                    total_energy=True, moves=True),
     # the structural options of make_solid_fermi_net
     "reference_shim_lih_tri": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
                                    opts=dict(distance_type="tri"), modes=("for",)),
@@ -308,6 +308,20 @@ def run_shim(case, seed):
         out.update(te_loss=np.float64(float(loss)), te_variance=np.float64(float(aux.variance)),
                    te_imaginary=np.float64(float(aux.imaginary)),
                    te_local_energy=aux.local_energy.numpy().astype(np.complex128))
+        # the energy-gradient estimator: the reference's custom JVP rule (train.py:90-142) applied to a fixed parameter
+        # tangent T gives sum_leaves <grad, T>; T = a second parameter-shaped numpy draw (seed stored)
+        tangent = O.params_to_torch(O.init_params(np.random.default_rng(seed + 7), cell.natm, simulation_cell.nelec, **init_kw))
+        batch_logdet = batched(nets["eval_logdet"].apply)
+        for clip_type in ("real", "complex"):
+            shim.LOOP_VMAP = True
+            try:
+                te = train.make_loss(nets["eval_logdet"].apply, batch_logdet, simulation_cell, clip_local_energy=5.0,
+                                     clip_type=clip_type, mode=modes[0], partition_number=pn)
+                _, (tdot, _) = te.jvp_rule((params, data), (tangent, torch.zeros_like(data)))
+            finally:
+                shim.LOOP_VMAP = False
+            out[f"te_jvp_{clip_type}"] = np.float64(float(tdot))
+        out["tangent_seed"] = np.int64(seed + 7)
     ewald = ewaldsum.EwaldSum(simulation_cell)
     parts = [ewald.energy(data[b]) for b in range(batch)]
     out["ee"], out["ei"], out["ii"] = (np.asarray([float(p[i]) for p in parts]) for i in range(3))
@@ -327,6 +341,31 @@ def run_shim(case, seed):
         x1, lp = x_new, lp_new
     out.update(xi=np.stack(xi), u=np.stack(u), masks=np.stack(masks), x_new=x1.numpy().astype(np.float64),
                pmove=np.float64(float(nacc) / (steps * batch)), width=np.float64(width))     # qmc.py:360
+
+    if case.get("moves", False):
+        # secondary samplers through the reference's own driver (qmc.py:290-364): one-electron Metropolis moves
+        # (mh_one_electron_update, qmc.py:227-287) and drift-diffusion importance sampling (importance_update +
+        # limdrift, qmc.py:63-150); the driver only returns the final walkers and pmove, which is what is stored
+        nel = n_up + n_dn
+        oe_steps, imp_steps = 1, 2
+        oe_xi = rng.standard_normal((oe_steps * nel, batch, 1, 3))
+        oe_u = rng.random((oe_steps * nel, batch))
+        shim.set_random_queue([a for pair in zip(oe_xi, oe_u) for a in pair])
+        step = qmc.make_mcmc_step(batch_slog, batch, latvec=latvec, steps=oe_steps, one_electron_moves=True)
+        oe_x, oe_p = step(params, data, key, 0.3)
+        imp_xi = rng.standard_normal((imp_steps, batch, 3 * nel))
+        imp_u = rng.random((imp_steps, batch))
+        shim.set_random_queue([a for pair in zip(imp_xi, imp_u) for a in pair])
+        shim.LOOP_VMAP = True
+        try:
+            step = qmc.make_mcmc_step(batch_slog, batch, latvec=latvec, steps=imp_steps,
+                                      importance_sampling=nets["eval_slogdet"].apply)
+            imp_x, imp_p = step(params, data, key, 0.2)
+        finally:
+            shim.LOOP_VMAP = False
+        out.update(oe_xi=oe_xi[:, :, 0, :], oe_u=oe_u, oe_x_new=oe_x.numpy().astype(np.float64), oe_pmove=np.float64(float(oe_p)),
+                   oe_width=np.float64(0.3), imp_xi=imp_xi, imp_u=imp_u, imp_x_new=imp_x.numpy().astype(np.float64),
+                   imp_pmove=np.float64(float(imp_p)), imp_width=np.float64(0.2))
 
     prim = simulation_cell.original_cell
     flat = _flatten({g: [{k: v.numpy() for k, v in d.items()} for d in params[g]] for g in params})

@@ -177,7 +177,17 @@ jnp.eye = lambda n, dtype=None: torch.eye(int(n), dtype=F64)
 jnp.ones = lambda shape, dtype=None: torch.ones(shape, dtype=F64)
 jnp.zeros = lambda shape, dtype=None: torch.zeros(shape, dtype=F64)
 jnp.where = lambda c, a, b: torch.where(c, _t(a), _t(b))
-jnp.clip = lambda x, a=None, b=None: torch.clamp(_t(x), a, b)
+
+
+def _clip(x, a=None, b=None, a_min=None, a_max=None):
+    lo = a if a is not None else a_min
+    hi = b if b is not None else a_max
+    lo = float(lo) if isinstance(lo, torch.Tensor) and lo.dim() == 0 else lo
+    hi = float(hi) if isinstance(hi, torch.Tensor) and hi.dim() == 0 else hi
+    return torch.clamp(_t(x), lo, hi)
+
+
+jnp.clip = _clip
 jnp.diagonal = lambda x, offset=0, axis1=0, axis2=1: torch.diagonal(_t(x), offset=offset, dim1=axis1, dim2=axis2)
 jnp.allclose = lambda a, b, rtol=1e-5, atol=1e-8: bool(torch.allclose(_t(a, F64), _t(b, F64), rtol=rtol, atol=atol))
 jnp.median = lambda x: torch.quantile(_t(x), 0.5)            # numpy's median (mean of the middle pair)
@@ -237,7 +247,8 @@ torch.func.grad_and_value_swapped = _grad_and_value_swapped
 
 
 def _jvp(f, primals, tangents):
-    return torch.func.jvp(f, tuple(_t(p) for p in primals), tuple(_t(t) for t in tangents))
+    tm = torch.utils._pytree.tree_map                       # primals / tangents may be pytrees (train.py:129)
+    return torch.func.jvp(f, tuple(tm(_t, p) for p in primals), tuple(tm(_t, t) for t in tangents))
 
 
 jax.jvp = _jvp
@@ -408,10 +419,34 @@ class _SizeDescriptor:
         return _orig_size if obj is None else _SizeProxy(obj)
 
 
+class _AtIndex:
+    def __init__(self, t, idx):
+        self.t, self.idx = t, idx
+
+    def add(self, v):                       # x.at[idx].add(v): functional update (qmc.py:269)
+        out = self.t.clone()
+        out[self.idx] = out[self.idx] + _t(v)
+        return out
+
+    def set(self, v):
+        out = self.t.clone()
+        out[self.idx] = _t(v)
+        return out
+
+
+class _At:
+    def __init__(self, t):
+        self.t = t
+
+    def __getitem__(self, idx):
+        return _AtIndex(self.t, idx)
+
+
 def install():
     """Put the stand-ins into sys.modules and make ``DeepSolid`` importable from /root/reference without running any
     module that needs the real JAX / pyscf / chex."""
     torch.Tensor.size = _SizeDescriptor()           # this process only (the generator script)
+    torch.Tensor.at = property(lambda self: _At(self))
     _orig_mm = torch.Tensor.__matmul__
 
     def _promoting_matmul(a, b):                    # `@` with jax's int / float / complex promotion (distance.py:68)

@@ -35,6 +35,13 @@ def case_opts(g):
     return json.loads(str(g["opts"])) if "opts" in g.files else {}
 
 
+def tangent_of(g, sc):
+    """The fixed parameter tangent of the gradient pin: a parameter-shaped numpy draw from the stored seed."""
+    o = case_opts(g)
+    ikw = {k: o[k] for k in ("envelope_type", "bias_orbitals", "use_last_layer", "full_det", "distance_type") if k in o}
+    return O.params_to_torch(O.init_params(np.random.default_rng(int(g["tangent_seed"])), sc.original_cell.natm, sc.nelec, **ikw))
+
+
 def case_modes(g):
     return tuple(str(g["modes"]).split(",")) if "modes" in g.files else ("for", "partition", "dim_batch")
 
@@ -101,6 +108,26 @@ def check_oracle(g, sc, klist, P, tol_e=1e-9, max_walkers=None, kinetic=True):
         loss, imag, var = O.total_energy_stats(torch.stack([torch.as_tensor(k) for k in kes]), torch.stack([torch.as_tensor(e) for e in ews]))
         assert abs(float(loss) - float(g["te_loss"])) < 1e-9 and abs(float(imag) - float(g["te_imaginary"])) < 1e-9
         assert abs(float(var) - float(g["te_variance"])) < 1e-8 * max(1.0, abs(float(g["te_variance"])))
+    if "te_jvp_real" in g.files and kinetic:      # train.py:90-142: <gradient estimator, fixed tangent>
+        T = tangent_of(g, sc)
+        f = O.make_solid_fermi_net(klist, sc, method_name="eval_phase_and_slogdet", **case_opts(g))
+        el = O.local_energy_seperate(nets["eval_logdet"], sc, mode=case_modes(g)[0], partition_number=pnum)
+        for clip_type in ("real", "complex"):
+            _, _, grads = O.total_energy_value_and_grad(f, el, P, X, clip_local_energy=5.0, clip_type=clip_type)
+            dot = sum(float((a * b).sum()) for a, b in zip(O._leaves(grads), O._leaves(T)))
+            want = float(g[f"te_jvp_{clip_type}"])
+            assert abs(dot - want) < 1e-8 * max(1.0, abs(want)), (clip_type, dot, want)
+    if "oe_x_new" in g.files:            # one-electron moves and importance sampling (qmc.py:63-150, 227-287)
+        lat = torch.as_tensor(sc.lattice_vectors())
+        B0 = X.shape[0]
+        N = sum(sc.nelec)
+        bs = lambda p, x: O.batch_apply(nets["eval_slogdet"], p, x)
+        xo, po, _ = O.make_mcmc_step_one_electron(bs, B0, lat, steps=g["oe_u"].shape[0] // N)(
+            P, X, (torch.as_tensor(g["oe_xi"]), torch.as_tensor(g["oe_u"])), float(g["oe_width"]))
+        assert np.abs(xo.numpy() - g["oe_x_new"]).max() < 1e-12 and abs(float(po) - float(g["oe_pmove"])) < 1e-15
+        xo, po, _ = O.make_mcmc_step_importance(nets["eval_slogdet"], B0, lat, steps=g["imp_u"].shape[0])(
+            P, X, (torch.as_tensor(g["imp_xi"]), torch.as_tensor(g["imp_u"])), float(g["imp_width"]))
+        assert np.abs(xo.numpy() - g["imp_x_new"]).max() < 1e-9 and abs(float(po) - float(g["imp_pmove"])) < 1e-15
     steps, B = g["u"].shape
     mc = O.make_mcmc_step(lambda p, x: O.batch_apply(nets["eval_slogdet"], p, x), B, sc.lattice_vectors(), steps=steps)
     xn, pmove, masks = mc(P, X, (torch.as_tensor(g["xi"]), torch.as_tensor(g["u"])), float(g["width"]))
@@ -135,8 +162,27 @@ def check_gpu(g, sc, klist, P):
         assert abs(float(loss) - float(g["te_loss"])) < 1e-8 and abs(float(aux.imaginary) - float(g["te_imaginary"])) < 1e-8
         assert abs(float(aux.variance) - float(g["te_variance"])) < 1e-7 * max(1.0, abs(float(g["te_variance"])))
         assert np.abs(aux.local_energy.cpu().numpy() - g["te_local_energy"]).max() < 1e-8
+    if "te_jvp_real" in g.files:
+        from deepsolid_b200 import train
+        T = tangent_of(g, sc)
+        for clip_type in ("real", "complex"):
+            lossf = train.make_loss(ld.apply, ld.apply, sc, clip_local_energy=5.0, clip_type=clip_type,
+                                    mode=case_modes(g)[0], partition_number=pnum)
+            _, grads = lossf.value_and_grad(P, X)
+            dot = sum(float((torch.as_tensor(a).cpu() * b).sum()) for a, b in zip(O._leaves(grads), O._leaves(T)))
+            want = float(g[f"te_jvp_{clip_type}"])
+            assert abs(dot - want) < 1e-7 * max(1.0, abs(want)), (clip_type, dot, want)
     ee, ei, ii = hp.ewald(X)
     assert np.abs(ee.cpu().numpy() - g["ee"]).max() < 1e-10 and np.abs(ei.cpu().numpy() - g["ei"]).max() < 1e-10
+    if "oe_x_new" in g.files:
+        lat = torch.as_tensor(sc.lattice_vectors())
+        B0, N = X.shape[0], sum(sc.nelec)
+        st = qmc.make_mcmc_step(sl.apply, B0, lat, steps=g["oe_u"].shape[0] // N, one_electron_moves=True)
+        xn, pm = st(P, X, (torch.as_tensor(g["oe_xi"]), torch.as_tensor(g["oe_u"])), float(g["oe_width"]))
+        assert np.abs(xn.cpu().numpy() - g["oe_x_new"]).max() < 1e-12 and abs(float(pm) - float(g["oe_pmove"])) < 1e-15
+        st = qmc.make_mcmc_step(sl.apply, B0, lat, steps=g["imp_u"].shape[0], importance_sampling=sl.apply)
+        xn, pm = st(P, X, (torch.as_tensor(g["imp_xi"]), torch.as_tensor(g["imp_u"])), float(g["imp_width"]))
+        assert np.abs(xn.cpu().numpy() - g["imp_x_new"]).max() < 1e-9 and abs(float(pm) - float(g["imp_pmove"])) < 1e-15
     steps, B = g["u"].shape
     step = qmc.make_mcmc_step(sl.apply, B, sc.lattice_vectors(), steps=steps)
     xn, pmove, masks = step(P, X, (torch.as_tensor(g["xi"]), torch.as_tensor(g["u"])), float(g["width"]), return_masks=True)
