@@ -163,7 +163,7 @@ SHIM_CASES = {
     # the cell of the reference's own tests (test/test_cell.py), all three Laplacian modes
     "reference_shim_lih_s111": dict(system="test_cell_lih", S=np.eye(3), batch=4, steps=3, burn=10),
     "reference_shim_lih_s211": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=4, steps=3, burn=10,
-                                    total_energy=True, moves=True),
+                                    total_energy=True, moves=True, observables=True),
     # the structural options of make_solid_fermi_net
     "reference_shim_lih_tri": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
                                    opts=dict(distance_type="tri"), modes=("for",)),
@@ -366,6 +366,12 @@ def run_shim(case, seed):
         out.update(oe_xi=oe_xi[:, :, 0, :], oe_u=oe_u, oe_x_new=oe_x.numpy().astype(np.float64), oe_pmove=np.float64(float(oe_p)),
                    oe_width=np.float64(0.3), imp_xi=imp_xi, imp_u=imp_u, imp_x_new=imp_x.numpy().astype(np.float64),
                    imp_pmove=np.float64(float(imp_p)), imp_width=np.float64(0.2))
+
+    if case.get("observables", False):              # estimator.py:15-85 on the walkers of the file
+        from DeepSolid import estimator
+        out["obs_sk"] = estimator.make_structure_factor(simulation_cell, nq=3)(data).numpy().astype(np.float64)
+        out["obs_pol"] = np.asarray([complex(estimator.make_complex_polarization(simulation_cell, direction=d)(data))
+                                     for d in range(3)])
 
     prim = simulation_cell.original_cell
     flat = _flatten({g: [{k: v.numpy() for k, v in d.items()} for d in params[g]] for g in params})

@@ -117,6 +117,10 @@ def check_oracle(g, sc, klist, P, tol_e=1e-9, max_walkers=None, kinetic=True):
             dot = sum(float((a * b).sum()) for a, b in zip(O._leaves(grads), O._leaves(T)))
             want = float(g[f"te_jvp_{clip_type}"])
             assert abs(dot - want) < 1e-8 * max(1.0, abs(want)), (clip_type, dot, want)
+    if "obs_sk" in g.files:              # estimator.py:15-85
+        assert np.abs(O.make_structure_factor(sc, nq=3)(X).numpy() - g["obs_sk"]).max() < 1e-12
+        for d in range(3):
+            assert abs(complex(O.make_complex_polarization(sc, direction=d)(X)) - g["obs_pol"][d]) < 1e-12
     if "oe_x_new" in g.files:            # one-electron moves and importance sampling (qmc.py:63-150, 227-287)
         lat = torch.as_tensor(sc.lattice_vectors())
         B0 = X.shape[0]
@@ -174,6 +178,12 @@ def check_gpu(g, sc, klist, P):
             assert abs(dot - want) < 1e-7 * max(1.0, abs(want)), (clip_type, dot, want)
     ee, ei, ii = hp.ewald(X)
     assert np.abs(ee.cpu().numpy() - g["ee"]).max() < 1e-10 and np.abs(ei.cpu().numpy() - g["ei"]).max() < 1e-10
+    if "obs_sk" in g.files:
+        from deepsolid_b200 import estimator
+        assert np.abs(estimator.make_structure_factor(sc, nq=3, hotpath=hp)(X).cpu().numpy() - g["obs_sk"]).max() < 1e-12
+        for d in range(3):
+            pol = estimator.make_complex_polarization(sc, direction=d, hotpath=hp)(X).cpu()
+            assert abs(complex(pol) - g["obs_pol"][d]) < 1e-12
     if "oe_x_new" in g.files:
         lat = torch.as_tensor(sc.lattice_vectors())
         B0, N = X.shape[0], sum(sc.nelec)
