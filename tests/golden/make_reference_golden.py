@@ -163,7 +163,7 @@ SHIM_CASES = {
     # the cell of the reference's own tests (test/test_cell.py), all three Laplacian modes
     "reference_shim_lih_s111": dict(system="test_cell_lih", S=np.eye(3), batch=4, steps=3, burn=10),
     "reference_shim_lih_s211": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=4, steps=3, burn=10,
-                                    total_energy=True, moves=True, observables=True),
+                                    total_energy=True, moves=True, observables=True, pretrain=True),
     # the structural options of make_solid_fermi_net
     "reference_shim_lih_tri": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
                                    opts=dict(distance_type="tri"), modes=("for",)),
@@ -172,7 +172,7 @@ SHIM_CASES = {
     "reference_shim_lih_fullenv": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
                                        opts=dict(envelope_type="full"), modes=("for",)),
     "reference_shim_lih_fulldet": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
-                                       opts=dict(full_det=True), modes=("for",)),
+                                       opts=dict(full_det=True), modes=("for",), pretrain=True),
     "reference_shim_lih_bias": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
                                     opts=dict(bias_orbitals=True), modes=("for",)),
     "reference_shim_lih_lastlayer": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
@@ -366,6 +366,33 @@ def run_shim(case, seed):
         out.update(oe_xi=oe_xi[:, :, 0, :], oe_u=oe_u, oe_x_new=oe_x.numpy().astype(np.float64), oe_pmove=np.float64(float(oe_p)),
                    oe_width=np.float64(0.3), imp_xi=imp_xi, imp_u=imp_u, imp_x_new=imp_x.numpy().astype(np.float64),
                    imp_pmove=np.float64(float(imp_p)), imp_width=np.float64(0.2))
+
+    if case.get("pretrain", False):
+        # pretraining loss and its parameter gradient (pretrain.py:43-107) through the reference's make_pretrain_step: the
+        # optimiser handed in only records the search direction (zero update), so the step returns the loss at `params`
+        from DeepSolid import pretrain as rpre
+        full_det = bool(opts.get("full_det", False))
+        target = [torch.as_tensor(rng.standard_normal((batch, ns, ns)) + 1j * rng.standard_normal((batch, ns, ns)))
+                  for ns in simulation_cell.nelec]
+        captured = {}
+
+        class RecordingOptimizer:
+            def update(self, grads, state, params=None):
+                captured["g"] = grads
+                return torch.utils._pytree.tree_map(torch.zeros_like, grads), state
+
+        def batch_mats(p, xs):
+            per = [nets["eval_mats"].apply(p, xs[b]) for b in range(xs.shape[0])]
+            return [torch.stack([m[s] for m in per]) for s in range(len(per[0]))]
+
+        pstep = rpre.make_pretrain_step(batch_mats, batch_slog, latvec, RecordingOptimizer(), full_det=full_det)
+        shim.set_random_queue([rng.standard_normal(tuple(data.shape)), rng.random((batch,))])
+        _, _, _, pt_loss, _, _ = pstep(data, target, params, None, key)
+        tangent = O.params_to_torch(O.init_params(np.random.default_rng(seed + 7), cell.natm, simulation_cell.nelec, **init_kw))
+        gl, tl = O._leaves(captured["g"]), O._leaves(tangent)
+        out.update(pt_target0=target[0].numpy(), pt_target1=target[1].numpy(), pt_loss=np.float64(float(pt_loss)),
+                   pt_dot=np.float64(sum(float((a * b).sum()) for a, b in zip(gl, tl))),
+                   pt_norms=np.asarray([float(a.norm()) for a in gl]), tangent_seed=np.int64(seed + 7))
 
     if case.get("observables", False):              # estimator.py:15-85 on the walkers of the file
         from DeepSolid import estimator

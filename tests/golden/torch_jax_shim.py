@@ -501,6 +501,22 @@ def install():
     tags.register_qmc = tags.register_qmc1
     sys.modules["DeepSolid.curvature_tags_and_blocks"] = tags
     pkg.curvature_tags_and_blocks = tags
+    # pretrain.py:24-28 imports optax and DeepSolid.hf (pyscf SCF) at module level; make_pretrain_step itself only needs
+    # optax.apply_updates (params + updates) -- the optimiser object is the caller's
+    optax = types.ModuleType("optax")
+    optax.apply_updates = lambda params, updates: torch.utils._pytree.tree_map(lambda p, u: p + u, params, updates)
+    sys.modules["optax"] = optax
+    hf = types.ModuleType("DeepSolid.hf")
+    hf.SCF = type("SCF", (), {})
+    sys.modules["DeepSolid.hf"] = hf
+    pkg.hf = hf
+    try:
+        import absl.logging  # noqa: F401
+    except Exception:
+        absl = types.ModuleType("absl")
+        import logging as _logging
+        absl.logging = _logging
+        sys.modules.update({"absl": absl, "absl.logging": _logging})
     # train.py:25,133: the KFAC loss tag (identity on values)
     utils_pkg = types.ModuleType("DeepSolid.utils")
     utils_pkg.__path__ = [REF_ROOT + "/DeepSolid/utils"]

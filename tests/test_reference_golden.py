@@ -117,6 +117,16 @@ def check_oracle(g, sc, klist, P, tol_e=1e-9, max_walkers=None, kinetic=True):
             dot = sum(float((a * b).sum()) for a, b in zip(O._leaves(grads), O._leaves(T)))
             want = float(g[f"te_jvp_{clip_type}"])
             assert abs(dot - want) < 1e-8 * max(1.0, abs(want)), (clip_type, dot, want)
+    if "pt_loss" in g.files:             # pretrain.py:43-107: loss and parameter gradient of the orbital matching
+        full_det = bool(case_opts(g).get("full_det", False))
+        target = [torch.as_tensor(g["pt_target0"]), torch.as_tensor(g["pt_target1"])]
+        loss, grads = O.pretrain_loss_and_grad(nets["eval_mats"], P, X, target, full_det)
+        T = tangent_of(g, sc)
+        dot = sum(float((a * b).sum()) for a, b in zip(O._leaves(grads), O._leaves(T)))
+        assert abs(float(loss) - float(g["pt_loss"])) < 1e-11 * max(1.0, abs(float(g["pt_loss"])))
+        assert abs(dot - float(g["pt_dot"])) < 1e-9 * max(1.0, abs(float(g["pt_dot"])))
+        norms = np.asarray([float(a.norm()) for a in O._leaves(grads)])
+        assert np.abs(norms - g["pt_norms"]).max() < 1e-9 * max(1.0, float(g["pt_norms"].max()))
     if "obs_sk" in g.files:              # estimator.py:15-85
         assert np.abs(O.make_structure_factor(sc, nq=3)(X).numpy() - g["obs_sk"]).max() < 1e-12
         for d in range(3):
@@ -178,6 +188,19 @@ def check_gpu(g, sc, klist, P):
             assert abs(dot - want) < 1e-7 * max(1.0, abs(want)), (clip_type, dot, want)
     ee, ei, ii = hp.ewald(X)
     assert np.abs(ee.cpu().numpy() - g["ee"]).max() < 1e-10 and np.abs(ei.cpu().numpy() - g["ei"]).max() < 1e-10
+    if "pt_loss" in g.files:
+        from deepsolid_b200 import pretrain
+        full_det = bool(case_opts(g).get("full_det", False))
+        target = [torch.as_tensor(g["pt_target0"]).to(dev), torch.as_tensor(g["pt_target1"]).to(dev)]
+        hp.set_params(P)
+        loss, cots = pretrain.pretrain_loss_cotangent(hp.orbitals(X), target, full_det)
+        grads = hp.orbitals_vjp(X, cots)
+        T = tangent_of(g, sc)
+        dot = sum(float((torch.as_tensor(a).cpu() * b).sum()) for a, b in zip(O._leaves(grads), O._leaves(T)))
+        assert abs(float(loss) - float(g["pt_loss"])) < 1e-10 * max(1.0, abs(float(g["pt_loss"])))
+        assert abs(dot - float(g["pt_dot"])) < 1e-8 * max(1.0, abs(float(g["pt_dot"])))
+        norms = np.asarray([float(torch.as_tensor(a).norm()) for a in O._leaves(grads)])
+        assert np.abs(norms - g["pt_norms"]).max() < 1e-8 * max(1.0, float(g["pt_norms"].max()))
     if "obs_sk" in g.files:
         from deepsolid_b200 import estimator
         assert np.abs(estimator.make_structure_factor(sc, nq=3, hotpath=hp)(X).cpu().numpy() - g["obs_sk"]).max() < 1e-12
