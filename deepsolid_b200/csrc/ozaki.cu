@@ -496,7 +496,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     __shared__ unsigned xown[JD ? 2 : 1][4][4][16], xpm[JD ? 2 : 1][4][16], xrem[JD ? 2 : 1][64];
     __shared__ __align__(8) uint64_t xbar[JD ? 2 : 1][4];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (the shuffle tells the compiler that `warp` is warp-uniform: role branches become uniform branches and the epilogue keeps
+    //  its memory descriptors and loop state in uniform registers instead of re-materialising them per access)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int nkb = p.K / OZ_BK;
     constexpr int ndiag = ND;                            // 6; 5 is an accuracy / speed experiment (DS_OZ_DIAGS=5)
 
