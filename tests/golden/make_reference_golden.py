@@ -177,6 +177,11 @@ SHIM_CASES = {
                                     opts=dict(bias_orbitals=True), modes=("for",)),
     "reference_shim_lih_lastlayer": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=1, burn=4,
                                          opts=dict(use_last_layer=True), modes=("for",)),
+    # spin-polarised cell (n_up != n_dn: network.py:322-323 splits, per-spin orbital blocks) and twisted k-points
+    "reference_shim_lih_spin": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=2, burn=4,
+                                    spin=2, modes=("for",)),
+    "reference_shim_lih_twist": dict(system="test_cell_lih", S=np.diag([2.0, 1.0, 1.0]), batch=2, steps=2, burn=4,
+                                     twist=(0.13, -0.21, 0.34), modes=("for",)),
     # minimal-image branches no config file reaches (distance.py:41-59, 91-108): an orthogonal lattice
     # that is not diagonal, and an obtuse one that the reference ALSO classifies as orthogonal (dot < tol without abs)
     "reference_shim_ortho": dict(custom=dict(a=[[3.0, 3.0, 0.0], [-2.0, 2.0, 0.0], [0.0, 0.0, 5.0]]), S=np.diag([2.0, 1.0, 1.0]),
@@ -233,7 +238,7 @@ def run_shim(case, seed):
     cell.ecp = charges if any(abs(z - shim._Z.get(sym, -1)) > 1e-12 for sym, z in charges.items()) else None
     cell.a = np.asarray(prim0.lattice_vectors(), dtype=np.float64)
     cell.unit = "B"
-    cell.spin = int(prim0.nelec[0] - prim0.nelec[1])
+    cell.spin = int(case.get("spin", prim0.nelec[0] - prim0.nelec[1]))
     cell.basis, cell.exp_to_discard = "sto-3g", 0.1
     cell.build()
     simulation_cell = supercell.get_supercell(cell, S=S)
@@ -241,6 +246,8 @@ def run_shim(case, seed):
     # k-points of the supercell (supercell.py:32-48, reference code); occupation: the lowest-index k-points take the
     # remainder (the HF solution that orders them in the reference run is an input, not part of the hot path)
     kpts = np.asarray(supercell.get_supercell_kpts(simulation_cell), dtype=np.float64)
+    if "twist" in case:               # twisted boundary conditions: every k-point shifted by twist . b (base_config.py:140, hf.py:60-66)
+        kpts = kpts + np.asarray(case["twist"], dtype=np.float64) @ simulation_cell.reciprocal_vectors()
     klist = []
     for ns in simulation_cell.nelec:
         per, rem = divmod(ns, len(kpts))

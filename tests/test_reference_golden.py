@@ -50,7 +50,8 @@ def load_case(path):
     g = np.load(path, allow_pickle=False)
     prim = C.Cell(a=g["prim_a"], coords=g["prim_atoms"], charges=g["prim_charges"],
                   nelec=tuple(int(v) // int(round(abs(np.linalg.det(g["S"])))) for v in g["nelec"]))
-    sc = C.get_supercell(prim, g["S"])
+    scale = int(round(abs(np.linalg.det(g["S"]))))
+    sc = C.get_supercell(prim, g["S"], spin=(int(g["nelec"][0]) - int(g["nelec"][1])) // scale)
     params = {"single": [], "double": [], "orbital": [], "envelope": []}
     for key in g.files:
         if key.startswith("param/"):
