@@ -1,7 +1,7 @@
 """A torch-backed stand-in for the parts of ``jax`` / ``jax.numpy`` / ``pyscf.pbc.gto`` that the hot-path modules of
 bytedance/DeepSolid touch, so that the reference's OWN SOURCE FILES (network.py, hamiltonian.py, ewaldsum.py,
 distance.py, supercell.py, qmc.py, imported unmodified from /root/reference) can be executed in an image that has
-neither JAX nor pyscf.  Test infrastructure only: used by ``make_reference_shim_golden.py`` in the build container;
+neither JAX nor pyscf.  Test infrastructure only: used by ``make_reference_golden.py --backend shim`` in the build container;
 nothing on the GPU box imports it.
 
 What is substituted, and what is not:
